@@ -1,0 +1,182 @@
+/*
+ * orbfe.h — C-ABI of the B200-native ORB front-end (liborbfe.so).
+ *
+ * This is the drop-in boundary for the one data-parallel hot path of Whitby-Li/monoORBSLAM3:
+ *   - ORBExtractor::operator()            modules/ORB/ORBExtractor.h:38-39, ORBExtractor.cpp:495-547
+ *   - ORBMatcher::DescriptorDistance      modules/ORB/ORBMatcher.h:18,      ORBMatcher.cpp:17-31
+ *   - ORBMatcher::SearchForInitialization modules/ORB/ORBMatcher.h:21-23,   ORBMatcher.cpp:33-116
+ *   - ORBMatcher::SearchByProjection      modules/ORB/ORBMatcher.h:28-37,   ORBMatcher.cpp:203-415
+ *   - ORBMatcher::SearchForTriangulation  modules/ORB/ORBMatcher.h:40-42,   ORBMatcher.cpp:417-522
+ * Plain pointers and sizes only; no C++/torch types cross this boundary.  Every entry point returns an
+ * int status (ORBFE_OK or a negative ORBFE_E_*), never throws, and records a message retrievable with
+ * orbfe_last_error().  One handle per host thread (a handle owns its CUDA stream, device arena and tensor
+ * maps); entry points are re-entrant across handles.  There is NO CPU fallback: without a CUDA device
+ * orbfe_create() fails with ORBFE_E_CUDA.
+ *
+ * INTEGRATION.md shows the reference-side binding (the C++ adapter classes with the reference's own
+ * signatures, and the ctypes stub used by the Python host mirror).
+ */
+#ifndef ORBFE_H
+#define ORBFE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBFE_OK            0
+#define ORBFE_E_ARG        -1   /* invalid argument / unsupported geometry                */
+#define ORBFE_E_CUDA       -2   /* CUDA runtime/driver error (see orbfe_last_error)        */
+#define ORBFE_E_CAPACITY   -3   /* caller-provided output capacity too small               */
+#define ORBFE_E_INTERNAL   -4   /* device-side scratch overflow (reported, never silent)   */
+
+#define ORBFE_MAX_LEVELS   16
+
+/* flags for orbfe_config.flags */
+#define ORBFE_FLAG_NO_TMA      1u   /* stage tiles with 16-byte vector loads instead of TMA (A/B + debugging) */
+#define ORBFE_FLAG_KEEP_STAGES 2u   /* keep per-stage outputs readable through orbfe_get_* (parity tests)     */
+
+/* Layout-compatible with cv::KeyPoint (7 x 4 bytes) — what ORBExtractor::operator() fills (ORBExtractor.cpp:537-545). */
+typedef struct orbfe_keypoint {
+    float   x, y;       /* pt, already multiplied by scale_factors[octave] (ORBExtractor.cpp:537-542) */
+    float   size;       /* = scale_factors[octave] (ORBExtractor.cpp:631; sic, not 31*scale)          */
+    float   angle;      /* IC_Angle / fastAtan2 in degrees [0,360)                                    */
+    float   response;   /* FAST score                                                                 */
+    int32_t octave;
+    int32_t class_id;   /* -1 */
+} orbfe_keypoint;
+
+/* Constructor arguments of ORBExtractor (ORBExtractor.h:29-30) plus device selection. */
+typedef struct orbfe_config {
+    int32_t  n_features;     /* nFeatures   (default 1000) */
+    float    scale_factor;   /* scaleFactor (default 1.2f) */
+    int32_t  n_levels;       /* nLevels     (default 8, <= ORBFE_MAX_LEVELS) */
+    int32_t  ini_th_fast;    /* iniThFast   (default 20)   */
+    int32_t  min_th_fast;    /* minThFast   (default 10; the yaml files use 7) */
+    int32_t  device;         /* CUDA device ordinal */
+    int32_t  max_batch;      /* frames processed per device pass (arena is sized for this); >=1 */
+    uint32_t flags;          /* ORBFE_FLAG_* */
+} orbfe_config;
+
+typedef struct orbfe_handle orbfe_handle;
+
+/* ---------------------------------------------------------------- lifecycle */
+int         orbfe_create(const orbfe_config *cfg, orbfe_handle **out);
+void        orbfe_destroy(orbfe_handle *h);
+const char *orbfe_last_error(const orbfe_handle *h);   /* h may be NULL: last error of a failed create on this thread */
+const char *orbfe_version(void);
+
+/* Static tables of ORBExtractor (ORBExtractor.h:44-86): scale_factors[level], features per level. */
+float orbfe_scale_factor(const orbfe_handle *h, int level);
+int   orbfe_features_per_level(const orbfe_handle *h, int level);
+/* Upper bound on keypoints returned per frame (sum over levels of quota+3). */
+int   orbfe_max_keypoints(const orbfe_handle *h);
+
+/* Pinned host memory helpers (optional; any host pointer is accepted by the entry points below). */
+int   orbfe_host_alloc(void **ptr, size_t bytes);
+void  orbfe_host_free(void *ptr);
+
+/* ---------------------------------------------------------------- extractor
+ * orbfe_extract == ORBExtractor::operator()(image, keyPoints, descriptors) for one CV_8UC1 image.
+ *   gray/stride : host pointer to row 0 and row pitch in bytes
+ *   kps, desc   : caller-allocated, capacity `cap` keypoints / cap*32 bytes
+ *   n_out       : number of keypoints written.  As in the reference, an empty image or zero keypoints
+ *                 returns ORBFE_OK with *n_out = 0 and leaves kps/desc untouched (ORBExtractor.cpp:497,512).
+ */
+int orbfe_extract(orbfe_handle *h, const uint8_t *gray, int width, int height, size_t stride,
+                  orbfe_keypoint *kps, uint8_t *desc, int cap, int *n_out);
+
+/* The same over a batch of equally-sized frames in HOST memory (frame b at frames + b*frame_stride).
+ * Outputs are slabs: kps[b*cap .. b*cap+n_per_frame[b]), desc[(b*cap+i)*32 ..].  Host<->device copies
+ * are part of the call (this is what bench.py's e2e times). */
+int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, int width, int height,
+                        size_t row_stride, size_t frame_stride,
+                        orbfe_keypoint *kps, uint8_t *desc, int cap, int *n_per_frame);
+
+/* The same with frames and outputs already resident in DEVICE memory (what bench.py's `value` times).
+ * `stream` is a cudaStream_t (NULL = the handle's own stream); the call is asynchronous on that stream
+ * unless `sync` != 0.  n_frames may exceed max_batch (processed in passes). */
+int orbfe_extract_batch_device(orbfe_handle *h, const uint8_t *d_frames, int n_frames, int width, int height,
+                               size_t row_stride, size_t frame_stride,
+                               orbfe_keypoint *d_kps, uint8_t *d_desc, int cap, int *d_n_per_frame,
+                               void *stream, int sync);
+
+/* Stage outputs of frame `frame` of the last pass (requires ORBFE_FLAG_KEEP_STAGES); used by the parity tests.
+ * All copy to host memory.  Images are written densely (w bytes per row). */
+int orbfe_level_size(orbfe_handle *h, int level, int *w, int *ht);
+int orbfe_get_level_image(orbfe_handle *h, int frame, int level, uint8_t *out);
+int orbfe_get_level_blurred(orbfe_handle *h, int frame, int level, uint8_t *out);
+/* FAST candidates after per-cell NMS/threshold fallback, reference order (cellRow, cellCol, y, x):
+ * xys[3*i] = x, y (relative to the 19-px border, as fed to DistributeOctree), score. */
+int orbfe_get_level_candidates(orbfe_handle *h, int frame, int level, int32_t *xys, int cap, int *n);
+/* keypoints selected by the quadtree, list order: x, y (level pixel coords), score. */
+int orbfe_get_level_keypoints(orbfe_handle *h, int frame, int level, int32_t *xys, int cap, int *n);
+
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+long long orbfe_launch_count(const orbfe_handle *h);
+
+/* ---------------------------------------------------------------- matcher
+ * All descriptor arrays are n x 32 bytes, row-major (cv::Mat N x 32 CV_8U as produced by the extractor).
+ */
+
+/* ORBMatcher::DescriptorDistance over explicit pairs: dist[i] = hamming(a[ia[i]], b[ib[i]]). */
+int orbfe_descriptor_distance(orbfe_handle *h, const uint8_t *a, int na, const uint8_t *b, int nb,
+                              const int32_t *ia, const int32_t *ib, int n_pairs, int32_t *dist);
+
+/* Brute-force best / second-best over all pairs (BASELINE configs 4/5): for each query row the train index of the
+ * minimum distance (first minimum wins), that distance and the second-smallest distance (257 if none). Host memory. */
+int orbfe_hamming_allpairs(orbfe_handle *h, const uint8_t *q, int nq, const uint8_t *t, int nt,
+                           int32_t *best_idx, int32_t *best_dist, int32_t *second_dist);
+/* Device-resident variant (asynchronous on `stream` unless sync). */
+int orbfe_hamming_allpairs_device(orbfe_handle *h, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt,
+                                  int32_t *d_best_idx, int32_t *d_best_dist, int32_t *d_second_dist,
+                                  void *stream, int sync);
+
+/* ORBMatcher::SearchForInitialization (ORBMatcher.cpp:33-116).  kps are the Frames' (undistorted) key points,
+ * prematched_xy (n1 x 2, in/out) is vecPreMatched, matches12 (n1, out) the result; returns the match count in
+ * *n_matches.  The candidate windows follow Frame::getFeaturesInArea on the 40-px grid (Frame.cpp:97-127). */
+int orbfe_search_for_initialization(orbfe_handle *h,
+                                    const orbfe_keypoint *kps1, const uint8_t *desc1, int n1,
+                                    const orbfe_keypoint *kps2, const uint8_t *desc2, int n2,
+                                    int img_w, int img_h, float *prematched_xy, int32_t *matches12,
+                                    int window, float nn_ratio, int check_orientation, int *n_matches);
+
+/* ORBMatcher::SearchByProjection(Frame|KeyFrame -> Frame) (ORBMatcher.cpp:203-348) after the adapter projected the
+ * map points: query i is considered iff q_valid[i]; window centre (q_u,q_v), radius q_radius (= th * kp.size),
+ * octave window [q_level-1, q_level+1]; occupied[j] != 0 marks current-frame slots that already hold a map point;
+ * assigned[j] (n2, out) = index of the query written into slot j, or -1. */
+int orbfe_search_by_projection(orbfe_handle *h,
+                               const float *q_u, const float *q_v, const float *q_radius, const int32_t *q_level,
+                               const float *q_angle, const uint8_t *q_desc, const uint8_t *q_valid, int nq,
+                               const orbfe_keypoint *kps2, const uint8_t *desc2, int n2, int img_w, int img_h,
+                               const uint8_t *occupied, int32_t *assigned, int check_orientation, int *n_matches);
+
+/* ORBMatcher::SearchByProjection(Frame, local map points) (ORBMatcher.cpp:350-415): octave window
+ * [q_level-1, q_level], best/second-best with the same-level ratio test. */
+int orbfe_search_local_points(orbfe_handle *h,
+                              const float *q_u, const float *q_v, const float *q_radius, const int32_t *q_level,
+                              const uint8_t *q_desc, const uint8_t *q_valid, int nq,
+                              const orbfe_keypoint *kps2, const uint8_t *desc2, int n2, int img_w, int img_h,
+                              const uint8_t *occupied, int32_t *assigned, float nn_ratio, int *n_matches);
+
+/* ORBMatcher::SearchForTriangulation (ORBMatcher.cpp:417-522).  DBoW2 feature vectors are passed as CSR: ascending
+ * node ids, offsets (n_nodes+1) and member key-point indices. */
+int orbfe_search_for_triangulation(orbfe_handle *h,
+                                   const uint8_t *desc1, const float *angle1, const uint8_t *has_mp1, int n1,
+                                   const int32_t *node_id1, const int32_t *node_off1, const int32_t *node_idx1, int n_nodes1,
+                                   const uint8_t *desc2, const float *angle2, const uint8_t *has_mp2, int n2,
+                                   const int32_t *node_id2, const int32_t *node_off2, const int32_t *node_idx2, int n_nodes2,
+                                   int32_t *matches12, int check_orientation, int *n_matches);
+
+#ifdef __cplusplus
+}
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#endif /* ORBFE_H */

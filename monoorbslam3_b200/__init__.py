@@ -1,0 +1,10 @@
+"""monoorbslam3_b200 — B200-native ORB front-end (extractor + Hamming matcher) for monoORBSLAM3's hot path.
+
+Only the path is here: csrc/ (CUDA kernels + C-ABI, built into lib/liborbfe.so), the ctypes binding, and host-side mirrors
+of the reference's ORBExtractor / ORBMatcher interfaces.  No CPU fallback: without the built library or a CUDA device the
+entry points raise."""
+from ._capi import KP_DTYPE, OrbfeError, lib      # noqa: F401
+from .extractor import ORBExtractor               # noqa: F401
+from .matcher import ORBMatcher, FrameView        # noqa: F401
+
+__all__ = ["ORBExtractor", "ORBMatcher", "FrameView", "KP_DTYPE", "OrbfeError", "lib"]

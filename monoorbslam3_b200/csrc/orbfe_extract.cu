@@ -1,0 +1,555 @@
+// orbfe_extract.cu — host side of the extractor path: handle, geometry, tensor maps, launches, C-ABI.
+// Replaces ORBExtractor (modules/ORB/ORBExtractor.{h,cpp}) behind include/orbfe.h.  No CPU fallback.
+#include "orbfe_kernels.cuh"
+
+#include <cudaTypedefs.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+
+namespace orbfe {
+
+static thread_local std::string g_create_error;
+
+int set_error(Handle *h, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+// ------------------------------------------------------------------------------------------------
+// constructor tables — ORBExtractor::ORBExtractor, ORBExtractor.cpp:424-475 (float32 semantics as written there)
+// ------------------------------------------------------------------------------------------------
+static int round_half_even(float v) { return (int) lrintf(v); }          // cvRound
+static int floor_f(float v) { int i = (int) v; return i - (v < (float) i); }
+static int ceil_f(float v) { int i = (int) v; return i + (v > (float) i); }
+
+static void build_ctor_tables(Handle *h) {
+    const orbfe_config &c = h->cfg;
+    h->scale[0] = 1.f; h->inv_scale[0] = 1.f;
+    for (int i = 1; i < c.n_levels; ++i) {                                  // :434-439
+        h->scale[i] = h->scale[i - 1] * c.scale_factor;
+        h->inv_scale[i] = 1.f / h->scale[i];
+    }
+    const float inv2 = 1.0f / (c.scale_factor * c.scale_factor);           // :443-452
+    float desired = (float) ((double) ((float) c.n_features * (1 - inv2)) / (1 - std::pow((double) inv2, (double) c.n_levels)));
+    int sum = 0;
+    for (int l = 0; l < c.n_levels - 1; ++l) {
+        h->quota[l] = round_half_even(desired);
+        sum += h->quota[l];
+        desired *= inv2;
+    }
+    h->quota[c.n_levels - 1] = std::max(c.n_features - sum, 1);
+}
+
+static void build_u_max(uint8_t *u_max) {                                   // :458-474
+    int um[kHalfPatch + 2] = {0};
+    const int v_max = floor_f(kHalfPatch * sqrtf(2.f) / 2 + 1);
+    const int v_min = ceil_f(kHalfPatch * sqrtf(2.f) / 2);
+    const double hp2 = kHalfPatch * kHalfPatch;
+    for (int v = 0; v <= v_max; ++v) um[v] = (int) lrint(std::sqrt(hp2 - v * v));
+    for (int v = kHalfPatch, v0 = 0; v >= v_min; --v) {
+        while (um[v0] == um[v0 + 1]) ++v0;
+        um[v] = v0;
+        ++v0;
+    }
+    for (int v = 0; v <= kHalfPatch; ++v) u_max[v] = (uint8_t) um[v];
+}
+
+// cv::resize INTER_LINEAR coefficient tables: per destination index the two source indices and the
+// two 11-bit weights.  The x axis zeroes the fraction at the borders, the y axis clamps the rows.
+static void build_axis_table(int dn, int sn, bool is_x, std::vector<int2> &tab) {
+    tab.resize(dn);
+    const double scale = 1.0 / ((double) dn / (double) sn);
+    for (int d = 0; d < dn; ++d) {
+        float f = (float) ((d + 0.5) * scale - 0.5);
+        int s = floor_f(f);
+        f -= (float) s;
+        int s0, s1;
+        if (is_x) {
+            if (s < 0) { f = 0.f; s = 0; }
+            if (s >= sn - 1) { f = 0.f; s = sn - 1; }
+            s0 = s; s1 = std::min(s + 1, sn - 1);
+        } else {
+            s0 = std::min(std::max(s, 0), sn - 1);
+            s1 = std::min(std::max(s + 1, 0), sn - 1);
+        }
+        const int c0 = (short) round_half_even((1.f - f) * 2048.f), c1 = (short) round_half_even(f * 2048.f);
+        tab[d] = make_int2(s0 | (s1 << 16), (c0 & 0xffff) | (c1 << 16));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensor maps
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_cuTensorMapEncodeTiled) p;
+    }
+    return fn;
+}
+
+// 3-D u8 tensor (x, y, frame) over `frames` images of w x h with the given pitch / frame stride; box = 256 x box_h x 1.
+static int make_tmap(Handle *h, CUtensorMap *m, const uint8_t *base, int w, int ht, size_t pitch, size_t frame_stride, int frames, int box_h) {
+    PFN_cuTensorMapEncodeTiled enc = get_encode_fn();
+    if (!enc) return set_error(h, ORBFE_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {(cuuint64_t) w, (cuuint64_t) ht, (cuuint64_t) std::max(frames, 1)};
+    cuuint64_t strides[2] = {(cuuint64_t) pitch, (cuuint64_t) frame_stride};
+    cuuint32_t box[3] = {(cuuint32_t) kBoxW, (cuuint32_t) box_h, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *) base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(h, ORBFE_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (w=%d h=%d pitch=%zu)", (int) r, w, ht, pitch);
+    return ORBFE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// geometry + arena
+// ------------------------------------------------------------------------------------------------
+static void free_arena(Handle *h) {
+    cudaFree(h->d_img); cudaFree(h->d_blur); cudaFree(h->d_slots); cudaFree(h->d_cell_cnt); cudaFree(h->d_cell_off);
+    cudaFree(h->d_cand); cudaFree(h->d_cur); cudaFree(h->d_nodes); cudaFree(h->d_lists); cudaFree(h->d_kp); cudaFree(h->d_nkp);
+    cudaFree(h->d_ncand); cudaFree(h->d_tables); cudaFree(h->d_out_kps); cudaFree(h->d_out_desc); cudaFree(h->d_out_n);
+    h->d_img = h->d_blur = nullptr; h->d_slots = nullptr; h->d_cell_cnt = h->d_cell_off = nullptr; h->d_cand = nullptr; h->d_cur = nullptr;
+    h->d_nodes = nullptr; h->d_lists = nullptr; h->d_kp = nullptr; h->d_nkp = h->d_ncand = nullptr; h->d_tables = nullptr;
+    h->d_out_kps = nullptr; h->d_out_desc = nullptr; h->d_out_n = nullptr; h->out_cap = 0;
+    h->batch_cap = 0; h->g.w = h->g.h = 0;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int configure(Handle *h, int w, int ht, int batch) {
+    if (h->g.w == w && h->g.h == ht && h->batch_cap >= batch) return ORBFE_OK;
+    ORBFE_CUDA(h, cudaStreamSynchronize(h->stream));
+    const int keep_batch = std::max(batch, (h->g.w == w && h->g.h == ht) ? h->batch_cap : 0);
+    free_arena(h);
+    Geometry &g = h->g;
+    g = Geometry();
+    const int nl = h->cfg.n_levels;
+    g.n_levels = nl;
+    std::vector<std::vector<int2>> xt(nl), yt(nl);
+    size_t img_off = 0, table_elems = 0;
+    int max_kp_cap = 1, max_node_cap = 1;
+    for (int l = 0; l < nl; ++l) {
+        LevelGeom &L = g.lv[l];
+        L.w = l ? round_half_even((float) w * h->inv_scale[l]) : w;          // ORBExtractor.cpp:563-564
+        L.h = l ? round_half_even((float) ht * h->inv_scale[l]) : ht;
+        if (L.w < 2 * kEdge + 1 || L.h < 2 * kEdge + 1 || L.w > 4000 || L.h > 4000)
+            return set_error(h, ORBFE_E_ARG, "level %d of a %dx%d image is %dx%d: every level must be within [39, 4000] px", l, w, ht, L.w, L.h);
+        L.pitch = (int) align_up((size_t) L.w, 64);
+        L.frame_stride = (unsigned long long) L.pitch * L.h;
+        L.img_off = img_off;
+        img_off += align_up((size_t) L.frame_stride * keep_batch, 256);
+        const int bw = L.w - 2 * kEdge, bh = L.h - 2 * kEdge;
+        L.n_cols = (bw + kCell - 1) / kCell; L.n_rows = (bh + kCell - 1) / kCell;          // :589-590
+        L.n_groups = (L.n_cols + kCellsPerBlk - 1) / kCellsPerBlk;
+        L.cell_base = g.cells_per_frame; g.cells_per_frame += L.n_cols * L.n_rows;
+        L.fast_blk_base = g.fast_blocks; g.fast_blocks += L.n_rows * L.n_groups;
+        L.blur_tx = (L.w + kBlurTileW - 1) / kBlurTileW; L.blur_ty = (L.h + kBlurTileH - 1) / kBlurTileH;
+        L.blur_blk_base = g.blur_blocks; g.blur_blocks += L.blur_tx * L.blur_ty;
+        L.quota = h->quota[l];
+        const int n_ini = ceil_f((float) bw / (float) bh);
+        L.cand_off = g.cand_per_frame; L.cand_cap = L.n_cols * L.n_rows * kSlotCap; g.cand_per_frame += L.cand_cap;
+        L.node_cap = 8 * (L.quota + 4) + 5 * n_ini + 64; L.node_off = g.nodes_per_frame; g.nodes_per_frame += L.node_cap;
+        L.kp_cap = std::max(L.quota + 4, 4 * n_ini + 4); L.kp_off = g.kp_per_frame; g.kp_per_frame += L.kp_cap;
+        L.list_off = g.lists_per_frame; g.lists_per_frame += 2 * L.kp_cap;
+        L.scale = h->scale[l];
+        max_kp_cap = std::max(max_kp_cap, L.kp_cap); max_node_cap = std::max(max_node_cap, L.node_cap);
+        if (l) {
+            build_axis_table(L.w, g.lv[l - 1].w, true, xt[l]);
+            build_axis_table(L.h, g.lv[l - 1].h, false, yt[l]);
+            // destination tile so that the staged source box (256 x 24) covers it
+            ResizeLevel &R = g.rs[l];
+            auto span_ok = [](const std::vector<int2> &tab, int tile, int limit) {
+                const int n = (int) tab.size();
+                for (int d0 = 0; d0 < n; d0 += tile) {
+                    const int o = tab[d0].x & 0xffff;
+                    int mx = 0;
+                    for (int d = d0; d < std::min(n, d0 + tile); ++d) mx = std::max(mx, (tab[d].x >> 16) - o);
+                    if (mx >= limit) return false;
+                }
+                return true;
+            };
+            R.tw = kRsMaxTW; while (R.tw > 16 && !span_ok(xt[l], R.tw, kBoxUsable)) R.tw -= 16;
+            R.th = kRsMaxTH; while (R.th > 1 && !span_ok(yt[l], R.th, kRsBoxH)) R.th -= 1;
+            if (!span_ok(xt[l], R.tw, kBoxUsable) || !span_ok(yt[l], R.th, kRsBoxH))
+                return set_error(h, ORBFE_E_ARG, "scale factor %f too large for the resize tile", (double) h->cfg.scale_factor);
+            R.tiles_x = (L.w + R.tw - 1) / R.tw; R.tiles_y = (L.h + R.th - 1) / R.th;
+            table_elems += xt[l].size() + yt[l].size();
+        }
+    }
+    g.w = w; g.h = ht;
+    g.img_bytes_per_frame = 0;
+    for (int l = 0; l < nl; ++l) g.img_bytes_per_frame += g.lv[l].frame_stride;
+    g.sort_cap = 1; while (g.sort_cap < max_kp_cap) g.sort_cap <<= 1;
+    if (g.sort_cap > 8192) return set_error(h, ORBFE_E_ARG, "n_features too large: %d key points on one level (limit 8188)", max_kp_cap);
+    {   // quadtree smem: sort keys + node pool (levels whose pool does not fit use the global pool)
+        const int budget = 100 * 1024 - g.sort_cap * 8;
+        int cap = std::min(max_node_cap, budget / 16);
+        g.oct_smem_bytes = g.sort_cap * 8 + cap * 16;
+        // stored in Geometry via oct_smem_bytes; smem_node_cap is recomputed at launch
+    }
+    h->max_kp = g.kp_per_frame;
+
+    const size_t B = (size_t) keep_batch;
+    ORBFE_CUDA(h, cudaMalloc(&h->d_img, img_off + 1024));
+    ORBFE_CUDA(h, cudaMalloc(&h->d_blur, img_off + 1024));
+    ORBFE_CUDA(h, cudaMemsetAsync(h->d_img, 0, img_off + 1024, h->stream));
+    ORBFE_CUDA(h, cudaMemsetAsync(h->d_blur, 0, img_off + 1024, h->stream));
+    ORBFE_CUDA(h, cudaMalloc(&h->d_slots, B * g.cells_per_frame * kSlotCap * sizeof(uint32_t)));
+    ORBFE_CUDA(h, cudaMalloc(&h->d_cell_cnt, B * g.cells_per_frame * sizeof(int)));
+    ORBFE_CUDA(h, cudaMalloc(&h->d_cell_off, B * g.cells_per_frame * sizeof(int)));
+    ORBFE_CUDA(h, cudaMalloc(&h->d_cand, B * g.cand_per_frame * sizeof(uint32_t)));
+    ORBFE_CUDA(h, cudaMalloc(&h->d_cur, B * g.cand_per_frame * sizeof(int)));
+    ORBFE_CUDA(h, cudaMalloc(&h->d_nodes, B * g.nodes_per_frame * 16));
+    ORBFE_CUDA(h, cudaMalloc(&h->d_lists, B * g.lists_per_frame * sizeof(int)));
+    ORBFE_CUDA(h, cudaMalloc(&h->d_kp, B * g.kp_per_frame * sizeof(uint32_t)));
+    ORBFE_CUDA(h, cudaMalloc(&h->d_nkp, B * ORBFE_MAX_LEVELS * sizeof(int)));
+    ORBFE_CUDA(h, cudaMalloc(&h->d_ncand, B * ORBFE_MAX_LEVELS * sizeof(int)));
+    ORBFE_CUDA(h, cudaMemsetAsync(h->d_nkp, 0, B * ORBFE_MAX_LEVELS * sizeof(int), h->stream));
+    ORBFE_CUDA(h, cudaMemsetAsync(h->d_ncand, 0, B * ORBFE_MAX_LEVELS * sizeof(int), h->stream));
+    // resize tables
+    ORBFE_CUDA(h, cudaMalloc(&h->d_tables, std::max<size_t>(table_elems, 1) * sizeof(int2)));
+    {
+        int2 *p = (int2 *) h->d_tables;
+        for (int l = 1; l < nl; ++l) {
+            ORBFE_CUDA(h, cudaMemcpyAsync(p, xt[l].data(), xt[l].size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+            g.rs[l].xtab = p; p += xt[l].size();
+            ORBFE_CUDA(h, cudaMemcpyAsync(p, yt[l].data(), yt[l].size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+            g.rs[l].ytab = p; p += yt[l].size();
+        }
+        ORBFE_CUDA(h, cudaStreamSynchronize(h->stream));      // the host vectors die with this scope
+    }
+    h->batch_cap = keep_batch;
+    if (h->use_tma) {
+        for (int l = 0; l < nl; ++l) {
+            const LevelGeom &L = g.lv[l];
+            int rc;
+            if ((rc = make_tmap(h, &h->tm_fast[l], h->d_img + L.img_off, L.w, L.h, L.pitch, L.frame_stride, keep_batch, kFastBoxH))) return rc;
+            if ((rc = make_tmap(h, &h->tm_blur[l], h->d_img + L.img_off, L.w, L.h, L.pitch, L.frame_stride, keep_batch, kBlurBoxH))) return rc;
+            if ((rc = make_tmap(h, &h->tm_rs[l], h->d_img + L.img_off, L.w, L.h, L.pitch, L.frame_stride, keep_batch, kRsBoxH))) return rc;
+        }
+    }
+    return ORBFE_OK;
+}
+
+static int ensure_out_staging(Handle *h, int cap) {
+    if (h->d_out_kps && h->out_cap >= cap) return ORBFE_OK;
+    ORBFE_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_out_kps); cudaFree(h->d_out_desc); cudaFree(h->d_out_n);
+    h->d_out_kps = nullptr; h->d_out_desc = nullptr; h->d_out_n = nullptr;
+    const size_t B = (size_t) h->batch_cap;
+    ORBFE_CUDA(h, cudaMalloc(&h->d_out_kps, B * cap * sizeof(orbfe_keypoint)));
+    ORBFE_CUDA(h, cudaMalloc(&h->d_out_desc, B * cap * 32));
+    ORBFE_CUDA(h, cudaMalloc(&h->d_out_n, B * sizeof(int)));
+    h->out_cap = cap;
+    return ORBFE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one device pass over nb <= batch_cap frames.  level-0 images are read from (l0, l0_pitch, l0_fstride), which is either
+// the arena (after an H2D / D2D copy) or the caller's device buffer used in place.
+// ------------------------------------------------------------------------------------------------
+// ORBFE_DEBUG_SYNC=1 synchronises after every launch and names the kernel that faulted (debugging aid, off by default)
+static bool debug_sync() { static int v = -1; if (v < 0) { const char *e = getenv("ORBFE_DEBUG_SYNC"); v = e && *e == '1'; } return v == 1; }
+#define ORBFE_AFTER_LAUNCH(h, st, name)                                                                          \
+    do { (h)->launches++;                                                                                        \
+         if (debug_sync()) { cudaError_t e__ = cudaStreamSynchronize(st);                                        \
+             if (e__ == cudaSuccess) e__ = cudaGetLastError();                                                   \
+             if (e__ != cudaSuccess) return set_error((h), ORBFE_E_CUDA, "kernel %s failed: %s", name, cudaGetErrorString(e__)); } } while (0)
+
+template <bool kTMA>
+static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, size_t l0_fstride,
+                      orbfe_keypoint *d_kps, uint8_t *d_desc, int *d_n, int cap, cudaStream_t st) {
+    const Geometry &g = h->g;
+    const int nl = g.n_levels;
+    LevelSet LS; memset(&LS, 0, sizeof LS);
+    LS.n_levels = nl;
+    for (int l = 0; l < nl; ++l) { LS.lv[l] = g.lv[l]; LS.img[l] = h->d_img + g.lv[l].img_off; }
+    TmapSet TF, TB; CUtensorMap tm_rs0;
+    memset(&TF, 0, sizeof TF); memset(&TB, 0, sizeof TB); memset(&tm_rs0, 0, sizeof tm_rs0);
+    if (kTMA) {
+        for (int l = 0; l < nl; ++l) { TF.m[l] = h->tm_fast[l]; TB.m[l] = h->tm_blur[l]; }
+        tm_rs0 = h->tm_rs[0];
+    }
+    const bool inplace = l0 != h->d_img + g.lv[0].img_off;
+    if (inplace) {
+        LS.img[0] = l0; LS.lv[0].pitch = (int) l0_pitch; LS.lv[0].frame_stride = l0_fstride;
+        if (kTMA) {
+            int rc;
+            if ((rc = make_tmap(h, &TF.m[0], l0, g.w, g.h, l0_pitch, l0_fstride, nb, kFastBoxH))) return rc;
+            if ((rc = make_tmap(h, &TB.m[0], l0, g.w, g.h, l0_pitch, l0_fstride, nb, kBlurBoxH))) return rc;
+            if ((rc = make_tmap(h, &tm_rs0, l0, g.w, g.h, l0_pitch, l0_fstride, nb, kRsBoxH))) return rc;
+        }
+    }
+    // K1 pyramid: level l from level l-1 (ComputePyramid, ORBExtractor.cpp:559-570)
+    for (int l = 1; l < nl; ++l) {
+        const LevelGeom &S = LS.lv[l - 1], &D = LS.lv[l];
+        const ResizeLevel &R = g.rs[l];
+        ResizeArgs ra;
+        ra.src = LS.img[l - 1]; ra.sw = S.w; ra.sh = S.h; ra.spitch = S.pitch; ra.sframe = S.frame_stride;
+        ra.dst = h->d_img + D.img_off; ra.dw = D.w; ra.dh = D.h; ra.dpitch = D.pitch; ra.dframe = D.frame_stride;
+        ra.tw = R.tw; ra.th = R.th; ra.tiles_x = R.tiles_x; ra.xtab = R.xtab; ra.ytab = R.ytab;
+        k_resize<kTMA><<<dim3(R.tiles_x * R.tiles_y, nb), 256, 0, st>>>(l == 1 ? tm_rs0 : h->tm_rs[l - 1], ra);
+        ORBFE_AFTER_LAUNCH(h, st, "k_resize");
+    }
+    // K2 FAST + per-cell NMS
+    FastArgs fa; fa.slots = h->d_slots; fa.cell_cnt = h->d_cell_cnt; fa.cells_per_frame = g.cells_per_frame;
+    fa.t_ini = h->cfg.ini_th_fast; fa.t_min = h->cfg.min_th_fast;
+    k_fast<kTMA><<<dim3(g.fast_blocks, nb), 256, 0, st>>>(LS, TF, fa);
+    ORBFE_AFTER_LAUNCH(h, st, "k_fast");
+    // K4 quadtree
+    OctArgs oa;
+    oa.slots = h->d_slots; oa.cell_cnt = h->d_cell_cnt; oa.cell_off = h->d_cell_off; oa.cand = h->d_cand; oa.cur = h->d_cur;
+    oa.nodes = h->d_nodes; oa.lists = h->d_lists; oa.kp = h->d_kp; oa.nkp = h->d_nkp; oa.ncand = h->d_ncand; oa.err = h->d_err;
+    oa.cells_per_frame = g.cells_per_frame; oa.cand_per_frame = g.cand_per_frame; oa.nodes_per_frame = g.nodes_per_frame;
+    oa.lists_per_frame = g.lists_per_frame; oa.kp_per_frame = g.kp_per_frame;
+    oa.sort_cap = g.sort_cap; oa.smem_node_cap = (g.oct_smem_bytes - g.sort_cap * 8) / 16;
+    k_octree<256><<<dim3(nl, nb), 256, g.oct_smem_bytes, st>>>(LS, oa);
+    ORBFE_AFTER_LAUNCH(h, st, "k_octree");
+    // K6 blur
+    BlurArgs ba; ba.blur = h->d_blur;
+    k_blur<kTMA><<<dim3(g.blur_blocks, nb), 256, 0, st>>>(LS, TB, ba);
+    ORBFE_AFTER_LAUNCH(h, st, "k_blur");
+    // K5 + K7 orientation and descriptors, final assembly
+    k_zero_counts<<<(nb + 255) / 256, 256, 0, st>>>(d_n, nb);
+    ORBFE_AFTER_LAUNCH(h, st, "k_zero_counts");
+    DescArgs da;
+    da.blur = h->d_blur; da.kp = h->d_kp; da.nkp = h->d_nkp; da.kp_per_frame = g.kp_per_frame;
+    da.out_kps = d_kps; da.out_desc = d_desc; da.out_n = d_n; da.cap = cap; da.err = h->d_err;
+    build_u_max(da.u_max);
+    k_describe<<<dim3((g.kp_per_frame + 7) / 8, nb), 256, 0, st>>>(LS, da);
+    ORBFE_AFTER_LAUNCH(h, st, "k_describe");
+    ORBFE_CUDA(h, cudaGetLastError());
+    h->last_batch = nb;
+    return ORBFE_OK;
+}
+
+static int run_pass(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, size_t l0_fstride,
+                    orbfe_keypoint *d_kps, uint8_t *d_desc, int *d_n, int cap, cudaStream_t st) {
+    return h->use_tma ? run_pass_t<true>(h, nb, l0, l0_pitch, l0_fstride, d_kps, d_desc, d_n, cap, st)
+                      : run_pass_t<false>(h, nb, l0, l0_pitch, l0_fstride, d_kps, d_desc, d_n, cap, st);
+}
+
+static int check_device_error(Handle *h, cudaStream_t st) {
+    int e = 0;
+    ORBFE_CUDA(h, cudaMemcpyAsync(&e, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaStreamSynchronize(st));
+    if (e) {
+        cudaMemsetAsync(h->d_err, 0, sizeof(int), st);
+        static const char *what[] = {"", "candidate capacity", "root nodes exceed the node pool", "quadtree node pool", "expandable-node list",
+                                     "key points per level", "caller key-point capacity (cap) too small"};
+        return set_error(h, e == 6 ? ORBFE_E_CAPACITY : ORBFE_E_INTERNAL, "device reported overflow: %s (code %d)", e >= 1 && e <= 6 ? what[e] : "?", e);
+    }
+    return ORBFE_OK;
+}
+
+}  // namespace orbfe
+
+using namespace orbfe;
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+extern "C" {
+
+const char *orbfe_version(void) { return "orbfe 0.1 (sm_100a)"; }
+
+int orbfe_create(const orbfe_config *cfg, orbfe_handle **out) {
+    if (!cfg || !out) return set_error(nullptr, ORBFE_E_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->n_levels < 1 || cfg->n_levels > ORBFE_MAX_LEVELS || cfg->n_features < 1 || !(cfg->scale_factor > 1.0f) || cfg->max_batch < 1 ||
+        cfg->ini_th_fast < 0 || cfg->min_th_fast < 0 || cfg->ini_th_fast > 254 || cfg->min_th_fast > 254)
+        return set_error(nullptr, ORBFE_E_ARG, "invalid config (n_levels 1..%d, n_features >= 1, scale_factor > 1, thresholds 0..254, max_batch >= 1)", ORBFE_MAX_LEVELS);
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return set_error(nullptr, ORBFE_E_CUDA, "no CUDA device: %s (this library has no CPU fallback)", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (cfg->device < 0 || cfg->device >= n_dev) return set_error(nullptr, ORBFE_E_ARG, "device %d out of range (%d devices)", cfg->device, n_dev);
+    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return set_error(nullptr, ORBFE_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) return set_error(nullptr, ORBFE_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major < 10) return set_error(nullptr, ORBFE_E_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+    orbfe_handle *h = new orbfe_handle();
+    h->cfg = *cfg; h->device = cfg->device; h->sm_count = prop.multiProcessorCount;
+    h->use_tma = !(cfg->flags & ORBFE_FLAG_NO_TMA);
+    h->keep_stages = (cfg->flags & ORBFE_FLAG_KEEP_STAGES) != 0;
+    build_ctor_tables(h);
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_err, sizeof(int))) != cudaSuccess || (e = cudaMemset(h->d_err, 0, sizeof(int))) != cudaSuccess) {
+        set_error(nullptr, ORBFE_E_CUDA, "handle setup: %s", cudaGetErrorString(e));
+        delete h; return ORBFE_E_CUDA;
+    }
+    cudaFuncSetAttribute(k_octree<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    *out = h;
+    return ORBFE_OK;
+}
+
+void orbfe_destroy(orbfe_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_arena(h);
+    cudaFree(h->d_err); cudaFree(h->d_match);
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char *orbfe_last_error(const orbfe_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+float orbfe_scale_factor(const orbfe_handle *h, int level) { return (h && level >= 0 && level < h->cfg.n_levels) ? h->scale[level] : 0.f; }
+int orbfe_features_per_level(const orbfe_handle *h, int level) { return (h && level >= 0 && level < h->cfg.n_levels) ? h->quota[level] : -1; }
+int orbfe_max_keypoints(const orbfe_handle *h) {
+    if (!h) return -1;
+    if (h->max_kp) return h->max_kp;
+    int s = 0;
+    for (int l = 0; l < h->cfg.n_levels; ++l) s += h->quota[l] + 40;
+    return s;
+}
+long long orbfe_launch_count(const orbfe_handle *h) { return h ? h->launches : 0; }
+
+int orbfe_host_alloc(void **ptr, size_t bytes) { return cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) == cudaSuccess ? ORBFE_OK : ORBFE_E_CUDA; }
+void orbfe_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }
+
+int orbfe_extract_batch_device(orbfe_handle *h, const uint8_t *d_frames, int n_frames, int width, int height, size_t row_stride,
+                               size_t frame_stride, orbfe_keypoint *d_kps, uint8_t *d_desc, int cap, int *d_n, void *stream, int sync) {
+    if (!h) return ORBFE_E_ARG;
+    if (!d_frames || !d_kps || !d_desc || !d_n || n_frames < 0 || cap < 1 || row_stride < (size_t) width) return set_error(h, ORBFE_E_ARG, "invalid argument");
+    if (n_frames == 0 || width <= 0 || height <= 0) return ORBFE_OK;
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t) stream : h->stream;
+    int rc = configure(h, width, height, std::min(n_frames, h->cfg.max_batch));
+    if (rc) return rc;
+    const bool inplace = ((uintptr_t) d_frames % 16 == 0) && row_stride % 16 == 0 && frame_stride % 16 == 0;
+    for (int b0 = 0; b0 < n_frames; b0 += h->batch_cap) {
+        const int nb = std::min(h->batch_cap, n_frames - b0);
+        const uint8_t *src = d_frames + (size_t) b0 * frame_stride;
+        const LevelGeom &L0 = h->g.lv[0];
+        if (inplace) {
+            rc = run_pass(h, nb, src, row_stride, frame_stride, d_kps + (size_t) b0 * cap, d_desc + (size_t) b0 * cap * 32, d_n + b0, cap, st);
+        } else {
+            // image.clone() into the pitched arena (ORBExtractor.cpp:567)
+            if (frame_stride == row_stride * (size_t) height)
+                ORBFE_CUDA(h, cudaMemcpy2DAsync(h->d_img + L0.img_off, L0.pitch, src, row_stride, width, (size_t) height * nb, cudaMemcpyDeviceToDevice, st));
+            else
+                for (int b = 0; b < nb; ++b)
+                    ORBFE_CUDA(h, cudaMemcpy2DAsync(h->d_img + L0.img_off + (size_t) b * L0.frame_stride, L0.pitch, src + (size_t) b * frame_stride,
+                                                    row_stride, width, height, cudaMemcpyDeviceToDevice, st));
+            rc = run_pass(h, nb, h->d_img + L0.img_off, L0.pitch, L0.frame_stride, d_kps + (size_t) b0 * cap, d_desc + (size_t) b0 * cap * 32, d_n + b0, cap, st);
+        }
+        if (rc) return rc;
+    }
+    if (sync) return check_device_error(h, st);
+    return ORBFE_OK;
+}
+
+int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, int width, int height, size_t row_stride, size_t frame_stride,
+                        orbfe_keypoint *kps, uint8_t *desc, int cap, int *n_per_frame) {
+    if (!h) return ORBFE_E_ARG;
+    if (!frames || !kps || !desc || !n_per_frame || n_frames < 0 || cap < 1 || row_stride < (size_t) width) return set_error(h, ORBFE_E_ARG, "invalid argument");
+    for (int b = 0; b < n_frames; ++b) n_per_frame[b] = 0;
+    if (n_frames == 0 || width <= 0 || height <= 0) return ORBFE_OK;                 // ORBExtractor.cpp:497
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    int rc = configure(h, width, height, std::min(n_frames, h->cfg.max_batch));
+    if (rc) return rc;
+    if ((rc = ensure_out_staging(h, cap))) return rc;
+    cudaStream_t st = h->stream;
+    const LevelGeom &L0 = h->g.lv[0];
+    for (int b0 = 0; b0 < n_frames; b0 += h->batch_cap) {
+        const int nb = std::min(h->batch_cap, n_frames - b0);
+        const uint8_t *src = frames + (size_t) b0 * frame_stride;
+        if (frame_stride == row_stride * (size_t) height)
+            ORBFE_CUDA(h, cudaMemcpy2DAsync(h->d_img + L0.img_off, L0.pitch, src, row_stride, width, (size_t) height * nb, cudaMemcpyHostToDevice, st));
+        else
+            for (int b = 0; b < nb; ++b)
+                ORBFE_CUDA(h, cudaMemcpy2DAsync(h->d_img + L0.img_off + (size_t) b * L0.frame_stride, L0.pitch, src + (size_t) b * frame_stride, row_stride,
+                                                width, height, cudaMemcpyHostToDevice, st));
+        if ((rc = run_pass(h, nb, h->d_img + L0.img_off, L0.pitch, L0.frame_stride, h->d_out_kps, h->d_out_desc, h->d_out_n, cap, st))) return rc;
+        ORBFE_CUDA(h, cudaMemcpyAsync(n_per_frame + b0, h->d_out_n, sizeof(int) * nb, cudaMemcpyDeviceToHost, st));
+        ORBFE_CUDA(h, cudaMemcpyAsync(kps + (size_t) b0 * cap, h->d_out_kps, sizeof(orbfe_keypoint) * (size_t) nb * cap, cudaMemcpyDeviceToHost, st));
+        ORBFE_CUDA(h, cudaMemcpyAsync(desc + (size_t) b0 * cap * 32, h->d_out_desc, (size_t) nb * cap * 32, cudaMemcpyDeviceToHost, st));
+        if ((rc = check_device_error(h, st))) return rc;
+    }
+    return ORBFE_OK;
+}
+
+int orbfe_extract(orbfe_handle *h, const uint8_t *gray, int width, int height, size_t stride, orbfe_keypoint *kps, uint8_t *desc, int cap, int *n_out) {
+    if (!h) return ORBFE_E_ARG;
+    if (!n_out) return set_error(h, ORBFE_E_ARG, "n_out is null");
+    *n_out = 0;
+    if (!gray || width <= 0 || height <= 0) return ORBFE_OK;                          // image.empty(): outputs untouched
+    if (!kps || !desc || cap < 1 || stride < (size_t) width) return set_error(h, ORBFE_E_ARG, "invalid argument");
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    int rc = configure(h, width, height, 1);
+    if (rc) return rc;
+    // device-side capacity is the handle's bound, so a too-small caller capacity is detected on the host without clobbering kps/desc
+    const int dcap = h->max_kp;
+    if ((rc = ensure_out_staging(h, dcap))) return rc;
+    cudaStream_t st = h->stream;
+    const LevelGeom &L0 = h->g.lv[0];
+    ORBFE_CUDA(h, cudaMemcpy2DAsync(h->d_img + L0.img_off, L0.pitch, gray, stride, width, height, cudaMemcpyHostToDevice, st));
+    if ((rc = run_pass(h, 1, h->d_img + L0.img_off, L0.pitch, L0.frame_stride, h->d_out_kps, h->d_out_desc, h->d_out_n, h->out_cap, st))) return rc;
+    int n = 0;
+    ORBFE_CUDA(h, cudaMemcpyAsync(&n, h->d_out_n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if ((rc = check_device_error(h, st))) return rc;
+    if (n == 0) return ORBFE_OK;                                                       // ORBExtractor.cpp:512
+    if (n > cap) return set_error(h, ORBFE_E_CAPACITY, "%d key points but capacity %d", n, cap);
+    ORBFE_CUDA(h, cudaMemcpyAsync(kps, h->d_out_kps, sizeof(orbfe_keypoint) * (size_t) n, cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaMemcpyAsync(desc, h->d_out_desc, (size_t) n * 32, cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaStreamSynchronize(st));
+    *n_out = n;
+    return ORBFE_OK;
+}
+
+// ---------------------------------------------------------------- stage getters (parity tests)
+int orbfe_level_size(orbfe_handle *h, int level, int *w, int *ht) {
+    if (!h || level < 0 || level >= h->g.n_levels) return h ? set_error(h, ORBFE_E_ARG, "no geometry / bad level") : ORBFE_E_ARG;
+    if (w) *w = h->g.lv[level].w;
+    if (ht) *ht = h->g.lv[level].h;
+    return ORBFE_OK;
+}
+
+static int get_image(orbfe_handle *h, const uint8_t *arena, int frame, int level, uint8_t *out) {
+    if (!h || !out || level < 0 || level >= h->g.n_levels || frame < 0 || frame >= h->last_batch) return h ? set_error(h, ORBFE_E_ARG, "bad frame/level") : ORBFE_E_ARG;
+    const LevelGeom &L = h->g.lv[level];
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    ORBFE_CUDA(h, cudaStreamSynchronize(h->stream));
+    ORBFE_CUDA(h, cudaMemcpy2D(out, L.w, arena + L.img_off + (size_t) frame * L.frame_stride, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    return ORBFE_OK;
+}
+int orbfe_get_level_image(orbfe_handle *h, int frame, int level, uint8_t *out) { return get_image(h, h ? h->d_img : nullptr, frame, level, out); }
+int orbfe_get_level_blurred(orbfe_handle *h, int frame, int level, uint8_t *out) { return get_image(h, h ? h->d_blur : nullptr, frame, level, out); }
+
+static int get_packed(orbfe_handle *h, const uint32_t *d_src, const int *d_cnt, size_t per_frame, int off, int frame, int level, int32_t *xys, int cap, int *n) {
+    if (!h || !n || level < 0 || level >= h->g.n_levels || frame < 0 || frame >= h->last_batch) return h ? set_error(h, ORBFE_E_ARG, "bad frame/level") : ORBFE_E_ARG;
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    ORBFE_CUDA(h, cudaStreamSynchronize(h->stream));
+    int cnt = 0;
+    ORBFE_CUDA(h, cudaMemcpy(&cnt, d_cnt + frame * ORBFE_MAX_LEVELS + level, sizeof(int), cudaMemcpyDeviceToHost));
+    *n = cnt;
+    if (!xys || cnt == 0) return ORBFE_OK;
+    if (cnt > cap) return set_error(h, ORBFE_E_CAPACITY, "%d entries but capacity %d", cnt, cap);
+    std::vector<uint32_t> tmp(cnt);
+    ORBFE_CUDA(h, cudaMemcpy(tmp.data(), d_src + (size_t) frame * per_frame + off, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < cnt; ++i) { xys[3 * i] = tmp[i] & 0xfff; xys[3 * i + 1] = (tmp[i] >> 12) & 0xfff; xys[3 * i + 2] = tmp[i] >> 24; }
+    return ORBFE_OK;
+}
+int orbfe_get_level_candidates(orbfe_handle *h, int frame, int level, int32_t *xys, int cap, int *n) {
+    if (!h || level < 0 || level >= h->g.n_levels) return ORBFE_E_ARG;
+    return get_packed(h, h->d_cand, h->d_ncand, h->g.cand_per_frame, h->g.lv[level].cand_off, frame, level, xys, cap, n);
+}
+int orbfe_get_level_keypoints(orbfe_handle *h, int frame, int level, int32_t *xys, int cap, int *n) {
+    if (!h || level < 0 || level >= h->g.n_levels) return ORBFE_E_ARG;
+    return get_packed(h, h->d_kp, h->d_nkp, h->g.kp_per_frame, h->g.lv[level].kp_off, frame, level, xys, cap, n);
+}
+
+}  // extern "C"

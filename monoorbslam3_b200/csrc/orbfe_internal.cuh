@@ -1,0 +1,112 @@
+// orbfe_internal.cuh — shared declarations of the B200-native ORB front-end (not part of the public C-ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/orbfe.h"
+
+namespace orbfe {
+
+constexpr int kEdge       = 19;   // EDGE_THRESHOLD   ORBExtractor.cpp:15
+constexpr int kHalfPatch  = 15;   // HALF_PATCH_SIZE  ORBExtractor.cpp:14
+constexpr int kCell       = 30;   // W                ORBExtractor.cpp:575
+constexpr int kCellsPerBlk = 8;   // FAST: one warp per cell, 8 cells (240 px) per CTA
+constexpr int kSlotCap    = 225;  // max NMS survivors of a 30x30 cell (one per 2x2 block)
+constexpr int kBoxW       = 256;  // TMA box width in bytes (max box dimension)
+constexpr int kBoxUsable  = kBoxW - 15;   // the box starts on a 16-byte boundary at or left of the wanted origin
+constexpr int kFastBoxH   = 36;   // 30 + 2*3
+constexpr int kBlurTileW  = 224;  // outputs per blur tile row (+6 halo +13 alignment slack <= 256)
+constexpr int kBlurTileH  = 32;
+constexpr int kBlurBoxH   = kBlurTileH + 6;
+constexpr int kRsBoxH     = 24;   // source rows staged per resize tile
+constexpr int kRsMaxTW    = 192;  // destination tile (chosen per level so the source span fits the box)
+constexpr int kRsMaxTH    = 16;
+
+// Per-level geometry, passed to kernels inside __grid_constant__ parameter blocks.
+struct LevelGeom {
+    int w, h, pitch;                 // level image size and row pitch (bytes, multiple of 64)
+    int n_cols, n_rows, n_groups;    // FAST cells (30 px), groups of 8 cells per cell row
+    int cell_base;                   // index of this level's first cell within a frame
+    int fast_blk_base;               // first FAST block of this level (blocks = n_rows * n_groups)
+    int blur_tx, blur_ty, blur_blk_base;
+    int quota;                       // n_features_per_level
+    int cand_off, cand_cap;          // per-frame candidate scratch (compact, reference order)
+    int node_off, node_cap;          // per-frame quadtree node pool
+    int kp_off, kp_cap;              // per-frame per-level selected key points
+    int list_off;                    // per-frame offset of the E/S work lists (2 * kp_cap ints)
+    float scale;                     // scale_factors[level]
+    unsigned long long img_off;      // byte offset of frame 0 of this level inside the image / blur arenas
+    unsigned long long frame_stride; // bytes between consecutive frames of this level
+};
+
+struct ResizeLevel {                 // destination level l (source = l-1)
+    int tw, th, tiles_x, tiles_y;
+    const int2 *xtab;                // per dst x: {sx0 | sx1<<16, a0 | a1<<16}
+    const int2 *ytab;                // per dst y: {sy0 | sy1<<16, b0 | b1<<16}
+};
+
+struct Geometry {
+    int w = 0, h = 0, n_levels = 0;
+    LevelGeom lv[ORBFE_MAX_LEVELS];
+    ResizeLevel rs[ORBFE_MAX_LEVELS];
+    int cells_per_frame = 0, fast_blocks = 0, blur_blocks = 0;
+    int cand_per_frame = 0, nodes_per_frame = 0, kp_per_frame = 0, lists_per_frame = 0;
+    size_t img_bytes_per_frame = 0;  // sum over levels of pitch*h (levels 0..n-1)
+    int oct_smem_bytes = 0;          // dynamic smem of the quadtree kernel
+    int sort_cap = 0;                // power of two >= max kp_cap
+};
+
+struct Handle {
+    orbfe_config cfg{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool use_tma = true, keep_stages = false;
+    float scale[ORBFE_MAX_LEVELS], inv_scale[ORBFE_MAX_LEVELS];
+    int quota[ORBFE_MAX_LEVELS];
+    int max_kp = 0;
+    int sm_count = 148;
+    long long launches = 0;
+
+    // geometry-dependent state (rebuilt when the frame size changes)
+    Geometry g;
+    int batch_cap = 0;               // frames the arena holds
+    uint8_t *d_img = nullptr;        // [level][frame][h][pitch]
+    uint8_t *d_blur = nullptr;
+    uint32_t *d_slots = nullptr;     // [frame][cell][kSlotCap] packed candidates
+    int *d_cell_cnt = nullptr;       // [frame][cell]
+    int *d_cell_off = nullptr;       // [frame][cell] exclusive prefix within the level
+    uint32_t *d_cand = nullptr;      // [frame][cand_per_frame]
+    int *d_cur = nullptr;            // [frame][cand_per_frame] current node of each candidate
+    uint8_t *d_nodes = nullptr;      // [frame][nodes_per_frame] * 16 B (global fallback of the node pool)
+    int *d_lists = nullptr;          // [frame][lists_per_frame]
+    uint32_t *d_kp = nullptr;        // [frame][kp_per_frame] packed selected key points
+    int *d_nkp = nullptr;            // [frame][ORBFE_MAX_LEVELS]
+    int *d_ncand = nullptr;          // [frame][ORBFE_MAX_LEVELS]
+    int *d_err = nullptr;            // device error flag
+    void *d_tables = nullptr;        // resize tables
+    // staging for the host entry points
+    orbfe_keypoint *d_out_kps = nullptr; uint8_t *d_out_desc = nullptr; int *d_out_n = nullptr; int out_cap = 0;
+    int last_batch = 0;              // frames of the last pass (for the stage getters)
+    // tensor maps (img arena; level 0 may be rebuilt for an in-place user buffer)
+    CUtensorMap tm_fast[ORBFE_MAX_LEVELS], tm_blur[ORBFE_MAX_LEVELS], tm_rs[ORBFE_MAX_LEVELS];
+    // matcher scratch
+    void *d_match = nullptr; size_t match_bytes = 0;
+    void *h_pinned = nullptr; size_t pinned_bytes = 0;
+
+    std::string err;
+};
+
+int set_error(Handle *h, int code, const char *fmt, ...);
+int ensure_match_scratch(Handle *h, size_t bytes);
+
+#define ORBFE_CUDA(h, call)                                                                     \
+    do { cudaError_t e__ = (call);                                                              \
+         if (e__ != cudaSuccess)                                                                \
+             return orbfe::set_error((h), ORBFE_E_CUDA, "%s failed: %s (%s:%d)", #call,       \
+                                     cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
+
+}  // namespace orbfe
+
+struct orbfe_handle : orbfe::Handle {};

@@ -1,0 +1,775 @@
+// orbfe_kernels.cuh — device code of the ORB extractor path, hand-written for sm_100a.
+//
+//   K1 k_resize    cv::resize INTER_LINEAR 8U, level l-1 -> l        (ORBExtractor.cpp:559-570)
+//   K2 k_fast      per-cell FAST-9/16 + NMS + threshold fallback     (ORBExtractor.cpp:592-617)
+//   K4 k_octree    DistributeOctree, deterministic, pointer-free     (ORBExtractor.cpp:367-413, 640-830)
+//   K6 k_blur      GaussianBlur 7x7 sigma 2, 8.8 fixed point         (ORBExtractor.cpp:527-528)
+//   K5/K7 k_describe  IC_Angle + fastAtan2 + rotated BRIEF-256        (ORBExtractor.cpp:18-97)
+//
+// Tiles are staged into shared memory with TMA (cp.async.bulk.tensor.3d over an (x, y, frame) tensor map,
+// out-of-range elements zero-filled) or, with ORBFE_FLAG_NO_TMA, with 16-byte vector loads.
+#pragma once
+#include "orbfe_internal.cuh"
+
+namespace orbfe {
+
+// ------------------------------------------------------------------------------------------------
+// small PTX helpers: mbarrier + TMA tile load
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
+// Stage a (kBoxW x box_h) byte box of frame `frame` into `tile` (pitch kBoxW).  TMA requires the box to start on a 16-byte
+// boundary in global memory, so both paths load from ax = ox rounded down to 16 and return xo = ox - ax: the pixel (ox + c, oy + r)
+// sits at tile[r * kBoxW + xo + c], and only kBoxW - xo columns are usable.
+//   TMA:      out-of-range bytes are zero-filled by the hardware.
+//   fallback: rows outside the image are zero; bytes right of the image width are whatever the (padded) row holds; neither is
+//             ever consumed un-fixed.
+// Must be called by all threads of the block; on return the tile is visible to all of them.
+template <bool kTMA, int NT>
+__device__ __forceinline__ int stage_box(uint8_t *tile, uint64_t *bar, const CUtensorMap *map, const uint8_t *frame_base,
+                                         int pitch, int h, int ox, int oy, int frame, int box_h) {
+    const int ax = ox & ~15;                           // floor to 16 (also for negative ox)
+    if constexpr (kTMA) {
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            fence_barrier_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, (uint32_t) (kBoxW * box_h));
+            tma_load_3d(tile, map, bar, ax, oy, frame);
+        }
+        mbar_wait(bar, 0);
+    } else {
+        constexpr int kVec = kBoxW / 16;
+        for (int idx = threadIdx.x; idx < box_h * kVec; idx += NT) {
+            const int r = idx / kVec, v = idx - r * kVec;
+            const int gy = oy + r, gx = ax + 16 * v;
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (gy >= 0 && gy < h && gx >= 0 && gx < pitch)
+                val = __ldg(reinterpret_cast<const uint4 *>(frame_base + (size_t) gy * pitch + gx));
+            *reinterpret_cast<uint4 *>(tile + r * kBoxW + 16 * v) = val;
+        }
+        __syncthreads();
+    }
+    return ox - ax;
+}
+
+template <bool kTMA> struct TilePitch { static constexpr int value = kBoxW; };
+
+// ------------------------------------------------------------------------------------------------
+// block-wide exclusive scan (NT threads, one value per thread)
+// ------------------------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ int block_scan_excl(int v, int &total, int *s_warp) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    int before = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) {
+        const int x = s_warp[w];
+        if (w < wid) before += x;
+        tot += x;
+    }
+    __syncthreads();
+    total = tot;
+    return before + inc - v;
+}
+
+#ifndef ORBFE_HELPERS_ONLY   // orbfe_match.cu only needs the helpers above
+// ------------------------------------------------------------------------------------------------
+// K1  resize (one launch per destination level; grid = (tiles, frames))
+// ------------------------------------------------------------------------------------------------
+struct ResizeArgs {
+    const uint8_t *src; int sw, sh, spitch; unsigned long long sframe;
+    uint8_t *dst; int dw, dh, dpitch; unsigned long long dframe;
+    int tw, th, tiles_x;
+    const int2 *xtab, *ytab;
+};
+
+template <bool kTMA>
+__global__ void __launch_bounds__(256) k_resize(const __grid_constant__ CUtensorMap tm_src, const ResizeArgs a) {
+    constexpr int SP = TilePitch<kTMA>::value;
+    __shared__ __align__(128) uint8_t tile[kRsBoxH * SP];
+    __shared__ __align__(8) uint64_t bar;
+    const int frame = blockIdx.y;
+    const int ty = blockIdx.x / a.tiles_x, tx = blockIdx.x - ty * a.tiles_x;
+    const int dx0 = tx * a.tw, dy0 = ty * a.th;
+    const int ox = (int) (short) (__ldg(&a.xtab[dx0]).x & 0xffff);
+    const int oy = (int) (short) (__ldg(&a.ytab[dy0]).x & 0xffff);
+    const int xo = stage_box<kTMA, 256>(tile, &bar, &tm_src, a.src + (size_t) frame * a.sframe, a.spitch, a.sh, ox, oy, frame, kRsBoxH);
+    uint8_t *dst = a.dst + (size_t) frame * a.dframe;
+    const int qpr = a.tw >> 2;
+    for (int it = threadIdx.x; it < qpr * a.th; it += 256) {
+        const int ry = it / qpr, qx = it - ry * qpr;
+        const int dy = dy0 + ry, dxb = dx0 + 4 * qx;
+        if (dy >= a.dh || dxb >= a.dw) continue;
+        const int2 ye = __ldg(&a.ytab[dy]);
+        const int r0 = (ye.x & 0xffff) - oy, r1 = (ye.x >> 16) - oy;
+        const int b0 = ye.y & 0xffff, b1 = ye.y >> 16;
+        const uint8_t *t0 = tile + r0 * SP + xo - ox, *t1 = tile + r1 * SP + xo - ox;
+        uint32_t out = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int dx = min(dxb + i, a.dw - 1);
+            const int2 xe = __ldg(&a.xtab[dx]);
+            const int c0 = xe.x & 0xffff, c1 = xe.x >> 16;
+            const int a0 = xe.y & 0xffff, a1 = xe.y >> 16;
+            const int h0 = t0[c0] * a0 + t0[c1] * a1;
+            const int h1 = t1[c0] * a0 + t1[c1] * a1;
+            const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            out |= (uint32_t) (v & 0xff) << (8 * i);
+        }
+        *reinterpret_cast<uint32_t *>(dst + (size_t) dy * a.dpitch + dxb) = out;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared parameter block of the all-level kernels
+// ------------------------------------------------------------------------------------------------
+struct LevelSet {
+    LevelGeom lv[ORBFE_MAX_LEVELS];
+    const uint8_t *img[ORBFE_MAX_LEVELS];     // frame 0 of each level (level 0 may be the caller's buffer)
+    int n_levels;
+};
+struct TmapSet { CUtensorMap m[ORBFE_MAX_LEVELS]; };
+
+// ------------------------------------------------------------------------------------------------
+// K2  FAST-9/16 per 30-px cell.  One warp per cell, 8 cells (a 246x36 patch) per CTA.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool has_arc9(unsigned m16) {
+    const unsigned r = m16 | (m16 << 16);
+    unsigned m = r;
+    m &= m >> 1; m &= m >> 2; m &= m >> 4;    // runs of 8
+    m &= r >> 8;                              // runs of 9
+    return (m & 0xffffu) != 0;
+}
+
+// full segment test + corner score for one pixel; returns m (> t) or 0.  SURVEY Appendix A3.
+template <int SP>
+__device__ __forceinline__ int fast_full(const uint8_t *c, int t) {
+    const int v = c[0];
+    int d[16];
+    d[0] = v - c[3 * SP];      d[1] = v - c[3 * SP + 1];   d[2] = v - c[2 * SP + 2];   d[3] = v - c[SP + 3];
+    d[4] = v - c[3];           d[5] = v - c[-SP + 3];      d[6] = v - c[-2 * SP + 2];  d[7] = v - c[-3 * SP + 1];
+    d[8] = v - c[-3 * SP];     d[9] = v - c[-3 * SP - 1];  d[10] = v - c[-2 * SP - 2]; d[11] = v - c[-SP - 3];
+    d[12] = v - c[-3];         d[13] = v - c[SP - 3];      d[14] = v - c[2 * SP - 2];  d[15] = v - c[3 * SP - 1];
+    unsigned dark = 0, bright = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        dark |= (unsigned) (d[k] > t) << k;
+        bright |= (unsigned) (d[k] < -t) << k;
+    }
+    const bool is_dark = has_arc9(dark);
+    if (!is_dark && !has_arc9(bright)) return 0;
+    // only one polarity can hold a 9-arc (two 9-arcs on a 16-ring overlap); the other side's minimum is <= t
+    int a1[16], a2[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) d[k] = is_dark ? d[k] : -d[k];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a1[k] = min(d[k], d[(k + 1) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a2[k] = min(a1[k], a1[(k + 2) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a1[k] = min(a2[k], a2[(k + 4) & 15]);     // 8 contiguous
+    int best = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) best = max(best, min(a1[k], d[(k + 8) & 15]));   // 9 contiguous
+    return best;
+}
+
+struct FastArgs {
+    uint32_t *slots; int *cell_cnt;
+    int cells_per_frame, t_ini, t_min;
+};
+
+template <bool kTMA>
+__global__ void __launch_bounds__(256) k_fast(const __grid_constant__ LevelSet L, const __grid_constant__ TmapSet T, const FastArgs a) {
+    constexpr int SP = TilePitch<kTMA>::value;
+    __shared__ __align__(128) uint8_t tile[kFastBoxH * SP];
+    __shared__ __align__(16) uint8_t mmap[kCellsPerBlk][32 * 32];
+    __shared__ uint16_t queue[kCellsPerBlk][kCell * kCell];
+    __shared__ __align__(8) uint64_t bar;
+
+    const int frame = blockIdx.y;
+    int l = 0;
+#pragma unroll 1
+    for (int k = 1; k < L.n_levels; ++k) if ((int) blockIdx.x >= L.lv[k].fast_blk_base) l = k;
+    const LevelGeom &G = L.lv[l];
+    const int rem = blockIdx.x - G.fast_blk_base;
+    const int ci = rem / G.n_groups, cg = rem - ci * G.n_groups;
+    const int px = kEdge - 3 + kCell * kCellsPerBlk * cg, py = kEdge - 3 + kCell * ci;     // 16-byte aligned x origin
+    stage_box<kTMA, 256>(tile, &bar, &T.m[l], L.img[l] + (size_t) frame * G.frame_stride, G.pitch, G.h, px, py, frame, kFastBoxH);
+
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cj = cg * kCellsPerBlk + wid;
+    if (cj >= G.n_cols) return;
+    const int max_bx = G.w - kEdge, max_by = G.h - kEdge;
+    const int ini_x = kEdge + cj * kCell, ini_y = kEdge + ci * kCell;
+    const int cw = min(ini_x + kCell, max_bx) - ini_x, ch = min(ini_y + kCell, max_by) - ini_y;
+    const int t_lo = min(a.t_ini, a.t_min);
+
+    uint8_t *mm = mmap[wid];
+    uint16_t *q = queue[wid];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) reinterpret_cast<uint32_t *>(mm)[lane + 32 * k] = 0;
+
+    // pass 1: high-speed rejection (every 9-arc contains ring pixel 0 or 8, and 4 or 12); survivors are queued densely
+    const uint8_t *cell0 = tile + 3 * SP + 3 + kCell * wid;
+    int qn = 0;
+    for (int cy = 0; cy < ch; ++cy) {
+        bool pass = false;
+        if (lane < cw) {
+            const uint8_t *c = cell0 + cy * SP + lane;
+            const int v = c[0];
+            const int d0 = abs(v - c[3 * SP]), d8 = abs(v - c[-3 * SP]);
+            const int d4 = abs(v - c[3]), d12 = abs(v - c[-3]);
+            pass = !((d0 <= t_lo && d8 <= t_lo) || (d4 <= t_lo && d12 <= t_lo));
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (pass) q[qn + __popc(bal & ((1u << lane) - 1u))] = (uint16_t) (cy * 32 + lane);
+        qn += __popc(bal);
+    }
+    __syncwarp();
+    // pass 2: full segment test + score on the dense queue
+    for (int k = lane; k < qn; k += 32) {
+        const int pos = q[k];
+        const int cy = pos >> 5, cx = pos & 31;
+        const int m = fast_full<SP>(cell0 + cy * SP + cx, t_lo);
+        if (m) mm[(cy + 1) * 32 + cx + 1] = (uint8_t) m;
+    }
+    __syncwarp();
+    // pass 3: 3x3 non-max suppression confined to the cell (outside = 0).  Because score = m-1 is monotone in m, the
+    // survivors at any threshold t >= t_lo are the t_lo survivors with m > t.
+    unsigned row_ini = 0, row_min = 0;     // lane r keeps the survivor masks of cell row r
+    for (int cy = 0; cy < ch; ++cy) {
+        int m = 0; bool s = false;
+        if (lane < cw) {
+            const uint8_t *p = mm + (cy + 1) * 32 + lane + 1;
+            m = p[0];
+            if (m) {
+                int nb = max(max(p[-1], p[1]), max(p[-33], p[-32]));
+                nb = max(nb, max(max(p[-31], p[31]), max(p[32], p[33])));
+                s = m > nb;
+            }
+        }
+        const unsigned bi = __ballot_sync(0xffffffffu, s && m > a.t_ini);
+        const unsigned bm = __ballot_sync(0xffffffffu, s && m > a.t_min);
+        if (lane == cy) { row_ini = bi; row_min = bm; }
+    }
+    const bool any_ini = __any_sync(0xffffffffu, row_ini != 0);     // ORBExtractor.cpp:604: fall back only if the cell is empty
+    unsigned mask = any_ini ? row_ini : row_min;
+    const int cnt = __popc(mask);
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    const int cell = G.cell_base + ci * G.n_cols + cj;
+    uint32_t *slot = a.slots + ((size_t) frame * a.cells_per_frame + cell) * kSlotCap + (inc - cnt);
+    while (mask) {
+        const int cx = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int m = mm[(lane + 1) * 32 + cx + 1];
+        *slot++ = (uint32_t) (cj * kCell + cx) | ((uint32_t) (ci * kCell + lane) << 12) | ((uint32_t) (m - 1) << 24);
+    }
+    if (lane == 0) a.cell_cnt[(size_t) frame * a.cells_per_frame + cell] = total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4  DistributeOctree.  One CTA per (level, frame).  See DESIGN.md "quadtree" for the derivation:
+// a node is a path prefix, its key points are the candidates (in reference order) whose coordinates descend to it,
+// so no per-node vectors are moved — only per-node counts; list order is recovered from the creation order of slots.
+// ------------------------------------------------------------------------------------------------
+struct OctArgs {
+    const uint32_t *slots; const int *cell_cnt; int *cell_off;
+    uint32_t *cand; int *cur; uint8_t *nodes; int *lists; uint32_t *kp; int *nkp; int *ncand; int *err;
+    int cells_per_frame, cand_per_frame, nodes_per_frame, lists_per_frame, kp_per_frame;
+    int smem_node_cap;      // nodes that fit the shared-memory pool
+    int sort_cap;           // power of two
+};
+
+struct NodeBounds { short x0, x1, y0, y1; };
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_octree(const __grid_constant__ LevelSet L, const OctArgs a) {
+    extern __shared__ __align__(16) uint8_t dyn[];
+    __shared__ int s_warp[NT / 32];
+    __shared__ int s_bcast[4];
+
+    const int l = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const LevelGeom &G = L.lv[l];
+    const int n_cells = G.n_cols * G.n_rows;
+    const int *cell_cnt = a.cell_cnt + (size_t) frame * a.cells_per_frame + G.cell_base;
+    int *cell_off = a.cell_off + (size_t) frame * a.cells_per_frame + G.cell_base;
+    const uint32_t *slots = a.slots + ((size_t) frame * a.cells_per_frame + G.cell_base) * kSlotCap;
+    uint32_t *cand = a.cand + (size_t) frame * a.cand_per_frame + G.cand_off;
+    int *cur = a.cur + (size_t) frame * a.cand_per_frame + G.cand_off;
+    int *E = a.lists + (size_t) frame * a.lists_per_frame + G.list_off;     // expandable nodes, creation order
+    int *S = E + G.kp_cap;                                                  // split list of the current pass
+    uint32_t *kp_out = a.kp + (size_t) frame * a.kp_per_frame + G.kp_off;
+
+    // dynamic smem: [sort keys: sort_cap u64][node pool: smem_node_cap * 16 B]
+    unsigned long long *skey = reinterpret_cast<unsigned long long *>(dyn);
+    uint8_t *pool = dyn + (size_t) a.sort_cap * 8;
+    if (G.node_cap > a.smem_node_cap) pool = a.nodes + ((size_t) frame * a.nodes_per_frame + G.node_off) * 16;
+    NodeBounds *nbnd = reinterpret_cast<NodeBounds *>(pool);
+    int *ncnt = reinterpret_cast<int *>(pool + (size_t) G.node_cap * 8);
+    int *nchild = ncnt + G.node_cap;
+
+    // ---- 1. candidates of this level in reference order: exclusive scan of the per-cell counts, then gather
+    int n = 0;
+    for (int base = 0; base < n_cells; base += NT) {
+        const int c = base + tid;
+        const int v = c < n_cells ? cell_cnt[c] : 0;
+        int tot;
+        const int ex = block_scan_excl<NT>(v, tot, s_warp);
+        if (c < n_cells) cell_off[c] = n + ex;
+        n += tot;
+    }
+    if (tid == 0) { a.ncand[frame * ORBFE_MAX_LEVELS + l] = n; a.nkp[frame * ORBFE_MAX_LEVELS + l] = 0; }
+    if (n == 0) return;
+    if (n > G.cand_cap || n >= (1 << 20)) { if (tid == 0) atomicExch(a.err, 1); return; }
+
+    const int W = G.w - 2 * kEdge, H = G.h - 2 * kEdge;                    // maxX-minX, maxY-minY
+    const int n_ini = (int) ceilf((float) W / (float) H);                   // ORBExtractor.cpp:645
+    const int h_x = (int) ceilf((float) W / (float) n_ini);                 // :646
+    if (n_ini * 5 > G.node_cap) { if (tid == 0) atomicExch(a.err, 2); return; }
+    for (int r = tid; r < n_ini; r += NT) {                                 // :652-670 (last root ends at maxX, sic)
+        NodeBounds b; b.x0 = (short) (h_x * r); b.x1 = (short) (r == n_ini - 1 ? G.w - kEdge : h_x * (r + 1)); b.y0 = 0; b.y1 = (short) H;
+        nbnd[r] = b; ncnt[r] = 0; nchild[r] = 0;
+    }
+    __syncthreads();
+    for (int c = wid; c < n_cells; c += NT / 32) {
+        const int cnt = cell_cnt[c], off = cell_off[c];
+        for (int k = lane; k < cnt; k += 32) {
+            const uint32_t v = slots[(size_t) c * kSlotCap + k];
+            cand[off + k] = v;
+            const int r = (int) (v & 0xfffu) / h_x;                         // :673-675
+            cur[off + k] = r;
+            const unsigned act = __activemask();
+            const unsigned same = __match_any_sync(act, r);
+            if (lane == __ffs(same) - 1) atomicAdd(&ncnt[r], __popc(same));
+        }
+    }
+    __syncthreads();
+
+    // ---- 2. list bookkeeping.  len = list size; pool_top = next free slot; E = expandable nodes in creation order.
+    int len = 0, ne = 0, pool_top = n_ini;
+    {   // roots: empty ones are erased, single-point ones are final (:677-686); the first pass splits the rest in root order
+        for (int base = 0; base < n_ini; base += NT) {
+            const int r = base + tid;
+            const int c = r < n_ini ? ncnt[r] : 0;
+            int tot_ne, tot_ex;
+            const int ex = block_scan_excl<NT>(c > 1 ? 1 : 0, tot_ex, s_warp);
+            block_scan_excl<NT>(c > 0 ? 1 : 0, tot_ne, s_warp);
+            if (c > 1) S[ne + ex] = r;
+            ne += tot_ex; len += tot_ne;
+        }
+        __syncthreads();
+    }
+    int ns = ne;                 // S currently holds the split list of the first breadth pass
+    bool careful = false;
+    const int nF = G.quota;
+
+    while (true) {
+        const int prev = len;
+        if (careful) {
+            // stable sort of E by size ascending (canonical tie-break = creation order; ORBExtractor.cpp:757)
+            int cap2 = 1; while (cap2 < ne) cap2 <<= 1;
+            for (int j = tid; j < cap2; j += NT)
+                skey[j] = j < ne ? (((unsigned long long) (unsigned) ncnt[E[j]]) << 32) | (unsigned) j : ~0ull;
+            __syncthreads();
+            for (int k = 2; k <= cap2; k <<= 1)
+                for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                    for (int i = tid; i < cap2; i += NT) {
+                        const int ixj = i ^ jj;
+                        if (ixj > i) {
+                            const unsigned long long x = skey[i], y = skey[ixj];
+                            const bool up = (i & k) == 0;
+                            if ((x > y) == up) { skey[i] = y; skey[ixj] = x; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            for (int j = tid; j < ne; j += NT) S[j] = E[(int) (skey[j] & 0xffffffffu)];
+            ns = ne;
+            __syncthreads();
+        }
+        if (ns == 0) break;                                    // nothing expandable: size == prevSize (:750 / :806)
+        if (pool_top + 4 * ns > G.node_cap) { if (tid == 0) atomicExch(a.err, 3); return; }
+        // ---- A. allocate 4 child slots per node of the split list (DivideNode geometry, :367-395)
+        for (int j = tid; j < ns; j += NT) {
+            const int nd = S[j];
+            const NodeBounds b = nbnd[nd];
+            const int base = pool_top + 4 * j;
+            nchild[nd] = base;
+            const short mx = (short) (b.x0 + (b.x1 - b.x0) / 2), my = (short) (b.y0 + (b.y1 - b.y0) / 2);
+            NodeBounds c0 = {b.x0, mx, b.y0, my}, c1 = {mx, b.x1, b.y0, my}, c2 = {b.x0, mx, my, b.y1}, c3 = {mx, b.x1, my, b.y1};
+            nbnd[base] = c0; nbnd[base + 1] = c1; nbnd[base + 2] = c2; nbnd[base + 3] = c3;
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) { ncnt[base + qd] = 0; nchild[base + qd] = 0; }
+        }
+        __syncthreads();
+        // ---- B. every candidate of a split node descends one level (:398-407); careful phase: count only (speculative)
+        for (int i = tid; i < n; i += NT) {
+            const int nd = cur[i];
+            const int base = nchild[nd];
+            if (base > 0) {
+                const NodeBounds b = nbnd[base];           // TL child: x1 = midX, y1 = midY
+                const uint32_t v = cand[i];
+                const int x = (int) (v & 0xfffu), y = (int) ((v >> 12) & 0xfffu);
+                const int ch = base + (x < b.x1 ? 0 : 1) + (y < b.y1 ? 0 : 2);
+                if (!careful) cur[i] = ch;
+                const unsigned act = __activemask();
+                const unsigned same = __match_any_sync(act, ch);
+                if (lane == __ffs(same) - 1) atomicAdd(&ncnt[ch], __popc(same));
+            }
+        }
+        __syncthreads();
+        // ---- C. how many of the split list are committed (careful phase stops as soon as len >= nFeatures, :802)
+        int n_commit = ns;
+        if (careful) {
+            int run = len, found = ns;
+            for (int base = 0; base < ns; base += NT) {
+                const int j = base + tid;
+                int delta = 0;
+                if (j < ns) {
+                    const int b = pool_top + 4 * j;
+                    delta = (ncnt[b] > 0) + (ncnt[b + 1] > 0) + (ncnt[b + 2] > 0) + (ncnt[b + 3] > 0) - 1;
+                }
+                int tot;
+                const int ex = block_scan_excl<NT>(delta, tot, s_warp);
+                const bool hit = j < ns && run + ex + delta >= nF;
+                // first j reaching the quota
+                const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                if (tid == 0) s_bcast[0] = 0x7fffffff;
+                __syncthreads();
+                if (bal && lane == 0) atomicMin(&s_bcast[0], base + wid * 32 + __ffs(bal) - 1);
+                __syncthreads();
+                const int first = s_bcast[0];
+                __syncthreads();
+                if (first != 0x7fffffff) { found = first; break; }
+                run += tot;
+            }
+            n_commit = found < ns ? found + 1 : ns;
+            // revert the uncommitted tail, move the committed candidates down
+            for (int j = n_commit + tid; j < ns; j += NT) nchild[S[j]] = 0;
+            __syncthreads();
+            for (int i = tid; i < n; i += NT) {
+                const int nd = cur[i];
+                const int base = nchild[nd];
+                if (base > 0) {
+                    const NodeBounds b = nbnd[base];
+                    const uint32_t v = cand[i];
+                    const int x = (int) (v & 0xfffu), y = (int) ((v >> 12) & 0xfffu);
+                    cur[i] = base + (x < b.x1 ? 0 : 1) + (y < b.y1 ? 0 : 2);
+                }
+            }
+            __syncthreads();
+        }
+        // ---- D. new list size and the expandable children in creation order
+        int new_ne = 0, added = 0;
+        const int n_slots = 4 * n_commit;
+        for (int base = 0; base < n_slots; base += NT) {
+            const int sidx = base + tid;
+            const int c = sidx < n_slots ? ncnt[pool_top + sidx] : 0;
+            int tot_ex, tot_ne;
+            const int ex = block_scan_excl<NT>(c > 1 ? 1 : 0, tot_ex, s_warp);
+            block_scan_excl<NT>(c > 0 ? 1 : 0, tot_ne, s_warp);
+            if (c > 1) {
+                if (new_ne + ex < G.kp_cap) E[new_ne + ex] = pool_top + sidx;
+            }
+            new_ne += tot_ex; added += tot_ne;
+        }
+        __syncthreads();
+        len = len - n_commit + added;
+        pool_top += n_slots;
+        if (new_ne > G.kp_cap) { if (tid == 0) atomicExch(a.err, 4); return; }
+        ne = new_ne;
+        if (careful) {
+            if (len >= nF || len == prev) break;                           // :806
+        } else {
+            if (len > nF || len == prev) break;                            // :750
+            if (len + 3 * ne > nF) careful = true;                         // :752
+            else {                                                         // next breadth pass walks the list front to back =
+                for (int j = tid; j < ne; j += NT) S[j] = E[ne - 1 - j];   // children in reverse creation order
+                ns = ne;
+                __syncthreads();
+            }
+        }
+    }
+    __syncthreads();
+    if (len > G.kp_cap) { if (tid == 0) atomicExch(a.err, 5); return; }
+
+    // ---- 3. list order: children slots newest first (push_front), then the surviving roots in order.
+    // leaves get nchild = -1 - position; best[] accumulates (score, first index) per leaf.
+    uint32_t *best = reinterpret_cast<uint32_t *>(S);      // S is free now (kp_cap entries)
+    for (int j = tid; j < len; j += NT) best[j] = 0;
+    int run = 0;
+    for (int base = 0; base < pool_top; base += NT) {
+        const int t = base + tid;
+        int slot = -1, leaf = 0;
+        if (t < pool_top) {
+            slot = t < pool_top - n_ini ? pool_top - 1 - t : t - (pool_top - n_ini);
+            leaf = ncnt[slot] > 0 && nchild[slot] == 0;
+        }
+        int tot;
+        const int ex = block_scan_excl<NT>(leaf, tot, s_warp);
+        if (leaf) nchild[slot] = -1 - (run + ex);
+        run += tot;
+    }
+    __syncthreads();
+    // ---- 4. best response per node, first one wins ties (:813-827)
+    for (int i = tid; i < n; i += NT) {
+        const int pos = -1 - nchild[cur[i]];
+        const uint32_t key = ((cand[i] >> 24) << 20) | (uint32_t) (0xfffff - i);
+        atomicMax(&best[pos], key);
+    }
+    __syncthreads();
+    for (int j = tid; j < len; j += NT) {
+        const int i = 0xfffff - (int) (best[j] & 0xfffffu);
+        const uint32_t v = cand[i];
+        kp_out[j] = ((v & 0xfffu) + kEdge) | ((((v >> 12) & 0xfffu) + kEdge) << 12) | (v & 0xff000000u);   // :625-632
+    }
+    if (tid == 0) a.nkp[frame * ORBFE_MAX_LEVELS + l] = len;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6  7x7 Gaussian blur, sigma 2, BORDER_REFLECT_101, OpenCV's 8.8 fixed-point path.
+// Tile: 224 x 32 outputs from a 256 x 38 staged box (the box starts 16-byte aligned, 13 px left of the halo).  Horizontal pass -> u16 in smem, vertical pass sliding in registers.
+// ------------------------------------------------------------------------------------------------
+struct BlurArgs { uint8_t *blur; };
+
+__device__ __forceinline__ int refl101(int p, int n) { return p < 0 ? -p : (p >= n ? 2 * n - 2 - p : p); }
+
+template <bool kTMA>
+__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ LevelSet L, const __grid_constant__ TmapSet T, const BlurArgs a) {
+    constexpr int SP = TilePitch<kTMA>::value;
+    __shared__ __align__(128) uint8_t tile[kBlurBoxH * SP];
+    __shared__ __align__(16) uint16_t hbuf[kBlurBoxH * kBlurTileW];
+    __shared__ __align__(8) uint64_t bar;
+    const int frame = blockIdx.y, tid = threadIdx.x;
+    int l = 0;
+#pragma unroll 1
+    for (int k = 1; k < L.n_levels; ++k) if ((int) blockIdx.x >= L.lv[k].blur_blk_base) l = k;
+    const LevelGeom &G = L.lv[l];
+    const int rem = blockIdx.x - G.blur_blk_base;
+    const int ty = rem / G.blur_tx, tx = rem - ty * G.blur_tx;
+    const int x0 = tx * kBlurTileW, y0 = ty * kBlurTileH;
+    const int xo = stage_box<kTMA, 256>(tile, &bar, &T.m[l], L.img[l] + (size_t) frame * G.frame_stride, G.pitch, G.h, x0 - 3, y0 - 3, frame, kBlurBoxH);
+    uint8_t *t = tile + xo;                       // t[r*SP + c] = pixel (x0-3+c, y0-3+r)
+    const int w = G.w, h = G.h;
+    // reflect-101 fix-up of the columns / rows of the box that lie outside the image (only border tiles)
+    const int need_w = min(kBlurTileW, w - x0) + 6, need_h = min(kBlurTileH, h - y0) + 6;
+    if (x0 == 0 || x0 + kBlurTileW + 3 > w) {
+        for (int idx = tid; idx < kBlurBoxH * 6; idx += 256) {
+            const int r = idx / 6, k = idx - r * 6;
+            const int c = k < 3 ? k : need_w - 6 + k;          // 3 columns left of x0, 3 right of the last needed column
+            const int gx = x0 - 3 + c;
+            if (gx < 0 || gx >= w) t[r * SP + c] = t[r * SP + refl101(gx, w) - (x0 - 3)];
+        }
+        __syncthreads();
+    }
+    if (y0 == 0 || y0 + kBlurTileH + 3 > h) {
+        for (int idx = tid; idx < 6 * kBoxW; idx += 256) {
+            const int k = idx / kBoxW, c = idx - k * kBoxW;
+            const int r = k < 3 ? k : need_h - 6 + k;
+            const int gy = y0 - 3 + r;
+            if ((gy < 0 || gy >= h) && c < need_w) t[r * SP + c] = t[(refl101(gy, h) - (y0 - 3)) * SP + c];
+        }
+        __syncthreads();
+    }
+    // horizontal pass: 4 outputs per item from 10 input bytes
+    for (int it = tid; it < kBlurBoxH * (kBlurTileW / 4); it += 256) {
+        const int r = it / (kBlurTileW / 4), qx = it - r * (kBlurTileW / 4);
+        const uint8_t *p = t + r * SP + 4 * qx;
+        int v[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) v[i] = p[i];
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            o[i] = 18 * (v[i] + v[i + 6]) + 34 * (v[i + 1] + v[i + 5]) + 48 * (v[i + 2] + v[i + 4]) + 56 * v[i + 3];
+        *reinterpret_cast<uint2 *>(hbuf + r * kBlurTileW + 4 * qx) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
+    }
+    __syncthreads();
+    // vertical pass: each thread owns a 4-column strip of 8 output rows
+    if (tid < (kBlurTileW / 4) * (kBlurTileH / 8)) {
+        const int seg = tid / (kBlurTileW / 4), qx = tid - seg * (kBlurTileW / 4);
+        const int gx = x0 + 4 * qx;
+        if (gx < w) {
+            uint32_t hv[14][4];
+#pragma unroll
+            for (int r = 0; r < 14; ++r) {
+                const uint2 u = *reinterpret_cast<const uint2 *>(hbuf + (seg * 8 + r) * kBlurTileW + 4 * qx);
+                hv[r][0] = u.x & 0xffff; hv[r][1] = u.x >> 16; hv[r][2] = u.y & 0xffff; hv[r][3] = u.y >> 16;
+            }
+            uint8_t *dst = a.blur + G.img_off + (size_t) frame * G.frame_stride;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int gy = y0 + seg * 8 + r;
+                if (gy < h) {
+                    uint32_t out = 0;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint32_t s = 18u * (hv[r][c] + hv[r + 6][c]) + 34u * (hv[r + 1][c] + hv[r + 5][c]) +
+                                           48u * (hv[r + 2][c] + hv[r + 4][c]) + 56u * hv[r + 3][c] + 32768u;
+                        out |= min(s >> 16, 255u) << (8 * c);
+                    }
+                    *reinterpret_cast<uint32_t *>(dst + (size_t) gy * G.pitch + gx) = out;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5 + K7  orientation (IC_Angle + fastAtan2) and rotated BRIEF.  One warp per key point.
+// ------------------------------------------------------------------------------------------------
+struct DescArgs {
+    const uint8_t *blur; const uint32_t *kp; const int *nkp; int kp_per_frame;
+    orbfe_keypoint *out_kps; uint8_t *out_desc; int *out_n; int cap; int *err;
+    uint8_t u_max[kHalfPatch + 1];
+};
+
+__constant__ int8_t c_pattern[1024] = {
+#include "brief_pattern.inc"
+};
+
+// cv::fastAtan2: float32, no FMA contraction.
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float scale = (float) (180.0 / 3.1415926535897932384626433832795);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale;
+    const float p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+    const float eps = (float) 2.2204460492503131e-16;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a;
+    if (ax >= ay) {
+        const float c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        const float c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        const float c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        const float c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__global__ void __launch_bounds__(256) k_describe(const __grid_constant__ LevelSet L, const DescArgs a) {
+    __shared__ int8_t s_pat[1024];
+    for (int i = threadIdx.x; i < 256; i += 256) reinterpret_cast<int *>(s_pat)[i] = reinterpret_cast<const int *>(c_pattern)[i];
+    __syncthreads();
+    const int frame = blockIdx.y, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (t >= a.kp_per_frame) return;
+    int l = 0;
+#pragma unroll 1
+    for (int k = 1; k < L.n_levels; ++k) if (t >= L.lv[k].kp_off) l = k;
+    const LevelGeom &G = L.lv[l];
+    const int k = t - G.kp_off;
+    const int *nkp = a.nkp + frame * ORBFE_MAX_LEVELS;
+    if (k >= nkp[l]) return;
+    int out_idx = k;
+    for (int q = 0; q < l; ++q) out_idx += nkp[q];
+    if (out_idx == 0) {                                // first key point of the frame also publishes the total
+        int tot = 0;
+        for (int q = 0; q < L.n_levels; ++q) tot += nkp[q];
+        if (lane == 0) a.out_n[frame] = tot;
+    }
+    if (out_idx >= a.cap) { if (lane == 0) atomicExch(a.err, 6); return; }
+    const uint32_t v = a.kp[(size_t) frame * a.kp_per_frame + t];
+    const int x = (int) (v & 0xfffu), y = (int) ((v >> 12) & 0xfffu), score = (int) (v >> 24);
+
+    // IC_Angle (ORBExtractor.cpp:18-42) on the un-blurred level: lane = u + 15, loop over v
+    const uint8_t *img = L.img[l] + (size_t) frame * G.frame_stride + (size_t) y * G.pitch + x;
+    int m01 = 0, m10 = 0;
+    const int u = lane - kHalfPatch;
+#pragma unroll 1
+    for (int vv = -kHalfPatch; vv <= kHalfPatch; ++vv) {
+        const int d = a.u_max[vv < 0 ? -vv : vv];
+        if (lane < 31 && u >= -d && u <= d) {
+            const int val = __ldg(img + vv * G.pitch + u);
+            m10 += u * val; m01 += vv * val;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = fast_atan2_deg((float) m01, (float) m10);
+
+    // computeOrbDescriptor (ORBExtractor.cpp:50-97) on the blurred level; cos/sin evaluated in double and rounded
+    const float factor_pi = (float) (3.1415926535897932384626433832795 / 180.f);
+    const float ang = __fmul_rn(angle, factor_pi);
+    const float ca = (float) cos((double) ang), sb = (float) sin((double) ang);
+    const uint8_t *ctr = a.blur + G.img_off + (size_t) frame * G.frame_stride + (size_t) y * G.pitch + x;
+    const int8_t *p = s_pat + lane * 32;
+    unsigned val = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j, p += 4) {
+        const float x0 = (float) p[0], y0 = (float) p[1], x1 = (float) p[2], y1 = (float) p[3];
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sb), __fmul_rn(y0, ca)));
+        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sb)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sb), __fmul_rn(y1, ca)));
+        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sb)));
+        const int t0 = __ldg(ctr + r0 * G.pitch + c0), t1 = __ldg(ctr + r1 * G.pitch + c1);
+        val |= (unsigned) (t0 < t1) << j;
+    }
+    a.out_desc[((size_t) frame * a.cap + out_idx) * 32 + lane] = (uint8_t) val;
+    if (lane == 0) {
+        orbfe_keypoint kp;
+        kp.x = l ? __fmul_rn((float) x, G.scale) : (float) x;             // ORBExtractor.cpp:537-542
+        kp.y = l ? __fmul_rn((float) y, G.scale) : (float) y;
+        kp.size = G.scale; kp.angle = angle; kp.response = (float) score; kp.octave = l; kp.class_id = -1;
+        a.out_kps[(size_t) frame * a.cap + out_idx] = kp;
+    }
+}
+
+// frames with zero key points never reach k_describe's publisher: clear the counts first
+__global__ void k_zero_counts(int *out_n, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out_n[i] = 0;
+}
+
+#endif  // ORBFE_HELPERS_ONLY
+
+}  // namespace orbfe

@@ -1,0 +1,655 @@
+// orbfe_match.cu — Hamming matching path of the B200-native ORB front-end.
+//
+//   K8  k_pair_distance      ORBMatcher::DescriptorDistance (ORBMatcher.cpp:17-31) over explicit pairs
+//   K11 k_hamming_allpairs   brute-force best / second-best (BASELINE configs 4/5): train tiles staged with TMA bulk copies
+//                            (cp.async.bulk + mbarrier, double buffered), uint4-packed descriptors, __popc, keyed min / second-min
+//   K9  k_win_count/fill     Frame::getFeaturesInArea windows (Frame.cpp:97-127) + distances, one warp per query
+//   K10 k_resolve_*          the order-preserving greedy resolves of SearchForInitialization (:33-116),
+//                            SearchByProjection (:203-348), SearchByProjection/local points (:350-415),
+//                            SearchForTriangulation (:417-522): one warp walks the queries in reference order
+#define ORBFE_HELPERS_ONLY
+#include "orbfe_kernels.cuh"
+
+#include <algorithm>
+#include <climits>
+#include <cstring>
+
+namespace orbfe {
+
+constexpr int TH_LOW = 50, TH_HIGH = 100, HISTO_LENGTH = 30, GRID_SIZE = 40;   // ORBMatcher.cpp:13-15, Frame.h:18
+
+int ensure_match_scratch(Handle *h, size_t bytes) {
+    if (h->match_bytes >= bytes) return ORBFE_OK;
+    ORBFE_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_match); h->d_match = nullptr; h->match_bytes = 0;
+    bytes = bytes + bytes / 4 + 4096;
+    ORBFE_CUDA(h, cudaMalloc(&h->d_match, bytes));
+    h->match_bytes = bytes;
+    return ORBFE_OK;
+}
+
+// bump allocator over the handle's matcher scratch
+struct Bump {
+    uint8_t *base; size_t off = 0;
+    template <class T> T *take(size_t n) { off = (off + 255) & ~(size_t) 255; T *p = base ? reinterpret_cast<T *>(base + off) : nullptr; off += n * sizeof(T); return p; }
+};
+
+__device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint4 b0, const uint4 b1) {
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pair_distance(const uint4 *a, const uint4 *b, const int *ia, const int *ib, int n, int *dist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 *pa = a + 2 * (size_t) ia[i], *pb = b + 2 * (size_t) ib[i];
+    dist[i] = hamming256(__ldg(pa), __ldg(pa + 1), __ldg(pb), __ldg(pb + 1));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K11 all-pairs.  CTA = 256 threads = 8 warps; lane <-> 2 queries (64 queries per CTA), warp <-> 1/8 of each train tile.
+// key = dist << 22 | train index  (first minimum wins, like the sequential `if (d < best)` loop).
+// ------------------------------------------------------------------------------------------------
+constexpr int kApTile = 512;          // train descriptors per stage (16 KB)
+constexpr int kApQ = 64;              // queries per CTA
+constexpr uint32_t kApNone = (257u << 22) | 0x3fffffu;
+
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(256) k_hamming_allpairs(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, int nt,
+                                                           int *best_idx, int *best_dist, int *second_dist) {
+    __shared__ __align__(128) uint4 tile[2][kApTile * 2];
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ uint32_t part[8][kApQ][2];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int q0 = blockIdx.x * kApQ;
+    uint4 qa[2][2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int qi = min(q0 + lane + 32 * r, nq - 1);
+        qa[r][0] = __ldg(q + 2 * (size_t) qi); qa[r][1] = __ldg(q + 2 * (size_t) qi + 1);
+    }
+    uint32_t k1[2] = {kApNone, kApNone}, k2[2] = {kApNone, kApNone};
+    const int n_tiles = (nt + kApTile - 1) / kApTile;
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_barrier_init(); }
+    __syncthreads();
+    if (tid == 0 && n_tiles > 0) {
+        const uint32_t bytes = (uint32_t) min(kApTile, nt) * 32u;
+        mbar_expect_tx(&bar[0], bytes);
+        bulk_g2s(tile[0], t, bytes, &bar[0]);
+    }
+    for (int it = 0; it < n_tiles; ++it) {
+        const int buf = it & 1;
+        if (tid == 0 && it + 1 < n_tiles) {                    // prefetch the next tile into the other buffer (freed by the barrier below)
+            const int j0 = (it + 1) * kApTile;
+            const uint32_t bytes = (uint32_t) min(kApTile, nt - j0) * 32u;
+            mbar_expect_tx(&bar[buf ^ 1], bytes);
+            bulk_g2s(tile[buf ^ 1], t + 2 * (size_t) j0, bytes, &bar[buf ^ 1]);
+        }
+        mbar_wait(&bar[buf], (uint32_t) ((it >> 1) & 1));
+        const int jbase = it * kApTile;
+        const int cnt = min(kApTile, nt - jbase);
+        const int lo = wid * (kApTile / 8), hi = min(lo + kApTile / 8, cnt);
+#pragma unroll 4
+        for (int j = lo; j < hi; ++j) {
+            const uint4 b0 = tile[buf][2 * j], b1 = tile[buf][2 * j + 1];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const uint32_t key = ((uint32_t) hamming256(qa[r][0], qa[r][1], b0, b1) << 22) | (uint32_t) (jbase + j);
+                k2[r] = min(k2[r], max(key, k1[r]));
+                k1[r] = min(k1[r], key);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) { part[wid][lane + 32 * r][0] = k1[r]; part[wid][lane + 32 * r][1] = k2[r]; }
+    __syncthreads();
+    if (tid < kApQ && q0 + tid < nq) {
+        uint32_t a1 = kApNone, a2 = kApNone;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t b1 = part[w][tid][0], b2 = part[w][tid][1];
+            const uint32_t n2 = min(max(a1, b1), min(a2, b2));
+            a1 = min(a1, b1); a2 = n2;
+        }
+        const int d1 = (int) (a1 >> 22), d2 = (int) (a2 >> 22);
+        best_idx[q0 + tid] = d1 >= 257 ? -1 : (int) (a1 & 0x3fffffu);
+        best_dist[q0 + tid] = d1; second_dist[q0 + tid] = d2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9 windows.  Grid of frame 2 as CSR (cell = cx*rows + cy, members in key-point index order) built by the host mirror of
+// Frame::Frame (Frame.cpp:32-51).  One warp per query; candidates come out in (cx, cy, insertion) order.
+// ------------------------------------------------------------------------------------------------
+struct WinArgs {
+    const float *qx, *qy, *qr; const int *qmin, *qmax; const uint8_t *qvalid; const uint4 *qdesc; int nq;
+    const orbfe_keypoint *kps2; const uint4 *desc2; const int *cell_off, *cell_idx; int cols, rows;
+    int *q_cnt; const int *q_off; int *c_idx; int *c_dist;
+};
+
+__device__ __forceinline__ int floor_div_cell(float v) { return (int) floorf(v) / GRID_SIZE; }   // cvFloor(v) / GRID_SIZE, C division
+
+template <bool kFill>
+__global__ void __launch_bounds__(256) k_window(const WinArgs a) {
+    const int qi = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (qi >= a.nq) return;
+    int total = 0;
+    if (a.qvalid[qi]) {
+        const float x = a.qx[qi], y = a.qy[qi], r = a.qr[qi];
+        const int min_l = a.qmin[qi], max_l = a.qmax[qi];
+        const int min_cx = max(0, floor_div_cell(__fsub_rn(x, r))), max_cx = min(a.cols - 1, floor_div_cell(__fadd_rn(x, r)));
+        const int min_cy = max(0, floor_div_cell(__fsub_rn(y, r))), max_cy = min(a.rows - 1, floor_div_cell(__fadd_rn(y, r)));
+        const bool check_level = min_l > 0 || max_l >= 0;
+        uint4 d0, d1; int out0 = 0;
+        if (kFill) { d0 = __ldg(a.qdesc + 2 * (size_t) qi); d1 = __ldg(a.qdesc + 2 * (size_t) qi + 1); out0 = a.q_off[qi]; }
+        if (min_cx <= max_cx && min_cy <= max_cy)
+            for (int cx = min_cx; cx <= max_cx; ++cx) {
+                // cells (cx, min_cy..max_cy) are contiguous in the CSR: walk their members as one run
+                const int beg = a.cell_off[cx * a.rows + min_cy], end = a.cell_off[cx * a.rows + max_cy + 1];
+                for (int k0 = beg; k0 < end; k0 += 32) {
+                    const int k = k0 + lane;
+                    bool ok = false; int idx = -1;
+                    if (k < end) {
+                        idx = a.cell_idx[k];
+                        const orbfe_keypoint kp = a.kps2[idx];
+                        ok = true;
+                        if (check_level) { if (kp.octave < min_l) ok = false; if (max_l >= 0 && kp.octave > max_l) ok = false; }
+                        if (!(fabsf(__fsub_rn(kp.x, x)) <= r && fabsf(__fsub_rn(kp.y, y)) <= r)) ok = false;
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+                    if (kFill && ok) {
+                        const int o = out0 + total + __popc(bal & ((1u << lane) - 1u));
+                        a.c_idx[o] = idx;
+                        a.c_dist[o] = hamming256(d0, d1, __ldg(a.desc2 + 2 * (size_t) idx), __ldg(a.desc2 + 2 * (size_t) idx + 1));
+                    }
+                    total += __popc(bal);
+                }
+            }
+    }
+    if (!kFill && lane == 0) a.q_cnt[qi] = total;
+}
+
+// exclusive scan of n ints by one CTA; out[n] = total
+__global__ void __launch_bounds__(1024) k_scan(const int *in, int *out, int n) {
+    __shared__ int s_warp[32];
+    int run = 0;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n ? in[i] : 0;
+        int tot;
+        const int ex = block_scan_excl<1024>(v, tot, s_warp);
+        if (i < n) out[i] = run + ex;
+        run += tot;
+    }
+    if (threadIdx.x == 0) out[n] = run;
+}
+
+// distances of CSR candidate lists given explicitly (SearchForTriangulation): one warp per query
+__global__ void __launch_bounds__(256) k_csr_distance(const uint4 *qdesc, const int *q_desc_idx, const int *q_off, int nq,
+                                                       const int *c_idx, const uint4 *desc2, int *c_dist) {
+    const int qi = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (qi >= nq) return;
+    const int di = q_desc_idx[qi];
+    const uint4 d0 = __ldg(qdesc + 2 * (size_t) di), d1 = __ldg(qdesc + 2 * (size_t) di + 1);
+    for (int k = q_off[qi] + lane; k < q_off[qi + 1]; k += 32) {
+        const int idx = c_idx[k];
+        c_dist[k] = hamming256(d0, d1, __ldg(desc2 + 2 * (size_t) idx), __ldg(desc2 + 2 * (size_t) idx + 1));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K10 resolves: one warp, queries in reference order, lanes over the query's candidates.
+// Candidate key = dist << 22 | position: the two smallest keys are exactly the sequential loop's (best, second).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_two_smallest(uint32_t &k1, uint32_t &k2) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1, o), o2 = __shfl_xor_sync(0xffffffffu, k2, o);
+        const uint32_t n2 = min(max(k1, o1), min(k2, o2));
+        k1 = min(k1, o1); k2 = n2;
+    }
+}
+
+__device__ __forceinline__ int cv_round_sat(float v) {       // cvRound via cvtss2si: out-of-range -> 0x80000000
+    if (!(v < 2147483648.f) || v < -2147483648.f) return INT_MIN;
+    return __float2int_rn(v);
+}
+
+__device__ __forceinline__ int rot_bin(float a1, float a2) {  // ORBMatcher.cpp:85-88
+    float rot = __fsub_rn(a1, a2);
+    if (rot < 0) rot = __fadd_rn(rot, 360.f);
+    int bin = __float2int_rn(__fmul_rn(rot, 1.f / HISTO_LENGTH));
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+// ComputeThreeMaxima (ORBMatcher.cpp:594-622) on the bin sizes
+__device__ void three_maxima(const int *cnt, int &ind1, int &ind2, int &ind3) {
+    int max1 = 0, max2 = -1, max3 = -2;
+    ind1 = ind2 = ind3 = -1;
+    for (int i = 0; i < HISTO_LENGTH; ++i) {
+        const int n = cnt[i];
+        if (n > max1) { max3 = max2; max2 = max1; max1 = n; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (n > max2) { max3 = max2; max2 = n; ind3 = ind2; ind2 = i; }
+        else if (n > max3) { max3 = n; ind3 = i; }
+    }
+    if (max2 < max1 / 10) { ind2 = -1; ind3 = -1; }
+    else if (max3 < max1 / 10) ind3 = -1;
+}
+
+struct ResolveArgs {
+    int nq, n2;
+    const int *q_off, *c_idx, *c_dist;
+    const uint8_t *qvalid;
+    const float *q_angle;            // angle of query i (kps1 angle / last key point angle)
+    const orbfe_keypoint *kps2;
+    const uint8_t *occupied;
+    const int *q_out_idx;            // triangulation: key-point index of query i in frame 1
+    const uint8_t *has_mp2;
+    int *matches12;                  // init / triangulation: per frame-1 key point
+    int *matches21, *matched_dist;   // init
+    int *assigned;                   // projection / local points: per frame-2 key point
+    int *bin_of;                     // rotation bin per entry (-1 = none)
+    float *prematched;               // init: n1 x 2
+    float nn_ratio; int check_orientation;
+    int *n_matches;
+};
+
+// variant 0: SearchForInitialization; 1: SearchByProjection (frame/keyframe -> frame); 2: local map points; 3: triangulation
+template <int kVariant>
+__global__ void __launch_bounds__(32) k_resolve(const ResolveArgs a) {
+    __shared__ int hist[HISTO_LENGTH];
+    const int lane = threadIdx.x;
+    if (lane < HISTO_LENGTH) hist[lane] = 0;
+    __syncwarp();
+    int n_match = 0;
+    for (int qi = 0; qi < a.nq; ++qi) {
+        if (kVariant != 3 && !a.qvalid[qi]) continue;
+        const int s = a.q_off[qi], e = a.q_off[qi + 1];
+        if (s == e) continue;
+        uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
+        for (int k = s + lane; k < e; k += 32) {
+            const int idx2 = a.c_idx[k], d = a.c_dist[k];
+            bool skip;
+            if (kVariant == 0) skip = a.matched_dist[idx2] <= d;
+            else if (kVariant == 3) skip = a.assigned[idx2] != 0 || a.has_mp2[idx2];      // vecBeMatched2 || kf2 map point
+            else skip = a.occupied[idx2] || a.assigned[idx2] >= 0;
+            if (!skip) {
+                const uint32_t key = ((uint32_t) d << 22) | (uint32_t) (k - s);
+                k2 = min(k2, max(key, k1));
+                k1 = min(k1, key);
+            }
+        }
+        warp_two_smallest(k1, k2);
+        if (k1 == 0xffffffffu) continue;                   // every candidate skipped: best stays at its initial value -> no match
+        const int best = (int) (k1 >> 22), best_idx2 = a.c_idx[s + (int) (k1 & 0x3fffffu)];
+        bool accept;
+        if (kVariant == 0) {
+            const int best2 = k2 == 0xffffffffu ? INT_MAX : (int) (k2 >> 22);
+            accept = best <= TH_LOW && best < cv_round_sat(__fmul_rn((float) best2, a.nn_ratio));      // :74
+        } else if (kVariant == 1) {
+            accept = best <= TH_HIGH;                                                                  // :245
+        } else if (kVariant == 2) {
+            accept = best <= TH_HIGH;
+            if (accept && k2 != 0xffffffffu) {
+                const int second = (int) (k2 >> 22);
+                const int lvl1 = a.kps2[best_idx2].octave, lvl2 = a.kps2[a.c_idx[s + (int) (k2 & 0x3fffffu)]].octave;
+                if (lvl1 == lvl2 && (float) best > __fmul_rn(a.nn_ratio, (float) second)) accept = false;   // :401-405
+            }
+        } else {
+            accept = best < TH_LOW && best_idx2 > 0;                                                   // :464-484 (sic: index 0 never accepted)
+        }
+        if (accept) {
+            if (lane == 0) {
+                if (kVariant == 0) {
+                    const int old = a.matches21[best_idx2];
+                    if (old >= 0) { a.matches12[old] = -1; n_match--; }
+                    a.matches12[qi] = best_idx2; a.matches21[best_idx2] = qi; a.matched_dist[best_idx2] = best;
+                    n_match++;
+                    if (a.check_orientation) { const int b = rot_bin(a.q_angle[qi], a.kps2[best_idx2].angle); hist[b]++; a.bin_of[qi] = b; }
+                } else if (kVariant == 3) {
+                    const int idx1 = a.q_out_idx[qi];
+                    a.matches12[idx1] = best_idx2; a.assigned[best_idx2] = 1; n_match++;
+                    if (a.check_orientation) { const int b = rot_bin(a.q_angle[qi], a.kps2[best_idx2].angle); hist[b]++; a.bin_of[idx1] = b; }
+                } else {
+                    a.assigned[best_idx2] = qi; n_match++;
+                    if (kVariant == 1 && a.check_orientation) { const int b = rot_bin(a.q_angle[qi], a.kps2[best_idx2].angle); hist[b]++; a.bin_of[best_idx2] = b; }
+                }
+                __threadfence_block();
+            }
+            __syncwarp();
+        }
+    }
+    // rotation consistency: keep the three dominant bins (ORBMatcher.cpp:95-108 and copies)
+    n_match = __shfl_sync(0xffffffffu, n_match, 0);
+    if (a.check_orientation && kVariant != 2) {
+        __syncwarp();
+        int i1, i2, i3;
+        three_maxima(hist, i1, i2, i3);
+        const int n_entries = (kVariant == 0 || kVariant == 3) ? a.nq : a.n2;
+        // variant 3 indexes bin_of by frame-1 key point; its caller passes nq = n1-sized arrays through n2 when needed
+        const int limit = kVariant == 3 ? a.n2 : n_entries;
+        int removed = 0;
+        for (int i = lane; i < limit; i += 32) {
+            const int b = a.bin_of[i];
+            if (b < 0 || b == i1 || b == i2 || b == i3) continue;
+            if (kVariant == 0 || kVariant == 3) { if (a.matches12[i] >= 0) { a.matches12[i] = -1; removed++; } }
+            else { a.assigned[i] = -1; removed++; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+        n_match -= removed;
+    }
+    if (kVariant == 0) {                                    // update previous match (:111-113)
+        __syncwarp();
+        for (int i = lane; i < a.nq; i += 32) {
+            const int m = a.matches12[i];
+            if (m >= 0) { a.prematched[2 * i] = a.kps2[m].x; a.prematched[2 * i + 1] = a.kps2[m].y; }
+        }
+    }
+    if (lane == 0) *a.n_matches = n_match;
+}
+
+__global__ void k_fill_int(int *p, int v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// host mirror of the Frame grid (Frame.cpp:32-51, PosInGrid :90-95): CSR with cell = cx*rows + cy
+static void build_grid(const orbfe_keypoint *kps, int n, int img_w, int img_h, int &cols, int &rows, std::vector<int> &off, std::vector<int> &idx) {
+    cols = img_w % GRID_SIZE == 0 ? img_w / GRID_SIZE : img_w / GRID_SIZE + 1;
+    rows = img_h % GRID_SIZE == 0 ? img_h / GRID_SIZE : img_h / GRID_SIZE + 1;
+    const int nc = cols * rows;
+    off.assign(nc + 1, 0); idx.assign(std::max(n, 1), 0);
+    std::vector<int> cell(std::max(n, 1));
+    for (int i = 0; i < n; ++i) {
+        const int x = (int) floorf(kps[i].x), y = (int) floorf(kps[i].y);
+        if (x < 0 || x >= img_w || y < 0 || y >= img_h) { cell[i] = -1; continue; }
+        cell[i] = (x / GRID_SIZE) * rows + y / GRID_SIZE;
+        off[cell[i] + 1]++;
+    }
+    for (int c = 0; c < nc; ++c) off[c + 1] += off[c];
+    std::vector<int> fill(nc, 0);
+    for (int i = 0; i < n; ++i) if (cell[i] >= 0) idx[off[cell[i]] + fill[cell[i]]++] = i;
+}
+
+static void fill_int(Handle *h, int *p, int v, int n, cudaStream_t st) {
+    if (n > 0) { k_fill_int<<<(n + 255) / 256, 256, 0, st>>>(p, v, n); h->launches++; }
+}
+
+// shared driver of the three grid-window searches
+struct WindowProblem {
+    const float *q_u, *q_v, *q_r; const int *q_min, *q_max; const uint8_t *q_valid; const uint8_t *q_desc; const float *q_angle; int nq;
+    const orbfe_keypoint *kps2; const uint8_t *desc2; int n2; int img_w, img_h; const uint8_t *occupied;
+};
+
+template <int kVariant>
+static int run_window_search(Handle *h, const WindowProblem &p, float nn_ratio, int check_orientation,
+                             int *out_n2 /*assigned*/, int *matches12 /*init*/, float *prematched, int *n_matches) {
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int nq = p.nq, n2 = p.n2;
+    int cols, rows; std::vector<int> goff, gidx;
+    build_grid(p.kps2, n2, p.img_w, p.img_h, cols, rows, goff, gidx);
+    float *qx, *qy, *qr, *qang, *pre; int *qmin, *qmax, *coff, *cidx, *qcnt, *qoff, *assigned, *m12, *m21, *mdist, *binof, *nmatch, *cand_idx, *cand_dist;
+    uint8_t *qvalid, *occ; uint4 *qdesc, *desc2; orbfe_keypoint *kps2;
+    auto layout = [&](Bump &b, size_t cand_cap) {
+        qx = b.take<float>(nq); qy = b.take<float>(nq); qr = b.take<float>(nq); qmin = b.take<int>(nq); qmax = b.take<int>(nq);
+        qvalid = b.take<uint8_t>(nq); qdesc = b.take<uint4>(2 * (size_t) nq); qang = b.take<float>(nq);
+        kps2 = b.take<orbfe_keypoint>(n2); desc2 = b.take<uint4>(2 * (size_t) n2); coff = b.take<int>(goff.size()); cidx = b.take<int>(gidx.size());
+        occ = b.take<uint8_t>(n2); qcnt = b.take<int>(nq); qoff = b.take<int>(nq + 1); assigned = b.take<int>(n2);
+        m12 = b.take<int>(nq); m21 = b.take<int>(n2); mdist = b.take<int>(n2); binof = b.take<int>(std::max(nq, n2)); pre = b.take<float>(2 * (size_t) nq);
+        nmatch = b.take<int>(4); cand_idx = b.take<int>(cand_cap); cand_dist = b.take<int>(cand_cap);
+    };
+#define UP(dst, src, bytes) ORBFE_CUDA(h, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, st))
+    WinArgs wa;
+    size_t cand_cap = (size_t) nq * 64 + 1024;      // first guess; the count pass tells the truth and the (rare) retry resizes
+    for (int attempt = 0;; ++attempt) {
+        Bump probe{nullptr}; layout(probe, cand_cap);
+        int rc = ensure_match_scratch(h, probe.off + 1024);
+        if (rc) return rc;
+        Bump b{(uint8_t *) h->d_match}; layout(b, cand_cap);
+        UP(qx, p.q_u, sizeof(float) * nq); UP(qy, p.q_v, sizeof(float) * nq); UP(qr, p.q_r, sizeof(float) * nq);
+        UP(qmin, p.q_min, sizeof(int) * nq); UP(qmax, p.q_max, sizeof(int) * nq); UP(qvalid, p.q_valid, nq); UP(qdesc, p.q_desc, 32 * (size_t) nq);
+        if (p.q_angle) UP(qang, p.q_angle, sizeof(float) * nq);
+        UP(kps2, p.kps2, sizeof(orbfe_keypoint) * (size_t) n2); UP(desc2, p.desc2, 32 * (size_t) n2);
+        UP(coff, goff.data(), sizeof(int) * goff.size()); UP(cidx, gidx.data(), sizeof(int) * gidx.size());
+        if (p.occupied) UP(occ, p.occupied, n2); else ORBFE_CUDA(h, cudaMemsetAsync(occ, 0, n2, st));
+        if (prematched) UP(pre, prematched, sizeof(float) * 2 * (size_t) nq);
+        wa.qx = qx; wa.qy = qy; wa.qr = qr; wa.qmin = qmin; wa.qmax = qmax; wa.qvalid = qvalid; wa.qdesc = qdesc; wa.nq = nq;
+        wa.kps2 = kps2; wa.desc2 = desc2; wa.cell_off = coff; wa.cell_idx = cidx; wa.cols = cols; wa.rows = rows;
+        wa.q_cnt = qcnt; wa.q_off = qoff; wa.c_idx = cand_idx; wa.c_dist = cand_dist;
+        k_window<false><<<(nq + 7) / 8, 256, 0, st>>>(wa);
+        k_scan<<<1, 1024, 0, st>>>(qcnt, qoff, nq);
+        h->launches += 2;
+        int total = 0;
+        ORBFE_CUDA(h, cudaMemcpyAsync(&total, qoff + nq, sizeof(int), cudaMemcpyDeviceToHost, st));
+        ORBFE_CUDA(h, cudaStreamSynchronize(st));
+        if ((size_t) total <= cand_cap) break;
+        if (attempt) return set_error(h, ORBFE_E_INTERNAL, "candidate count changed between passes");
+        cand_cap = (size_t) total;
+    }
+    k_window<true><<<(nq + 7) / 8, 256, 0, st>>>(wa);
+    h->launches++;
+    ResolveArgs ra; memset(&ra, 0, sizeof ra);
+    ra.nq = nq; ra.n2 = n2; ra.q_off = qoff; ra.c_idx = cand_idx; ra.c_dist = cand_dist; ra.qvalid = qvalid; ra.q_angle = qang; ra.kps2 = kps2;
+    ra.occupied = occ; ra.matches12 = m12; ra.matches21 = m21; ra.matched_dist = mdist; ra.assigned = assigned; ra.bin_of = binof;
+    ra.prematched = pre; ra.nn_ratio = nn_ratio; ra.check_orientation = check_orientation; ra.n_matches = nmatch;
+    fill_int(h, binof, -1, std::max(nq, n2), st);
+    if (kVariant == 0) { fill_int(h, m12, -1, nq, st); fill_int(h, m21, -1, n2, st); fill_int(h, mdist, INT_MAX, n2, st); }
+    else fill_int(h, assigned, -1, n2, st);
+    k_resolve<kVariant><<<1, 32, 0, st>>>(ra);
+    h->launches++;
+    ORBFE_CUDA(h, cudaGetLastError());
+    if (kVariant == 0) {
+        ORBFE_CUDA(h, cudaMemcpyAsync(matches12, m12, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
+        ORBFE_CUDA(h, cudaMemcpyAsync(prematched, pre, sizeof(float) * 2 * (size_t) nq, cudaMemcpyDeviceToHost, st));
+    } else {
+        ORBFE_CUDA(h, cudaMemcpyAsync(out_n2, assigned, sizeof(int) * n2, cudaMemcpyDeviceToHost, st));
+    }
+    ORBFE_CUDA(h, cudaMemcpyAsync(n_matches, nmatch, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaStreamSynchronize(st));
+#undef UP
+    return ORBFE_OK;
+}
+
+}  // namespace orbfe
+
+using namespace orbfe;
+
+extern "C" {
+
+int orbfe_descriptor_distance(orbfe_handle *h, const uint8_t *a, int na, const uint8_t *b, int nb, const int32_t *ia, const int32_t *ib, int n_pairs, int32_t *dist) {
+    if (!h) return ORBFE_E_ARG;
+    if (!a || !b || !ia || !ib || !dist || na < 0 || nb < 0 || n_pairs < 0) return set_error(h, ORBFE_E_ARG, "invalid argument");
+    if (n_pairs == 0) return ORBFE_OK;
+    for (int i = 0; i < n_pairs; ++i) if (ia[i] < 0 || ia[i] >= na || ib[i] < 0 || ib[i] >= nb) return set_error(h, ORBFE_E_ARG, "pair %d out of range", i);
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    Bump probe{nullptr};
+    probe.take<uint4>(2 * (size_t) na); probe.take<uint4>(2 * (size_t) nb); probe.take<int>(n_pairs); probe.take<int>(n_pairs); probe.take<int>(n_pairs);
+    int rc = ensure_match_scratch(h, probe.off + 1024);
+    if (rc) return rc;
+    Bump bp{(uint8_t *) h->d_match};
+    uint4 *da = bp.take<uint4>(2 * (size_t) na), *db = bp.take<uint4>(2 * (size_t) nb);
+    int *dia = bp.take<int>(n_pairs), *dib = bp.take<int>(n_pairs), *dd = bp.take<int>(n_pairs);
+    ORBFE_CUDA(h, cudaMemcpyAsync(da, a, 32 * (size_t) na, cudaMemcpyHostToDevice, st));
+    ORBFE_CUDA(h, cudaMemcpyAsync(db, b, 32 * (size_t) nb, cudaMemcpyHostToDevice, st));
+    ORBFE_CUDA(h, cudaMemcpyAsync(dia, ia, sizeof(int) * n_pairs, cudaMemcpyHostToDevice, st));
+    ORBFE_CUDA(h, cudaMemcpyAsync(dib, ib, sizeof(int) * n_pairs, cudaMemcpyHostToDevice, st));
+    k_pair_distance<<<(n_pairs + 255) / 256, 256, 0, st>>>(da, db, dia, dib, n_pairs, dd);
+    h->launches++;
+    ORBFE_CUDA(h, cudaGetLastError());
+    ORBFE_CUDA(h, cudaMemcpyAsync(dist, dd, sizeof(int) * n_pairs, cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaStreamSynchronize(st));
+    return ORBFE_OK;
+}
+
+int orbfe_hamming_allpairs_device(orbfe_handle *h, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, int32_t *d_best_idx, int32_t *d_best_dist,
+                                  int32_t *d_second_dist, void *stream, int sync) {
+    if (!h) return ORBFE_E_ARG;
+    if (nq < 0 || nt < 0 || (nq && (!d_q || !d_best_idx || !d_best_dist || !d_second_dist)) || (nt && !d_t)) return set_error(h, ORBFE_E_ARG, "invalid argument");
+    if (nt >= (1 << 22)) return set_error(h, ORBFE_E_ARG, "at most %d train descriptors per call", (1 << 22) - 1);
+    if (((uintptr_t) d_q | (uintptr_t) d_t) & 15) return set_error(h, ORBFE_E_ARG, "descriptor arrays must be 16-byte aligned");
+    if (nq == 0) return ORBFE_OK;
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t) stream : h->stream;
+    k_hamming_allpairs<<<(nq + kApQ - 1) / kApQ, 256, 0, st>>>((const uint4 *) d_q, nq, (const uint4 *) d_t, nt, d_best_idx, d_best_dist, d_second_dist);
+    h->launches++;
+    ORBFE_CUDA(h, cudaGetLastError());
+    if (sync) ORBFE_CUDA(h, cudaStreamSynchronize(st));
+    return ORBFE_OK;
+}
+
+int orbfe_hamming_allpairs(orbfe_handle *h, const uint8_t *q, int nq, const uint8_t *t, int nt, int32_t *best_idx, int32_t *best_dist, int32_t *second_dist) {
+    if (!h) return ORBFE_E_ARG;
+    if (nq < 0 || nt < 0 || (nq && (!q || !best_idx || !best_dist || !second_dist)) || (nt && !t)) return set_error(h, ORBFE_E_ARG, "invalid argument");
+    if (nq == 0) return ORBFE_OK;
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    Bump probe{nullptr};
+    probe.take<uint4>(2 * (size_t) nq); probe.take<uint4>(2 * (size_t) std::max(nt, 1)); probe.take<int>(nq); probe.take<int>(nq); probe.take<int>(nq);
+    int rc = ensure_match_scratch(h, probe.off + 1024);
+    if (rc) return rc;
+    Bump bp{(uint8_t *) h->d_match};
+    uint4 *dq = bp.take<uint4>(2 * (size_t) nq), *dt = bp.take<uint4>(2 * (size_t) std::max(nt, 1));
+    int *bi = bp.take<int>(nq), *bd = bp.take<int>(nq), *sd = bp.take<int>(nq);
+    ORBFE_CUDA(h, cudaMemcpyAsync(dq, q, 32 * (size_t) nq, cudaMemcpyHostToDevice, st));
+    if (nt) ORBFE_CUDA(h, cudaMemcpyAsync(dt, t, 32 * (size_t) nt, cudaMemcpyHostToDevice, st));
+    rc = orbfe_hamming_allpairs_device(h, (const uint8_t *) dq, nq, (const uint8_t *) dt, nt, bi, bd, sd, st, 0);
+    if (rc) return rc;
+    ORBFE_CUDA(h, cudaMemcpyAsync(best_idx, bi, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaMemcpyAsync(best_dist, bd, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaMemcpyAsync(second_dist, sd, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaStreamSynchronize(st));
+    return ORBFE_OK;
+}
+
+int orbfe_search_for_initialization(orbfe_handle *h, const orbfe_keypoint *kps1, const uint8_t *desc1, int n1, const orbfe_keypoint *kps2,
+                                    const uint8_t *desc2, int n2, int img_w, int img_h, float *prematched_xy, int32_t *matches12, int window,
+                                    float nn_ratio, int check_orientation, int *n_matches) {
+    if (!h) return ORBFE_E_ARG;
+    if (!n_matches || n1 < 0 || n2 < 0 || (n1 && (!kps1 || !desc1 || !prematched_xy || !matches12)) || (n2 && (!kps2 || !desc2)) || img_w <= 0 || img_h <= 0)
+        return set_error(h, ORBFE_E_ARG, "invalid argument");
+    *n_matches = 0;
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    if (n1 == 0 || n2 == 0) return ORBFE_OK;
+    // the adapter's part of the loop head (ORBMatcher.cpp:46-52): level-0 key points only, window centre = vecPreMatched
+    std::vector<float> qx(n1), qy(n1), qr(n1, (float) window), qa(n1);
+    std::vector<int> qmin(n1), qmax(n1); std::vector<uint8_t> qv(n1);
+    for (int i = 0; i < n1; ++i) {
+        qx[i] = prematched_xy[2 * i]; qy[i] = prematched_xy[2 * i + 1]; qa[i] = kps1[i].angle;
+        qmin[i] = qmax[i] = kps1[i].octave; qv[i] = kps1[i].octave <= 0;
+    }
+    WindowProblem p{qx.data(), qy.data(), qr.data(), qmin.data(), qmax.data(), qv.data(), desc1, qa.data(), n1, kps2, desc2, n2, img_w, img_h, nullptr};
+    return run_window_search<0>(h, p, nn_ratio, check_orientation, nullptr, matches12, prematched_xy, n_matches);
+}
+
+int orbfe_search_by_projection(orbfe_handle *h, const float *q_u, const float *q_v, const float *q_radius, const int32_t *q_level, const float *q_angle,
+                               const uint8_t *q_desc, const uint8_t *q_valid, int nq, const orbfe_keypoint *kps2, const uint8_t *desc2, int n2,
+                               int img_w, int img_h, const uint8_t *occupied, int32_t *assigned, int check_orientation, int *n_matches) {
+    if (!h) return ORBFE_E_ARG;
+    if (!n_matches || nq < 0 || n2 < 0 || (nq && (!q_u || !q_v || !q_radius || !q_level || !q_angle || !q_desc || !q_valid)) ||
+        (n2 && (!kps2 || !desc2 || !assigned)) || img_w <= 0 || img_h <= 0)
+        return set_error(h, ORBFE_E_ARG, "invalid argument");
+    *n_matches = 0;
+    for (int j = 0; j < n2; ++j) assigned[j] = -1;
+    if (nq == 0 || n2 == 0) return ORBFE_OK;
+    std::vector<int> qmin(nq), qmax(nq);
+    for (int i = 0; i < nq; ++i) { qmin[i] = q_level[i] - 1; qmax[i] = q_level[i] + 1; }             // ORBMatcher.cpp:229
+    WindowProblem p{q_u, q_v, q_radius, qmin.data(), qmax.data(), q_valid, q_desc, q_angle, nq, kps2, desc2, n2, img_w, img_h, occupied};
+    return run_window_search<1>(h, p, 0.f, check_orientation, assigned, nullptr, nullptr, n_matches);
+}
+
+int orbfe_search_local_points(orbfe_handle *h, const float *q_u, const float *q_v, const float *q_radius, const int32_t *q_level, const uint8_t *q_desc,
+                              const uint8_t *q_valid, int nq, const orbfe_keypoint *kps2, const uint8_t *desc2, int n2, int img_w, int img_h,
+                              const uint8_t *occupied, int32_t *assigned, float nn_ratio, int *n_matches) {
+    if (!h) return ORBFE_E_ARG;
+    if (!n_matches || nq < 0 || n2 < 0 || (nq && (!q_u || !q_v || !q_radius || !q_level || !q_desc || !q_valid)) || (n2 && (!kps2 || !desc2 || !assigned)) ||
+        img_w <= 0 || img_h <= 0)
+        return set_error(h, ORBFE_E_ARG, "invalid argument");
+    *n_matches = 0;
+    for (int j = 0; j < n2; ++j) assigned[j] = -1;
+    if (nq == 0 || n2 == 0) return ORBFE_OK;
+    std::vector<int> qmin(nq), qmax(nq);
+    for (int i = 0; i < nq; ++i) { qmin[i] = q_level[i] - 1; qmax[i] = q_level[i]; }                  // ORBMatcher.cpp:367-369
+    WindowProblem p{q_u, q_v, q_radius, qmin.data(), qmax.data(), q_valid, q_desc, nullptr, nq, kps2, desc2, n2, img_w, img_h, occupied};
+    return run_window_search<2>(h, p, nn_ratio, 0, assigned, nullptr, nullptr, n_matches);
+}
+
+int orbfe_search_for_triangulation(orbfe_handle *h, const uint8_t *desc1, const float *angle1, const uint8_t *has_mp1, int n1, const int32_t *node_id1,
+                                   const int32_t *node_off1, const int32_t *node_idx1, int n_nodes1, const uint8_t *desc2, const float *angle2,
+                                   const uint8_t *has_mp2, int n2, const int32_t *node_id2, const int32_t *node_off2, const int32_t *node_idx2,
+                                   int n_nodes2, int32_t *matches12, int check_orientation, int *n_matches) {
+    if (!h) return ORBFE_E_ARG;
+    if (!n_matches || n1 < 0 || n2 < 0 || n_nodes1 < 0 || n_nodes2 < 0 || (n1 && (!desc1 || !angle1 || !has_mp1 || !matches12)) ||
+        (n2 && (!desc2 || !angle2 || !has_mp2)) || (n_nodes1 && (!node_id1 || !node_off1 || !node_idx1)) || (n_nodes2 && (!node_id2 || !node_off2 || !node_idx2)))
+        return set_error(h, ORBFE_E_ARG, "invalid argument");
+    *n_matches = 0;
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    if (n1 == 0 || n2 == 0 || n_nodes1 == 0 || n_nodes2 == 0) return ORBFE_OK;
+    // merge-join of the two feature vectors (ORBMatcher.cpp:443-512): the query list in reference order, candidates = node members of kf2
+    std::vector<int> q_idx1, q_off(1, 0), c_idx; std::vector<float> q_ang;
+    int a = 0, b = 0;
+    while (a < n_nodes1 && b < n_nodes2) {
+        if (node_id1[a] == node_id2[b]) {
+            for (int i = node_off1[a]; i < node_off1[a + 1]; ++i) {
+                const int idx1 = node_idx1[i];
+                if (idx1 < 0 || idx1 >= n1) return set_error(h, ORBFE_E_ARG, "feature vector 1 index out of range");
+                if (has_mp1[idx1]) continue;                                     // :452
+                q_idx1.push_back(idx1); q_ang.push_back(angle1[idx1]);
+                for (int k = node_off2[b]; k < node_off2[b + 1]; ++k) {
+                    if (node_idx2[k] < 0 || node_idx2[k] >= n2) return set_error(h, ORBFE_E_ARG, "feature vector 2 index out of range");
+                    c_idx.push_back(node_idx2[k]);
+                }
+                q_off.push_back((int) c_idx.size());
+            }
+            ++a; ++b;
+        } else if (node_id1[a] < node_id2[b]) { while (a < n_nodes1 && node_id1[a] < node_id2[b]) ++a; }
+        else { while (b < n_nodes2 && node_id2[b] < node_id1[a]) ++b; }
+    }
+    const int nq = (int) q_idx1.size(), total = (int) c_idx.size();
+    if (nq == 0) return ORBFE_OK;
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    std::vector<orbfe_keypoint> kps2(n2);
+    for (int j = 0; j < n2; ++j) { memset(&kps2[j], 0, sizeof(orbfe_keypoint)); kps2[j].angle = angle2[j]; }
+    auto layout = [&](Bump &bp, uint4 *&d1, uint4 *&d2, int *&qi, int *&qo, int *&ci, int *&cd, float *&qa, orbfe_keypoint *&k2, uint8_t *&mp2, int *&m12,
+                      int *&asg, int *&binof, int *&nm) {
+        d1 = bp.take<uint4>(2 * (size_t) n1); d2 = bp.take<uint4>(2 * (size_t) n2); qi = bp.take<int>(nq); qo = bp.take<int>(nq + 1);
+        ci = bp.take<int>(std::max(total, 1)); cd = bp.take<int>(std::max(total, 1)); qa = bp.take<float>(nq); k2 = bp.take<orbfe_keypoint>(n2);
+        mp2 = bp.take<uint8_t>(n2); m12 = bp.take<int>(n1); asg = bp.take<int>(n2); binof = bp.take<int>(n1); nm = bp.take<int>(4);
+    };
+    uint4 *d1, *d2; int *qi, *qo, *ci, *cd, *m12, *asg, *binof, *nm; float *qa; orbfe_keypoint *k2; uint8_t *mp2;
+    Bump probe{nullptr}; layout(probe, d1, d2, qi, qo, ci, cd, qa, k2, mp2, m12, asg, binof, nm);
+    int rc = ensure_match_scratch(h, probe.off + 1024);
+    if (rc) return rc;
+    Bump bp{(uint8_t *) h->d_match}; layout(bp, d1, d2, qi, qo, ci, cd, qa, k2, mp2, m12, asg, binof, nm);
+#define UP(dst, src, bytes) ORBFE_CUDA(h, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, st))
+    UP(d1, desc1, 32 * (size_t) n1); UP(d2, desc2, 32 * (size_t) n2); UP(qi, q_idx1.data(), sizeof(int) * nq); UP(qo, q_off.data(), sizeof(int) * (nq + 1));
+    if (total) UP(ci, c_idx.data(), sizeof(int) * total);
+    UP(qa, q_ang.data(), sizeof(float) * nq); UP(k2, kps2.data(), sizeof(orbfe_keypoint) * (size_t) n2); UP(mp2, has_mp2, n2);
+#undef UP
+    fill_int(h, m12, -1, n1, st); fill_int(h, asg, 0, n2, st); fill_int(h, binof, -1, n1, st);
+    k_csr_distance<<<(nq + 7) / 8, 256, 0, st>>>(d1, qi, qo, nq, ci, d2, cd);
+    ResolveArgs ra; memset(&ra, 0, sizeof ra);
+    ra.nq = nq; ra.n2 = n1 /* bin_of / matches12 are indexed by frame-1 key points */; ra.q_off = qo; ra.c_idx = ci; ra.c_dist = cd; ra.q_angle = qa; ra.kps2 = k2;
+    ra.q_out_idx = qi; ra.has_mp2 = mp2; ra.matches12 = m12; ra.assigned = asg; ra.bin_of = binof; ra.check_orientation = check_orientation; ra.n_matches = nm;
+    k_resolve<3><<<1, 32, 0, st>>>(ra);
+    h->launches += 2;
+    ORBFE_CUDA(h, cudaGetLastError());
+    ORBFE_CUDA(h, cudaMemcpyAsync(matches12, m12, sizeof(int) * n1, cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaMemcpyAsync(n_matches, nm, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaStreamSynchronize(st));
+    return ORBFE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+"""Host-side mirror of the reference's ORBMatcher (modules/ORB/ORBMatcher.h:12-52) on top of the C-ABI.
+
+The reference's methods take Frame/KeyFrame objects; here a frame is anything with `key_points` (KP_DTYPE array),
+`descriptors` ([N,32] uint8) and `width`/`height` — see FrameView.  The adapters do what the C++ adapters of INTEGRATION.md do:
+flatten the objects, call the C-ABI, write the results back in the reference's order."""
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _capi
+from ._capi import KP_DTYPE
+
+TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30      # ORBMatcher.cpp:13-15
+
+
+@dataclass
+class FrameView:
+    """The part of Frame/KeyFrame the matcher reads (BasicObject/Frame.h): undistorted key points, descriptors, image size,
+    and the map-point slots (None = empty)."""
+    key_points: np.ndarray
+    descriptors: np.ndarray
+    width: int
+    height: int
+    map_points: list = field(default_factory=list)
+
+    @property
+    def num_kps(self):
+        return len(self.key_points)
+
+
+_shared_handle = None
+
+
+def _handle(device=0):
+    global _shared_handle
+    if _shared_handle is None:
+        _shared_handle = _capi.create(1000, 1.2, 8, 20, 7, device, 1, 0)
+    return _shared_handle
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+class ORBMatcher:
+    """ORBMatcher(nnRatio=0.6, checkOrientation=True) — ORBMatcher.h:14."""
+
+    def __init__(self, nnRatio=0.6, checkOrientation=True, handle=None, device=0):
+        self.nn_ratio = float(nnRatio)
+        self.be_check_orientation = bool(checkOrientation)
+        self._h = handle if handle is not None else _handle(device)
+        self._lib = _capi.lib()
+
+    # ---- static int DescriptorDistance(a, b) — ORBMatcher.cpp:17-31
+    def DescriptorDistance(self, a, b):
+        a = _c(a, np.uint8).reshape(1, 32); b = _c(b, np.uint8).reshape(1, 32)
+        return int(self.descriptor_distances(a, b, [0], [0])[0])
+
+    def descriptor_distances(self, a, b, ia, ib):
+        a = _c(a, np.uint8); b = _c(b, np.uint8); ia = _c(ia, np.int32); ib = _c(ib, np.int32)
+        out = np.zeros(len(ia), np.int32)
+        _capi.check(self._h, self._lib.orbfe_descriptor_distance(self._h, _capi.ptr(a), len(a), _capi.ptr(b), len(b), _capi.ptr(ia), _capi.ptr(ib),
+                                                                 len(ia), _capi.ptr(out)))
+        return out
+
+    # ---- brute force best / second best (BASELINE configs 4/5)
+    def hamming_allpairs(self, q, t):
+        q = _c(q, np.uint8); t = _c(t, np.uint8)
+        bi = np.zeros(len(q), np.int32); bd = np.zeros(len(q), np.int32); sd = np.zeros(len(q), np.int32)
+        _capi.check(self._h, self._lib.orbfe_hamming_allpairs(self._h, _capi.ptr(q), len(q), _capi.ptr(t), len(t), _capi.ptr(bi), _capi.ptr(bd),
+                                                              _capi.ptr(sd)))
+        return bi, bd, sd
+
+    def hamming_allpairs_device(self, d_q, nq, d_t, nt, d_bi, d_bd, d_sd, stream=None, sync=True):
+        _capi.check(self._h, self._lib.orbfe_hamming_allpairs_device(self._h, _capi.ptr(d_q), nq, _capi.ptr(d_t), nt, _capi.ptr(d_bi), _capi.ptr(d_bd),
+                                                                     _capi.ptr(d_sd), C.c_void_p(stream) if stream else None, int(sync)))
+
+    # ---- int SearchForInitialization(frame1, frame2, vecPreMatched, matches12, windowSize=100) — ORBMatcher.cpp:33-116
+    def SearchForInitialization(self, frame1, frame2, vecPreMatched, windowSize=100):
+        """Returns (numMatches, matches12); vecPreMatched ([n1,2] float32) is updated in place like the reference's reference argument."""
+        k1 = _c(frame1.key_points, KP_DTYPE); k2 = _c(frame2.key_points, KP_DTYPE)
+        d1 = _c(frame1.descriptors, np.uint8); d2 = _c(frame2.descriptors, np.uint8)
+        pre = _c(vecPreMatched, np.float32).reshape(-1, 2).copy()
+        m12 = np.full(max(len(k1), 1), -1, np.int32)
+        n = C.c_int()
+        _capi.check(self._h, self._lib.orbfe_search_for_initialization(self._h, _capi.ptr(k1), _capi.ptr(d1), len(k1), _capi.ptr(k2), _capi.ptr(d2), len(k2),
+                                                                       frame2.width, frame2.height, _capi.ptr(pre), _capi.ptr(m12), int(windowSize),
+                                                                       self.nn_ratio, int(self.be_check_orientation), C.byref(n)))
+        vecPreMatched[...] = pre.reshape(np.shape(vecPreMatched))
+        return n.value, m12[:len(k1)]
+
+    # ---- SearchByProjection(lastFrame|lastKF, curFrame, th) — ORBMatcher.cpp:203-348, after the adapter projected the map points
+    def SearchByProjection(self, q_u, q_v, q_radius, q_level, q_angle, q_desc, q_valid, curFrame, occupied):
+        """Returns (numMatch, assigned) where assigned[j] = query index written into curFrame.map_points[j] or -1."""
+        k2 = _c(curFrame.key_points, KP_DTYPE); d2 = _c(curFrame.descriptors, np.uint8)
+        args = [_c(q_u, np.float32), _c(q_v, np.float32), _c(q_radius, np.float32), _c(q_level, np.int32), _c(q_angle, np.float32),
+                _c(q_desc, np.uint8), _c(q_valid, np.uint8)]
+        occ = _c(occupied, np.uint8)
+        assigned = np.full(max(len(k2), 1), -1, np.int32)
+        n = C.c_int()
+        _capi.check(self._h, self._lib.orbfe_search_by_projection(self._h, *[_capi.ptr(a) for a in args], len(args[0]), _capi.ptr(k2), _capi.ptr(d2), len(k2),
+                                                                  curFrame.width, curFrame.height, _capi.ptr(occ), _capi.ptr(assigned),
+                                                                  int(self.be_check_orientation), C.byref(n)))
+        return n.value, assigned[:len(k2)]
+
+    # ---- SearchByProjection(frame, mapPoints, th) — ORBMatcher.cpp:350-415
+    def SearchLocalPoints(self, q_u, q_v, q_radius, q_level, q_desc, q_valid, frame, occupied):
+        k2 = _c(frame.key_points, KP_DTYPE); d2 = _c(frame.descriptors, np.uint8)
+        args = [_c(q_u, np.float32), _c(q_v, np.float32), _c(q_radius, np.float32), _c(q_level, np.int32), _c(q_desc, np.uint8), _c(q_valid, np.uint8)]
+        occ = _c(occupied, np.uint8)
+        assigned = np.full(max(len(k2), 1), -1, np.int32)
+        n = C.c_int()
+        _capi.check(self._h, self._lib.orbfe_search_local_points(self._h, *[_capi.ptr(a) for a in args], len(args[0]), _capi.ptr(k2), _capi.ptr(d2), len(k2),
+                                                                 frame.width, frame.height, _capi.ptr(occ), _capi.ptr(assigned), self.nn_ratio, C.byref(n)))
+        return n.value, assigned[:len(k2)]
+
+    # ---- int SearchForTriangulation(keyFrame1, keyFrame2, matches12) — ORBMatcher.cpp:417-522
+    def SearchForTriangulation(self, desc1, angle1, has_mp1, fv1, desc2, angle2, has_mp2, fv2):
+        """fv = (node ids ascending, CSR offsets, key-point indices): the DBoW2 FeatureVector of a key frame."""
+        d1 = _c(desc1, np.uint8); d2 = _c(desc2, np.uint8)
+        a1 = _c(angle1, np.float32); a2 = _c(angle2, np.float32); m1 = _c(has_mp1, np.uint8); m2 = _c(has_mp2, np.uint8)
+        f1 = [_c(x, np.int32) for x in fv1]; f2 = [_c(x, np.int32) for x in fv2]
+        m12 = np.full(max(len(d1), 1), -1, np.int32)
+        n = C.c_int()
+        _capi.check(self._h, self._lib.orbfe_search_for_triangulation(self._h, _capi.ptr(d1), _capi.ptr(a1), _capi.ptr(m1), len(d1), _capi.ptr(f1[0]),
+                                                                      _capi.ptr(f1[1]), _capi.ptr(f1[2]), len(f1[0]), _capi.ptr(d2), _capi.ptr(a2), _capi.ptr(m2),
+                                                                      len(d2), _capi.ptr(f2[0]), _capi.ptr(f2[1]), _capi.ptr(f2[2]), len(f2[0]), _capi.ptr(m12),
+                                                                      int(self.be_check_orientation), C.byref(n)))
+        return n.value, m12[:len(d1)]
