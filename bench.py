@@ -1,0 +1,314 @@
+#!/usr/bin/env python3
+"""bench.py — ORB extract+describe frames/s on the BASELINE.json headline config (752x480, 1000 key points, euroc settings
+1.2 / 8 levels / FAST 20,7), plus all-pairs Hamming GMatch/s, on N B200s of one node.
+
+A step = one pass of the hot path (pyramid, FAST, quadtree, blur, descriptors) over one batch of B synthetic frames per GPU.
+  value : frames/s with the frames already resident in HBM (device API), CUDA events on the launching stream, max over ranks
+  e2e   : frames/s through the host C-ABI call (orbfe_extract_batch) with pinned HOST buffers — H2D and D2H inside the timed region
+  roofline : the dominant stage, algorithmic bytes per launch / its CUDA-event duration, against MEASURED_PEAKS.json
+  cpu_baseline : the reference's own ORBExtractor.cpp (oracle/_ref, compiled verbatim) on the host cores, bounded sample
+`--impl reference` runs only that CPU arm.  N > 1: frames are sharded by rank (weak scaling), results gathered with NCCL."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, NF = 752, 480, 1000
+ORB = dict(nFeatures=NF, scaleFactor=1.2, nLevels=8, iniThFast=20, minThFast=7)
+WORKLOAD = "C1: %dx%d grayscale frames, %d features, 8 levels, scale 1.2, FAST 20/7 (euroc-shaped), dense synthetic profile" % (W, H, NF)
+
+
+def level_sizes(w, h, n_levels=8, sf=1.2):
+    sc = [np.float32(1.0)]
+    for _ in range(1, n_levels):
+        sc.append(np.float32(sc[-1] * np.float32(sf)))
+    out = [(w, h)]
+    for l in range(1, n_levels):
+        inv = np.float32(1.0) / sc[l]
+        out.append((int(np.rint(np.float32(w) * inv)), int(np.rint(np.float32(h) * inv))))
+    return out
+
+
+def algorithmic_bytes(w, h, n_kp):
+    """per-frame algorithmic bytes of each stage."""
+    a = [x * y for x, y in level_sizes(w, h)]
+    s = sum(a)
+    return {"pyramid": (s - a[-1]) + (s - a[0]), "fast": s, "blur": 2 * s, "describe": 60 * n_kp, "quadtree": 0,
+            "frame_total": (s - a[-1]) + (s - a[0]) + s + 2 * s + 60 * n_kp}
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.samples, self.reasons, self.stop_flag, self.max_mhz = gpu, [], set(), False, None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_fps(frames, threads, min_seconds=8.0, max_frames=None):
+    """Time the reference's own extractor (oracle/_ref/libref_orb.so = ORBExtractor.cpp compiled verbatim + cv shim) frame-parallel
+    on `threads` host threads; falls back to the C oracle port when the verbatim build is not there.  Returns (fps, kind, sample)."""
+    from oracle import orb_oracle as orc
+    kind = "reference"
+    try:
+        ref = orc.ReferenceExtractor(NF, 1.2, 8, 20, 7, canonical=False)
+    except (FileNotFoundError, OSError):
+        ref, kind = None, "port"
+    n = max(threads, 8)
+    total_t, total_n = 0.0, 0
+    while True:
+        idx = [i % len(frames) for i in range(total_n, total_n + n)]
+        batch = np.ascontiguousarray(frames[idx])
+        if ref is not None:
+            sec, counts = ref.time_batch(batch, threads)
+            assert counts.min() > 0
+        else:
+            ex = orc.Extractor(NF, 1.2, 8, 20, 7)
+            t0 = time.perf_counter()
+            for f in batch:
+                ex(f)
+            sec = time.perf_counter() - t0
+        total_t += sec; total_n += n
+        if total_t >= min_seconds or (max_frames and total_n >= max_frames):
+            break
+        n = min(4 * n, max(n, int(n * (min_seconds - total_t) / max(sec, 1e-6)) + threads))
+    used = threads if ref is not None else 1
+    return total_n / total_t, kind, "%d frames of the workload in %.1f s on %d thread(s)" % (total_n, total_t, used), used
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from monoorbslam3_b200 import synth
+    cores = host_cores()
+    frames = synth.frames(16, H, W, 1000, "dense")
+    for _ in range(max(args.warmup, 0)):
+        cpu_reference_fps(frames, cores, min_seconds=0.5)
+    vals, samples = [], []
+    t_all = time.perf_counter()
+    kind = used = None
+    for _ in range(args.steps):
+        fps, kind, sample, used = cpu_reference_fps(frames, cores, min_seconds=args.ref_seconds)
+        vals.append(fps); samples.append(sample)
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": "ORB extract+describe frames/s (752x480, 1000 kp)", "value": v, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (time.perf_counter() - t_all) / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": "bounded CPU sample", "l2": "n/a (CPU)"},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": used, "kind": kind, "sample": samples[-1]},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from monoorbslam3_b200 import ORBExtractor, ORBMatcher, KP_DTYPE, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
+
+    # synthetic frames: `distinct` different scenes, repeated to fill the batch (B*H*W = 185 MB at B=512 > the 126 MB L2)
+    distinct = min(args.distinct, B)
+    base = synth.frames(distinct, H, W, 1000 + 100000 * rank, "dense")
+    reps = (B + distinct - 1) // distinct
+    host_frames = torch.from_numpy(np.concatenate([base] * reps)[:B]).pin_memory()
+    d_frames = host_frames.to(dev, non_blocking=True)
+
+    ex = ORBExtractor(device=local, max_batch=B, **ORB)
+    cap = NF + 64
+    d_kps = torch.zeros((B, cap, 7), dtype=torch.float32, device=dev)
+    d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device=dev)
+    d_n = torch.zeros(B, dtype=torch.int32, device=dev)
+    # a real (non-default) stream: the library launches on it and the timing events are recorded on it
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
+
+    gather_bufs = None
+    if world > 1:   # NCCL gather of the fixed-capacity result slabs
+        gather_bufs = (torch.empty((world,) + tuple(d_kps.shape), dtype=d_kps.dtype, device=dev),
+                       torch.empty((world,) + tuple(d_desc.shape), dtype=d_desc.dtype, device=dev),
+                       torch.empty((world, B), dtype=torch.int32, device=dev))
+
+    def step_device():
+        ex.extract_batch_device(d_frames, B, H, W, d_kps, d_desc, cap, d_n, stream=stream, sync=False)
+        if world > 1:
+            dist.all_gather_into_tensor(gather_bufs[0], d_kps)
+            dist.all_gather_into_tensor(gather_bufs[1], d_desc)
+            dist.all_gather_into_tensor(gather_bufs[2], d_n)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(Wm):
+        step_device()
+    barrier()
+    n_kp_mean = float(d_n.float().mean().item())
+    assert n_kp_mean > 900, n_kp_mean
+
+    # ---- timed region 1: frames resident in HBM
+    sampler = ClockSampler(local); sampler.start()
+    ex.profile(True); ex.profile_read(reset=True)
+    launches0 = ex.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        step_device()
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    stage_ms, passes = ex.profile_read(reset=True)
+    ex.profile(False)
+    launches = ex.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms_dev], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev = float(t.item())
+    value = world * B * K / (ms_dev * 1e-3)
+
+    # ---- timed region 2: end to end through the host C-ABI with pinned host buffers (H2D + kernels + D2H every step)
+    h_n = torch.zeros(B, dtype=torch.int32).pin_memory()
+    h_kps = torch.zeros((B, cap, 7), dtype=torch.float32).pin_memory()
+    h_desc = torch.zeros((B, cap, 32), dtype=torch.uint8).pin_memory()
+    frames_np = host_frames.numpy()
+    out = (h_n.numpy(), h_kps.numpy().view(KP_DTYPE).reshape(B, cap), h_desc.numpy())
+    for _ in range(2):
+        ex.extract_batch(frames_np, cap=cap, out=out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        ex.extract_batch(frames_np, cap=cap, out=out)
+        _ = int(out[0][0])            # the step's result is read on the host
+    barrier()
+    sec_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([sec_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec_e2e = float(t.item())
+    e2e = world * B * K / sec_e2e
+    sampler.stop_flag = True; sampler.join(timeout=2)
+
+    # ---- all-pairs Hamming (BASELINE config 4: 20 key frames x 2000 descriptors = 40k x 40k), device resident
+    nq = 40000
+    g = torch.Generator(device="cpu"); g.manual_seed(7 + rank)
+    descs = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, generator=g).to(dev)
+    bi = torch.zeros(nq, dtype=torch.int32, device=dev); bd = torch.zeros_like(bi); sd = torch.zeros_like(bi)
+    mt = ORBMatcher(0.6, False, handle=ex._h)
+    for _ in range(2):
+        mt.hamming_allpairs_device(descs, nq, descs, nq, bi, bd, sd, stream=stream, sync=False)
+    torch.cuda.synchronize()
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps_m = 5
+    m0.record()
+    for _ in range(reps_m):
+        mt.hamming_allpairs_device(descs, nq, descs, nq, bi, bd, sd, stream=stream, sync=False)
+    m1.record()
+    torch.cuda.synchronize()
+    ms_match = m0.elapsed_time(m1) / reps_m
+    gmatch = nq * nq / (ms_match * 1e-3) / 1e9
+    launches += 0   # the matcher launches above are outside the timed extractor region and are not counted
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+        ab = algorithmic_bytes(W, H, n_kp_mean)
+        per_launch_ms = {k: v / max(passes, 1) for k, v in stage_ms.items()}
+        hbm_stages = ("pyramid", "fast", "blur")
+        dom = max(hbm_stages, key=lambda k: per_launch_ms[k])
+        achieved = ab[dom] * B / (per_launch_ms[dom] * 1e-3) / 1e9
+        stage_report = {k: {"ms_per_step": per_launch_ms[k], "algorithmic_GBps": (ab[k] * B / (per_launch_ms[k] * 1e-3) / 1e9) if per_launch_ms[k] > 0 else None}
+                        for k in stage_ms}
+        line = {
+            "metric": "ORB extract+describe frames/s (752x480, 1000 kp)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
+            "warmup": Wm, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "distinct_scenes": distinct, "sharding": "frames by rank, NCCL all_gather of result slabs" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (%.0f MB of frames per step)" % (B * H * W / 1e6), "mean_keypoints_per_frame": n_kp_mean},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * H * W, "d2h_bytes_per_step": B * (4 + cap * 60),
+                    "api": "orbfe_extract_batch (host C-ABI, pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab[dom] * B,
+                         "whole_step_algorithmic_GBps": ab["frame_total"] * B / (ms_dev / K * 1e-3) / 1e9},
+            "stages": stage_report,
+            "match": {"metric": "Hamming GMatch/s (all-pairs 40000 x 40000, best/second-best)", "value": gmatch, "unit": "GMatch/s", "ms": ms_match},
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu:
+            fps, kind, sample, used = cpu_reference_fps(base, host_cores(), min_seconds=args.ref_seconds)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": used, "kind": kind, "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU")
+    ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic scenes per rank (repeated to fill the batch)")
+    ap.add_argument("--ref-seconds", type=float, default=10.0, help="CPU work per reference step / cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

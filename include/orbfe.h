@@ -120,6 +120,13 @@ int orbfe_get_level_keypoints(orbfe_handle *h, int frame, int level, int32_t *xy
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 long long orbfe_launch_count(const orbfe_handle *h);
 
+/* Per-stage device timing with CUDA events recorded on the launching stream inside every extractor pass.
+ * Stages: 0 pyramid (n_levels-1 launches), 1 FAST+NMS, 2 quadtree, 3 blur, 4 orientation+descriptors. */
+#define ORBFE_N_STAGES 5
+int orbfe_profile(orbfe_handle *h, int enable);
+/* Accumulated milliseconds per stage and the number of passes since the last reset. */
+int orbfe_profile_read(orbfe_handle *h, float *stage_ms, int *n_passes, int reset);
+
 /* ---------------------------------------------------------------- matcher
  * All descriptor arrays are n x 32 bytes, row-major (cv::Mat N x 32 CV_8U as produced by the extractor).
  */

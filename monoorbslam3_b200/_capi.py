@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "lib", "liborbfe.so")
 ORBFE_OK, ORBFE_E_ARG, ORBFE_E_CUDA, ORBFE_E_CAPACITY, ORBFE_E_INTERNAL = 0, -1, -2, -3, -4
 ORBFE_MAX_LEVELS = 16
 FLAG_NO_TMA, FLAG_KEEP_STAGES = 1, 2
+STAGES = ("pyramid", "fast", "quadtree", "blur", "describe")
 
 # cv::KeyPoint layout (7 x 4 bytes), see include/orbfe.h
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
@@ -51,6 +52,8 @@ SIGNATURES = {
     "orbfe_get_level_candidates": (_i, [_vp, _i, _i, _vp, _i, C.POINTER(_i)]),
     "orbfe_get_level_keypoints": (_i, [_vp, _i, _i, _vp, _i, C.POINTER(_i)]),
     "orbfe_launch_count": (C.c_longlong, [_vp]),
+    "orbfe_profile": (_i, [_vp, _i]),
+    "orbfe_profile_read": (_i, [_vp, _vp, C.POINTER(_i), _i]),
     "orbfe_descriptor_distance": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp]),
     "orbfe_hamming_allpairs": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "orbfe_hamming_allpairs_device": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i]),

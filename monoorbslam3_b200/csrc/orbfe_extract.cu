@@ -266,6 +266,20 @@ static bool debug_sync() { static int v = -1; if (v < 0) { const char *e = geten
              if (e__ == cudaSuccess) e__ = cudaGetLastError();                                                   \
              if (e__ != cudaSuccess) return set_error((h), ORBFE_E_CUDA, "kernel %s failed: %s", name, cudaGetErrorString(e__)); } } while (0)
 
+static int prof_collect(Handle *h) {
+    if (!h->prof_pending) return ORBFE_OK;
+    ORBFE_CUDA(h, cudaEventSynchronize(h->prof_ev[ORBFE_N_STAGES]));
+    for (int s = 0; s < ORBFE_N_STAGES; ++s) {
+        float ms = 0.f;
+        ORBFE_CUDA(h, cudaEventElapsedTime(&ms, h->prof_ev[s], h->prof_ev[s + 1]));
+        h->prof_ms[s] += ms;
+    }
+    h->prof_passes++;
+    h->prof_pending = false;
+    return ORBFE_OK;
+}
+#define ORBFE_PROF_MARK(h, st, i) do { if ((h)->prof) ORBFE_CUDA(h, cudaEventRecord((h)->prof_ev[i], st)); } while (0)
+
 template <bool kTMA>
 static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, size_t l0_fstride,
                       orbfe_keypoint *d_kps, uint8_t *d_desc, int *d_n, int cap, cudaStream_t st) {
@@ -290,6 +304,8 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
             if ((rc = make_tmap(h, &tm_rs0, l0, g.w, g.h, l0_pitch, l0_fstride, nb, kRsBoxH))) return rc;
         }
     }
+    if (h->prof) { int rc = prof_collect(h); if (rc) return rc; }
+    ORBFE_PROF_MARK(h, st, 0);
     // K1 pyramid: level l from level l-1 (ComputePyramid, ORBExtractor.cpp:559-570)
     for (int l = 1; l < nl; ++l) {
         const LevelGeom &S = LS.lv[l - 1], &D = LS.lv[l];
@@ -301,11 +317,13 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
         k_resize<kTMA><<<dim3(R.tiles_x * R.tiles_y, nb), 256, 0, st>>>(l == 1 ? tm_rs0 : h->tm_rs[l - 1], ra);
         ORBFE_AFTER_LAUNCH(h, st, "k_resize");
     }
+    ORBFE_PROF_MARK(h, st, 1);
     // K2 FAST + per-cell NMS
     FastArgs fa; fa.slots = h->d_slots; fa.cell_cnt = h->d_cell_cnt; fa.cells_per_frame = g.cells_per_frame;
     fa.t_ini = h->cfg.ini_th_fast; fa.t_min = h->cfg.min_th_fast;
     k_fast<kTMA><<<dim3(g.fast_blocks, nb), 256, 0, st>>>(LS, TF, fa);
     ORBFE_AFTER_LAUNCH(h, st, "k_fast");
+    ORBFE_PROF_MARK(h, st, 2);
     // K4 quadtree
     OctArgs oa;
     oa.slots = h->d_slots; oa.cell_cnt = h->d_cell_cnt; oa.cell_off = h->d_cell_off; oa.cand = h->d_cand; oa.cur = h->d_cur;
@@ -315,10 +333,12 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
     oa.sort_cap = g.sort_cap; oa.smem_node_cap = (g.oct_smem_bytes - g.sort_cap * 8) / 16;
     k_octree<256><<<dim3(nl, nb), 256, g.oct_smem_bytes, st>>>(LS, oa);
     ORBFE_AFTER_LAUNCH(h, st, "k_octree");
+    ORBFE_PROF_MARK(h, st, 3);
     // K6 blur
     BlurArgs ba; ba.blur = h->d_blur;
     k_blur<kTMA><<<dim3(g.blur_blocks, nb), 256, 0, st>>>(LS, TB, ba);
     ORBFE_AFTER_LAUNCH(h, st, "k_blur");
+    ORBFE_PROF_MARK(h, st, 4);
     // K5 + K7 orientation and descriptors, final assembly
     k_zero_counts<<<(nb + 255) / 256, 256, 0, st>>>(d_n, nb);
     ORBFE_AFTER_LAUNCH(h, st, "k_zero_counts");
@@ -328,6 +348,8 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
     build_u_max(da.u_max);
     k_describe<<<dim3((g.kp_per_frame + 7) / 8, nb), 256, 0, st>>>(LS, da);
     ORBFE_AFTER_LAUNCH(h, st, "k_describe");
+    ORBFE_PROF_MARK(h, st, 5);
+    if (h->prof) h->prof_pending = true;
     ORBFE_CUDA(h, cudaGetLastError());
     h->last_batch = nb;
     return ORBFE_OK;
@@ -399,6 +421,7 @@ void orbfe_destroy(orbfe_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_arena(h);
     cudaFree(h->d_err); cudaFree(h->d_match);
+    for (int i = 0; i <= ORBFE_N_STAGES; ++i) if (h->prof_ev[i]) cudaEventDestroy(h->prof_ev[i]);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -417,13 +440,36 @@ int orbfe_max_keypoints(const orbfe_handle *h) {
 }
 long long orbfe_launch_count(const orbfe_handle *h) { return h ? h->launches : 0; }
 
+int orbfe_profile(orbfe_handle *h, int enable) {
+    if (!h) return ORBFE_E_ARG;
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    if (enable && !h->prof_ev[0])
+        for (int i = 0; i <= ORBFE_N_STAGES; ++i) ORBFE_CUDA(h, cudaEventCreate(&h->prof_ev[i]));
+    if (!enable) { int rc = prof_collect(h); if (rc) return rc; }
+    h->prof = enable != 0;
+    return ORBFE_OK;
+}
+
+int orbfe_profile_read(orbfe_handle *h, float *stage_ms, int *n_passes, int reset) {
+    if (!h || !stage_ms || !n_passes) return ORBFE_E_ARG;
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    int rc = prof_collect(h);
+    if (rc) return rc;
+    for (int s = 0; s < ORBFE_N_STAGES; ++s) stage_ms[s] = (float) h->prof_ms[s];
+    *n_passes = h->prof_passes;
+    if (reset) { for (int s = 0; s < ORBFE_N_STAGES; ++s) h->prof_ms[s] = 0; h->prof_passes = 0; }
+    return ORBFE_OK;
+}
+
 int orbfe_host_alloc(void **ptr, size_t bytes) { return cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) == cudaSuccess ? ORBFE_OK : ORBFE_E_CUDA; }
 void orbfe_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }
 
 int orbfe_extract_batch_device(orbfe_handle *h, const uint8_t *d_frames, int n_frames, int width, int height, size_t row_stride,
                                size_t frame_stride, orbfe_keypoint *d_kps, uint8_t *d_desc, int cap, int *d_n, void *stream, int sync) {
     if (!h) return ORBFE_E_ARG;
-    if (!d_frames || !d_kps || !d_desc || !d_n || n_frames < 0 || cap < 1 || row_stride < (size_t) width) return set_error(h, ORBFE_E_ARG, "invalid argument");
+    if (!d_frames || !d_kps || !d_desc || !d_n || n_frames < 0 || cap < 1 || row_stride < (size_t) width)
+        return set_error(h, ORBFE_E_ARG, "orbfe_extract_batch_device: invalid argument (frames=%p kps=%p desc=%p n=%p n_frames=%d cap=%d row_stride=%zu width=%d)",
+                         (const void *) d_frames, (void *) d_kps, (void *) d_desc, (void *) d_n, n_frames, cap, row_stride, width);
     if (n_frames == 0 || width <= 0 || height <= 0) return ORBFE_OK;
     ORBFE_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t) stream : h->stream;
@@ -455,7 +501,9 @@ int orbfe_extract_batch_device(orbfe_handle *h, const uint8_t *d_frames, int n_f
 int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, int width, int height, size_t row_stride, size_t frame_stride,
                         orbfe_keypoint *kps, uint8_t *desc, int cap, int *n_per_frame) {
     if (!h) return ORBFE_E_ARG;
-    if (!frames || !kps || !desc || !n_per_frame || n_frames < 0 || cap < 1 || row_stride < (size_t) width) return set_error(h, ORBFE_E_ARG, "invalid argument");
+    if (!frames || !kps || !desc || !n_per_frame || n_frames < 0 || cap < 1 || row_stride < (size_t) width)
+        return set_error(h, ORBFE_E_ARG, "orbfe_extract_batch: invalid argument (frames=%p kps=%p desc=%p n=%p n_frames=%d cap=%d row_stride=%zu width=%d)",
+                         (const void *) frames, (void *) kps, (void *) desc, (void *) n_per_frame, n_frames, cap, row_stride, width);
     for (int b = 0; b < n_frames; ++b) n_per_frame[b] = 0;
     if (n_frames == 0 || width <= 0 || height <= 0) return ORBFE_OK;                 // ORBExtractor.cpp:497
     ORBFE_CUDA(h, cudaSetDevice(h->device));
@@ -487,7 +535,7 @@ int orbfe_extract(orbfe_handle *h, const uint8_t *gray, int width, int height, s
     if (!n_out) return set_error(h, ORBFE_E_ARG, "n_out is null");
     *n_out = 0;
     if (!gray || width <= 0 || height <= 0) return ORBFE_OK;                          // image.empty(): outputs untouched
-    if (!kps || !desc || cap < 1 || stride < (size_t) width) return set_error(h, ORBFE_E_ARG, "invalid argument");
+    if (!kps || !desc || cap < 1 || stride < (size_t) width) return set_error(h, ORBFE_E_ARG, "orbfe_extract: invalid argument (kps/desc null, cap < 1 or stride < width)");
     ORBFE_CUDA(h, cudaSetDevice(h->device));
     int rc = configure(h, width, height, 1);
     if (rc) return rc;

@@ -95,6 +95,12 @@ struct Handle {
     void *d_match = nullptr; size_t match_bytes = 0;
     void *h_pinned = nullptr; size_t pinned_bytes = 0;
 
+    // optional per-stage timing (orbfe_profile)
+    bool prof = false, prof_pending = false;
+    cudaEvent_t prof_ev[ORBFE_N_STAGES + 1] = {};
+    double prof_ms[ORBFE_N_STAGES] = {};
+    int prof_passes = 0;
+
     std::string err;
 };
 

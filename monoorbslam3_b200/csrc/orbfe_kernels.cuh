@@ -167,47 +167,51 @@ struct LevelSet {
 struct TmapSet { CUtensorMap m[ORBFE_MAX_LEVELS]; };
 
 // ------------------------------------------------------------------------------------------------
-// K2  FAST-9/16 per 30-px cell.  One warp per cell, 8 cells (a 246x36 patch) per CTA.
+// K2  FAST-9/16 per 30-px cell (cv::FAST on every cell, ORBExtractor.cpp:592-617).
+// One CTA per strip of 8 cells (240 x 30 px, a 256 x 36 byte TMA box).  The corner measure m(x, y) does not depend on the cell
+// grid, only NMS and the threshold fallback do, so the strip is processed in four block-wide stages:
+//   A  high-speed rejection, 4 pixels per thread on packed bytes (VABSDIFF4 + SWAR compares); survivors -> shared queue
+//   B  exact m for the queued pixels, 2 pixels per thread on packed s16x2 (VIMNMX3): m = max over the 16 arcs of
+//      max(min_arc(p - v), -max_arc(p - v)); corner iff m > t; corners are compacted in place into the queue
+//   C  3x3 non-max suppression of the corners inside their own cell (outside = 0) -> per-cell row bit masks
+//   D  one warp per cell: ordered (y, x) emission into the cell's slot, cell count
+// Cells without a survivor at iniThFAST repeat A-D with minThFAST (the reference's second cv::FAST call).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool has_arc9(unsigned m16) {
-    const unsigned r = m16 | (m16 << 16);
-    unsigned m = r;
-    m &= m >> 1; m &= m >> 2; m &= m >> 4;    // runs of 8
-    m &= r >> 8;                              // runs of 9
-    return (m & 0xffffu) != 0;
+constexpr int kStripW = kCell * kCellsPerBlk;      // 240
+
+__device__ __forceinline__ uint32_t bytes_gt(uint32_t x, uint32_t k7, bool t_ge_128) {
+    // per byte: x > t ? 0x80 : 0, with k7 = (127 - (t & 127)) replicated
+    const uint32_t low = (x & 0x7f7f7f7fu) + k7;
+    return (t_ge_128 ? (low & x) : (low | x)) & 0x80808080u;
 }
 
-// full segment test + corner score for one pixel; returns m (> t) or 0.  SURVEY Appendix A3.
-template <int SP>
-__device__ __forceinline__ int fast_full(const uint8_t *c, int t) {
-    const int v = c[0];
-    int d[16];
-    d[0] = v - c[3 * SP];      d[1] = v - c[3 * SP + 1];   d[2] = v - c[2 * SP + 2];   d[3] = v - c[SP + 3];
-    d[4] = v - c[3];           d[5] = v - c[-SP + 3];      d[6] = v - c[-2 * SP + 2];  d[7] = v - c[-3 * SP + 1];
-    d[8] = v - c[-3 * SP];     d[9] = v - c[-3 * SP - 1];  d[10] = v - c[-2 * SP - 2]; d[11] = v - c[-SP - 3];
-    d[12] = v - c[-3];         d[13] = v - c[SP - 3];      d[14] = v - c[2 * SP - 2];  d[15] = v - c[3 * SP - 1];
-    unsigned dark = 0, bright = 0;
+// exact corner measure of two pixels (centres cA, cB in the staged tile, pitch kBoxW); halves of the s16x2 lanes = (A, B)
+__device__ __forceinline__ void fast_measure2(const uint8_t *cA, const uint8_t *cB, int &mA, int &mB) {
+    constexpr int SP = kBoxW;
+    constexpr int ofs[16] = {3 * SP, 3 * SP + 1, 2 * SP + 2, SP + 3, 3, -SP + 3, -2 * SP + 2, -3 * SP + 1,
+                             -3 * SP, -3 * SP - 1, -2 * SP - 2, -SP - 3, -3, SP - 3, 2 * SP - 2, 3 * SP - 1};
+    const uint32_t negv = ((uint32_t) (-(int) cA[0]) & 0xffffu) | ((uint32_t) (-(int) cB[0]) << 16);
+    uint32_t e[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) e[k] = __vadd2((uint32_t) cA[ofs[k]] | ((uint32_t) cB[ofs[k]] << 16), negv);      // p - v
+    uint32_t mn[16], mx[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        dark |= (unsigned) (d[k] > t) << k;
-        bright |= (unsigned) (d[k] < -t) << k;
+        mn[k] = __vimin3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
+        mx[k] = __vimax3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
     }
-    const bool is_dark = has_arc9(dark);
-    if (!is_dark && !has_arc9(bright)) return 0;
-    // only one polarity can hold a 9-arc (two 9-arcs on a 16-ring overlap); the other side's minimum is <= t
-    int a1[16], a2[16];
+    uint32_t bright = 0x80008000u, dark = 0x7fff7fffu;      // max_k min9(e),  min_k max9(e)
 #pragma unroll
-    for (int k = 0; k < 16; ++k) d[k] = is_dark ? d[k] : -d[k];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) a1[k] = min(d[k], d[(k + 1) & 15]);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) a2[k] = min(a1[k], a1[(k + 2) & 15]);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) a1[k] = min(a2[k], a2[(k + 4) & 15]);     // 8 contiguous
-    int best = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) best = max(best, min(a1[k], d[(k + 8) & 15]));   // 9 contiguous
-    return best;
+    for (int k = 0; k < 16; k += 2) {
+        const uint32_t a = __vimin3_s16x2(mn[k], mn[(k + 3) & 15], mn[(k + 6) & 15]);
+        const uint32_t b = __vimin3_s16x2(mn[k + 1], mn[(k + 4) & 15], mn[(k + 7) & 15]);
+        bright = __vimax3_s16x2(bright, a, b);
+        const uint32_t c = __vimax3_s16x2(mx[k], mx[(k + 3) & 15], mx[(k + 6) & 15]);
+        const uint32_t d = __vimax3_s16x2(mx[k + 1], mx[(k + 4) & 15], mx[(k + 7) & 15]);
+        dark = __vimin3_s16x2(dark, c, d);
+    }
+    mA = max((int) (short) (bright & 0xffffu), -(int) (short) (dark & 0xffffu));
+    mB = max((int) (short) (bright >> 16), -(int) (short) (dark >> 16));
 }
 
 struct FastArgs {
@@ -217,97 +221,160 @@ struct FastArgs {
 
 template <bool kTMA>
 __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ LevelSet L, const __grid_constant__ TmapSet T, const FastArgs a) {
-    constexpr int SP = TilePitch<kTMA>::value;
+    constexpr int SP = kBoxW;
     __shared__ __align__(128) uint8_t tile[kFastBoxH * SP];
-    __shared__ __align__(16) uint8_t mmap[kCellsPerBlk][32 * 32];
-    __shared__ uint16_t queue[kCellsPerBlk][kCell * kCell];
+    __shared__ __align__(16) uint8_t mmap[kCellsPerBlk][32 * 32];      // per cell, 1-px zero frame: m at [(cy+1)*32 + cx+1]
+    __shared__ uint16_t queue[kStripW * kCell];                         // y << 8 | x  (strip coordinates)
+    __shared__ uint32_t rowmask[kCellsPerBlk][32];                      // NMS survivors of cell row r, bit = cx
+    __shared__ int s_qn, s_cn;
     __shared__ __align__(8) uint64_t bar;
 
-    const int frame = blockIdx.y;
+    const int frame = blockIdx.y, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     int l = 0;
 #pragma unroll 1
     for (int k = 1; k < L.n_levels; ++k) if ((int) blockIdx.x >= L.lv[k].fast_blk_base) l = k;
     const LevelGeom &G = L.lv[l];
     const int rem = blockIdx.x - G.fast_blk_base;
     const int ci = rem / G.n_groups, cg = rem - ci * G.n_groups;
-    const int px = kEdge - 3 + kCell * kCellsPerBlk * cg, py = kEdge - 3 + kCell * ci;     // 16-byte aligned x origin
+    const int px = kEdge - 3 + kStripW * cg, py = kEdge - 3 + kCell * ci;               // 16-byte aligned x origin
     stage_box<kTMA, 256>(tile, &bar, &T.m[l], L.img[l] + (size_t) frame * G.frame_stride, G.pitch, G.h, px, py, frame, kFastBoxH);
 
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cj = cg * kCellsPerBlk + wid;
-    if (cj >= G.n_cols) return;
-    const int max_bx = G.w - kEdge, max_by = G.h - kEdge;
-    const int ini_x = kEdge + cj * kCell, ini_y = kEdge + ci * kCell;
-    const int cw = min(ini_x + kCell, max_bx) - ini_x, ch = min(ini_y + kCell, max_by) - ini_y;
-    const int t_lo = min(a.t_ini, a.t_min);
+    const int strip_w = min(kStripW, G.w - kEdge - (kEdge + kStripW * cg));             // pixels of this strip inside maxBorderX
+    const int ch = min(kCell, G.h - kEdge - (kEdge + kCell * ci));                      // rows inside maxBorderY
+    const int cj = cg * kCellsPerBlk + wid;                                             // this warp's cell (stage D)
+    const int cw = min(kCell, strip_w - kCell * wid);                                   // <= 0: no such cell
+    bool cell_open = cw > 0;                                                            // still needs a result
+    const uint8_t *strip = tile + 3 * SP + 3;                                           // pixel (x, y) at strip[y * SP + x]
 
-    uint8_t *mm = mmap[wid];
-    uint16_t *q = queue[wid];
+#pragma unroll 1
+    for (int round = 0; round < 2; ++round) {
+        const int t = round == 0 ? a.t_ini : a.t_min;
+        unsigned open_cells = __ballot_sync(0xffffffffu, cell_open) ? 1u << wid : 0u;
+        // every thread needs the set of open cells: gather through shared memory
+        if (tid == 0) { s_qn = 0; s_cn = 0; }
+        if (lane == 0) rowmask[wid][0] = open_cells;       // temporary use of rowmask[w][0]
+        __syncthreads();
+        unsigned open_all = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) reinterpret_cast<uint32_t *>(mm)[lane + 32 * k] = 0;
+        for (int w = 0; w < kCellsPerBlk; ++w) open_all |= rowmask[w][0];
+        __syncthreads();
+        if (open_all == 0) break;
+        for (int i = tid; i < kCellsPerBlk * 256; i += 256) if ((open_all >> (i >> 8)) & 1u) reinterpret_cast<uint32_t *>(mmap)[i] = 0;
+        rowmask[wid][lane] = 0;
+        __syncthreads();
 
-    // pass 1: high-speed rejection (every 9-arc contains ring pixel 0 or 8, and 4 or 12); survivors are queued densely
-    const uint8_t *cell0 = tile + 3 * SP + 3 + kCell * wid;
-    int qn = 0;
-    for (int cy = 0; cy < ch; ++cy) {
-        bool pass = false;
-        if (lane < cw) {
-            const uint8_t *c = cell0 + cy * SP + lane;
-            const int v = c[0];
-            const int d0 = abs(v - c[3 * SP]), d8 = abs(v - c[-3 * SP]);
-            const int d4 = abs(v - c[3]), d12 = abs(v - c[-3]);
-            pass = !((d0 <= t_lo && d8 <= t_lo) || (d4 <= t_lo && d12 <= t_lo));
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, pass);
-        if (pass) q[qn + __popc(bal & ((1u << lane) - 1u))] = (uint16_t) (cy * 32 + lane);
-        qn += __popc(bal);
-    }
-    __syncwarp();
-    // pass 2: full segment test + score on the dense queue
-    for (int k = lane; k < qn; k += 32) {
-        const int pos = q[k];
-        const int cy = pos >> 5, cx = pos & 31;
-        const int m = fast_full<SP>(cell0 + cy * SP + cx, t_lo);
-        if (m) mm[(cy + 1) * 32 + cx + 1] = (uint8_t) m;
-    }
-    __syncwarp();
-    // pass 3: 3x3 non-max suppression confined to the cell (outside = 0).  Because score = m-1 is monotone in m, the
-    // survivors at any threshold t >= t_lo are the t_lo survivors with m > t.
-    unsigned row_ini = 0, row_min = 0;     // lane r keeps the survivor masks of cell row r
-    for (int cy = 0; cy < ch; ++cy) {
-        int m = 0; bool s = false;
-        if (lane < cw) {
-            const uint8_t *p = mm + (cy + 1) * 32 + lane + 1;
-            m = p[0];
-            if (m) {
-                int nb = max(max(p[-1], p[1]), max(p[-33], p[-32]));
-                nb = max(nb, max(max(p[-31], p[31]), max(p[32], p[33])));
-                s = m > nb;
+        // ---- A: high-speed test on aligned words of the tile rows: word j = strip pixels 4j-3 .. 4j
+        {
+            const uint32_t k7 = (uint32_t) (127 - (t & 127)) * 0x01010101u;
+            const bool tge = t >= 128;
+            for (int idx = tid; idx < ch * 64; idx += 256) {
+                const int y = idx >> 6, j = idx & 63;
+                uint32_t pass = 0;
+                if (j <= kStripW / 4) {
+                    const uint32_t *rc = reinterpret_cast<const uint32_t *>(tile + (3 + y) * SP);
+                    const uint32_t w1 = rc[j], w0 = j ? rc[j - 1] : 0u, w2 = rc[j + 1];
+                    const uint32_t up = reinterpret_cast<const uint32_t *>(tile + y * SP)[j];
+                    const uint32_t dn = reinterpret_cast<const uint32_t *>(tile + (6 + y) * SP)[j];
+                    const uint32_t lf = __funnelshift_r(w0, w1, 8), rt = __funnelshift_r(w1, w2, 24);
+                    const uint32_t m0 = bytes_gt(__vabsdiffu4(w1, dn), k7, tge), m8 = bytes_gt(__vabsdiffu4(w1, up), k7, tge);
+                    const uint32_t m4 = bytes_gt(__vabsdiffu4(w1, rt), k7, tge), m12 = bytes_gt(__vabsdiffu4(w1, lf), k7, tge);
+                    pass = (m0 | m8) & (m4 | m12);           // every 9-arc holds ring 0 or 8, and ring 4 or 12
+                    // keep only pixels inside the strip whose cell is still open
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int x = 4 * j - 3 + b;
+                        const bool ok = x >= 0 && x < strip_w && ((open_all >> ((x * 2185) >> 16)) & 1u);
+                        if (!ok) pass &= ~(0x80u << (8 * b));
+                    }
+                }
+                const int c = __popc(pass);
+                int inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+                const int total = __shfl_sync(0xffffffffu, inc, 31);
+                if (total) {
+                    int base = 0;
+                    if (lane == 31) base = atomicAdd(&s_qn, total);
+                    base = __shfl_sync(0xffffffffu, base, 31);
+                    int o = base + inc - c;
+                    while (pass) {
+                        const int b = (__ffs(pass) - 1) >> 3;
+                        pass &= pass - 1;
+                        queue[o++] = (uint16_t) ((y << 8) | (4 * j - 3 + b));
+                    }
+                }
             }
         }
-        const unsigned bi = __ballot_sync(0xffffffffu, s && m > a.t_ini);
-        const unsigned bm = __ballot_sync(0xffffffffu, s && m > a.t_min);
-        if (lane == cy) { row_ini = bi; row_min = bm; }
-    }
-    const bool any_ini = __any_sync(0xffffffffu, row_ini != 0);     // ORBExtractor.cpp:604: fall back only if the cell is empty
-    unsigned mask = any_ini ? row_ini : row_min;
-    const int cnt = __popc(mask);
-    int inc = cnt;
+        __syncthreads();
+
+        // ---- B: exact measure, two queued pixels per thread; corners (m > t) are compacted in place at the queue head
+        {
+            const int n = s_qn;
+            for (int base = 0; base < n; base += 512) {
+                const int k = base + 2 * tid;
+                int pa = 0, pb = 0;
+                if (k < n) { pa = queue[k]; pb = queue[min(k + 1, n - 1)]; }
+                __syncthreads();                            // all entries of this round are in registers: the head may be overwritten
+                int ma = 0, mb = 0;
+                if (k < n) {
+                    fast_measure2(strip + (pa >> 8) * SP + (pa & 255), strip + (pb >> 8) * SP + (pb & 255), ma, mb);
+                    if (k + 1 >= n) mb = 0;
+                }
+                const bool ca = ma > t, cb = mb > t;
+                if (ca) { const int x = pa & 255, c = (x * 2185) >> 16; mmap[c][((pa >> 8) + 1) * 32 + (x - kCell * c) + 1] = (uint8_t) ma; }
+                if (cb) { const int x = pb & 255, c = (x * 2185) >> 16; mmap[c][((pb >> 8) + 1) * 32 + (x - kCell * c) + 1] = (uint8_t) mb; }
+                const unsigned ba = __ballot_sync(0xffffffffu, ca), bb = __ballot_sync(0xffffffffu, cb);
+                const int total = __popc(ba) + __popc(bb);
+                if (total) {
+                    int o = 0;
+                    if (lane == 0) o = atomicAdd(&s_cn, total);
+                    o = __shfl_sync(0xffffffffu, o, 0);
+                    const unsigned lt = (1u << lane) - 1u;
+                    if (ca) queue[o + __popc(ba & lt)] = (uint16_t) pa;
+                    if (cb) queue[o + __popc(ba) + __popc(bb & lt)] = (uint16_t) pb;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- C: non-max suppression inside the cell (strictly greater than the 8 neighbours; outside the cell = 0)
+        {
+            const int n = s_cn;
+            for (int k = tid; k < n; k += 256) {
+                const int pos = queue[k];
+                const int x = pos & 255, y = pos >> 8, c = (x * 2185) >> 16, cx = x - kCell * c;
+                const uint8_t *p = mmap[c] + (y + 1) * 32 + cx + 1;
+                const int m = p[0];
+                int nb = max(max(p[-1], p[1]), max(p[-33], p[-32]));
+                nb = max(nb, max(max(p[-31], p[31]), max(p[32], p[33])));
+                if (m > nb) atomicOr(&rowmask[c][y], 1u << cx);
+            }
+        }
+        __syncthreads();
+
+        // ---- D: one warp per cell, lane = cell row: ordered emission (ORBExtractor.cpp:609-615)
+        if (cell_open) {
+            unsigned mask = rowmask[wid][lane];
+            const int cnt = __popc(mask);
+            int inc = cnt;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+            const int total = __shfl_sync(0xffffffffu, inc, 31);
+            if (total > 0 || round == 1) {
+                const int cell = G.cell_base + ci * G.n_cols + cj;
+                uint32_t *slot = a.slots + ((size_t) frame * a.cells_per_frame + cell) * kSlotCap + (inc - cnt);
+                while (mask) {
+                    const int cx = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int m = mmap[wid][(lane + 1) * 32 + cx + 1];
+                    *slot++ = (uint32_t) (cj * kCell + cx) | ((uint32_t) (ci * kCell + lane) << 12) | ((uint32_t) (m - 1) << 24);
+                }
+                if (lane == 0) a.cell_cnt[(size_t) frame * a.cells_per_frame + cell] = total;
+                cell_open = false;
+            }
+        }
+        // (the loop head synchronises before shared state is reused)
     }
-    const int total = __shfl_sync(0xffffffffu, inc, 31);
-    const int cell = G.cell_base + ci * G.n_cols + cj;
-    uint32_t *slot = a.slots + ((size_t) frame * a.cells_per_frame + cell) * kSlotCap + (inc - cnt);
-    while (mask) {
-        const int cx = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int m = mm[(lane + 1) * 32 + cx + 1];
-        *slot++ = (uint32_t) (cj * kCell + cx) | ((uint32_t) (ci * kCell + lane) << 12) | ((uint32_t) (m - 1) << 24);
-    }
-    if (lane == 0) a.cell_cnt[(size_t) frame * a.cells_per_frame + cell] = total;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -53,6 +53,17 @@ class ORBExtractor:
     def launch_count(self):
         return int(self._lib.orbfe_launch_count(self._h))
 
+    def profile(self, enable=True):
+        """Record CUDA events around every stage of every pass (on the launching stream)."""
+        _capi.check(self._h, self._lib.orbfe_profile(self._h, int(enable)))
+
+    def profile_read(self, reset=True):
+        """-> ({stage: accumulated ms}, passes) since the last reset."""
+        ms = np.zeros(len(_capi.STAGES), np.float32)
+        n = C.c_int()
+        _capi.check(self._h, self._lib.orbfe_profile_read(self._h, _capi.ptr(ms), C.byref(n), int(reset)))
+        return dict(zip(_capi.STAGES, ms.tolist())), n.value
+
     # ---- operator()
     def __call__(self, image):
         """image: HxW uint8 (CV_8UC1).  Returns (keypoints[KP_DTYPE], descriptors[N,32] uint8).  An empty image or an image
@@ -76,6 +87,8 @@ class ORBExtractor:
         """frames: [B,H,W] uint8 host array (pinned or pageable).  Returns (n[B], kps[B,cap], desc[B,cap,32]) host arrays."""
         if frames.dtype != np.uint8 or frames.ndim != 3:
             raise TypeError("frames must be a [B,H,W] uint8 array")
+        if frames.strides[2] != 1 or frames.strides[1] < frames.shape[2]:
+            frames = np.ascontiguousarray(frames)
         B, H, W = frames.shape
         if cap is None:
             cap = self.n_features + 40 * self.n_levels + 64

@@ -30,11 +30,11 @@ def frame(h, w, seed, profile="dense"):
         rw = int(rng.integers(5, 80)); rh = int(rng.integers(5, 80)); v = float(rng.uniform(0, 256))
         img[y0:y0 + rh, x0:x0 + rw] = 0.5 * img[y0:y0 + rh, x0:x0 + rw] + 0.5 * v
     img += rng.normal(0, sigma, (h, w))
-    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(np.clip(np.rint(img), 0, 255).astype(np.uint8))
 
 
 def frames(n, h, w, seed0=1000, profile="dense"):
-    return np.stack([frame(h, w, seed0 + k, profile) for k in range(n)])
+    return np.ascontiguousarray(np.stack([frame(h, w, seed0 + k, profile) for k in range(n)]))
 
 
 def shifted_pair(h, w, seed, dx=7, dy=3, profile="dense"):
@@ -44,4 +44,4 @@ def shifted_pair(h, w, seed, dx=7, dy=3, profile="dense"):
     b = big[4 + dy:4 + dy + h, 4 + dx:4 + dx + w].astype(np.int16)
     rng = np.random.default_rng(seed + 7919)
     b = b + np.rint(rng.normal(0, 1.5, b.shape)).astype(np.int16)
-    return np.clip(a, 0, 255).astype(np.uint8), np.clip(b, 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(np.clip(a, 0, 255).astype(np.uint8)), np.ascontiguousarray(np.clip(b, 0, 255).astype(np.uint8))
