@@ -220,13 +220,13 @@ struct FastArgs {
 };
 
 template <bool kTMA>
-__global__ void __launch_bounds__(256) k_fast(const __grid_constant__ LevelSet L, const __grid_constant__ TmapSet T, const FastArgs a) {
+__global__ void __launch_bounds__(256, 4) k_fast(const __grid_constant__ LevelSet L, const __grid_constant__ TmapSet T, const FastArgs a) {
     constexpr int SP = kBoxW;
     __shared__ __align__(128) uint8_t tile[kFastBoxH * SP];
-    __shared__ __align__(16) uint8_t mmap[kCellsPerBlk][32 * 32];      // per cell, 1-px zero frame: m at [(cy+1)*32 + cx+1]
+    __shared__ __align__(16) uint8_t mmap[32 * SP];                     // m of strip pixel (x, y) at [(y+1)*SP + x+1], zero elsewhere
     __shared__ uint16_t queue[kStripW * kCell];                         // y << 8 | x  (strip coordinates)
     __shared__ uint32_t rowmask[kCellsPerBlk][32];                      // NMS survivors of cell row r, bit = cx
-    __shared__ int s_qn, s_cn;
+    __shared__ int s_qn, s_cn, s_has[kCellsPerBlk];
     __shared__ __align__(8) uint64_t bar;
 
     const int frame = blockIdx.y, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
@@ -241,66 +241,67 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ LevelSet L
 
     const int strip_w = min(kStripW, G.w - kEdge - (kEdge + kStripW * cg));             // pixels of this strip inside maxBorderX
     const int ch = min(kCell, G.h - kEdge - (kEdge + kCell * ci));                      // rows inside maxBorderY
-    const int cj = cg * kCellsPerBlk + wid;                                             // this warp's cell (stage D)
-    const int cw = min(kCell, strip_w - kCell * wid);                                   // <= 0: no such cell
-    bool cell_open = cw > 0;                                                            // still needs a result
     const uint8_t *strip = tile + 3 * SP + 3;                                           // pixel (x, y) at strip[y * SP + x]
+    unsigned open = (1u << ((strip_w + kCell - 1) / kCell)) - 1u;                       // cells that still need a result
+    const unsigned lt = (1u << lane) - 1u;
 
 #pragma unroll 1
     for (int round = 0; round < 2; ++round) {
         const int t = round == 0 ? a.t_ini : a.t_min;
-        unsigned open_cells = __ballot_sync(0xffffffffu, cell_open) ? 1u << wid : 0u;
-        // every thread needs the set of open cells: gather through shared memory
         if (tid == 0) { s_qn = 0; s_cn = 0; }
-        if (lane == 0) rowmask[wid][0] = open_cells;       // temporary use of rowmask[w][0]
-        __syncthreads();
-        unsigned open_all = 0;
-#pragma unroll
-        for (int w = 0; w < kCellsPerBlk; ++w) open_all |= rowmask[w][0];
-        __syncthreads();
-        if (open_all == 0) break;
-        for (int i = tid; i < kCellsPerBlk * 256; i += 256) if ((open_all >> (i >> 8)) & 1u) reinterpret_cast<uint32_t *>(mmap)[i] = 0;
+        if (tid < kCellsPerBlk) s_has[tid] = 0;
         rowmask[wid][lane] = 0;
+        if (round == 0) {
+            for (int i = tid; i < 32 * SP / 16; i += 256) reinterpret_cast<uint4 *>(mmap)[i] = make_uint4(0, 0, 0, 0);
+        } else {
+            for (int i = tid; i < 32 * SP; i += 256) {
+                const int x = (i & 255) - 1;
+                if (x >= 0 && x < kStripW && ((open >> ((x * 2185) >> 16)) & 1u)) mmap[i] = 0;
+            }
+        }
         __syncthreads();
 
-        // ---- A: high-speed test on aligned words of the tile rows: word j = strip pixels 4j-3 .. 4j
+        // ---- A: high-speed test, one warp per strip row, lane = aligned words `lane` and `lane + 32` (word j = pixels 4j-3 .. 4j)
         {
             const uint32_t k7 = (uint32_t) (127 - (t & 127)) * 0x01010101u;
             const bool tge = t >= 128;
-            for (int idx = tid; idx < ch * 64; idx += 256) {
-                const int y = idx >> 6, j = idx & 63;
-                uint32_t pass = 0;
-                if (j <= kStripW / 4) {
-                    const uint32_t *rc = reinterpret_cast<const uint32_t *>(tile + (3 + y) * SP);
-                    const uint32_t w1 = rc[j], w0 = j ? rc[j - 1] : 0u, w2 = rc[j + 1];
-                    const uint32_t up = reinterpret_cast<const uint32_t *>(tile + y * SP)[j];
-                    const uint32_t dn = reinterpret_cast<const uint32_t *>(tile + (6 + y) * SP)[j];
+            for (int y = wid; y < ch; y += 8) {
+                const uint32_t *rc = reinterpret_cast<const uint32_t *>(tile + (3 + y) * SP);
+                const uint32_t *ru = reinterpret_cast<const uint32_t *>(tile + y * SP);
+                const uint32_t *rd = reinterpret_cast<const uint32_t *>(tile + (6 + y) * SP);
+                uint32_t pass[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int j = lane + 32 * h;
+                    const uint32_t w1 = rc[j], w0 = rc[max(j - 1, 0)], w2 = rc[min(j + 1, 63)];
                     const uint32_t lf = __funnelshift_r(w0, w1, 8), rt = __funnelshift_r(w1, w2, 24);
-                    const uint32_t m0 = bytes_gt(__vabsdiffu4(w1, dn), k7, tge), m8 = bytes_gt(__vabsdiffu4(w1, up), k7, tge);
+                    const uint32_t m0 = bytes_gt(__vabsdiffu4(w1, rd[j]), k7, tge), m8 = bytes_gt(__vabsdiffu4(w1, ru[j]), k7, tge);
                     const uint32_t m4 = bytes_gt(__vabsdiffu4(w1, rt), k7, tge), m12 = bytes_gt(__vabsdiffu4(w1, lf), k7, tge);
-                    pass = (m0 | m8) & (m4 | m12);           // every 9-arc holds ring 0 or 8, and ring 4 or 12
-                    // keep only pixels inside the strip whose cell is still open
+                    uint32_t p = (m0 | m8) & (m4 | m12);      // every 9-arc holds ring 0 or 8, and ring 4 or 12
+                    // pixels 4j-3+b must lie in [0, strip_w)
+                    const int nb = min(max(strip_w + 3 - 4 * j, 0), 4);
+                    p &= nb >= 4 ? 0xffffffffu : ((1u << (8 * nb)) - 1u);
+                    if (j == 0) p &= 0xff000000u;
+                    if (round) {                              // second pass: only cells without a survivor
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const int x = 4 * j - 3 + b;
-                        const bool ok = x >= 0 && x < strip_w && ((open_all >> ((x * 2185) >> 16)) & 1u);
-                        if (!ok) pass &= ~(0x80u << (8 * b));
+                        for (int b = 0; b < 4; ++b) {
+                            const int x = max(4 * j - 3 + b, 0);
+                            if (!((open >> ((x * 2185) >> 16)) & 1u)) p &= ~(0x80u << (8 * b));
+                        }
                     }
+                    pass[h] = p;
                 }
-                const int c = __popc(pass);
-                int inc = c;
+                unsigned bal[8]; int total = 0;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-                const int total = __shfl_sync(0xffffffffu, inc, 31);
+                for (int i = 0; i < 8; ++i) { bal[i] = __ballot_sync(0xffffffffu, (pass[i >> 2] >> (8 * (i & 3) + 7)) & 1u); total += __popc(bal[i]); }
                 if (total) {
-                    int base = 0;
-                    if (lane == 31) base = atomicAdd(&s_qn, total);
-                    base = __shfl_sync(0xffffffffu, base, 31);
-                    int o = base + inc - c;
-                    while (pass) {
-                        const int b = (__ffs(pass) - 1) >> 3;
-                        pass &= pass - 1;
-                        queue[o++] = (uint16_t) ((y << 8) | (4 * j - 3 + b));
+                    int o = 0;
+                    if (lane == 0) o = atomicAdd(&s_qn, total);
+                    o = __shfl_sync(0xffffffffu, o, 0);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if ((bal[i] >> lane) & 1u) queue[o + __popc(bal[i] & lt)] = (uint16_t) ((y << 8) | (4 * (lane + 32 * (i >> 2)) - 3 + (i & 3)));
+                        o += __popc(bal[i]);
                     }
                 }
             }
@@ -321,15 +322,14 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ LevelSet L
                     if (k + 1 >= n) mb = 0;
                 }
                 const bool ca = ma > t, cb = mb > t;
-                if (ca) { const int x = pa & 255, c = (x * 2185) >> 16; mmap[c][((pa >> 8) + 1) * 32 + (x - kCell * c) + 1] = (uint8_t) ma; }
-                if (cb) { const int x = pb & 255, c = (x * 2185) >> 16; mmap[c][((pb >> 8) + 1) * 32 + (x - kCell * c) + 1] = (uint8_t) mb; }
+                if (ca) mmap[pa + SP + 1] = (uint8_t) ma;
+                if (cb) mmap[pb + SP + 1] = (uint8_t) mb;
                 const unsigned ba = __ballot_sync(0xffffffffu, ca), bb = __ballot_sync(0xffffffffu, cb);
                 const int total = __popc(ba) + __popc(bb);
                 if (total) {
                     int o = 0;
                     if (lane == 0) o = atomicAdd(&s_cn, total);
                     o = __shfl_sync(0xffffffffu, o, 0);
-                    const unsigned lt = (1u << lane) - 1u;
                     if (ca) queue[o + __popc(ba & lt)] = (uint16_t) pa;
                     if (cb) queue[o + __popc(ba) + __popc(bb & lt)] = (uint16_t) pb;
                 }
@@ -343,37 +343,41 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ LevelSet L
             for (int k = tid; k < n; k += 256) {
                 const int pos = queue[k];
                 const int x = pos & 255, y = pos >> 8, c = (x * 2185) >> 16, cx = x - kCell * c;
-                const uint8_t *p = mmap[c] + (y + 1) * 32 + cx + 1;
+                const uint8_t *p = mmap + pos + SP + 1;
                 const int m = p[0];
-                int nb = max(max(p[-1], p[1]), max(p[-33], p[-32]));
-                nb = max(nb, max(max(p[-31], p[31]), max(p[32], p[33])));
-                if (m > nb) atomicOr(&rowmask[c][y], 1u << cx);
+                int nb = max(p[-SP], p[SP]);
+                if (cx > 0) nb = max(nb, max(max(p[-SP - 1], p[-1]), p[SP - 1]));
+                if (cx < kCell - 1 && x + 1 < strip_w) nb = max(nb, max(max(p[-SP + 1], p[1]), p[SP + 1]));
+                if (m > nb) { atomicOr(&rowmask[c][y], 1u << cx); s_has[c] = 1; }
             }
         }
         __syncthreads();
 
         // ---- D: one warp per cell, lane = cell row: ordered emission (ORBExtractor.cpp:609-615)
-        if (cell_open) {
+        unsigned has = 0;
+#pragma unroll
+        for (int c = 0; c < kCellsPerBlk; ++c) has |= s_has[c] ? 1u << c : 0u;
+        if (((open >> wid) & 1u) && (((has >> wid) & 1u) || round == 1)) {
             unsigned mask = rowmask[wid][lane];
             const int cnt = __popc(mask);
             int inc = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
             const int total = __shfl_sync(0xffffffffu, inc, 31);
-            if (total > 0 || round == 1) {
-                const int cell = G.cell_base + ci * G.n_cols + cj;
-                uint32_t *slot = a.slots + ((size_t) frame * a.cells_per_frame + cell) * kSlotCap + (inc - cnt);
-                while (mask) {
-                    const int cx = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const int m = mmap[wid][(lane + 1) * 32 + cx + 1];
-                    *slot++ = (uint32_t) (cj * kCell + cx) | ((uint32_t) (ci * kCell + lane) << 12) | ((uint32_t) (m - 1) << 24);
-                }
-                if (lane == 0) a.cell_cnt[(size_t) frame * a.cells_per_frame + cell] = total;
-                cell_open = false;
+            const int cj = cg * kCellsPerBlk + wid;
+            const int cell = G.cell_base + ci * G.n_cols + cj;
+            uint32_t *slot = a.slots + ((size_t) frame * a.cells_per_frame + cell) * kSlotCap + (inc - cnt);
+            while (mask) {
+                const int cx = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int m = mmap[(lane + 1) * SP + kCell * wid + cx + 1];
+                *slot++ = (uint32_t) (cj * kCell + cx) | ((uint32_t) (ci * kCell + lane) << 12) | ((uint32_t) (m - 1) << 24);
             }
+            if (lane == 0) a.cell_cnt[(size_t) frame * a.cells_per_frame + cell] = total;
         }
-        // (the loop head synchronises before shared state is reused)
+        open &= ~has;
+        if (open == 0) break;
+        __syncthreads();                                     // stage D reads of mmap / rowmask precede the re-initialisation
     }
 }
 
