@@ -120,7 +120,9 @@ static void free_arena(Handle *h) {
     cudaFree(h->d_ncand); cudaFree(h->d_tables); cudaFree(h->d_out_kps); cudaFree(h->d_out_desc); cudaFree(h->d_out_n);
     h->d_img = h->d_blur = nullptr; h->d_slots = nullptr; h->d_cell_cnt = h->d_cell_off = nullptr; h->d_cand = nullptr; h->d_cur = nullptr;
     h->d_nodes = nullptr; h->d_lists = nullptr; h->d_kp = nullptr; h->d_nkp = h->d_ncand = nullptr; h->d_tables = nullptr;
-    h->d_out_kps = nullptr; h->d_out_desc = nullptr; h->d_out_n = nullptr; h->out_cap = 0;
+    h->d_out_kps = nullptr; h->d_out_desc = nullptr; h->d_out_n = nullptr; h->out_cap = 0; h->out_frames = 0;
+    for (int i = 0; i < 2; ++i) { cudaFree(h->d_stage[i]); h->d_stage[i] = nullptr; }
+    h->stage_bytes = 0;
     h->batch_cap = 0; h->g.w = h->g.h = 0;
 }
 
@@ -242,7 +244,7 @@ static int configure(Handle *h, int w, int ht, int batch) {
 }
 
 static int ensure_out_staging(Handle *h, int cap) {
-    if (h->d_out_kps && h->out_cap >= cap) return ORBFE_OK;
+    if (h->d_out_kps && h->out_cap >= cap && h->out_frames >= h->batch_cap) return ORBFE_OK;
     ORBFE_CUDA(h, cudaStreamSynchronize(h->stream));
     cudaFree(h->d_out_kps); cudaFree(h->d_out_desc); cudaFree(h->d_out_n);
     h->d_out_kps = nullptr; h->d_out_desc = nullptr; h->d_out_n = nullptr;
@@ -250,7 +252,37 @@ static int ensure_out_staging(Handle *h, int cap) {
     ORBFE_CUDA(h, cudaMalloc(&h->d_out_kps, B * cap * sizeof(orbfe_keypoint)));
     ORBFE_CUDA(h, cudaMalloc(&h->d_out_desc, B * cap * 32));
     ORBFE_CUDA(h, cudaMalloc(&h->d_out_n, B * sizeof(int)));
-    h->out_cap = cap;
+    h->out_cap = cap; h->out_frames = (int) B;
+    return ORBFE_OK;
+}
+
+// staging of the pipelined host entry point: two dense input slots, two output slots, copy streams and events
+static int ensure_pipeline(Handle *h, size_t stage_bytes, int chunk, int cap) {
+    if (!h->s_up) {
+        ORBFE_CUDA(h, cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
+        ORBFE_CUDA(h, cudaStreamCreateWithFlags(&h->s_down, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            ORBFE_CUDA(h, cudaEventCreateWithFlags(&h->ev_up[i], cudaEventDisableTiming));
+            ORBFE_CUDA(h, cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+            ORBFE_CUDA(h, cudaEventCreateWithFlags(&h->ev_down[i], cudaEventDisableTiming));
+        }
+    }
+    if (h->stage_bytes < stage_bytes) {
+        ORBFE_CUDA(h, cudaDeviceSynchronize());
+        for (int i = 0; i < 2; ++i) { cudaFree(h->d_stage[i]); h->d_stage[i] = nullptr; }
+        for (int i = 0; i < 2; ++i) ORBFE_CUDA(h, cudaMalloc(&h->d_stage[i], stage_bytes + 256));
+        h->stage_bytes = stage_bytes;
+    }
+    if (!h->d_out_kps || h->out_cap < cap || h->out_frames < 2 * chunk) {
+        ORBFE_CUDA(h, cudaDeviceSynchronize());
+        cudaFree(h->d_out_kps); cudaFree(h->d_out_desc); cudaFree(h->d_out_n);
+        h->d_out_kps = nullptr; h->d_out_desc = nullptr; h->d_out_n = nullptr;
+        const size_t B = (size_t) std::max(2 * chunk, h->batch_cap);
+        ORBFE_CUDA(h, cudaMalloc(&h->d_out_kps, B * cap * sizeof(orbfe_keypoint)));
+        ORBFE_CUDA(h, cudaMalloc(&h->d_out_desc, B * cap * 32));
+        ORBFE_CUDA(h, cudaMalloc(&h->d_out_n, B * sizeof(int)));
+        h->out_cap = cap; h->out_frames = (int) B;
+    }
     return ORBFE_OK;
 }
 
@@ -424,6 +456,13 @@ void orbfe_destroy(orbfe_handle *h) {
     for (int i = 0; i <= ORBFE_N_STAGES; ++i) if (h->prof_ev[i]) cudaEventDestroy(h->prof_ev[i]);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->s_up) cudaStreamDestroy(h->s_up);
+    if (h->s_down) cudaStreamDestroy(h->s_down);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+        if (h->ev_down[i]) cudaEventDestroy(h->ev_down[i]);
+    }
     delete h;
 }
 
@@ -498,6 +537,9 @@ int orbfe_extract_batch_device(orbfe_handle *h, const uint8_t *d_frames, int n_f
     return ORBFE_OK;
 }
 
+// Host batch entry point: a 3-stream software pipeline over chunks of frames.  Chunk c is copied host->device into one of two
+// dense staging buffers on the copy stream while chunk c-1 runs on the compute stream and the results of chunk c-2 go back to the
+// host on the download stream; level 0 is read in place from the staging buffer when the row size allows TMA (multiple of 16).
 int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, int width, int height, size_t row_stride, size_t frame_stride,
                         orbfe_keypoint *kps, uint8_t *desc, int cap, int *n_per_frame) {
     if (!h) return ORBFE_E_ARG;
@@ -507,27 +549,49 @@ int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, in
     for (int b = 0; b < n_frames; ++b) n_per_frame[b] = 0;
     if (n_frames == 0 || width <= 0 || height <= 0) return ORBFE_OK;                 // ORBExtractor.cpp:497
     ORBFE_CUDA(h, cudaSetDevice(h->device));
-    int rc = configure(h, width, height, std::min(n_frames, h->cfg.max_batch));
+    const int chunk = std::min(h->cfg.max_batch, std::max(16, std::min(128, (n_frames + 3) / 4)));
+    int rc = configure(h, width, height, std::min(n_frames, chunk));
     if (rc) return rc;
-    if ((rc = ensure_out_staging(h, cap))) return rc;
-    cudaStream_t st = h->stream;
+    const int cn = std::min(h->batch_cap, chunk);                                   // frames per pipeline stage
+    if ((rc = ensure_pipeline(h, (size_t) cn * width * height, cn, cap))) return rc;
+    const size_t frame_bytes = (size_t) width * height;
+    const bool dense_rows = row_stride == (size_t) width, dense_frames = dense_rows && frame_stride == frame_bytes;
+    const bool inplace = width % 16 == 0;
     const LevelGeom &L0 = h->g.lv[0];
-    for (int b0 = 0; b0 < n_frames; b0 += h->batch_cap) {
-        const int nb = std::min(h->batch_cap, n_frames - b0);
+    cudaStream_t sc = h->stream, su = h->s_up, sd = h->s_down;
+    int c = 0;
+    for (int b0 = 0; b0 < n_frames; b0 += cn, ++c) {
+        const int nb = std::min(cn, n_frames - b0), slot = c & 1;
         const uint8_t *src = frames + (size_t) b0 * frame_stride;
-        if (frame_stride == row_stride * (size_t) height)
-            ORBFE_CUDA(h, cudaMemcpy2DAsync(h->d_img + L0.img_off, L0.pitch, src, row_stride, width, (size_t) height * nb, cudaMemcpyHostToDevice, st));
+        uint8_t *stage = h->d_stage[slot];
+        if (c >= 2) ORBFE_CUDA(h, cudaStreamWaitEvent(su, h->ev_done[slot], 0));      // the pass that read this slot has finished
+        if (dense_frames) ORBFE_CUDA(h, cudaMemcpyAsync(stage, src, frame_bytes * nb, cudaMemcpyHostToDevice, su));
         else
             for (int b = 0; b < nb; ++b)
-                ORBFE_CUDA(h, cudaMemcpy2DAsync(h->d_img + L0.img_off + (size_t) b * L0.frame_stride, L0.pitch, src + (size_t) b * frame_stride, row_stride,
-                                                width, height, cudaMemcpyHostToDevice, st));
-        if ((rc = run_pass(h, nb, h->d_img + L0.img_off, L0.pitch, L0.frame_stride, h->d_out_kps, h->d_out_desc, h->d_out_n, cap, st))) return rc;
-        ORBFE_CUDA(h, cudaMemcpyAsync(n_per_frame + b0, h->d_out_n, sizeof(int) * nb, cudaMemcpyDeviceToHost, st));
-        ORBFE_CUDA(h, cudaMemcpyAsync(kps + (size_t) b0 * cap, h->d_out_kps, sizeof(orbfe_keypoint) * (size_t) nb * cap, cudaMemcpyDeviceToHost, st));
-        ORBFE_CUDA(h, cudaMemcpyAsync(desc + (size_t) b0 * cap * 32, h->d_out_desc, (size_t) nb * cap * 32, cudaMemcpyDeviceToHost, st));
-        if ((rc = check_device_error(h, st))) return rc;
+                ORBFE_CUDA(h, cudaMemcpy2DAsync(stage + (size_t) b * frame_bytes, width, src + (size_t) b * frame_stride, row_stride, width, height,
+                                                cudaMemcpyHostToDevice, su));
+        ORBFE_CUDA(h, cudaEventRecord(h->ev_up[slot], su));
+        ORBFE_CUDA(h, cudaStreamWaitEvent(sc, h->ev_up[slot], 0));
+        if (c >= 2) ORBFE_CUDA(h, cudaStreamWaitEvent(sc, h->ev_down[slot], 0));      // the output slot has been downloaded
+        orbfe_keypoint *okps = h->d_out_kps + (size_t) slot * cn * cap;
+        uint8_t *odesc = h->d_out_desc + (size_t) slot * cn * cap * 32;
+        int *on = h->d_out_n + (size_t) slot * cn;
+        if (inplace) rc = run_pass(h, nb, stage, width, frame_bytes, okps, odesc, on, cap, sc);
+        else {
+            ORBFE_CUDA(h, cudaMemcpy2DAsync(h->d_img + L0.img_off, L0.pitch, stage, width, width, (size_t) height * nb, cudaMemcpyDeviceToDevice, sc));
+            rc = run_pass(h, nb, h->d_img + L0.img_off, L0.pitch, L0.frame_stride, okps, odesc, on, cap, sc);
+        }
+        if (rc) return rc;
+        ORBFE_CUDA(h, cudaEventRecord(h->ev_done[slot], sc));
+        ORBFE_CUDA(h, cudaStreamWaitEvent(sd, h->ev_done[slot], 0));
+        ORBFE_CUDA(h, cudaMemcpyAsync(n_per_frame + b0, on, sizeof(int) * nb, cudaMemcpyDeviceToHost, sd));
+        ORBFE_CUDA(h, cudaMemcpyAsync(kps + (size_t) b0 * cap, okps, sizeof(orbfe_keypoint) * (size_t) nb * cap, cudaMemcpyDeviceToHost, sd));
+        ORBFE_CUDA(h, cudaMemcpyAsync(desc + (size_t) b0 * cap * 32, odesc, (size_t) nb * cap * 32, cudaMemcpyDeviceToHost, sd));
+        ORBFE_CUDA(h, cudaEventRecord(h->ev_down[slot], sd));
     }
-    return ORBFE_OK;
+    ORBFE_CUDA(h, cudaStreamSynchronize(sd));
+    ORBFE_CUDA(h, cudaStreamSynchronize(su));
+    return check_device_error(h, sc);
 }
 
 int orbfe_extract(orbfe_handle *h, const uint8_t *gray, int width, int height, size_t stride, orbfe_keypoint *kps, uint8_t *desc, int cap, int *n_out) {
