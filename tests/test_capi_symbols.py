@@ -1,0 +1,61 @@
+"""The C-ABI library loads on a CPU-only box, exports every symbol include/orbfe.h declares, and refuses to run without a GPU."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from monoorbslam3_b200 import _capi, build
+    if not os.path.exists(_capi.LIB_PATH):
+        build.build()
+    return _capi
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "orbfe.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(orbfe_[a-z_0-9]+)\s*\(", txt)))
+
+
+def test_header_declares_the_reference_facing_entry_points():
+    syms = header_symbols()
+    for s in ("orbfe_create", "orbfe_extract", "orbfe_extract_batch", "orbfe_extract_batch_device", "orbfe_hamming_allpairs",
+              "orbfe_descriptor_distance", "orbfe_search_for_initialization", "orbfe_search_by_projection", "orbfe_search_local_points",
+              "orbfe_search_for_triangulation"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(capi):
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    for s in header_symbols():
+        assert hasattr(lib, s), s
+    assert set(header_symbols()) == set(capi.SIGNATURES)          # the ctypes table covers the header, nothing more
+
+
+def test_library_contains_sm100a_code_only(capi):
+    out = subprocess.run(["cuobjdump", "-lelf", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert not re.search(r"sm_(5|6|7|8|9)\d", out)
+
+
+def test_no_cpu_fallback(capi):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(capi.OrbfeError) as e:
+        capi.create(1000, 1.2, 8, 20, 7)
+    assert e.value.code == capi.ORBFE_E_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "monoorbslam3_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                assert "oracle" not in open(os.path.join(dirpath, f), errors="ignore").read().replace("ORBFE", ""), os.path.join(dirpath, f)

@@ -1,0 +1,122 @@
+"""T3 (GPU): the Hamming matchers, called through the C-ABI, against the flat-array oracle restatements of ORBMatcher.cpp.
+Integer work: everything is compared bit-exactly (indices, distances, match counts, updated vecPreMatched)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from monoorbslam3_b200 import ORBExtractor, ORBMatcher, FrameView, synth
+    ex = ORBExtractor(2000, 1.2, 8, 20, 7)
+    a, b = synth.shifted_pair(480, 752, 1000)
+    ka, da = ex(a); kb, db = ex(b)
+    return dict(ORBMatcher=ORBMatcher, FrameView=FrameView, synth=synth, ex=ex, ka=ka, da=da, kb=kb, db=db, w=752, h=480)
+
+
+def test_descriptor_distance(ctx, oracle):
+    m = ctx["ORBMatcher"]()
+    rng = np.random.default_rng(0)
+    ia = rng.integers(0, len(ctx["da"]), 500); ib = rng.integers(0, len(ctx["db"]), 500)
+    got = m.descriptor_distances(ctx["da"], ctx["db"], ia, ib)
+    exp = [oracle.descriptor_distance(ctx["da"][i], ctx["db"][j]) for i, j in zip(ia, ib)]
+    assert got.tolist() == exp
+    assert m.DescriptorDistance(ctx["da"][0], ctx["da"][0]) == 0
+    assert m.DescriptorDistance(np.zeros(32, np.uint8), np.full(32, 255, np.uint8)) == 256
+
+
+@pytest.mark.parametrize("nq,nt", [(1, 1), (7, 513), (64, 512), (65, 1025), (2012, 2009), (300, 5000)])
+def test_allpairs(ctx, oracle, nq, nt):
+    m = ctx["ORBMatcher"]()
+    rng = np.random.default_rng(nq * 7 + nt)
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8); t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    t[rng.integers(0, nt, max(nt // 10, 1))] = q[rng.integers(0, nq, max(nt // 10, 1))]      # exact duplicates: distance-0 ties, first index must win
+    bi, bd, sd = m.hamming_allpairs(q, t)
+    obi, obd, osd = oracle.hamming_allpairs(q, t)
+    assert np.array_equal(bi, obi) and np.array_equal(bd, obd) and np.array_equal(sd, osd)
+
+
+def test_allpairs_real_descriptors_and_empty(ctx, oracle):
+    m = ctx["ORBMatcher"]()
+    bi, bd, sd = m.hamming_allpairs(ctx["da"], ctx["db"])
+    obi, obd, osd = oracle.hamming_allpairs(ctx["da"], ctx["db"])
+    assert np.array_equal(bi, obi) and np.array_equal(bd, obd) and np.array_equal(sd, osd)
+    bi, bd, sd = m.hamming_allpairs(ctx["da"][:5], np.zeros((0, 32), np.uint8))
+    assert bi.tolist() == [-1] * 5 and bd.tolist() == [257] * 5 and sd.tolist() == [257] * 5
+
+
+@pytest.mark.parametrize("window,ratio,orient", [(100, 0.9, True), (100, 0.9, False), (30, 0.7, True), (200, 1.0, True)])
+def test_search_for_initialization(ctx, oracle, window, ratio, orient):
+    m = ctx["ORBMatcher"](ratio, orient)
+    FV = ctx["FrameView"]
+    f1 = FV(ctx["ka"], ctx["da"], ctx["w"], ctx["h"]); f2 = FV(ctx["kb"], ctx["db"], ctx["w"], ctx["h"])
+    pre = np.stack([ctx["ka"]["x"], ctx["ka"]["y"]], 1).astype(np.float32)
+    opre = pre.copy()
+    n, m12 = m.SearchForInitialization(f1, f2, pre, window)
+    on, om12, opre = oracle.search_for_initialization(ctx["ka"], ctx["da"], ctx["kb"], ctx["db"], ctx["w"], ctx["h"], opre, window, ratio, orient)
+    assert n == on and n > 50
+    assert np.array_equal(m12, om12) and np.array_equal(pre, opre)
+    # second call with the updated vecPreMatched (what Tracking::Initialization does frame after frame)
+    n2, m12b = m.SearchForInitialization(f1, f2, pre, window)
+    on2, om12b, _ = oracle.search_for_initialization(ctx["ka"], ctx["da"], ctx["kb"], ctx["db"], ctx["w"], ctx["h"], opre, window, ratio, orient)
+    assert n2 == on2 and np.array_equal(m12b, om12b)
+
+
+def _projection_queries(ctx, rng, th):
+    """Stand-in for the adapter's projection step: last-frame key points re-projected with a small motion + noise."""
+    ka = ctx["ka"]
+    nq = len(ka)
+    q_u = (ka["x"] + 7 + rng.normal(0, 1.0, nq)).astype(np.float32); q_v = (ka["y"] + 3 + rng.normal(0, 1.0, nq)).astype(np.float32)
+    q_r = (th * ka["size"]).astype(np.float32)
+    q_valid = (rng.random(nq) < 0.8).astype(np.uint8)
+    occupied = (rng.random(len(ctx["kb"])) < 0.1).astype(np.uint8)
+    return q_u, q_v, q_r, ka["octave"].astype(np.int32), ka["angle"].astype(np.float32), ctx["da"], q_valid, occupied
+
+
+@pytest.mark.parametrize("th,orient", [(15, True), (30, True), (15, False)])
+def test_search_by_projection(ctx, oracle, th, orient):
+    rng = np.random.default_rng(th)
+    q_u, q_v, q_r, q_l, q_a, q_d, q_valid, occ = _projection_queries(ctx, rng, th)
+    m = ctx["ORBMatcher"](0.9, orient)
+    cur = ctx["FrameView"](ctx["kb"], ctx["db"], ctx["w"], ctx["h"])
+    n, assigned = m.SearchByProjection(q_u, q_v, q_r, q_l, q_a, q_d, q_valid, cur, occ)
+    on, oassigned = oracle.search_by_projection(q_u, q_v, q_r, q_l, q_a, q_d, q_valid, ctx["kb"], ctx["db"], ctx["w"], ctx["h"], occ, orient)
+    assert n == on and n > 50 and np.array_equal(assigned, oassigned)
+
+
+@pytest.mark.parametrize("th,ratio", [(1, 0.8), (2, 0.8), (15, 0.6)])
+def test_search_local_points(ctx, oracle, th, ratio):
+    rng = np.random.default_rng(100 + th)
+    q_u, q_v, _, q_l, _, q_d, q_valid, occ = _projection_queries(ctx, rng, th)
+    scale = np.array([ctx["ex"].getScaleFactor(int(l)) for l in q_l], np.float32)
+    q_r = (np.float32(th) * np.where(rng.random(len(q_l)) < 0.5, np.float32(2.5), np.float32(4.0)).astype(np.float32) * scale).astype(np.float32)
+    m = ctx["ORBMatcher"](ratio, True)
+    fr = ctx["FrameView"](ctx["kb"], ctx["db"], ctx["w"], ctx["h"])
+    n, assigned = m.SearchLocalPoints(q_u, q_v, q_r, q_l, q_d, q_valid, fr, occ)
+    on, oassigned = oracle.search_local_points(q_u, q_v, q_r, q_l, q_d, q_valid, ctx["kb"], ctx["db"], ctx["w"], ctx["h"], occ, ratio)
+    assert n == on and n > 20 and np.array_equal(assigned, oassigned)
+
+
+def _feature_vector(desc, n_bits):
+    """Synthetic DBoW2 FeatureVector (no vocabulary file in the reference repo): node id = leading descriptor bits."""
+    node = (desc[:, 0].astype(np.int32) >> (8 - n_bits))
+    ids = np.unique(node)
+    off = [0]; idx = []
+    for i in ids:
+        members = np.nonzero(node == i)[0]
+        idx.extend(members.tolist()); off.append(len(idx))
+    return ids.astype(np.int32), np.array(off, np.int32), np.array(idx, np.int32)
+
+
+@pytest.mark.parametrize("bits,orient", [(3, False), (5, False), (4, True)])
+def test_search_for_triangulation(ctx, oracle, bits, orient):
+    rng = np.random.default_rng(bits)
+    da, db = ctx["da"], ctx["db"]
+    has1 = (rng.random(len(da)) < 0.3).astype(np.uint8); has2 = (rng.random(len(db)) < 0.3).astype(np.uint8)
+    fv1, fv2 = _feature_vector(da, bits), _feature_vector(db, bits)
+    m = ctx["ORBMatcher"](0.6, orient)
+    n, m12 = m.SearchForTriangulation(da, ctx["ka"]["angle"], has1, fv1, db, ctx["kb"]["angle"], has2, fv2)
+    on, om12 = oracle.search_for_triangulation(da, ctx["ka"]["angle"], has1, fv1, db, ctx["kb"]["angle"], has2, fv2, orient)
+    assert n == on and n > 20 and np.array_equal(m12, om12)
+    assert not (m12 == 0).any()                       # ORBMatcher.cpp:484: index 0 is never accepted (sic)
