@@ -291,18 +291,18 @@ __global__ void __launch_bounds__(256, 4) k_fast(const __grid_constant__ LevelSe
                     }
                     pass[h] = p;
                 }
-                unsigned bal[8]; int total = 0;
+                const int c = __popc(pass[0]) + __popc(pass[1]);
+                int inc = c;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { bal[i] = __ballot_sync(0xffffffffu, (pass[i >> 2] >> (8 * (i & 3) + 7)) & 1u); total += __popc(bal[i]); }
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+                const int total = __shfl_sync(0xffffffffu, inc, 31);
                 if (total) {
                     int o = 0;
-                    if (lane == 0) o = atomicAdd(&s_qn, total);
-                    o = __shfl_sync(0xffffffffu, o, 0);
+                    if (lane == 31) o = atomicAdd(&s_qn, total);
+                    o = __shfl_sync(0xffffffffu, o, 31) + inc - c;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if ((bal[i] >> lane) & 1u) queue[o + __popc(bal[i] & lt)] = (uint16_t) ((y << 8) | (4 * (lane + 32 * (i >> 2)) - 3 + (i & 3)));
-                        o += __popc(bal[i]);
-                    }
+                    for (int i = 0; i < 8; ++i)
+                        if ((pass[i >> 2] >> (8 * (i & 3) + 7)) & 1u) queue[o++] = (uint16_t) ((y << 8) + (4 * (lane + 32 * (i >> 2)) - 3 + (i & 3)));
                 }
             }
         }
@@ -793,13 +793,18 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ LevelS
     const uint8_t *img = L.img[l] + (size_t) frame * G.frame_stride + (size_t) y * G.pitch + x;
     int m01 = 0, m10 = 0;
     const int u = lane - kHalfPatch;
-#pragma unroll 1
-    for (int vv = -kHalfPatch; vv <= kHalfPatch; ++vv) {
-        const int d = a.u_max[vv < 0 ? -vv : vv];
-        if (lane < 31 && u >= -d && u <= d) {
-            const int val = __ldg(img + vv * G.pitch + u);
-            m10 += u * val; m01 += vv * val;
+    {   // all 31 row loads are issued before the first use (the loop is latency-bound otherwise)
+        int val[2 * kHalfPatch + 1];
+        const int au = u < 0 ? -u : u;
+#pragma unroll
+        for (int vv = -kHalfPatch; vv <= kHalfPatch; ++vv) {
+            const int d = a.u_max[vv < 0 ? -vv : vv];
+            val[vv + kHalfPatch] = (lane < 31 && au <= d) ? (int) __ldg(img + vv * G.pitch + u) : 0;
         }
+        int row_sum = 0;
+#pragma unroll
+        for (int vv = -kHalfPatch; vv <= kHalfPatch; ++vv) { row_sum += val[vv + kHalfPatch]; m01 += vv * val[vv + kHalfPatch]; }
+        m10 = u * row_sum;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
