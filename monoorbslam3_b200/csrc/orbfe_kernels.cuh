@@ -685,42 +685,57 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ LevelSet L
         }
         __syncthreads();
     }
-    // horizontal pass: 4 outputs per item from 10 input bytes
-    for (int it = tid; it < kBlurBoxH * (kBlurTileW / 4); it += 256) {
-        const int r = it / (kBlurTileW / 4), qx = it - r * (kBlurTileW / 4);
-        const uint8_t *p = t + r * SP + 4 * qx;
-        int v[10];
+    // horizontal pass on packed bytes: H[x] = dp4a(src[x-3..x], {18,34,48,56}) + dp4a(src[x+1..x+4], {48,34,18,0})  (exact, <= 65280).
+    // One item = 4 outputs of two consecutive rows, stored as u16x2 pairs (row 2p | row 2p+1 << 16) for the dp2a vertical pass.
+    constexpr uint32_t K0123 = 18u | (34u << 8) | (48u << 16) | (56u << 24), K456 = 48u | (34u << 8) | (18u << 16);
+    constexpr int QW = kBlurTileW / 4;
+    static_assert(kBlurTileW % 16 == 0 && kBlurBoxH % 2 == 0, "tile origin must keep xo == 13 and rows must pair up");
+    uint32_t *hp = reinterpret_cast<uint32_t *>(hbuf);          // [kBlurBoxH / 2][kBlurTileW]
+    for (int it = tid; it < (kBlurBoxH / 2) * QW; it += 256) {
+        const int rp = it / QW, qx = it - rp * QW;
+        uint32_t h[2][4];
 #pragma unroll
-        for (int i = 0; i < 10; ++i) v[i] = p[i];
-        uint32_t o[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            o[i] = 18 * (v[i] + v[i + 6]) + 34 * (v[i + 1] + v[i + 5]) + 48 * (v[i + 2] + v[i + 4]) + 56 * v[i + 3];
-        *reinterpret_cast<uint2 *>(hbuf + r * kBlurTileW + 4 * qx) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
+        for (int rr = 0; rr < 2; ++rr) {
+            // tile column of output o's first tap is xo + o; xo is 13 for every tile (x0 is a multiple of 16), so words are aligned
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(tile + (2 * rp + rr) * SP + (xo & ~3)) + qx;
+            const uint32_t wa = w[0], wb = w[1], wc = w[2];
+            const int sh = 8 * (xo & 3);                       // = 8: first tap of output 0 is byte 1 of wa
+            h[rr][0] = __dp4a(__funnelshift_r(wa, wb, sh), K0123, __dp4a(__funnelshift_r(wb, wc, sh), K456, 0u));
+            h[rr][1] = __dp4a(__funnelshift_r(wa, wb, sh + 8), K0123, __dp4a(__funnelshift_r(wb, wc, sh + 8), K456, 0u));
+            h[rr][2] = __dp4a(__funnelshift_r(wa, wb, sh + 16), K0123, __dp4a(__funnelshift_r(wb, wc, sh + 16), K456, 0u));
+            h[rr][3] = __dp4a(wb, K0123, __dp4a(wc, K456, 0u));
+        }
+        *reinterpret_cast<uint4 *>(hp + rp * kBlurTileW + 4 * qx) =
+            make_uint4(h[0][0] | (h[1][0] << 16), h[0][1] | (h[1][1] << 16), h[0][2] | (h[1][2] << 16), h[0][3] | (h[1][3] << 16));
     }
     __syncthreads();
-    // vertical pass: each thread owns a 4-column strip of 8 output rows
-    if (tid < (kBlurTileW / 4) * (kBlurTileH / 8)) {
-        const int seg = tid / (kBlurTileW / 4), qx = tid - seg * (kBlurTileW / 4);
+    // vertical pass: dst = (sum_j k[j] * H[y + j] + 32768) >> 16 with dp2a on the row pairs; a thread owns 4 columns x 8 rows
+    if (tid < QW * (kBlurTileH / 8)) {
+        const int seg = tid / QW, qx = tid - seg * QW;
         const int gx = x0 + 4 * qx;
         if (gx < w) {
-            uint32_t hv[14][4];
+            uint4 pr[7];                                        // row pairs 4*seg .. 4*seg+6  (rows 8*seg .. 8*seg+13)
 #pragma unroll
-            for (int r = 0; r < 14; ++r) {
-                const uint2 u = *reinterpret_cast<const uint2 *>(hbuf + (seg * 8 + r) * kBlurTileW + 4 * qx);
-                hv[r][0] = u.x & 0xffff; hv[r][1] = u.x >> 16; hv[r][2] = u.y & 0xffff; hv[r][3] = u.y >> 16;
-            }
+            for (int p = 0; p < 7; ++p) pr[p] = *reinterpret_cast<const uint4 *>(hp + (4 * seg + p) * kBlurTileW + 4 * qx);
             uint8_t *dst = a.blur + G.img_off + (size_t) frame * G.frame_stride;
+            constexpr uint32_t E0 = 18u | (34u << 8), E1 = 48u | (56u << 8), E2 = 48u | (34u << 8), E3 = 18u;              // even output row
+            constexpr uint32_t O0 = 18u << 8, O1 = 34u | (48u << 8), O2 = 56u | (48u << 8), O3 = 34u | (18u << 8);        // odd output row
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 const int gy = y0 + seg * 8 + r;
                 if (gy < h) {
+                    const int p0 = r >> 1;
                     uint32_t out = 0;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const uint32_t s = 18u * (hv[r][c] + hv[r + 6][c]) + 34u * (hv[r + 1][c] + hv[r + 5][c]) +
-                                           48u * (hv[r + 2][c] + hv[r + 4][c]) + 56u * hv[r + 3][c] + 32768u;
-                        out |= min(s >> 16, 255u) << (8 * c);
+                        const uint32_t a0 = c == 0 ? pr[p0].x : c == 1 ? pr[p0].y : c == 2 ? pr[p0].z : pr[p0].w;
+                        const uint32_t a1 = c == 0 ? pr[p0 + 1].x : c == 1 ? pr[p0 + 1].y : c == 2 ? pr[p0 + 1].z : pr[p0 + 1].w;
+                        const uint32_t a2 = c == 0 ? pr[p0 + 2].x : c == 1 ? pr[p0 + 2].y : c == 2 ? pr[p0 + 2].z : pr[p0 + 2].w;
+                        const uint32_t a3 = c == 0 ? pr[p0 + 3].x : c == 1 ? pr[p0 + 3].y : c == 2 ? pr[p0 + 3].z : pr[p0 + 3].w;
+                        uint32_t sacc = 32768u;
+                        if ((r & 1) == 0) sacc = __dp2a_lo(a3, E3, __dp2a_lo(a2, E2, __dp2a_lo(a1, E1, __dp2a_lo(a0, E0, sacc))));
+                        else sacc = __dp2a_lo(a3, O3, __dp2a_lo(a2, O2, __dp2a_lo(a1, O1, __dp2a_lo(a0, O0, sacc))));
+                        out |= (sacc >> 16) << (8 * c);         // <= 255: the kernel sums to 256
                     }
                     *reinterpret_cast<uint32_t *>(dst + (size_t) gy * G.pitch + gx) = out;
                 }
