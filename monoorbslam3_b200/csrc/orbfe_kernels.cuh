@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256, 4) k_fast(const __grid_constant__ LevelSe
     constexpr int SP = kBoxW;
     __shared__ __align__(128) uint8_t tile[kFastBoxH * SP];
     __shared__ __align__(16) uint8_t mmap[32 * SP];                     // m of strip pixel (x, y) at [(y+1)*SP + x+1], zero elsewhere
-    __shared__ uint16_t queue[kStripW * kCell];                         // y << 8 | x  (strip coordinates)
+    __shared__ uint16_t queue[kStripW * kCell + 32];                    // y << 8 | x  (strip coordinates); +32 dummy slots
     __shared__ uint32_t rowmask[kCellsPerBlk][32];                      // NMS survivors of cell row r, bit = cx
     __shared__ int s_qn, s_cn, s_has[kCellsPerBlk];
     __shared__ __align__(8) uint64_t bar;
@@ -300,9 +300,14 @@ __global__ void __launch_bounds__(256, 4) k_fast(const __grid_constant__ LevelSe
                     int o = 0;
                     if (lane == 31) o = atomicAdd(&s_qn, total);
                     o = __shfl_sync(0xffffffffu, o, 31) + inc - c;
+                    // branch-free: lanes without the bit store to a private dummy slot behind the queue
+                    const int val0 = (y << 8) + 4 * lane - 3;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if ((pass[i >> 2] >> (8 * (i & 3) + 7)) & 1u) queue[o++] = (uint16_t) ((y << 8) + (4 * (lane + 32 * (i >> 2)) - 3 + (i & 3)));
+                    for (int i = 0; i < 8; ++i) {
+                        const int bit = (int) ((pass[i >> 2] >> (8 * (i & 3) + 7)) & 1u);
+                        queue[bit ? o : kStripW * kCell + lane] = (uint16_t) (val0 + 128 * (i >> 2) + (i & 3));
+                        o += bit;
+                    }
                 }
             }
         }
