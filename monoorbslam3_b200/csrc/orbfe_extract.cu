@@ -168,7 +168,7 @@ static int configure(Handle *h, int w, int ht, int batch) {
         if (l) {
             build_axis_table(L.w, g.lv[l - 1].w, true, xt[l]);
             build_axis_table(L.h, g.lv[l - 1].h, false, yt[l]);
-            // destination tile so that the staged source box (256 x 24) covers it
+            // destination tile so that the staged source box (256 x kRsBoxH) covers it
             ResizeLevel &R = g.rs[l];
             auto span_ok = [](const std::vector<int2> &tab, int tile, int limit) {
                 const int n = (int) tab.size();
@@ -346,7 +346,7 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
         ra.src = LS.img[l - 1]; ra.sw = S.w; ra.sh = S.h; ra.spitch = S.pitch; ra.sframe = S.frame_stride;
         ra.dst = h->d_img + D.img_off; ra.dw = D.w; ra.dh = D.h; ra.dpitch = D.pitch; ra.dframe = D.frame_stride;
         ra.tw = R.tw; ra.th = R.th; ra.tiles_x = R.tiles_x; ra.xtab = R.xtab; ra.ytab = R.ytab;
-        k_resize<kTMA><<<dim3(R.tiles_x * R.tiles_y, nb), 256, 0, st>>>(l == 1 ? tm_rs0 : h->tm_rs[l - 1], ra);
+        k_resize<kTMA><<<dim3(R.tiles_x * R.tiles_y, nb), kRsThreads, 0, st>>>(l == 1 ? tm_rs0 : h->tm_rs[l - 1], ra);
         ORBFE_AFTER_LAUNCH(h, st, "k_resize");
     }
     ORBFE_PROF_MARK(h, st, 1);

@@ -119,40 +119,66 @@ struct ResizeArgs {
     const int2 *xtab, *ytab;
 };
 
+// A thread owns 4 destination columns (their coefficient-table entries stay in registers) and walks down a run of destination
+// rows, re-using the horizontal interpolation of a source row when consecutive destination rows share it (5 times out of 6 at
+// scale 1.2).  192 threads = 48 column quads x 4 row runs.
+constexpr int kRsThreads = 192;
+
 template <bool kTMA>
-__global__ void __launch_bounds__(256) k_resize(const __grid_constant__ CUtensorMap tm_src, const ResizeArgs a) {
+__global__ void __launch_bounds__(kRsThreads) k_resize(const __grid_constant__ CUtensorMap tm_src, const ResizeArgs a) {
     constexpr int SP = TilePitch<kTMA>::value;
     __shared__ __align__(128) uint8_t tile[kRsBoxH * SP];
     __shared__ __align__(8) uint64_t bar;
     const int frame = blockIdx.y;
     const int ty = blockIdx.x / a.tiles_x, tx = blockIdx.x - ty * a.tiles_x;
     const int dx0 = tx * a.tw, dy0 = ty * a.th;
-    const int ox = (int) (short) (__ldg(&a.xtab[dx0]).x & 0xffff);
-    const int oy = (int) (short) (__ldg(&a.ytab[dy0]).x & 0xffff);
-    const int xo = stage_box<kTMA, 256>(tile, &bar, &tm_src, a.src + (size_t) frame * a.sframe, a.spitch, a.sh, ox, oy, frame, kRsBoxH);
-    uint8_t *dst = a.dst + (size_t) frame * a.dframe;
-    const int qpr = a.tw >> 2;
-    for (int it = threadIdx.x; it < qpr * a.th; it += 256) {
-        const int ry = it / qpr, qx = it - ry * qpr;
-        const int dy = dy0 + ry, dxb = dx0 + 4 * qx;
-        if (dy >= a.dh || dxb >= a.dw) continue;
+    const int ox = __ldg(&a.xtab[dx0]).x & 0xffff, oy = __ldg(&a.ytab[dy0]).x & 0xffff;
+    const int xo = stage_box<kTMA, kRsThreads>(tile, &bar, &tm_src, a.src + (size_t) frame * a.sframe, a.spitch, a.sh, ox, oy, frame, kRsBoxH);
+    const int qx = threadIdx.x % (kRsMaxTW / 4), grp = threadIdx.x / (kRsMaxTW / 4);
+    const int dxb = dx0 + 4 * qx;
+    if (4 * qx >= a.tw || dxb >= a.dw) return;
+    int c0[4], c1[4], w0[4], w1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int2 xe = __ldg(&a.xtab[min(dxb + i, a.dw - 1)]);
+        c0[i] = (xe.x & 0xffff) - ox + xo; c1[i] = (xe.x >> 16) - ox + xo;
+        w0[i] = xe.y & 0xffff; w1[i] = xe.y >> 16;
+    }
+    const int rows_per = (a.th + 3) >> 2;
+    const int ry_end = min(min((grp + 1) * rows_per, a.th), a.dh - dy0);
+    uint8_t *dst = a.dst + (size_t) frame * a.dframe + dxb;
+    int prev_r = -1, hp[4] = {0, 0, 0, 0};
+    for (int ry = grp * rows_per; ry < ry_end; ++ry) {
+        const int dy = dy0 + ry;
         const int2 ye = __ldg(&a.ytab[dy]);
         const int r0 = (ye.x & 0xffff) - oy, r1 = (ye.x >> 16) - oy;
         const int b0 = ye.y & 0xffff, b1 = ye.y >> 16;
-        const uint8_t *t0 = tile + r0 * SP + xo - ox, *t1 = tile + r1 * SP + xo - ox;
+        int h0[4], h1[4];
+        if (r0 == prev_r) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h0[i] = hp[i];
+        } else {
+            const uint8_t *t = tile + r0 * SP;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h0[i] = t[c0[i]] * w0[i] + t[c1[i]] * w1[i];
+        }
+        if (r1 == r0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h1[i] = h0[i];
+        } else {
+            const uint8_t *t = tile + r1 * SP;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h1[i] = t[c0[i]] * w0[i] + t[c1[i]] * w1[i];
+        }
         uint32_t out = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int dx = min(dxb + i, a.dw - 1);
-            const int2 xe = __ldg(&a.xtab[dx]);
-            const int c0 = xe.x & 0xffff, c1 = xe.x >> 16;
-            const int a0 = xe.y & 0xffff, a1 = xe.y >> 16;
-            const int h0 = t0[c0] * a0 + t0[c1] * a1;
-            const int h1 = t1[c0] * a0 + t1[c1] * a1;
-            const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            const int v = (((b0 * (h0[i] >> 4)) >> 16) + ((b1 * (h1[i] >> 4)) >> 16) + 2) >> 2;
             out |= (uint32_t) (v & 0xff) << (8 * i);
+            hp[i] = h1[i];
         }
-        *reinterpret_cast<uint32_t *>(dst + (size_t) dy * a.dpitch + dxb) = out;
+        prev_r = r1;
+        *reinterpret_cast<uint32_t *>(dst + (size_t) dy * a.dpitch) = out;
     }
 }
 
