@@ -378,7 +378,13 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
     da.blur = h->d_blur; da.kp = h->d_kp; da.nkp = h->d_nkp; da.kp_per_frame = g.kp_per_frame;
     da.out_kps = d_kps; da.out_desc = d_desc; da.out_n = d_n; da.cap = cap; da.err = h->d_err;
     build_u_max(da.u_max);
-    k_describe<<<dim3((g.kp_per_frame + 7) / 8, nb), 256, 0, st>>>(LS, da);
+    {   // the kernel's compile-time u_max table must be what the reference's formula gives
+        static const uint8_t expect[kHalfPatch + 1] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+        if (memcmp(da.u_max, expect, sizeof expect) != 0) return set_error(h, ORBFE_E_INTERNAL, "u_max table mismatch");
+    }
+    int max_kp_cap = 1;
+    for (int l = 0; l < nl; ++l) max_kp_cap = std::max(max_kp_cap, g.lv[l].kp_cap);
+    k_describe<<<dim3((max_kp_cap + 7) / 8, nb, nl), 256, 0, st>>>(LS, da);
     ORBFE_AFTER_LAUNCH(h, st, "k_describe");
     ORBFE_PROF_MARK(h, st, 5);
     if (h->prof) h->prof_pending = true;

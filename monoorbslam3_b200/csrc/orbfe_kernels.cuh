@@ -810,19 +810,27 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
+// u_max of the reference (ORBExtractor.cpp:458-474) for HALF_PATCH_SIZE = 15: a compile-time table; the host recomputes it with
+// the reference's float32 formula at handle creation and refuses to run if the two ever disagree (DescArgs::u_max is that copy).
+__device__ __forceinline__ constexpr int umax15(int v) {
+    constexpr int t[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    return t[v < 0 ? -v : v];
+}
+
+// grid = (ceil(max kp_cap / 8), frames, levels): one warp per key-point slot of one level
 __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ LevelSet L, const DescArgs a) {
-    __shared__ int8_t s_pat[1024];
-    for (int i = threadIdx.x; i < 256; i += 256) reinterpret_cast<int *>(s_pat)[i] = reinterpret_cast<const int *>(c_pattern)[i];
-    __syncthreads();
-    const int frame = blockIdx.y, lane = threadIdx.x & 31;
-    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (t >= a.kp_per_frame) return;
-    int l = 0;
-#pragma unroll 1
-    for (int k = 1; k < L.n_levels; ++k) if (t >= L.lv[k].kp_off) l = k;
-    const LevelGeom &G = L.lv[l];
-    const int k = t - G.kp_off;
+    __shared__ __align__(16) float s_pat[1024];
+    const int frame = blockIdx.y, l = blockIdx.z, lane = threadIdx.x & 31;
     const int *nkp = a.nkp + frame * ORBFE_MAX_LEVELS;
+    if ((int) blockIdx.x * 8 >= nkp[l]) return;        // whole block beyond this level's key points
+    // pair (lane * 8 + j) is stored at float4 slot j * 32 + lane: the lanes of a warp read consecutive 16-byte slots (no bank conflicts)
+    for (int i = threadIdx.x; i < 1024; i += 256) {
+        const int pair = i >> 2, c = i & 3;
+        s_pat[(((pair & 7) * 32) + (pair >> 3)) * 4 + c] = (float) c_pattern[i];
+    }
+    __syncthreads();
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const LevelGeom &G = L.lv[l];
     if (k >= nkp[l]) return;
     int out_idx = k;
     for (int q = 0; q < l; ++q) out_idx += nkp[q];
@@ -832,26 +840,22 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ LevelS
         if (lane == 0) a.out_n[frame] = tot;
     }
     if (out_idx >= a.cap) { if (lane == 0) atomicExch(a.err, 6); return; }
-    const uint32_t v = a.kp[(size_t) frame * a.kp_per_frame + t];
+    const uint32_t v = a.kp[(size_t) frame * a.kp_per_frame + G.kp_off + k];
     const int x = (int) (v & 0xfffu), y = (int) ((v >> 12) & 0xfffu), score = (int) (v >> 24);
 
-    // IC_Angle (ORBExtractor.cpp:18-42) on the un-blurred level: lane = u + 15, loop over v
-    const uint8_t *img = L.img[l] + (size_t) frame * G.frame_stride + (size_t) y * G.pitch + x;
-    int m01 = 0, m10 = 0;
-    const int u = lane - kHalfPatch;
-    {   // all 31 row loads are issued before the first use (the loop is latency-bound otherwise)
-        int val[2 * kHalfPatch + 1];
-        const int au = u < 0 ? -u : u;
+    // IC_Angle (ORBExtractor.cpp:18-42) on the un-blurred level: lane = u + 15, rows v = -15..15 all in flight
+    const int u = lane - kHalfPatch, au = u < 0 ? -u : u;
+    const uint8_t *row = L.img[l] + (size_t) frame * G.frame_stride + (size_t) (y - kHalfPatch) * G.pitch + (x + u);
+    int val[2 * kHalfPatch + 1];
 #pragma unroll
-        for (int vv = -kHalfPatch; vv <= kHalfPatch; ++vv) {
-            const int d = a.u_max[vv < 0 ? -vv : vv];
-            val[vv + kHalfPatch] = (lane < 31 && au <= d) ? (int) __ldg(img + vv * G.pitch + u) : 0;
-        }
-        int row_sum = 0;
-#pragma unroll
-        for (int vv = -kHalfPatch; vv <= kHalfPatch; ++vv) { row_sum += val[vv + kHalfPatch]; m01 += vv * val[vv + kHalfPatch]; }
-        m10 = u * row_sum;
+    for (int vv = -kHalfPatch; vv <= kHalfPatch; ++vv) {
+        val[vv + kHalfPatch] = (au <= umax15(vv)) ? (int) __ldg(row) : 0;      // lane 31: au = 16 > every u_max
+        row += G.pitch;
     }
+    int m01 = 0, row_sum = 0;
+#pragma unroll
+    for (int vv = -kHalfPatch; vv <= kHalfPatch; ++vv) { row_sum += val[vv + kHalfPatch]; m01 += vv * val[vv + kHalfPatch]; }
+    int m10 = u * row_sum;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         m10 += __shfl_xor_sync(0xffffffffu, m10, o);
@@ -864,19 +868,19 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ LevelS
     const float ang = __fmul_rn(angle, factor_pi);
     const float ca = (float) cos((double) ang), sb = (float) sin((double) ang);
     const uint8_t *ctr = a.blur + G.img_off + (size_t) frame * G.frame_stride + (size_t) y * G.pitch + x;
-    const int8_t *p = s_pat + lane * 32;
-    unsigned val = 0;
+    const float4 *p = reinterpret_cast<const float4 *>(s_pat) + lane;
+    unsigned desc_byte = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j, p += 4) {
-        const float x0 = (float) p[0], y0 = (float) p[1], x1 = (float) p[2], y1 = (float) p[3];
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sb), __fmul_rn(y0, ca)));
-        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sb)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sb), __fmul_rn(y1, ca)));
-        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sb)));
+    for (int j = 0; j < 8; ++j) {
+        const float4 q = p[j * 32];                                         // x0, y0, x1, y1
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(q.x, sb), __fmul_rn(q.y, ca)));
+        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(q.x, ca), __fmul_rn(q.y, sb)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(q.z, sb), __fmul_rn(q.w, ca)));
+        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(q.z, ca), __fmul_rn(q.w, sb)));
         const int t0 = __ldg(ctr + r0 * G.pitch + c0), t1 = __ldg(ctr + r1 * G.pitch + c1);
-        val |= (unsigned) (t0 < t1) << j;
+        desc_byte |= (unsigned) (t0 < t1) << j;
     }
-    a.out_desc[((size_t) frame * a.cap + out_idx) * 32 + lane] = (uint8_t) val;
+    a.out_desc[((size_t) frame * a.cap + out_idx) * 32 + lane] = (uint8_t) desc_byte;
     if (lane == 0) {
         orbfe_keypoint kp;
         kp.x = l ? __fmul_rn((float) x, G.scale) : (float) x;             // ORBExtractor.cpp:537-542
