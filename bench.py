@@ -128,7 +128,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "ORB extract+describe frames/s (752x480, 1000 kp)", "value": v, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (time.perf_counter() - t_all) / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": "bounded CPU sample", "l2": "n/a (CPU)"},
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": "bounded CPU sample of the same frames (%s)" % samples[-1],
+                       "sharding": "rank 0 only, all host threads", "l2": "n/a (CPU arm)"},
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": used, "kind": kind, "sample": samples[-1]},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -266,8 +267,16 @@ def run_ours(args):
         hbm_stages = ("pyramid", "fast", "blur")
         dom = max(hbm_stages, key=lambda k: per_launch_ms[k])
         achieved = ab[dom] * B / (per_launch_ms[dom] * 1e-3) / 1e9
-        stage_report = {k: {"ms_per_step": per_launch_ms[k], "algorithmic_GBps": (ab[k] * B / (per_launch_ms[k] * 1e-3) / 1e9) if per_launch_ms[k] > 0 else None}
+        stage_report = {k: {"ms_per_step": per_launch_ms[k], "algorithmic_GBps": (ab[k] * B / (per_launch_ms[k] * 1e-3) / 1e9) if per_launch_ms[k] > 0 else None,
+                            "frac_of_hbm_peak": (ab[k] * B / (per_launch_ms[k] * 1e-3) / 1e9 / peak_gbs) if per_launch_ms[k] > 0 and ab[k] else None}
                         for k in stage_ms}
+        traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if tj.get("batch") == B:
+                traffic = tj["stages"][dom]["dram_read_bytes"] + tj["stages"][dom]["dram_write_bytes"]
+        except Exception:
+            pass
         line = {
             "metric": "ORB extract+describe frames/s (752x480, 1000 kp)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
@@ -278,7 +287,7 @@ def run_ours(args):
                     "api": "orbfe_extract_batch (host C-ABI, pinned host buffers)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab[dom] * B,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab[dom] * B,
                          "whole_step_algorithmic_GBps": ab["frame_total"] * B / (ms_dev / K * 1e-3) / 1e9},
             "stages": stage_report,
             "match": {"metric": "Hamming GMatch/s (all-pairs 40000 x 40000, best/second-best)", "value": gmatch, "unit": "GMatch/s", "ms": ms_match},

@@ -31,3 +31,14 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+
+
+def build_cpp_adapter_test(out=None):
+    """g++ build of the C++ host adapters + tests/cpp/adapter_test.cpp against liborbfe.so (used by the GPU test-suite)."""
+    root = os.path.dirname(HERE)
+    out = out or os.path.join(HERE, "lib", "adapter_test")
+    srcs = [os.path.join(HERE, "host", "ORBExtractor.cpp"), os.path.join(HERE, "host", "ORBMatcher.cpp"), os.path.join(root, "tests", "cpp", "adapter_test.cpp")]
+    if os.path.exists(out) and all(os.path.getmtime(s) < os.path.getmtime(out) for s in srcs + [LIB]):
+        return out
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", out] + srcs + ["-L" + os.path.dirname(LIB), "-lorbfe", "-Wl,-rpath," + os.path.dirname(LIB)])
+    return out
