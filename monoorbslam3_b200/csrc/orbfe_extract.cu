@@ -350,6 +350,22 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
         ORBFE_AFTER_LAUNCH(h, st, "k_resize");
     }
     ORBFE_PROF_MARK(h, st, 1);
+    // The blur only depends on the pyramid: it runs on an auxiliary stream next to FAST + quadtree (which are issue- and
+    // latency-bound) and is joined before the descriptors.
+    BlurArgs ba; ba.blur = h->d_blur;
+    const bool fork_blur = !h->prof && !debug_sync();
+    if (fork_blur) {
+        if (!h->s_aux) {
+            ORBFE_CUDA(h, cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking));
+            ORBFE_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+            ORBFE_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        }
+        ORBFE_CUDA(h, cudaEventRecord(h->ev_fork, st));
+        ORBFE_CUDA(h, cudaStreamWaitEvent(h->s_aux, h->ev_fork, 0));
+        k_blur<kTMA><<<dim3(g.blur_blocks, nb), 256, 0, h->s_aux>>>(LS, TB, ba);
+        h->launches++;
+        ORBFE_CUDA(h, cudaEventRecord(h->ev_join, h->s_aux));
+    }
     // K2 FAST + per-cell NMS
     FastArgs fa; fa.slots = h->d_slots; fa.cell_cnt = h->d_cell_cnt; fa.cells_per_frame = g.cells_per_frame;
     fa.t_ini = h->cfg.ini_th_fast; fa.t_min = h->cfg.min_th_fast;
@@ -366,10 +382,13 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
     k_octree<256><<<dim3(nl, nb), 256, g.oct_smem_bytes, st>>>(LS, oa);
     ORBFE_AFTER_LAUNCH(h, st, "k_octree");
     ORBFE_PROF_MARK(h, st, 3);
-    // K6 blur
-    BlurArgs ba; ba.blur = h->d_blur;
-    k_blur<kTMA><<<dim3(g.blur_blocks, nb), 256, 0, st>>>(LS, TB, ba);
-    ORBFE_AFTER_LAUNCH(h, st, "k_blur");
+    // K6 blur (launched above on the auxiliary stream unless profiling / debugging serialises the stages)
+    if (!fork_blur) {
+        k_blur<kTMA><<<dim3(g.blur_blocks, nb), 256, 0, st>>>(LS, TB, ba);
+        ORBFE_AFTER_LAUNCH(h, st, "k_blur");
+    } else {
+        ORBFE_CUDA(h, cudaStreamWaitEvent(st, h->ev_join, 0));
+    }
     ORBFE_PROF_MARK(h, st, 4);
     // K5 + K7 orientation and descriptors, final assembly
     k_zero_counts<<<(nb + 255) / 256, 256, 0, st>>>(d_n, nb);
@@ -462,6 +481,7 @@ void orbfe_destroy(orbfe_handle *h) {
     for (int i = 0; i <= ORBFE_N_STAGES; ++i) if (h->prof_ev[i]) cudaEventDestroy(h->prof_ev[i]);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->s_aux) { cudaStreamDestroy(h->s_aux); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
     if (h->s_up) cudaStreamDestroy(h->s_up);
     if (h->s_down) cudaStreamDestroy(h->s_down);
     for (int i = 0; i < 2; ++i) {

@@ -90,7 +90,8 @@ struct Handle {
     orbfe_keypoint *d_out_kps = nullptr; uint8_t *d_out_desc = nullptr; int *d_out_n = nullptr; int out_cap = 0;
     int out_frames = 0;              // frames the output staging holds
     uint8_t *d_stage[2] = {nullptr, nullptr}; size_t stage_bytes = 0;          // dense H2D staging of the pipelined host path
-    cudaStream_t s_up = nullptr, s_down = nullptr;
+    cudaStream_t s_up = nullptr, s_down = nullptr, s_aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_up[2] = {}, ev_done[2] = {}, ev_down[2] = {};
     int last_batch = 0;              // frames of the last pass (for the stage getters)
     // tensor maps (img arena; level 0 may be rebuilt for an in-place user buffer)
