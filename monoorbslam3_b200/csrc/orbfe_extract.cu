@@ -575,7 +575,9 @@ int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, in
     for (int b = 0; b < n_frames; ++b) n_per_frame[b] = 0;
     if (n_frames == 0 || width <= 0 || height <= 0) return ORBFE_OK;                 // ORBExtractor.cpp:497
     ORBFE_CUDA(h, cudaSetDevice(h->device));
-    const int chunk = std::min(h->cfg.max_batch, std::max(16, std::min(128, (n_frames + 3) / 4)));
+    int chunk_target = 128;                               // frames per pipeline stage (ORBFE_CHUNK overrides, for tuning)
+    if (const char *e = getenv("ORBFE_CHUNK")) chunk_target = std::max(1, atoi(e));
+    const int chunk = std::min(h->cfg.max_batch, std::max(std::min(16, chunk_target), std::min(chunk_target, (n_frames + 3) / 4)));
     int rc = configure(h, width, height, std::min(n_frames, chunk));
     if (rc) return rc;
     const int cn = std::min(h->batch_cap, chunk);                                   // frames per pipeline stage
@@ -585,9 +587,12 @@ int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, in
     const bool inplace = width % 16 == 0;
     const LevelGeom &L0 = h->g.lv[0];
     cudaStream_t sc = h->stream, su = h->s_up, sd = h->s_down;
+    // a short first chunk keeps the un-overlapped head of the pipeline (its upload) small; later chunks are full-sized
+    const int first = n_frames > cn ? std::max(1, cn / 4) : cn;
     int c = 0;
-    for (int b0 = 0; b0 < n_frames; b0 += cn, ++c) {
-        const int nb = std::min(cn, n_frames - b0), slot = c & 1;
+    for (int b0 = 0, nb = 0; b0 < n_frames; b0 += nb, ++c) {
+        nb = std::min(c == 0 ? first : cn, n_frames - b0);
+        const int slot = c & 1;
         const uint8_t *src = frames + (size_t) b0 * frame_stride;
         uint8_t *stage = h->d_stage[slot];
         if (c >= 2) ORBFE_CUDA(h, cudaStreamWaitEvent(su, h->ev_done[slot], 0));      // the pass that read this slot has finished
