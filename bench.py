@@ -109,6 +109,23 @@ def cpu_reference_fps(frames, threads, min_seconds=8.0, max_frames=None):
     return total_n / total_t, kind, "%d frames of the workload in %.1f s on %d thread(s)" % (total_n, total_t, used), used
 
 
+def cpu_hamming_gmatch(threads, nt=40000, q_per_thread=1024):
+    """The reference's DescriptorDistance arithmetic (ORBMatcher.cpp:17-31, SWAR popcount; oracle port) in a best/second-best loop,
+    one slice of queries per host thread against the 40k-descriptor table."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import orb_oracle as orc
+    rng = np.random.default_rng(5)
+    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    qs = [rng.integers(0, 256, (q_per_thread, 32), dtype=np.uint8) for _ in range(threads)]
+    orc.hamming_allpairs(qs[0][:8], t)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as pool:
+        list(pool.map(lambda q: orc.hamming_allpairs(q, t), qs))
+    sec = time.perf_counter() - t0
+    return {"value": threads * q_per_thread * nt / sec / 1e9, "unit": "GMatch/s", "cores": threads, "kind": "port",
+            "sample": "%d x %d pairs in %.2f s on %d thread(s)" % (threads * q_per_thread, nt, sec, threads)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -262,7 +279,35 @@ def run_ours(args):
     torch.cuda.synchronize()
     ms_match = m0.elapsed_time(m1) / reps_m
     gmatch = nq * nq / (ms_match * 1e-3) / 1e9
-    launches += 0   # the matcher launches above are outside the timed extractor region and are not counted
+    popc_peak = mt.popc_peak()            # measured 10^9 popc/s; one match = 8 popc
+
+    # ---- single-frame latency through the reference-shaped call (ORBExtractor::operator(), host image in, host vectors out)
+    one = base[0]
+    ex1 = ORBExtractor(device=local, max_batch=1, **ORB)
+    for _ in range(5):
+        ex1(one)
+    t0 = time.perf_counter()
+    for _ in range(100):
+        ex1(one)
+    ms_single = (time.perf_counter() - t0) * 1e3 / 100
+
+    # ---- SearchForInitialization on a frame pair of the workload (window 100, ratio 0.9), GPU call vs the CPU restatement
+    init = None
+    if rank == 0:
+        from monoorbslam3_b200 import FrameView
+        fa_, fb_ = synth.shifted_pair(H, W, 1000)
+        ex2 = ORBExtractor(device=local, max_batch=1, **dict(ORB, nFeatures=2 * NF))       # the initial extractor uses 2 x nFeatures (Tracking.cpp:24)
+        ka, da = ex2(fa_); kb, db = ex2(fb_)
+        f1, f2 = FrameView(ka, da, W, H), FrameView(kb, db, W, H)
+        mi = ORBMatcher(0.9, True, handle=ex2._h)
+        pre0 = np.stack([ka["x"], ka["y"]], 1).astype(np.float32)
+        for _ in range(3):
+            mi.SearchForInitialization(f1, f2, pre0.copy(), 100)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            n_init, _ = mi.SearchForInitialization(f1, f2, pre0.copy(), 100)
+        ms_init = (time.perf_counter() - t0) * 1e3 / 20
+        init = {"matches": int(n_init), "gpu_ms_per_call": ms_init, "queries": int((ka["octave"] == 0).sum())}
 
     if rank == 0:
         peaks = {}
@@ -299,12 +344,24 @@ def run_ours(args):
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab[dom] * B,
                          "whole_step_algorithmic_GBps": ab["frame_total"] * B / (ms_dev / K * 1e-3) / 1e9},
             "stages": stage_report, "ms_per_step_serialised_with_stage_events": ms_prof / K,
-            "match": {"metric": "Hamming GMatch/s (all-pairs 40000 x 40000, best/second-best)", "value": gmatch, "unit": "GMatch/s", "ms": ms_match},
+            "match": {"metric": "Hamming GMatch/s (all-pairs 40000 x 40000, best/second-best)", "value": gmatch, "unit": "GMatch/s", "ms": ms_match,
+                      "roofline": {"bound": "integer pipe (popc)", "achieved": gmatch, "peak": popc_peak / 8, "unit": "GMatch/s", "frac": gmatch / (popc_peak / 8),
+                                   "peak_source": "measured popc micro-benchmark (orbfe_popc_peak), 8 popc per 256-bit match"}},
+            "single_frame": {"ms_per_call": ms_single, "frames_per_s": 1e3 / ms_single, "api": "ORBExtractor.__call__ -> orbfe_extract (host image in, host key points out)"},
+            "search_for_initialization": init,
             "clocks": sampler.summary(),
         }
         if world == 1 and not args.no_cpu:
             fps, kind, sample, used = cpu_reference_fps(base, host_cores(), min_seconds=args.ref_seconds)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": used, "kind": kind, "sample": sample}
+            line["match"]["cpu_baseline"] = cpu_hamming_gmatch(host_cores())
+            if init is not None:
+                from oracle import orb_oracle as orc
+                t0 = time.perf_counter()
+                for _ in range(5):
+                    on, _, _ = orc.search_for_initialization(ka, da, kb, db, W, H, pre0.copy(), 100, 0.9, True)
+                init["cpu_port_ms_per_call"] = (time.perf_counter() - t0) * 1e3 / 5
+                init["cpu_matches"] = int(on)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -131,6 +131,10 @@ int orbfe_profile_read(orbfe_handle *h, float *stage_ms, int *n_passes, int rese
  * All descriptor arrays are n x 32 bytes, row-major (cv::Mat N x 32 CV_8U as produced by the extractor).
  */
 
+/* Measured popc throughput of the device (10^9 32-bit popc per second; 8 popc = one 256-bit match): the roofline
+ * denominator bench.py quotes the matching kernels against. */
+int orbfe_popc_peak(orbfe_handle *h, double *gpopc_per_s);
+
 /* ORBMatcher::DescriptorDistance over explicit pairs: dist[i] = hamming(a[ia[i]], b[ib[i]]). */
 int orbfe_descriptor_distance(orbfe_handle *h, const uint8_t *a, int na, const uint8_t *b, int nb,
                               const int32_t *ia, const int32_t *ib, int n_pairs, int32_t *dist);

@@ -54,6 +54,7 @@ SIGNATURES = {
     "orbfe_launch_count": (C.c_longlong, [_vp]),
     "orbfe_profile": (_i, [_vp, _i]),
     "orbfe_profile_read": (_i, [_vp, _vp, C.POINTER(_i), _i]),
+    "orbfe_popc_peak": (_i, [_vp, C.POINTER(C.c_double)]),
     "orbfe_descriptor_distance": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp]),
     "orbfe_hamming_allpairs": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "orbfe_hamming_allpairs_device": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i]),

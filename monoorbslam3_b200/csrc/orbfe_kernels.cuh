@@ -246,7 +246,7 @@ struct FastArgs {
 };
 
 template <bool kTMA>
-__global__ void __launch_bounds__(256, 4) k_fast(const __grid_constant__ LevelSet L, const __grid_constant__ TmapSet T, const FastArgs a) {
+__global__ void __launch_bounds__(256, 6) k_fast(const __grid_constant__ LevelSet L, const __grid_constant__ TmapSet T, const FastArgs a) {
     constexpr int SP = kBoxW;
     __shared__ __align__(128) uint8_t tile[kFastBoxH * SP];
     __shared__ __align__(16) uint8_t mmap[32 * SP];                     // m of strip pixel (x, y) at [(y+1)*SP + x+1], zero elsewhere
@@ -680,7 +680,7 @@ struct BlurArgs { uint8_t *blur; };
 __device__ __forceinline__ int refl101(int p, int n) { return p < 0 ? -p : (p >= n ? 2 * n - 2 - p : p); }
 
 template <bool kTMA>
-__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ LevelSet L, const __grid_constant__ TmapSet T, const BlurArgs a) {
+__global__ void __launch_bounds__(256, 6) k_blur(const __grid_constant__ LevelSet L, const __grid_constant__ TmapSet T, const BlurArgs a) {
     constexpr int SP = TilePitch<kTMA>::value;
     __shared__ __align__(128) uint8_t tile[kBlurBoxH * SP];
     __shared__ __align__(16) uint16_t hbuf[kBlurBoxH * kBlurTileW];
@@ -818,7 +818,7 @@ __device__ __forceinline__ constexpr int umax15(int v) {
 }
 
 // grid = (ceil(max kp_cap / 8), frames, levels): one warp per key-point slot of one level
-__global__ void __launch_bounds__(256) k_describe(const __grid_constant__ LevelSet L, const DescArgs a) {
+__global__ void __launch_bounds__(256, 6) k_describe(const __grid_constant__ LevelSet L, const DescArgs a) {
     __shared__ __align__(16) float s_pat[1024];
     const int frame = blockIdx.y, l = blockIdx.z, lane = threadIdx.x & 31;
     const int *nkp = a.nkp + frame * ORBFE_MAX_LEVELS;

@@ -40,6 +40,24 @@ __device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// popc micro-benchmark: the roofline denominator of the matching kernels (SURVEY.md §8d asks for a measured figure).
+// Every thread runs 8 independent xor+popc chains; 8 popc = one 256-bit "match".
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_popc_peak(unsigned *out, unsigned seed, int iters) {
+    unsigned x[8], acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x[i] = seed * (threadIdx.x + 1) + i * 0x9e3779b9u + blockIdx.x; acc[i] = 0; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { acc[i] += __popc(x[i] ^ acc[i]); }
+    }
+    unsigned r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r ^= acc[i];
+    if (r == 0xdeadbeefu) out[0] = r;          // keeps the chains alive without a store in practice
+}
+
+// ------------------------------------------------------------------------------------------------
 // K8
 // ------------------------------------------------------------------------------------------------
 __global__ void k_pair_distance(const uint4 *a, const uint4 *b, const int *ia, const int *ib, int n, int *dist) {
@@ -466,6 +484,32 @@ static int run_window_search(Handle *h, const WindowProblem &p, float nn_ratio, 
 using namespace orbfe;
 
 extern "C" {
+
+int orbfe_popc_peak(orbfe_handle *h, double *gpopc_per_s) {
+    if (!h || !gpopc_per_s) return ORBFE_E_ARG;
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_match_scratch(h, 4096);
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    cudaEvent_t e0, e1;
+    ORBFE_CUDA(h, cudaEventCreate(&e0)); ORBFE_CUDA(h, cudaEventCreate(&e1));
+    const int blocks = h->sm_count * 8, iters = 4096;
+    k_popc_peak<<<blocks, 256, 0, st>>>((unsigned *) h->d_match, 12345u, 64);       // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        ORBFE_CUDA(h, cudaEventRecord(e0, st));
+        k_popc_peak<<<blocks, 256, 0, st>>>((unsigned *) h->d_match, 12345u + rep, iters);
+        ORBFE_CUDA(h, cudaEventRecord(e1, st));
+        ORBFE_CUDA(h, cudaEventSynchronize(e1));
+        float ms = 0;
+        ORBFE_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+        best = std::max(best, (double) blocks * 256 * 8 * iters / (ms * 1e-3) / 1e9);
+    }
+    h->launches += 6;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *gpopc_per_s = best;
+    return ORBFE_OK;
+}
 
 int orbfe_descriptor_distance(orbfe_handle *h, const uint8_t *a, int na, const uint8_t *b, int nb, const int32_t *ia, const int32_t *ib, int n_pairs, int32_t *dist) {
     if (!h) return ORBFE_E_ARG;

@@ -64,6 +64,12 @@ class ORBMatcher:
                                                                  len(ia), _capi.ptr(out)))
         return out
 
+    def popc_peak(self):
+        """Measured 32-bit popc throughput of the device in 10^9/s (the matching roofline denominator)."""
+        v = C.c_double()
+        _capi.check(self._h, self._lib.orbfe_popc_peak(self._h, C.byref(v)))
+        return v.value
+
     # ---- brute force best / second best (BASELINE configs 4/5)
     def hamming_allpairs(self, q, t):
         q = _c(q, np.uint8); t = _c(t, np.uint8)
