@@ -117,7 +117,7 @@ static int make_tmap(Handle *h, CUtensorMap *m, const uint8_t *base, int w, int 
 static void free_arena(Handle *h) {
     cudaFree(h->d_img); cudaFree(h->d_blur); cudaFree(h->d_slots); cudaFree(h->d_cell_cnt); cudaFree(h->d_cell_off);
     cudaFree(h->d_cand); cudaFree(h->d_cur); cudaFree(h->d_nodes); cudaFree(h->d_lists); cudaFree(h->d_kp); cudaFree(h->d_nkp);
-    cudaFree(h->d_ncand); cudaFree(h->d_tables); cudaFree(h->d_out_kps); cudaFree(h->d_out_desc); cudaFree(h->d_out_n);
+    cudaFree(h->d_ncand); cudaFree(h->d_tables); cudaFree(h->d_fast_tab); h->d_fast_tab = nullptr; cudaFree(h->d_out_kps); cudaFree(h->d_out_desc); cudaFree(h->d_out_n);
     h->d_img = h->d_blur = nullptr; h->d_slots = nullptr; h->d_cell_cnt = h->d_cell_off = nullptr; h->d_cand = nullptr; h->d_cur = nullptr;
     h->d_nodes = nullptr; h->d_lists = nullptr; h->d_kp = nullptr; h->d_nkp = h->d_ncand = nullptr; h->d_tables = nullptr;
     h->d_out_kps = nullptr; h->d_out_desc = nullptr; h->d_out_n = nullptr; h->out_cap = 0; h->out_frames = 0;
@@ -228,6 +228,13 @@ static int configure(Handle *h, int w, int ht, int batch) {
             ORBFE_CUDA(h, cudaMemcpyAsync(p, yt[l].data(), yt[l].size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
             g.rs[l].ytab = p; p += yt[l].size();
         }
+        // FAST block table: block -> (level, cell row, strip of 8 cells)
+        std::vector<int> tab((size_t) g.fast_blocks);
+        for (int l = 0; l < nl; ++l)
+            for (int ci = 0; ci < g.lv[l].n_rows; ++ci)
+                for (int cg = 0; cg < g.lv[l].n_groups; ++cg) tab[(size_t) g.lv[l].fast_blk_base + ci * g.lv[l].n_groups + cg] = l | (ci << 4) | (cg << 16);
+        ORBFE_CUDA(h, cudaMalloc(&h->d_fast_tab, tab.size() * sizeof(int)));
+        ORBFE_CUDA(h, cudaMemcpyAsync(h->d_fast_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
         ORBFE_CUDA(h, cudaStreamSynchronize(h->stream));      // the host vectors die with this scope
     }
     h->batch_cap = keep_batch;
@@ -367,7 +374,7 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
         ORBFE_CUDA(h, cudaEventRecord(h->ev_join, h->s_aux));
     }
     // K2 FAST + per-cell NMS
-    FastArgs fa; fa.slots = h->d_slots; fa.cell_cnt = h->d_cell_cnt; fa.cells_per_frame = g.cells_per_frame;
+    FastArgs fa; fa.slots = h->d_slots; fa.cell_cnt = h->d_cell_cnt; fa.blk_tab = h->d_fast_tab; fa.cells_per_frame = g.cells_per_frame;
     fa.t_ini = h->cfg.ini_th_fast; fa.t_min = h->cfg.min_th_fast;
     k_fast<kTMA><<<dim3(g.fast_blocks, nb), 256, 0, st>>>(LS, TF, fa);
     ORBFE_AFTER_LAUNCH(h, st, "k_fast");

@@ -86,6 +86,7 @@ struct Handle {
     int *d_ncand = nullptr;          // [frame][ORBFE_MAX_LEVELS]
     int *d_err = nullptr;            // device error flag
     void *d_tables = nullptr;        // resize tables
+    int *d_fast_tab = nullptr;       // FAST block -> (level, cell row, strip)
     // staging for the host entry points
     orbfe_keypoint *d_out_kps = nullptr; uint8_t *d_out_desc = nullptr; int *d_out_n = nullptr; int out_cap = 0;
     int out_frames = 0;              // frames the output staging holds

@@ -241,7 +241,7 @@ __device__ __forceinline__ void fast_measure2(const uint8_t *cA, const uint8_t *
 }
 
 struct FastArgs {
-    uint32_t *slots; int *cell_cnt;
+    uint32_t *slots; int *cell_cnt; const int *blk_tab;
     int cells_per_frame, t_ini, t_min;
 };
 
@@ -250,18 +250,16 @@ __global__ void __launch_bounds__(256, 6) k_fast(const __grid_constant__ LevelSe
     constexpr int SP = kBoxW;
     __shared__ __align__(128) uint8_t tile[kFastBoxH * SP];
     __shared__ __align__(16) uint8_t mmap[32 * SP];                     // m of strip pixel (x, y) at [(y+1)*SP + x+1], zero elsewhere
-    __shared__ uint16_t queue[kStripW * kCell + 32];                    // y << 8 | x  (strip coordinates); +32 dummy slots
+    __shared__ uint16_t queue[kStripW * kCell];                         // y << 8 | x  (strip coordinates)
     __shared__ uint32_t rowmask[kCellsPerBlk][32];                      // NMS survivors of cell row r, bit = cx
-    __shared__ int s_qn, s_cn, s_has[kCellsPerBlk];
+    __shared__ int s_qn, s_cn, s_has[kCellsPerBlk], s_scan[8];
+    __shared__ uint32_t passbits[32][8];                                // stage-A result: [row][half * 4 + byte] bit = word index within the half
     __shared__ __align__(8) uint64_t bar;
 
     const int frame = blockIdx.y, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-    int l = 0;
-#pragma unroll 1
-    for (int k = 1; k < L.n_levels; ++k) if ((int) blockIdx.x >= L.lv[k].fast_blk_base) l = k;
+    const int packed = __ldg(&a.blk_tab[blockIdx.x]);                                   // level | cell row << 4 | strip << 16
+    const int l = packed & 15, ci = (packed >> 4) & 0xfff, cg = packed >> 16;
     const LevelGeom &G = L.lv[l];
-    const int rem = blockIdx.x - G.fast_blk_base;
-    const int ci = rem / G.n_groups, cg = rem - ci * G.n_groups;
     const int px = kEdge - 3 + kStripW * cg, py = kEdge - 3 + kCell * ci;               // 16-byte aligned x origin
     stage_box<kTMA, 256>(tile, &bar, &T.m[l], L.img[l] + (size_t) frame * G.frame_stride, G.pitch, G.h, px, py, frame, kFastBoxH);
 
@@ -317,24 +315,30 @@ __global__ void __launch_bounds__(256, 6) k_fast(const __grid_constant__ LevelSe
                     }
                     pass[h] = p;
                 }
-                const int c = __popc(pass[0]) + __popc(pass[1]);
-                int inc = c;
+                // bit planes: plane i = (half h, byte b), bit = lane; lanes 0..7 keep one plane each and store it
+                unsigned mine = 0;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-                const int total = __shfl_sync(0xffffffffu, inc, 31);
-                if (total) {
-                    int o = 0;
-                    if (lane == 31) o = atomicAdd(&s_qn, total);
-                    o = __shfl_sync(0xffffffffu, o, 31) + inc - c;
-                    // branch-free: lanes without the bit store to a private dummy slot behind the queue
-                    const int val0 = (y << 8) + 4 * lane - 3;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int bit = (int) ((pass[i >> 2] >> (8 * (i & 3) + 7)) & 1u);
-                        queue[bit ? o : kStripW * kCell + lane] = (uint16_t) (val0 + 128 * (i >> 2) + (i & 3));
-                        o += bit;
-                    }
+                for (int i = 0; i < 8; ++i) {
+                    const unsigned bal = __ballot_sync(0xffffffffu, (pass[i >> 2] >> (8 * (i & 3) + 7)) & 1u);
+                    if (lane == i) mine = bal;
                 }
+                if (lane < 8) passbits[y][lane] = mine;
+            }
+        }
+        __syncthreads();
+        // ---- A2: expand the bit planes into the queue (order is irrelevant): thread = one 32-bit plane word
+        {
+            unsigned word = 0;
+            const int y = tid >> 3, plane = tid & 7;
+            if (y < ch) word = passbits[y][plane];
+            int total;
+            int o = block_scan_excl<256>(__popc(word), total, s_scan);
+            if (tid == 0) s_qn = total;
+            const int xbase = (y << 8) + 128 * (plane >> 2) - 3 + (plane & 3);
+            while (word) {
+                const int b = __ffs(word) - 1;
+                word &= word - 1;
+                queue[o++] = (uint16_t) (xbase + 4 * b);
             }
         }
         __syncthreads();
