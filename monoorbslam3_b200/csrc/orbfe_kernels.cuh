@@ -196,9 +196,10 @@ struct TmapSet { CUtensorMap m[ORBFE_MAX_LEVELS]; };
 // K2  FAST-9/16 per 30-px cell (cv::FAST on every cell, ORBExtractor.cpp:592-617).
 // One CTA per strip of 8 cells (240 x 30 px, a 256 x 36 byte TMA box).  The corner measure m(x, y) does not depend on the cell
 // grid, only NMS and the threshold fallback do, so the strip is processed in four block-wide stages:
-//   A  high-speed rejection, 4 pixels per thread on packed bytes (VABSDIFF4 + SWAR compares); survivors -> shared queue
-//   B  exact m for the queued pixels, 2 pixels per thread on packed s16x2 (VIMNMX3): m = max over the 16 arcs of
-//      max(min_arc(p - v), -max_arc(p - v)); corner iff m > t; corners are compacted in place into the queue
+//   A  rejection test on packed bytes, 8 pixels per thread: all eight opposite ring pairs (k, k+8) must hold a pixel with
+//      |p - v| > t (VABSDIFF4 + SWAR compare; necessary for any 9-arc of either polarity); survivors -> shared queue
+//   B  exact m for the queued pixels, one per thread, both polarities in one u16x2 register (IMAD packing, VIMNMX3.U16x2):
+//      m = max over the 16 arcs of max(min_arc(p - v), min_arc(v - p)); corner iff m > t -> strip-wide score map
 //   C  3x3 non-max suppression of the corners inside their own cell (outside = 0) -> per-cell row bit masks
 //   D  one warp per cell: ordered (y, x) emission into the cell's slot, cell count
 // Cells without a survivor at iniThFAST repeat A-D with minThFAST (the reference's second cv::FAST call).
@@ -211,49 +212,111 @@ __device__ __forceinline__ uint32_t bytes_gt(uint32_t x, uint32_t k7, bool t_ge_
     return (t_ge_128 ? (low & x) : (low | x)) & 0x80808080u;
 }
 
-// exact corner measure of two pixels (centres cA, cB in the staged tile, pitch kBoxW); halves of the s16x2 lanes = (A, B)
-__device__ __forceinline__ void fast_measure2(const uint8_t *cA, const uint8_t *cB, int &mA, int &mB) {
+// exact corner measure of one pixel (centre c in the staged tile, pitch kBoxW).  Both polarities ride in one register:
+// e_k = (256 + d_k) | (256 - d_k) << 16 with d_k = p_k - v, built by one IMAD per ring pixel (p * 0xFFFF0001 + bias; both halves
+// stay in [1, 511], so nothing borrows across the halves).  m = max over the 16 arcs of min over the arc, per half (VIMNMX3.U16x2).
+__device__ __forceinline__ int fast_measure1(const uint8_t *c) {
     constexpr int SP = kBoxW;
     constexpr int ofs[16] = {3 * SP, 3 * SP + 1, 2 * SP + 2, SP + 3, 3, -SP + 3, -2 * SP + 2, -3 * SP + 1,
                              -3 * SP, -3 * SP - 1, -2 * SP - 2, -SP - 3, -3, SP - 3, 2 * SP - 2, 3 * SP - 1};
-    const uint32_t negv = ((uint32_t) (-(int) cA[0]) & 0xffffu) | ((uint32_t) (-(int) cB[0]) << 16);
+    const uint32_t v = c[0];
+    const uint32_t bias = (256u - v) | ((256u + v) << 16);
     uint32_t e[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) e[k] = __vadd2((uint32_t) cA[ofs[k]] | ((uint32_t) cB[ofs[k]] << 16), negv);      // p - v
-    uint32_t mn[16], mx[16];
+    for (int k = 0; k < 16; ++k) e[k] = (uint32_t) c[ofs[k]] * 0xFFFF0001u + bias;
+    uint32_t mn[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        mn[k] = __vimin3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
-        mx[k] = __vimax3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
-    }
-    uint32_t bright = 0x80008000u, dark = 0x7fff7fffu;      // max_k min9(e),  min_k max9(e)
+    for (int k = 0; k < 16; ++k) mn[k] = __vimin3_u16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
+    uint32_t best = 0;
 #pragma unroll
     for (int k = 0; k < 16; k += 2) {
-        const uint32_t a = __vimin3_s16x2(mn[k], mn[(k + 3) & 15], mn[(k + 6) & 15]);
-        const uint32_t b = __vimin3_s16x2(mn[k + 1], mn[(k + 4) & 15], mn[(k + 7) & 15]);
-        bright = __vimax3_s16x2(bright, a, b);
-        const uint32_t c = __vimax3_s16x2(mx[k], mx[(k + 3) & 15], mx[(k + 6) & 15]);
-        const uint32_t d = __vimax3_s16x2(mx[k + 1], mx[(k + 4) & 15], mx[(k + 7) & 15]);
-        dark = __vimin3_s16x2(dark, c, d);
+        const uint32_t a = __vimin3_u16x2(mn[k], mn[(k + 3) & 15], mn[(k + 6) & 15]);
+        const uint32_t b = __vimin3_u16x2(mn[k + 1], mn[(k + 4) & 15], mn[(k + 7) & 15]);
+        best = __vimax3_u16x2(best, a, b);
     }
-    mA = max((int) (short) (bright & 0xffffu), -(int) (short) (dark & 0xffffu));
-    mB = max((int) (short) (bright >> 16), -(int) (short) (dark >> 16));
+    return (int) max(best & 0xffffu, best >> 16) - 256;
 }
+
+// |a - b| > t per byte -> bit 7 of each byte of (x, y) OR-ed together (the low 7 bits are garbage).  k7 = (127 - (t & 127)) replicated.
+//   exact form (any t):   ((x & 0x7f..) + k7)  |/&  x
+//   fast form (t < 128):  (x + k7) | x  with the add issued as an IMAD (x * one + k7, `one` is a kernel argument equal to 1) so it
+//   runs on the FMA pipe.  Without the 7-bit mask a byte >= 129 + t carries into its left neighbour, which can only turn a
+//   neighbour byte equal to t into a pass: the test stays a superset of the exact one (stage B is exact), never a subset.
+template <int kMode>      // 0: fast t < 128, 1: exact t < 128, 2: exact t >= 128
+__device__ __forceinline__ uint32_t pair_gt(uint32_t v, uint32_t pa, uint32_t pb, uint32_t k7, uint32_t one, uint32_t acc) {
+    const uint32_t xa = __vabsdiffu4(v, pa), xb = __vabsdiffu4(v, pb);
+    if constexpr (kMode == 0) {
+        const uint32_t ya = xa * one + k7, yb = xb * one + k7;
+        return ((ya | xa | yb) | xb) & acc;
+    } else {
+        const uint32_t ya = (xa & 0x7f7f7f7fu) + k7, yb = (xb & 0x7f7f7f7fu) + k7;
+        return kMode == 2 ? ((ya & xa) | (yb & xb)) & acc : ((ya | xa | yb) | xb) & acc;
+    }
+}
+
+// Stage A of k_fast for one strip row y: a lane owns the aligned words 2*lane and 2*lane+1 (8 pixels).  A 9-arc of the 16-ring
+// holds ring k or ring k+8 for every k, so a corner needs |p_k - v| > t or |p_(k+8) - v| > t for all eight opposite pairs.
+// Returns the pass flags of the two words in bit 7 of each byte.
+template <int kMode>
+__device__ __forceinline__ void fast_pairs_row(const uint8_t *tile, int y, int lane, uint32_t k7, uint32_t one, uint32_t &acc0, uint32_t &acc1) {
+    constexpr int SP = kBoxW;
+    const uint8_t *base = tile + y * SP + 8 * lane;
+    const int lo = lane == 0 ? 0 : -4, hi = lane == 31 ? 4 : 8;          // clamp the neighbour words at the box edge (never candidates)
+#define ORBFE_ROW(r, Wm, W0, W1, W2)                                                     \
+    const uint2 c##r = *reinterpret_cast<const uint2 *>(base + (r) * SP);               \
+    const uint32_t Wm = *reinterpret_cast<const uint32_t *>(base + (r) * SP + lo);      \
+    const uint32_t W2 = *reinterpret_cast<const uint32_t *>(base + (r) * SP + hi);      \
+    const uint32_t W0 = c##r.x, W1 = c##r.y;
+#define ORBFE_PAIR(A0, A1, B0, B1)                                   \
+    acc0 = pair_gt<kMode>(v0, A0, B0, k7, one, acc0);                \
+    acc1 = pair_gt<kMode>(v1, A1, B1, k7, one, acc1);
+    // centre row (ring 4 = (+3, 0), ring 12 = (-3, 0))
+    ORBFE_ROW(3, m3, v0, v1, p3)
+    acc0 = acc1 = 0xffffffffu;
+    ORBFE_PAIR(__funnelshift_r(v0, v1, 24), __funnelshift_r(v1, p3, 24), __funnelshift_r(m3, v0, 8), __funnelshift_r(v0, v1, 8))
+    {   // rows y+6 (dy = +3) and y (dy = -3): pairs (0, 8), (1, 9), (15, 7)
+        ORBFE_ROW(6, dm, d0, d1, d2)
+        ORBFE_ROW(0, um, u0, u1, u2)
+        ORBFE_PAIR(d0, d1, u0, u1)
+        ORBFE_PAIR(__funnelshift_r(d0, d1, 8), __funnelshift_r(d1, d2, 8), __funnelshift_r(um, u0, 24), __funnelshift_r(u0, u1, 24))
+        ORBFE_PAIR(__funnelshift_r(dm, d0, 24), __funnelshift_r(d0, d1, 24), __funnelshift_r(u0, u1, 8), __funnelshift_r(u1, u2, 8))
+    }
+    {   // rows y+5 (dy = +2) and y+1 (dy = -2): pairs (2, 10), (14, 6)
+        ORBFE_ROW(5, dm, d0, d1, d2)
+        ORBFE_ROW(1, um, u0, u1, u2)
+        const uint32_t dmid = __funnelshift_r(d0, d1, 16), umid = __funnelshift_r(u0, u1, 16);
+        ORBFE_PAIR(dmid, __funnelshift_r(d1, d2, 16), __funnelshift_r(um, u0, 16), umid)
+        ORBFE_PAIR(__funnelshift_r(dm, d0, 16), dmid, umid, __funnelshift_r(u1, u2, 16))
+    }
+    {   // rows y+4 (dy = +1) and y+2 (dy = -1): pairs (3, 11), (13, 5)
+        ORBFE_ROW(4, dm, d0, d1, d2)
+        ORBFE_ROW(2, um, u0, u1, u2)
+        ORBFE_PAIR(__funnelshift_r(d0, d1, 24), __funnelshift_r(d1, d2, 24), __funnelshift_r(um, u0, 8), __funnelshift_r(u0, u1, 8))
+        ORBFE_PAIR(__funnelshift_r(dm, d0, 8), __funnelshift_r(d0, d1, 8), __funnelshift_r(u0, u1, 24), __funnelshift_r(u1, u2, 24))
+    }
+#undef ORBFE_PAIR
+#undef ORBFE_ROW
+}
+
+// bytes [0, n) set, n in [0, 4]
+__device__ __forceinline__ uint32_t low_bytes(int n) { return n >= 4 ? 0xffffffffu : ((1u << (8 * n)) - 1u); }
 
 struct FastArgs {
     uint32_t *slots; int *cell_cnt; const int *blk_tab;
     int cells_per_frame, t_ini, t_min;
+    int one;        // 1: multiplier that keeps the stage-A adds on the FMA pipe (an immediate would be folded into an IADD)
+    int flags;      // bit 0: exact (masked) stage-A compares, for A/B testing
 };
 
 template <bool kTMA>
 __global__ void __launch_bounds__(256, 6) k_fast(const __grid_constant__ LevelSet L, const __grid_constant__ TmapSet T, const FastArgs a) {
     constexpr int SP = kBoxW;
     __shared__ __align__(128) uint8_t tile[kFastBoxH * SP];
-    __shared__ __align__(16) uint8_t mmap[32 * SP];                     // m of strip pixel (x, y) at [(y+1)*SP + x+1], zero elsewhere
+    // m of strip pixel (x, y) at [(y+1)*SP + x+1], zero elsewhere; between stages A and A2 rows 0..ch-1 hold the pass words of stage A
+    __shared__ __align__(16) uint8_t mmap[32 * SP];
     __shared__ uint16_t queue[kStripW * kCell];                         // y << 8 | x  (strip coordinates)
     __shared__ uint32_t rowmask[kCellsPerBlk][32];                      // NMS survivors of cell row r, bit = cx
-    __shared__ int s_qn, s_cn, s_has[kCellsPerBlk], s_scan[8];
-    __shared__ uint32_t passbits[32][8];                                // stage-A result: [row][half * 4 + byte] bit = word index within the half
+    __shared__ int s_has[kCellsPerBlk], s_scan[8];
     __shared__ __align__(8) uint64_t bar;
 
     const int frame = blockIdx.y, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
@@ -267,152 +330,113 @@ __global__ void __launch_bounds__(256, 6) k_fast(const __grid_constant__ LevelSe
     const int ch = min(kCell, G.h - kEdge - (kEdge + kCell * ci));                      // rows inside maxBorderY
     const uint8_t *strip = tile + 3 * SP + 3;                                           // pixel (x, y) at strip[y * SP + x]
     unsigned open = (1u << ((strip_w + kCell - 1) / kCell)) - 1u;                       // cells that still need a result
-    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t one = (uint32_t) a.one;
 
 #pragma unroll 1
     for (int round = 0; round < 2; ++round) {
         const int t = round == 0 ? a.t_ini : a.t_min;
-        if (tid == 0) { s_qn = 0; s_cn = 0; }
-        if (tid < kCellsPerBlk) s_has[tid] = 0;
         rowmask[wid][lane] = 0;
-        if (round == 0) {
-            for (int i = tid; i < 32 * SP / 16; i += 256) reinterpret_cast<uint4 *>(mmap)[i] = make_uint4(0, 0, 0, 0);
-        } else {
-            for (int i = tid; i < 32 * SP; i += 256) {
-                const int x = (i & 255) - 1;
-                if (x >= 0 && x < kStripW && ((open >> ((x * 2185) >> 16)) & 1u)) mmap[i] = 0;
-            }
-        }
+        for (int i = tid; i < 32 * SP / 16; i += 256) reinterpret_cast<uint4 *>(mmap)[i] = make_uint4(0, 0, 0, 0);
         __syncthreads();
 
-        // ---- A: high-speed test, one warp per strip row, lane = aligned words `lane` and `lane + 32` (word j = pixels 4j-3 .. 4j)
+        // ---- A: opposite-pair rejection test, one warp per strip row, lane = aligned words 2*lane, 2*lane+1 (word j = pixels 4j-3 .. 4j)
         {
             const uint32_t k7 = (uint32_t) (127 - (t & 127)) * 0x01010101u;
-            const bool tge = t >= 128;
+            // candidate pixels of this lane: strip x = 8*lane + p - 3 in [0, strip_w), in a cell that is still open
+            const int nv = strip_w + 3 - 8 * lane;
+            uint32_t vm0 = low_bytes(max(nv, 0)) & 0x80808080u, vm1 = low_bytes(max(nv - 4, 0)) & 0x80808080u;
+            if (lane == 0) vm0 &= 0xff000000u;
+            if (round) {
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    const int x = max(8 * lane + p - 3, 0);
+                    if (!((open >> ((x * 2185) >> 16)) & 1u)) { if (p < 4) vm0 &= ~(0x80u << (8 * p)); else vm1 &= ~(0x80u << (8 * (p - 4))); }
+                }
+            }
+            const int mode = t >= 128 ? 2 : (a.flags & 1) ? 1 : 0;
             for (int y = wid; y < ch; y += 8) {
-                const uint32_t *rc = reinterpret_cast<const uint32_t *>(tile + (3 + y) * SP);
-                const uint32_t *ru = reinterpret_cast<const uint32_t *>(tile + y * SP);
-                const uint32_t *rd = reinterpret_cast<const uint32_t *>(tile + (6 + y) * SP);
-                uint32_t pass[2];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int j = lane + 32 * h;
-                    const uint32_t w1 = rc[j], w0 = rc[max(j - 1, 0)], w2 = rc[min(j + 1, 63)];
-                    const uint32_t lf = __funnelshift_r(w0, w1, 8), rt = __funnelshift_r(w1, w2, 24);
-                    const uint32_t m0 = bytes_gt(__vabsdiffu4(w1, rd[j]), k7, tge), m8 = bytes_gt(__vabsdiffu4(w1, ru[j]), k7, tge);
-                    const uint32_t m4 = bytes_gt(__vabsdiffu4(w1, rt), k7, tge), m12 = bytes_gt(__vabsdiffu4(w1, lf), k7, tge);
-                    uint32_t p = (m0 | m8) & (m4 | m12);      // every 9-arc holds ring 0 or 8, and ring 4 or 12
-                    // pixels 4j-3+b must lie in [0, strip_w)
-                    const int nb = min(max(strip_w + 3 - 4 * j, 0), 4);
-                    p &= nb >= 4 ? 0xffffffffu : ((1u << (8 * nb)) - 1u);
-                    if (j == 0) p &= 0xff000000u;
-                    if (round) {                              // second pass: only cells without a survivor
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            const int x = max(4 * j - 3 + b, 0);
-                            if (!((open >> ((x * 2185) >> 16)) & 1u)) p &= ~(0x80u << (8 * b));
-                        }
-                    }
-                    pass[h] = p;
-                }
-                // bit planes: plane i = (half h, byte b), bit = lane; lanes 0..7 keep one plane each and store it
-                unsigned mine = 0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const unsigned bal = __ballot_sync(0xffffffffu, (pass[i >> 2] >> (8 * (i & 3) + 7)) & 1u);
-                    if (lane == i) mine = bal;
-                }
-                if (lane < 8) passbits[y][lane] = mine;
+                uint32_t a0, a1;
+                if (mode == 0) fast_pairs_row<0>(tile, y, lane, k7, one, a0, a1);
+                else if (mode == 1) fast_pairs_row<1>(tile, y, lane, k7, one, a0, a1);
+                else fast_pairs_row<2>(tile, y, lane, k7, one, a0, a1);
+                *reinterpret_cast<uint2 *>(mmap + y * SP + 8 * lane) = make_uint2(a0 & vm0, a1 & vm1);
             }
         }
         __syncthreads();
-        // ---- A2: expand the bit planes into the queue (order is irrelevant): thread = one 32-bit plane word
+        // ---- A2: expand the pass words into the queue (order is irrelevant): thread = 8 consecutive words of one row; the words
+        // are cleared on the way, which leaves the score map zeroed for stage B
+        int n;
         {
-            unsigned word = 0;
-            const int y = tid >> 3, plane = tid & 7;
-            if (y < ch) word = passbits[y][plane];
-            int total;
-            int o = block_scan_excl<256>(__popc(word), total, s_scan);
-            if (tid == 0) s_qn = total;
-            const int xbase = (y << 8) + 128 * (plane >> 2) - 3 + (plane & 3);
-            while (word) {
-                const int b = __ffs(word) - 1;
-                word &= word - 1;
-                queue[o++] = (uint16_t) (xbase + 4 * b);
+            unsigned bits = 0;                                          // bit 8b + i = byte b of word i
+            const int y = tid >> 3, seg = tid & 7;
+            if (y < ch) {
+                uint4 *w = reinterpret_cast<uint4 *>(mmap + y * SP + 32 * seg);
+                const uint4 wa = w[0], wb = w[1];
+                w[0] = make_uint4(0, 0, 0, 0); w[1] = make_uint4(0, 0, 0, 0);
+                // the stored words only hold bit 7 of each byte
+                bits = (wa.x >> 7) | (wa.y >> 6) | (wa.z >> 5) | (wa.w >> 4) | (wb.x >> 3) | (wb.y >> 2) | (wb.z >> 1) | wb.w;
+            }
+            int o = block_scan_excl<256>(__popc(bits), n, s_scan);
+            const int xbase = (y << 8) + 32 * seg - 3;
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                queue[o++] = (uint16_t) (xbase + 4 * (b & 7) + (b >> 3));
             }
         }
         __syncthreads();
 
-        // ---- B: exact measure, two queued pixels per thread; corners (m > t) are compacted in place at the queue head
-        {
-            const int n = s_qn;
-            for (int base = 0; base < n; base += 512) {
-                const int k = base + 2 * tid;
-                int pa = 0, pb = 0;
-                if (k < n) { pa = queue[k]; pb = queue[min(k + 1, n - 1)]; }
-                __syncthreads();                            // all entries of this round are in registers: the head may be overwritten
-                int ma = 0, mb = 0;
-                if (k < n) {
-                    fast_measure2(strip + (pa >> 8) * SP + (pa & 255), strip + (pb >> 8) * SP + (pb & 255), ma, mb);
-                    if (k + 1 >= n) mb = 0;
-                }
-                const bool ca = ma > t, cb = mb > t;
-                if (ca) mmap[pa + SP + 1] = (uint8_t) ma;
-                if (cb) mmap[pb + SP + 1] = (uint8_t) mb;
-                const unsigned ba = __ballot_sync(0xffffffffu, ca), bb = __ballot_sync(0xffffffffu, cb);
-                const int total = __popc(ba) + __popc(bb);
-                if (total) {
-                    int o = 0;
-                    if (lane == 0) o = atomicAdd(&s_cn, total);
-                    o = __shfl_sync(0xffffffffu, o, 0);
-                    if (ca) queue[o + __popc(ba & lt)] = (uint16_t) pa;
-                    if (cb) queue[o + __popc(ba) + __popc(bb & lt)] = (uint16_t) pb;
-                }
-            }
+        // ---- B: exact measure of the queued pixels, one per thread; corners (m > t) go into the strip-wide score map
+        for (int k = tid; k < n; k += 256) {
+            const int pos = queue[k];
+            const int m = fast_measure1(strip + (pos >> 8) * SP + (pos & 255));
+            if (m > t) mmap[pos + SP + 1] = (uint8_t) m;
         }
         __syncthreads();
 
         // ---- C: non-max suppression inside the cell (strictly greater than the 8 neighbours; outside the cell = 0)
-        {
-            const int n = s_cn;
-            for (int k = tid; k < n; k += 256) {
-                const int pos = queue[k];
-                const int x = pos & 255, y = pos >> 8, c = (x * 2185) >> 16, cx = x - kCell * c;
-                const uint8_t *p = mmap + pos + SP + 1;
-                const int m = p[0];
-                int nb = max(p[-SP], p[SP]);
-                if (cx > 0) nb = max(nb, max(max(p[-SP - 1], p[-1]), p[SP - 1]));
-                if (cx < kCell - 1 && x + 1 < strip_w) nb = max(nb, max(max(p[-SP + 1], p[1]), p[SP + 1]));
-                if (m > nb) { atomicOr(&rowmask[c][y], 1u << cx); s_has[c] = 1; }
-            }
+        for (int k = tid; k < n; k += 256) {
+            const int pos = queue[k];
+            const uint8_t *p = mmap + pos + SP + 1;
+            const int m = p[0];
+            if (m == 0) continue;                            // rejected by the exact measure
+            const int x = pos & 255, y = pos >> 8, c = (x * 2185) >> 16, cx = x - kCell * c;
+            int nb = max(p[-SP], p[SP]);
+            if (cx > 0) nb = max(nb, max(max(p[-SP - 1], p[-1]), p[SP - 1]));
+            if (cx < kCell - 1 && x + 1 < strip_w) nb = max(nb, max(max(p[-SP + 1], p[1]), p[SP + 1]));
+            if (m > nb) atomicOr(&rowmask[c][y], 1u << cx);
         }
         __syncthreads();
 
         // ---- D: one warp per cell, lane = cell row: ordered emission (ORBExtractor.cpp:609-615)
+        {
+            unsigned mask = rowmask[wid][lane];
+            const bool has = __any_sync(0xffffffffu, mask != 0);
+            if (lane == 0) s_has[wid] = has;
+            if (((open >> wid) & 1u) && (has || round == 1)) {
+                const int cnt = __popc(mask);
+                int inc = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+                const int total = __shfl_sync(0xffffffffu, inc, 31);
+                const int cj = cg * kCellsPerBlk + wid;
+                const int cell = G.cell_base + ci * G.n_cols + cj;
+                uint32_t *slot = a.slots + ((size_t) frame * a.cells_per_frame + cell) * kSlotCap + (inc - cnt);
+                while (mask) {
+                    const int cx = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int m = mmap[(lane + 1) * SP + kCell * wid + cx + 1];
+                    *slot++ = (uint32_t) (cj * kCell + cx) | ((uint32_t) (ci * kCell + lane) << 12) | ((uint32_t) (m - 1) << 24);
+                }
+                if (lane == 0) a.cell_cnt[(size_t) frame * a.cells_per_frame + cell] = total;
+            }
+        }
+        __syncthreads();                                     // s_has is complete; stage D reads of mmap / rowmask precede the next round
         unsigned has = 0;
 #pragma unroll
         for (int c = 0; c < kCellsPerBlk; ++c) has |= s_has[c] ? 1u << c : 0u;
-        if (((open >> wid) & 1u) && (((has >> wid) & 1u) || round == 1)) {
-            unsigned mask = rowmask[wid][lane];
-            const int cnt = __popc(mask);
-            int inc = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-            const int total = __shfl_sync(0xffffffffu, inc, 31);
-            const int cj = cg * kCellsPerBlk + wid;
-            const int cell = G.cell_base + ci * G.n_cols + cj;
-            uint32_t *slot = a.slots + ((size_t) frame * a.cells_per_frame + cell) * kSlotCap + (inc - cnt);
-            while (mask) {
-                const int cx = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const int m = mmap[(lane + 1) * SP + kCell * wid + cx + 1];
-                *slot++ = (uint32_t) (cj * kCell + cx) | ((uint32_t) (ci * kCell + lane) << 12) | ((uint32_t) (m - 1) << 24);
-            }
-            if (lane == 0) a.cell_cnt[(size_t) frame * a.cells_per_frame + cell] = total;
-        }
         open &= ~has;
         if (open == 0) break;
-        __syncthreads();                                     // stage D reads of mmap / rowmask precede the re-initialisation
     }
 }
 
