@@ -185,6 +185,10 @@ static int configure(Handle *h, int w, int ht, int batch) {
             if (!span_ok(xt[l], R.tw, kBoxUsable) || !span_ok(yt[l], R.th, kRsBoxH))
                 return set_error(h, ORBFE_E_ARG, "scale factor %f too large for the resize tile", (double) h->cfg.scale_factor);
             R.tiles_x = (L.w + R.tw - 1) / R.tw; R.tiles_y = (L.h + R.th - 1) / R.th;
+            R.packed = true;                              // quads start at multiples of 4 (tw is a multiple of 16)
+            for (int d0 = 0; d0 < L.w && R.packed; d0 += 4)
+                for (int i = 0; i < 4; ++i)
+                    if ((xt[l][std::min(d0 + i, L.w - 1)].x >> 16) - (xt[l][d0].x & 0xffff) > 7) R.packed = false;
             table_elems += xt[l].size() + yt[l].size();
         }
     }
@@ -229,10 +233,14 @@ static int configure(Handle *h, int w, int ht, int batch) {
             g.rs[l].ytab = p; p += yt[l].size();
         }
         // FAST block table: block -> (level, cell row, strip of 8 cells)
-        std::vector<int> tab((size_t) g.fast_blocks);
-        for (int l = 0; l < nl; ++l)
+        // followed by the blur block table: block -> (level, tile row, tile column)
+        std::vector<int> tab((size_t) g.fast_blocks + g.blur_blocks);
+        for (int l = 0; l < nl; ++l) {
             for (int ci = 0; ci < g.lv[l].n_rows; ++ci)
                 for (int cg = 0; cg < g.lv[l].n_groups; ++cg) tab[(size_t) g.lv[l].fast_blk_base + ci * g.lv[l].n_groups + cg] = l | (ci << 4) | (cg << 16);
+            for (int ty = 0; ty < g.lv[l].blur_ty; ++ty)
+                for (int tx = 0; tx < g.lv[l].blur_tx; ++tx) tab[(size_t) g.fast_blocks + g.lv[l].blur_blk_base + ty * g.lv[l].blur_tx + tx] = l | (ty << 4) | (tx << 16);
+        }
         ORBFE_CUDA(h, cudaMalloc(&h->d_fast_tab, tab.size() * sizeof(int)));
         ORBFE_CUDA(h, cudaMemcpyAsync(h->d_fast_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
         ORBFE_CUDA(h, cudaStreamSynchronize(h->stream));      // the host vectors die with this scope
@@ -353,13 +361,14 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
         ra.src = LS.img[l - 1]; ra.sw = S.w; ra.sh = S.h; ra.spitch = S.pitch; ra.sframe = S.frame_stride;
         ra.dst = h->d_img + D.img_off; ra.dw = D.w; ra.dh = D.h; ra.dpitch = D.pitch; ra.dframe = D.frame_stride;
         ra.tw = R.tw; ra.th = R.th; ra.tiles_x = R.tiles_x; ra.xtab = R.xtab; ra.ytab = R.ytab;
-        k_resize<kTMA><<<dim3(R.tiles_x * R.tiles_y, nb), kRsThreads, 0, st>>>(l == 1 ? tm_rs0 : h->tm_rs[l - 1], ra);
+        if (R.packed) k_resize<kTMA, true><<<dim3(R.tiles_x * R.tiles_y, nb), kRsThreads, 0, st>>>(l == 1 ? tm_rs0 : h->tm_rs[l - 1], ra);
+        else k_resize<kTMA, false><<<dim3(R.tiles_x * R.tiles_y, nb), kRsThreads, 0, st>>>(l == 1 ? tm_rs0 : h->tm_rs[l - 1], ra);
         ORBFE_AFTER_LAUNCH(h, st, "k_resize");
     }
     ORBFE_PROF_MARK(h, st, 1);
     // The blur only depends on the pyramid: it runs on an auxiliary stream next to FAST + quadtree (which are issue- and
     // latency-bound) and is joined before the descriptors.
-    BlurArgs ba; ba.blur = h->d_blur;
+    BlurArgs ba; ba.blur = h->d_blur; ba.blk_tab = h->d_fast_tab + g.fast_blocks;
     const bool fork_blur = !h->prof && !debug_sync();
     if (fork_blur) {
         if (!h->s_aux) {

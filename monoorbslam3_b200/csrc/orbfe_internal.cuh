@@ -43,6 +43,7 @@ struct LevelGeom {
 
 struct ResizeLevel {                 // destination level l (source = l-1)
     int tw, th, tiles_x, tiles_y;
+    bool packed;                     // every 4-column quad reads a source span of at most 8 bytes (k_resize packed path)
     const int2 *xtab;                // per dst x: {sx0 | sx1<<16, a0 | a1<<16}
     const int2 *ytab;                // per dst y: {sy0 | sy1<<16, b0 | b1<<16}
 };

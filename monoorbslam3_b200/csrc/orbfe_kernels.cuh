@@ -122,12 +122,15 @@ struct ResizeArgs {
 // A thread owns 4 destination columns (their coefficient-table entries stay in registers) and walks down a run of destination
 // rows, re-using the horizontal interpolation of a source row when consecutive destination rows share it (5 times out of 6 at
 // scale 1.2).  192 threads = 48 column quads x 4 row runs.
+// kPacked (every quad's source span fits 8 bytes, true for scale factors up to 2): a source row costs three aligned word loads,
+// two funnel shifts, and per column one PRMT (byte pair s0, s1) + one DP2A (s0 * a0 + s1 * a1); otherwise bytes are gathered.
+// The horizontal results are kept pre-shifted (H >> 4), the vertical blend is two IMAD.HI with the row weights pre-shifted by 16.
 constexpr int kRsThreads = 192;
 
-template <bool kTMA>
+template <bool kTMA, bool kPacked>
 __global__ void __launch_bounds__(kRsThreads) k_resize(const __grid_constant__ CUtensorMap tm_src, const ResizeArgs a) {
     constexpr int SP = TilePitch<kTMA>::value;
-    __shared__ __align__(128) uint8_t tile[kRsBoxH * SP];
+    __shared__ __align__(128) uint8_t tile[kRsBoxH * SP + 16];                // + 16: the packed path may read one word past a row
     __shared__ __align__(8) uint64_t bar;
     const int frame = blockIdx.y;
     const int ty = blockIdx.x / a.tiles_x, tx = blockIdx.x - ty * a.tiles_x;
@@ -137,48 +140,62 @@ __global__ void __launch_bounds__(kRsThreads) k_resize(const __grid_constant__ C
     const int qx = threadIdx.x % (kRsMaxTW / 4), grp = threadIdx.x / (kRsMaxTW / 4);
     const int dxb = dx0 + 4 * qx;
     if (4 * qx >= a.tw || dxb >= a.dw) return;
-    int c0[4], c1[4], w0[4], w1[4];
+    int c0[4], c1[4];
+    uint32_t wq[4];                                       // a0 | a1 << 16
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int2 xe = __ldg(&a.xtab[min(dxb + i, a.dw - 1)]);
         c0[i] = (xe.x & 0xffff) - ox + xo; c1[i] = (xe.x >> 16) - ox + xo;
-        w0[i] = xe.y & 0xffff; w1[i] = xe.y >> 16;
+        wq[i] = (uint32_t) xe.y;
     }
+    const int cw = c0[0] >> 2, sh = (c0[0] & 3) * 8;
+    uint32_t sel[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sel[i] = (uint32_t) (c0[i] - c0[0]) | ((uint32_t) (c1[i] - c0[0]) << 4);
+    // horizontal interpolation of one staged source row, >> 4
+    auto hrow = [&](int r, uint32_t (&hs)[4]) {
+        if constexpr (kPacked) {
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(tile + r * SP) + cw;
+            const uint32_t wa = wp[0], wb = wp[1], wc = wp[2];
+            const uint32_t lo = __funnelshift_r(wa, wb, sh), hi = __funnelshift_r(wb, wc, sh);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hs[i] = __dp2a_lo(wq[i], __byte_perm(lo, hi, sel[i]), 0u) >> 4;
+        } else {
+            const uint8_t *t = tile + r * SP;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hs[i] = (t[c0[i]] * (wq[i] & 0xffffu) + t[c1[i]] * (wq[i] >> 16)) >> 4;
+        }
+    };
     const int rows_per = (a.th + 3) >> 2;
     const int ry_end = min(min((grp + 1) * rows_per, a.th), a.dh - dy0);
-    uint8_t *dst = a.dst + (size_t) frame * a.dframe + dxb;
-    int prev_r = -1, hp[4] = {0, 0, 0, 0};
-    for (int ry = grp * rows_per; ry < ry_end; ++ry) {
-        const int dy = dy0 + ry;
-        const int2 ye = __ldg(&a.ytab[dy]);
+    const int ry0 = grp * rows_per;
+    if (ry0 >= ry_end) return;
+    uint8_t *dst = a.dst + (size_t) frame * a.dframe + (size_t) (dy0 + ry0) * a.dpitch + dxb;
+    const int2 *yt = a.ytab + dy0;
+    int prev_r = -1;
+    uint32_t hp[4] = {0, 0, 0, 0};
+    for (int ry = ry0; ry < ry_end; ++ry) {
+        const int2 ye = __ldg(&yt[ry]);
         const int r0 = (ye.x & 0xffff) - oy, r1 = (ye.x >> 16) - oy;
-        const int b0 = ye.y & 0xffff, b1 = ye.y >> 16;
-        int h0[4], h1[4];
+        const uint32_t b0 = (uint32_t) ye.y << 16, b1 = (uint32_t) ye.y & 0xffff0000u;        // row weights << 16
+        uint32_t h0[4], h1[4];
         if (r0 == prev_r) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) h0[i] = hp[i];
-        } else {
-            const uint8_t *t = tile + r0 * SP;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) h0[i] = t[c0[i]] * w0[i] + t[c1[i]] * w1[i];
-        }
+        } else hrow(r0, h0);
         if (r1 == r0) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) h1[i] = h0[i];
-        } else {
-            const uint8_t *t = tile + r1 * SP;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) h1[i] = t[c0[i]] * w0[i] + t[c1[i]] * w1[i];
-        }
-        uint32_t out = 0;
+        } else hrow(r1, h1);
+        uint32_t v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int v = (((b0 * (h0[i] >> 4)) >> 16) + ((b1 * (h1[i] >> 4)) >> 16) + 2) >> 2;
-            out |= (uint32_t) (v & 0xff) << (8 * i);
+            v[i] = (__umulhi(b0, h0[i]) + __umulhi(b1, h1[i]) + 2u) >> 2;           // ((b0 * (H0 >> 4)) >> 16) + ...
             hp[i] = h1[i];
         }
         prev_r = r1;
-        *reinterpret_cast<uint32_t *>(dst + (size_t) dy * a.dpitch) = out;
+        *reinterpret_cast<uint32_t *>(dst) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+        dst += a.dpitch;
     }
 }
 
@@ -703,26 +720,25 @@ __global__ void __launch_bounds__(NT) k_octree(const __grid_constant__ LevelSet 
 // K6  7x7 Gaussian blur, sigma 2, BORDER_REFLECT_101, OpenCV's 8.8 fixed-point path.
 // Tile: 224 x 32 outputs from a 256 x 38 staged box (the box starts 16-byte aligned, 13 px left of the halo).  Horizontal pass -> u16 in smem, vertical pass sliding in registers.
 // ------------------------------------------------------------------------------------------------
-struct BlurArgs { uint8_t *blur; };
+struct BlurArgs { uint8_t *blur; const int *blk_tab; };      // blk_tab: block -> level | tile row << 4 | tile column << 16
 
 __device__ __forceinline__ int refl101(int p, int n) { return p < 0 ? -p : (p >= n ? 2 * n - 2 - p : p); }
 
 template <bool kTMA>
 __global__ void __launch_bounds__(256, 6) k_blur(const __grid_constant__ LevelSet L, const __grid_constant__ TmapSet T, const BlurArgs a) {
     constexpr int SP = TilePitch<kTMA>::value;
+    constexpr int XO = 13;                        // the box starts 16 px left of x0 (16-byte aligned), the 3-px halo at column 13
+    static_assert(kBlurTileW % 16 == 0 && kBlurBoxH % 2 == 0, "tile origin must keep the halo at column 13 and rows must pair up");
     __shared__ __align__(128) uint8_t tile[kBlurBoxH * SP];
-    __shared__ __align__(16) uint16_t hbuf[kBlurBoxH * kBlurTileW];
+    __shared__ __align__(16) uint32_t hp[(kBlurBoxH / 2) * kBlurTileW];     // horizontal pass, rows paired: H[2p][x] | H[2p+1][x] << 16
     __shared__ __align__(8) uint64_t bar;
     const int frame = blockIdx.y, tid = threadIdx.x;
-    int l = 0;
-#pragma unroll 1
-    for (int k = 1; k < L.n_levels; ++k) if ((int) blockIdx.x >= L.lv[k].blur_blk_base) l = k;
+    const int packed = __ldg(&a.blk_tab[blockIdx.x]);
+    const int l = packed & 15, ty = (packed >> 4) & 0xfff, tx = packed >> 16;
     const LevelGeom &G = L.lv[l];
-    const int rem = blockIdx.x - G.blur_blk_base;
-    const int ty = rem / G.blur_tx, tx = rem - ty * G.blur_tx;
     const int x0 = tx * kBlurTileW, y0 = ty * kBlurTileH;
-    const int xo = stage_box<kTMA, 256>(tile, &bar, &T.m[l], L.img[l] + (size_t) frame * G.frame_stride, G.pitch, G.h, x0 - 3, y0 - 3, frame, kBlurBoxH);
-    uint8_t *t = tile + xo;                       // t[r*SP + c] = pixel (x0-3+c, y0-3+r)
+    stage_box<kTMA, 256>(tile, &bar, &T.m[l], L.img[l] + (size_t) frame * G.frame_stride, G.pitch, G.h, x0 - 3, y0 - 3, frame, kBlurBoxH);
+    uint8_t *t = tile + XO;                       // t[r*SP + c] = pixel (x0-3+c, y0-3+r)
     const int w = G.w, h = G.h;
     // reflect-101 fix-up of the columns / rows of the box that lie outside the image (only border tiles)
     const int need_w = min(kBlurTileW, w - x0) + 6, need_h = min(kBlurTileH, h - y0) + 6;
@@ -737,7 +753,7 @@ __global__ void __launch_bounds__(256, 6) k_blur(const __grid_constant__ LevelSe
     }
     if (y0 == 0 || y0 + kBlurTileH + 3 > h) {
         for (int idx = tid; idx < 6 * kBoxW; idx += 256) {
-            const int k = idx / kBoxW, c = idx - k * kBoxW;
+            const int k = idx >> 8, c = idx & 255;
             const int r = k < 3 ? k : need_h - 6 + k;
             const int gy = y0 - 3 + r;
             if ((gy < 0 || gy >= h) && c < need_w) t[r * SP + c] = t[(refl101(gy, h) - (y0 - 3)) * SP + c];
@@ -746,26 +762,24 @@ __global__ void __launch_bounds__(256, 6) k_blur(const __grid_constant__ LevelSe
     }
     // horizontal pass on packed bytes: H[x] = dp4a(src[x-3..x], {18,34,48,56}) + dp4a(src[x+1..x+4], {48,34,18,0})  (exact, <= 65280).
     // One item = 4 outputs of two consecutive rows, stored as u16x2 pairs (row 2p | row 2p+1 << 16) for the dp2a vertical pass.
+    // The first tap of output 4*qx sits at tile column 13 + 4*qx = byte 1 of the aligned word at column 12 + 4*qx.
     constexpr uint32_t K0123 = 18u | (34u << 8) | (48u << 16) | (56u << 24), K456 = 48u | (34u << 8) | (18u << 16);
     constexpr int QW = kBlurTileW / 4;
-    static_assert(kBlurTileW % 16 == 0 && kBlurBoxH % 2 == 0, "tile origin must keep xo == 13 and rows must pair up");
-    uint32_t *hp = reinterpret_cast<uint32_t *>(hbuf);          // [kBlurBoxH / 2][kBlurTileW]
     for (int it = tid; it < (kBlurBoxH / 2) * QW; it += 256) {
         const int rp = it / QW, qx = it - rp * QW;
-        uint32_t h[2][4];
+        uint32_t hh[2][4];
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
-            // tile column of output o's first tap is xo + o; xo is 13 for every tile (x0 is a multiple of 16), so words are aligned
-            const uint32_t *w = reinterpret_cast<const uint32_t *>(tile + (2 * rp + rr) * SP + (xo & ~3)) + qx;
-            const uint32_t wa = w[0], wb = w[1], wc = w[2];
-            const int sh = 8 * (xo & 3);                       // = 8: first tap of output 0 is byte 1 of wa
-            h[rr][0] = __dp4a(__funnelshift_r(wa, wb, sh), K0123, __dp4a(__funnelshift_r(wb, wc, sh), K456, 0u));
-            h[rr][1] = __dp4a(__funnelshift_r(wa, wb, sh + 8), K0123, __dp4a(__funnelshift_r(wb, wc, sh + 8), K456, 0u));
-            h[rr][2] = __dp4a(__funnelshift_r(wa, wb, sh + 16), K0123, __dp4a(__funnelshift_r(wb, wc, sh + 16), K456, 0u));
-            h[rr][3] = __dp4a(wb, K0123, __dp4a(wc, K456, 0u));
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(tile + (2 * rp + rr) * SP + (XO - 1)) + qx;
+            const uint32_t wa = wp[0], wb = wp[1], wc = wp[2];
+            hh[rr][0] = __dp4a(__funnelshift_r(wa, wb, 8), K0123, __dp4a(__funnelshift_r(wb, wc, 8), K456, 0u));
+            hh[rr][1] = __dp4a(__funnelshift_r(wa, wb, 16), K0123, __dp4a(__funnelshift_r(wb, wc, 16), K456, 0u));
+            hh[rr][2] = __dp4a(__funnelshift_r(wa, wb, 24), K0123, __dp4a(__funnelshift_r(wb, wc, 24), K456, 0u));
+            hh[rr][3] = __dp4a(wb, K0123, __dp4a(wc, K456, 0u));
         }
         *reinterpret_cast<uint4 *>(hp + rp * kBlurTileW + 4 * qx) =
-            make_uint4(h[0][0] | (h[1][0] << 16), h[0][1] | (h[1][1] << 16), h[0][2] | (h[1][2] << 16), h[0][3] | (h[1][3] << 16));
+            make_uint4(__byte_perm(hh[0][0], hh[1][0], 0x5410), __byte_perm(hh[0][1], hh[1][1], 0x5410),
+                       __byte_perm(hh[0][2], hh[1][2], 0x5410), __byte_perm(hh[0][3], hh[1][3], 0x5410));
     }
     __syncthreads();
     // vertical pass: dst = (sum_j k[j] * H[y + j] + 32768) >> 16 with dp2a on the row pairs; a thread owns 4 columns x 8 rows
@@ -776,27 +790,28 @@ __global__ void __launch_bounds__(256, 6) k_blur(const __grid_constant__ LevelSe
             uint4 pr[7];                                        // row pairs 4*seg .. 4*seg+6  (rows 8*seg .. 8*seg+13)
 #pragma unroll
             for (int p = 0; p < 7; ++p) pr[p] = *reinterpret_cast<const uint4 *>(hp + (4 * seg + p) * kBlurTileW + 4 * qx);
-            uint8_t *dst = a.blur + G.img_off + (size_t) frame * G.frame_stride;
+            const int gy0 = y0 + seg * 8;
+            uint8_t *dst = a.blur + G.img_off + (size_t) frame * G.frame_stride + (size_t) gy0 * G.pitch + gx;
+            const int rows = min(8, h - gy0);
             constexpr uint32_t E0 = 18u | (34u << 8), E1 = 48u | (56u << 8), E2 = 48u | (34u << 8), E3 = 18u;              // even output row
             constexpr uint32_t O0 = 18u << 8, O1 = 34u | (48u << 8), O2 = 56u | (48u << 8), O3 = 34u | (18u << 8);        // odd output row
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                const int gy = y0 + seg * 8 + r;
-                if (gy < h) {
+                if (r < rows) {
                     const int p0 = r >> 1;
-                    uint32_t out = 0;
+                    uint32_t sa[4];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const uint32_t a0 = c == 0 ? pr[p0].x : c == 1 ? pr[p0].y : c == 2 ? pr[p0].z : pr[p0].w;
                         const uint32_t a1 = c == 0 ? pr[p0 + 1].x : c == 1 ? pr[p0 + 1].y : c == 2 ? pr[p0 + 1].z : pr[p0 + 1].w;
                         const uint32_t a2 = c == 0 ? pr[p0 + 2].x : c == 1 ? pr[p0 + 2].y : c == 2 ? pr[p0 + 2].z : pr[p0 + 2].w;
                         const uint32_t a3 = c == 0 ? pr[p0 + 3].x : c == 1 ? pr[p0 + 3].y : c == 2 ? pr[p0 + 3].z : pr[p0 + 3].w;
-                        uint32_t sacc = 32768u;
-                        if ((r & 1) == 0) sacc = __dp2a_lo(a3, E3, __dp2a_lo(a2, E2, __dp2a_lo(a1, E1, __dp2a_lo(a0, E0, sacc))));
-                        else sacc = __dp2a_lo(a3, O3, __dp2a_lo(a2, O2, __dp2a_lo(a1, O1, __dp2a_lo(a0, O0, sacc))));
-                        out |= (sacc >> 16) << (8 * c);         // <= 255: the kernel sums to 256
+                        if ((r & 1) == 0) sa[c] = __dp2a_lo(a3, E3, __dp2a_lo(a2, E2, __dp2a_lo(a1, E1, __dp2a_lo(a0, E0, 32768u))));
+                        else sa[c] = __dp2a_lo(a3, O3, __dp2a_lo(a2, O2, __dp2a_lo(a1, O1, __dp2a_lo(a0, O0, 32768u))));
                     }
-                    *reinterpret_cast<uint32_t *>(dst + (size_t) gy * G.pitch + gx) = out;
+                    // result of column c = byte 2 of sa[c] (<= 255: the kernel sums to 256)
+                    *reinterpret_cast<uint32_t *>(dst) = __byte_perm(__byte_perm(sa[0], sa[1], 0x0062), __byte_perm(sa[2], sa[3], 0x0062), 0x5410);
+                    dst += G.pitch;
                 }
             }
         }
