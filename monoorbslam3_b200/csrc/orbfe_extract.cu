@@ -28,6 +28,11 @@ static int round_half_even(float v) { return (int) lrintf(v); }          // cvRo
 static int floor_f(float v) { int i = (int) v; return i - (v < (float) i); }
 static int ceil_f(float v) { int i = (int) v; return i + (v > (float) i); }
 
+// bit_pattern_31_ (ORBExtractor.cpp:108-365): 256 pairs (x0, y0, x1, y1)
+static const int8_t kBriefPattern[1024] = {
+#include "brief_pattern.inc"
+};
+
 static void build_ctor_tables(Handle *h) {
     const orbfe_config &c = h->cfg;
     h->scale[0] = 1.f; h->inv_scale[0] = 1.f;
@@ -98,12 +103,12 @@ static PFN_cuTensorMapEncodeTiled get_encode_fn() {
 }
 
 // 3-D u8 tensor (x, y, frame) over `frames` images of w x h with the given pitch / frame stride; box = 256 x box_h x 1.
-static int make_tmap(Handle *h, CUtensorMap *m, const uint8_t *base, int w, int ht, size_t pitch, size_t frame_stride, int frames, int box_h) {
+static int make_tmap(Handle *h, CUtensorMap *m, const uint8_t *base, int w, int ht, size_t pitch, size_t frame_stride, int frames, int box_h, int box_w = kBoxW) {
     PFN_cuTensorMapEncodeTiled enc = get_encode_fn();
     if (!enc) return set_error(h, ORBFE_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[3] = {(cuuint64_t) w, (cuuint64_t) ht, (cuuint64_t) std::max(frames, 1)};
     cuuint64_t strides[2] = {(cuuint64_t) pitch, (cuuint64_t) frame_stride};
-    cuuint32_t box[3] = {(cuuint32_t) kBoxW, (cuuint32_t) box_h, 1};
+    cuuint32_t box[3] = {(cuuint32_t) box_w, (cuuint32_t) box_h, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *) base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -252,6 +257,8 @@ static int configure(Handle *h, int w, int ht, int batch) {
             int rc;
             if ((rc = make_tmap(h, &h->tm_fast[l], h->d_img + L.img_off, L.w, L.h, L.pitch, L.frame_stride, keep_batch, kFastBoxH))) return rc;
             if ((rc = make_tmap(h, &h->tm_blur[l], h->d_img + L.img_off, L.w, L.h, L.pitch, L.frame_stride, keep_batch, kBlurBoxH))) return rc;
+            if ((rc = make_tmap(h, &h->tm_pimg[l], h->d_img + L.img_off, L.w, L.h, L.pitch, L.frame_stride, keep_batch, kPatchH, kPatchW))) return rc;
+            if ((rc = make_tmap(h, &h->tm_pblur[l], h->d_blur + L.img_off, L.w, L.h, L.pitch, L.frame_stride, keep_batch, kBPatchH, kBPatchW))) return rc;
             if ((rc = make_tmap(h, &h->tm_rs[l], h->d_img + L.img_off, L.w, L.h, L.pitch, L.frame_stride, keep_batch, kRsBoxH))) return rc;
         }
     }
@@ -335,10 +342,10 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
     LevelSet LS; memset(&LS, 0, sizeof LS);
     LS.n_levels = nl;
     for (int l = 0; l < nl; ++l) { LS.lv[l] = g.lv[l]; LS.img[l] = h->d_img + g.lv[l].img_off; }
-    TmapSet TF, TB; CUtensorMap tm_rs0;
-    memset(&TF, 0, sizeof TF); memset(&TB, 0, sizeof TB); memset(&tm_rs0, 0, sizeof tm_rs0);
+    TmapSet TF, TB; CUtensorMap tm_rs0; PatchMaps PM;
+    memset(&TF, 0, sizeof TF); memset(&TB, 0, sizeof TB); memset(&tm_rs0, 0, sizeof tm_rs0); memset(&PM, 0, sizeof PM);
     if (kTMA) {
-        for (int l = 0; l < nl; ++l) { TF.m[l] = h->tm_fast[l]; TB.m[l] = h->tm_blur[l]; }
+        for (int l = 0; l < nl; ++l) { TF.m[l] = h->tm_fast[l]; TB.m[l] = h->tm_blur[l]; PM.img[l] = h->tm_pimg[l]; PM.blur[l] = h->tm_pblur[l]; }
         tm_rs0 = h->tm_rs[0];
     }
     const bool inplace = l0 != h->d_img + g.lv[0].img_off;
@@ -349,6 +356,7 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
             if ((rc = make_tmap(h, &TF.m[0], l0, g.w, g.h, l0_pitch, l0_fstride, nb, kFastBoxH))) return rc;
             if ((rc = make_tmap(h, &TB.m[0], l0, g.w, g.h, l0_pitch, l0_fstride, nb, kBlurBoxH))) return rc;
             if ((rc = make_tmap(h, &tm_rs0, l0, g.w, g.h, l0_pitch, l0_fstride, nb, kRsBoxH))) return rc;
+            if ((rc = make_tmap(h, &PM.img[0], l0, g.w, g.h, l0_pitch, l0_fstride, nb, kPatchH, kPatchW))) return rc;
         }
     }
     if (h->prof) { int rc = prof_collect(h); if (rc) return rc; }
@@ -368,7 +376,7 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
     ORBFE_PROF_MARK(h, st, 1);
     // The blur only depends on the pyramid: it runs on an auxiliary stream next to FAST + quadtree (which are issue- and
     // latency-bound) and is joined before the descriptors.
-    BlurArgs ba; ba.blur = h->d_blur; ba.blk_tab = h->d_fast_tab + g.fast_blocks;
+    BlurArgs ba; ba.blur = h->d_blur; ba.blk_tab = h->d_fast_tab + g.fast_blocks; blur_taps(ba.kc);
     const bool fork_blur = !h->prof && !debug_sync();
     if (fork_blur) {
         if (!h->s_aux) {
@@ -378,7 +386,7 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
         }
         ORBFE_CUDA(h, cudaEventRecord(h->ev_fork, st));
         ORBFE_CUDA(h, cudaStreamWaitEvent(h->s_aux, h->ev_fork, 0));
-        k_blur<kTMA><<<dim3(g.blur_blocks, nb), 256, 0, h->s_aux>>>(LS, TB, ba);
+        k_blur<kTMA><<<dim3(g.blur_blocks, nb), kBlurThreads, 0, h->s_aux>>>(LS, TB, ba);
         h->launches++;
         ORBFE_CUDA(h, cudaEventRecord(h->ev_join, h->s_aux));
     }
@@ -401,7 +409,7 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
     ORBFE_PROF_MARK(h, st, 3);
     // K6 blur (launched above on the auxiliary stream unless profiling / debugging serialises the stages)
     if (!fork_blur) {
-        k_blur<kTMA><<<dim3(g.blur_blocks, nb), 256, 0, st>>>(LS, TB, ba);
+        k_blur<kTMA><<<dim3(g.blur_blocks, nb), kBlurThreads, 0, st>>>(LS, TB, ba);
         ORBFE_AFTER_LAUNCH(h, st, "k_blur");
     } else {
         ORBFE_CUDA(h, cudaStreamWaitEvent(st, h->ev_join, 0));
@@ -418,9 +426,8 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
         static const uint8_t expect[kHalfPatch + 1] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
         if (memcmp(da.u_max, expect, sizeof expect) != 0) return set_error(h, ORBFE_E_INTERNAL, "u_max table mismatch");
     }
-    int max_kp_cap = 1;
-    for (int l = 0; l < nl; ++l) max_kp_cap = std::max(max_kp_cap, g.lv[l].kp_cap);
-    k_describe<<<dim3((max_kp_cap + 7) / 8, nb, nl), 256, 0, st>>>(LS, da);
+    da.pattern = h->d_pattern;
+    k_describe<kTMA><<<dim3((g.kp_per_frame + 7) / 8, nb), 256, 0, st>>>(LS, PM, da);
     ORBFE_AFTER_LAUNCH(h, st, "k_describe");
     ORBFE_PROF_MARK(h, st, 5);
     if (h->prof) h->prof_pending = true;
@@ -485,6 +492,16 @@ int orbfe_create(const orbfe_config *cfg, orbfe_handle **out) {
         set_error(nullptr, ORBFE_E_CUDA, "handle setup: %s", cudaGetErrorString(e));
         delete h; return ORBFE_E_CUDA;
     }
+    {   // pattern table of k_describe: pair p = 8 * lane + j (bit j of descriptor byte `lane`) at float4 slot j * 32 + lane
+        std::vector<float> pat(1024);
+        for (int pair = 0; pair < 256; ++pair)
+            for (int c = 0; c < 4; ++c) pat[(size_t) (((pair & 7) * 32) + (pair >> 3)) * 4 + c] = (float) kBriefPattern[pair * 4 + c];
+        if ((e = cudaMalloc(&h->d_pattern, pat.size() * sizeof(float))) != cudaSuccess ||
+            (e = cudaMemcpy(h->d_pattern, pat.data(), pat.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
+            set_error(nullptr, ORBFE_E_CUDA, "pattern table: %s", cudaGetErrorString(e));
+            orbfe_destroy(h); return ORBFE_E_CUDA;
+        }
+    }
     cudaFuncSetAttribute(k_octree<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     *out = h;
     return ORBFE_OK;
@@ -495,7 +512,7 @@ void orbfe_destroy(orbfe_handle *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_arena(h);
-    cudaFree(h->d_err); cudaFree(h->d_match);
+    cudaFree(h->d_err); cudaFree(h->d_match); cudaFree(h->d_pattern);
     for (int i = 0; i <= ORBFE_N_STAGES; ++i) if (h->prof_ev[i]) cudaEventDestroy(h->prof_ev[i]);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->stream) cudaStreamDestroy(h->stream);

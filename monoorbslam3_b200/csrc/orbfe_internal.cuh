@@ -99,6 +99,8 @@ struct Handle {
     int last_batch = 0;              // frames of the last pass (for the stage getters)
     // tensor maps (img arena; level 0 may be rebuilt for an in-place user buffer)
     CUtensorMap tm_fast[ORBFE_MAX_LEVELS], tm_blur[ORBFE_MAX_LEVELS], tm_rs[ORBFE_MAX_LEVELS];
+    CUtensorMap tm_pimg[ORBFE_MAX_LEVELS], tm_pblur[ORBFE_MAX_LEVELS];   // per-key-point patch boxes of k_describe (image / blurred arena)
+    float4 *d_pattern = nullptr;     // rotated-BRIEF pattern as floats, lane-major (DescArgs::pattern)
     // matcher scratch
     void *d_match = nullptr; size_t match_bytes = 0;
     void *h_pinned = nullptr; size_t pinned_bytes = 0;

@@ -720,30 +720,43 @@ __global__ void __launch_bounds__(NT) k_octree(const __grid_constant__ LevelSet 
 // K6  7x7 Gaussian blur, sigma 2, BORDER_REFLECT_101, OpenCV's 8.8 fixed-point path.
 // Tile: 224 x 32 outputs from a 256 x 38 staged box (the box starts 16-byte aligned, 13 px left of the halo).  Horizontal pass -> u16 in smem, vertical pass sliding in registers.
 // ------------------------------------------------------------------------------------------------
-struct BlurArgs { uint8_t *blur; const int *blk_tab; };      // blk_tab: block -> level | tile row << 4 | tile column << 16
+// kc: the packed 8.8 kernel taps, passed as arguments so they live in the constant bank / registers (as literals the compiler
+// re-materialises them through uniform registers before every IDP):
+//   [0] = {18,34,48,56} bytes, [1] = {48,34,18,0} bytes                    horizontal DP4A pair
+//   [2..5] = even output row, [6..9] = odd output row                       vertical DP2A over row pairs (u16x2 . u8x2)
+struct BlurArgs { uint8_t *blur; const int *blk_tab; uint32_t kc[10]; };      // blk_tab: block -> level | tile row << 4 | tile column << 16
+
+__host__ __device__ inline void blur_taps(uint32_t (&kc)[10]) {
+    kc[0] = 18u | (34u << 8) | (48u << 16) | (56u << 24); kc[1] = 48u | (34u << 8) | (18u << 16);
+    kc[2] = 18u | (34u << 8); kc[3] = 48u | (56u << 8); kc[4] = 48u | (34u << 8); kc[5] = 18u;
+    kc[6] = 18u << 8; kc[7] = 34u | (48u << 8); kc[8] = 56u | (48u << 8); kc[9] = 34u | (18u << 8);
+}
 
 __device__ __forceinline__ int refl101(int p, int n) { return p < 0 ? -p : (p >= n ? 2 * n - 2 - p : p); }
 
+constexpr int kBlurThreads = (kBlurTileW / 4) * (kBlurTileH / 8);      // 224: 56 column quads x 4 row groups, in both passes
+
 template <bool kTMA>
-__global__ void __launch_bounds__(256, 6) k_blur(const __grid_constant__ LevelSet L, const __grid_constant__ TmapSet T, const BlurArgs a) {
+__global__ void __launch_bounds__(kBlurThreads, 6) k_blur(const __grid_constant__ LevelSet L, const __grid_constant__ TmapSet T, const __grid_constant__ BlurArgs a) {
     constexpr int SP = TilePitch<kTMA>::value;
     constexpr int XO = 13;                        // the box starts 16 px left of x0 (16-byte aligned), the 3-px halo at column 13
+    constexpr int NT = kBlurThreads, QW = kBlurTileW / 4, NRP = kBlurBoxH / 2;
     static_assert(kBlurTileW % 16 == 0 && kBlurBoxH % 2 == 0, "tile origin must keep the halo at column 13 and rows must pair up");
     __shared__ __align__(128) uint8_t tile[kBlurBoxH * SP];
-    __shared__ __align__(16) uint32_t hp[(kBlurBoxH / 2) * kBlurTileW];     // horizontal pass, rows paired: H[2p][x] | H[2p+1][x] << 16
+    __shared__ __align__(16) uint32_t hp[NRP * kBlurTileW];     // horizontal pass, rows paired: H[2p][x] | H[2p+1][x] << 16
     __shared__ __align__(8) uint64_t bar;
     const int frame = blockIdx.y, tid = threadIdx.x;
     const int packed = __ldg(&a.blk_tab[blockIdx.x]);
     const int l = packed & 15, ty = (packed >> 4) & 0xfff, tx = packed >> 16;
     const LevelGeom &G = L.lv[l];
     const int x0 = tx * kBlurTileW, y0 = ty * kBlurTileH;
-    stage_box<kTMA, 256>(tile, &bar, &T.m[l], L.img[l] + (size_t) frame * G.frame_stride, G.pitch, G.h, x0 - 3, y0 - 3, frame, kBlurBoxH);
+    stage_box<kTMA, NT>(tile, &bar, &T.m[l], L.img[l] + (size_t) frame * G.frame_stride, G.pitch, G.h, x0 - 3, y0 - 3, frame, kBlurBoxH);
     uint8_t *t = tile + XO;                       // t[r*SP + c] = pixel (x0-3+c, y0-3+r)
     const int w = G.w, h = G.h;
     // reflect-101 fix-up of the columns / rows of the box that lie outside the image (only border tiles)
     const int need_w = min(kBlurTileW, w - x0) + 6, need_h = min(kBlurTileH, h - y0) + 6;
     if (x0 == 0 || x0 + kBlurTileW + 3 > w) {
-        for (int idx = tid; idx < kBlurBoxH * 6; idx += 256) {
+        for (int idx = tid; idx < kBlurBoxH * 6; idx += NT) {
             const int r = idx / 6, k = idx - r * 6;
             const int c = k < 3 ? k : need_w - 6 + k;          // 3 columns left of x0, 3 right of the last needed column
             const int gx = x0 - 3 + c;
@@ -752,7 +765,7 @@ __global__ void __launch_bounds__(256, 6) k_blur(const __grid_constant__ LevelSe
         __syncthreads();
     }
     if (y0 == 0 || y0 + kBlurTileH + 3 > h) {
-        for (int idx = tid; idx < 6 * kBoxW; idx += 256) {
+        for (int idx = tid; idx < 6 * kBoxW; idx += NT) {
             const int k = idx >> 8, c = idx & 255;
             const int r = k < 3 ? k : need_h - 6 + k;
             const int gy = y0 - 3 + r;
@@ -760,75 +773,86 @@ __global__ void __launch_bounds__(256, 6) k_blur(const __grid_constant__ LevelSe
         }
         __syncthreads();
     }
+    const int seg = tid / QW, qx = tid - seg * QW;      // column quad, row group (both passes)
     // horizontal pass on packed bytes: H[x] = dp4a(src[x-3..x], {18,34,48,56}) + dp4a(src[x+1..x+4], {48,34,18,0})  (exact, <= 65280).
     // One item = 4 outputs of two consecutive rows, stored as u16x2 pairs (row 2p | row 2p+1 << 16) for the dp2a vertical pass.
     // The first tap of output 4*qx sits at tile column 13 + 4*qx = byte 1 of the aligned word at column 12 + 4*qx.
-    constexpr uint32_t K0123 = 18u | (34u << 8) | (48u << 16) | (56u << 24), K456 = 48u | (34u << 8) | (18u << 16);
-    constexpr int QW = kBlurTileW / 4;
-    for (int it = tid; it < (kBlurBoxH / 2) * QW; it += 256) {
-        const int rp = it / QW, qx = it - rp * QW;
-        uint32_t hh[2][4];
+    {
+        const uint32_t K0123 = a.kc[0], K456 = a.kc[1];
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(tile + (XO - 1)) + qx + seg * (2 * SP / 4);
+        uint32_t *hq = hp + seg * kBlurTileW + 4 * qx;
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            const uint32_t *wp = reinterpret_cast<const uint32_t *>(tile + (2 * rp + rr) * SP + (XO - 1)) + qx;
-            const uint32_t wa = wp[0], wb = wp[1], wc = wp[2];
-            hh[rr][0] = __dp4a(__funnelshift_r(wa, wb, 8), K0123, __dp4a(__funnelshift_r(wb, wc, 8), K456, 0u));
-            hh[rr][1] = __dp4a(__funnelshift_r(wa, wb, 16), K0123, __dp4a(__funnelshift_r(wb, wc, 16), K456, 0u));
-            hh[rr][2] = __dp4a(__funnelshift_r(wa, wb, 24), K0123, __dp4a(__funnelshift_r(wb, wc, 24), K456, 0u));
-            hh[rr][3] = __dp4a(wb, K0123, __dp4a(wc, K456, 0u));
+        for (int i = 0; i < (NRP + 3) / 4; ++i) {                   // row pairs seg, seg + 4, ...
+            if (4 * i + 3 < NRP || seg + 4 * i < NRP) {
+                uint32_t hh[2][4];
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const uint32_t wa = wp[(8 * i + rr) * (SP / 4)], wb = wp[(8 * i + rr) * (SP / 4) + 1], wc = wp[(8 * i + rr) * (SP / 4) + 2];
+                    hh[rr][0] = __dp4a(__funnelshift_r(wa, wb, 8), K0123, __dp4a(__funnelshift_r(wb, wc, 8), K456, 0u));
+                    hh[rr][1] = __dp4a(__funnelshift_r(wa, wb, 16), K0123, __dp4a(__funnelshift_r(wb, wc, 16), K456, 0u));
+                    hh[rr][2] = __dp4a(__funnelshift_r(wa, wb, 24), K0123, __dp4a(__funnelshift_r(wb, wc, 24), K456, 0u));
+                    hh[rr][3] = __dp4a(wb, K0123, __dp4a(wc, K456, 0u));
+                }
+                *reinterpret_cast<uint4 *>(hq + 4 * i * kBlurTileW) =
+                    make_uint4(__byte_perm(hh[0][0], hh[1][0], 0x5410), __byte_perm(hh[0][1], hh[1][1], 0x5410),
+                               __byte_perm(hh[0][2], hh[1][2], 0x5410), __byte_perm(hh[0][3], hh[1][3], 0x5410));
+            }
         }
-        *reinterpret_cast<uint4 *>(hp + rp * kBlurTileW + 4 * qx) =
-            make_uint4(__byte_perm(hh[0][0], hh[1][0], 0x5410), __byte_perm(hh[0][1], hh[1][1], 0x5410),
-                       __byte_perm(hh[0][2], hh[1][2], 0x5410), __byte_perm(hh[0][3], hh[1][3], 0x5410));
     }
     __syncthreads();
     // vertical pass: dst = (sum_j k[j] * H[y + j] + 32768) >> 16 with dp2a on the row pairs; a thread owns 4 columns x 8 rows
-    if (tid < QW * (kBlurTileH / 8)) {
-        const int seg = tid / QW, qx = tid - seg * QW;
-        const int gx = x0 + 4 * qx;
-        if (gx < w) {
-            uint4 pr[7];                                        // row pairs 4*seg .. 4*seg+6  (rows 8*seg .. 8*seg+13)
+    const int gx = x0 + 4 * qx;
+    if (gx >= w) return;
+    uint4 pr[7];                                        // row pairs 4*seg .. 4*seg+6  (rows 8*seg .. 8*seg+13)
 #pragma unroll
-            for (int p = 0; p < 7; ++p) pr[p] = *reinterpret_cast<const uint4 *>(hp + (4 * seg + p) * kBlurTileW + 4 * qx);
-            const int gy0 = y0 + seg * 8;
-            uint8_t *dst = a.blur + G.img_off + (size_t) frame * G.frame_stride + (size_t) gy0 * G.pitch + gx;
-            const int rows = min(8, h - gy0);
-            constexpr uint32_t E0 = 18u | (34u << 8), E1 = 48u | (56u << 8), E2 = 48u | (34u << 8), E3 = 18u;              // even output row
-            constexpr uint32_t O0 = 18u << 8, O1 = 34u | (48u << 8), O2 = 56u | (48u << 8), O3 = 34u | (18u << 8);        // odd output row
+    for (int p = 0; p < 7; ++p) pr[p] = *reinterpret_cast<const uint4 *>(hp + (4 * seg + p) * kBlurTileW + 4 * qx);
+    const int gy0 = y0 + seg * 8;
+    uint8_t *dst = a.blur + G.img_off + (size_t) frame * G.frame_stride + (size_t) gy0 * G.pitch + gx;
+    const int rows = min(8, h - gy0);
+    const size_t pitch = (size_t) G.pitch;
+    auto out_row = [&](int r) -> uint32_t {             // r is a compile-time constant after unrolling
+        const int p0 = r >> 1;
+        const uint32_t c0 = a.kc[(r & 1) ? 6 : 2], c1 = a.kc[(r & 1) ? 7 : 3], c2 = a.kc[(r & 1) ? 8 : 4], c3 = a.kc[(r & 1) ? 9 : 5];
+        uint32_t sa[4];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                if (r < rows) {
-                    const int p0 = r >> 1;
-                    uint32_t sa[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const uint32_t a0 = c == 0 ? pr[p0].x : c == 1 ? pr[p0].y : c == 2 ? pr[p0].z : pr[p0].w;
-                        const uint32_t a1 = c == 0 ? pr[p0 + 1].x : c == 1 ? pr[p0 + 1].y : c == 2 ? pr[p0 + 1].z : pr[p0 + 1].w;
-                        const uint32_t a2 = c == 0 ? pr[p0 + 2].x : c == 1 ? pr[p0 + 2].y : c == 2 ? pr[p0 + 2].z : pr[p0 + 2].w;
-                        const uint32_t a3 = c == 0 ? pr[p0 + 3].x : c == 1 ? pr[p0 + 3].y : c == 2 ? pr[p0 + 3].z : pr[p0 + 3].w;
-                        if ((r & 1) == 0) sa[c] = __dp2a_lo(a3, E3, __dp2a_lo(a2, E2, __dp2a_lo(a1, E1, __dp2a_lo(a0, E0, 32768u))));
-                        else sa[c] = __dp2a_lo(a3, O3, __dp2a_lo(a2, O2, __dp2a_lo(a1, O1, __dp2a_lo(a0, O0, 32768u))));
-                    }
-                    // result of column c = byte 2 of sa[c] (<= 255: the kernel sums to 256)
-                    *reinterpret_cast<uint32_t *>(dst) = __byte_perm(__byte_perm(sa[0], sa[1], 0x0062), __byte_perm(sa[2], sa[3], 0x0062), 0x5410);
-                    dst += G.pitch;
-                }
-            }
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t a0 = c == 0 ? pr[p0].x : c == 1 ? pr[p0].y : c == 2 ? pr[p0].z : pr[p0].w;
+            const uint32_t a1 = c == 0 ? pr[p0 + 1].x : c == 1 ? pr[p0 + 1].y : c == 2 ? pr[p0 + 1].z : pr[p0 + 1].w;
+            const uint32_t a2 = c == 0 ? pr[p0 + 2].x : c == 1 ? pr[p0 + 2].y : c == 2 ? pr[p0 + 2].z : pr[p0 + 2].w;
+            const uint32_t a3 = c == 0 ? pr[p0 + 3].x : c == 1 ? pr[p0 + 3].y : c == 2 ? pr[p0 + 3].z : pr[p0 + 3].w;
+            sa[c] = __dp2a_lo(a3, c3, __dp2a_lo(a2, c2, __dp2a_lo(a1, c1, __dp2a_lo(a0, c0, 32768u))));
         }
+        // result of column c = byte 2 of sa[c] (<= 255: the kernel sums to 256)
+        return __byte_perm(__byte_perm(sa[0], sa[1], 0x0062), __byte_perm(sa[2], sa[3], 0x0062), 0x5410);
+    };
+    if (rows == 8) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) *reinterpret_cast<uint32_t *>(dst + r * pitch) = out_row(r);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) if (r < rows) *reinterpret_cast<uint32_t *>(dst + r * pitch) = out_row(r);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K5 + K7  orientation (IC_Angle + fastAtan2) and rotated BRIEF.  One warp per key point.
+// K5 + K7  orientation (IC_Angle + fastAtan2) and rotated BRIEF.  One warp per key point, in output order.
+// The two patches a key point needs — 31 rows of the un-blurred level (radius-15 disc) and 37 rows of the blurred level (the
+// rotated pattern reaches 18 px) — are staged into the warp's own shared-memory buffers by two TMA box loads (48 x 31 and
+// 64 x 37 bytes, x origin rounded down to 16), so every pixel access afterwards is an LDS with a compile-time row stride
+// instead of a 64-bit global address computation, and the blurred patch arrives while the angle is being computed.
 // ------------------------------------------------------------------------------------------------
+constexpr int kPatchW = 48, kPatchH = 2 * kHalfPatch + 1;            // un-blurred patch box (x-15 .. x+15 after alignment)
+constexpr int kBPatchR = 18, kBPatchW = 64, kBPatchH = 2 * kBPatchR + 1;   // blurred patch box
+constexpr int kPatchBytes = 1536, kBPatchBytes = 2432;               // box sizes rounded up to 128 (TMA destination alignment)
+static_assert(kPatchW * kPatchH <= kPatchBytes && kBPatchW * kBPatchH <= kBPatchBytes, "patch buffers");
+
+struct PatchMaps { CUtensorMap img[ORBFE_MAX_LEVELS], blur[ORBFE_MAX_LEVELS]; };
+
 struct DescArgs {
     const uint8_t *blur; const uint32_t *kp; const int *nkp; int kp_per_frame;
     orbfe_keypoint *out_kps; uint8_t *out_desc; int *out_n; int cap; int *err;
+    const float4 *pattern;      // pair p = 8 * lane + j at [j * 32 + lane]: (x0, y0, x1, y1) as floats
     uint8_t u_max[kHalfPatch + 1];
-};
-
-__constant__ int8_t c_pattern[1024] = {
-#include "brief_pattern.inc"
 };
 
 // cv::fastAtan2: float32, no FMA contraction.
@@ -860,45 +884,101 @@ __device__ __forceinline__ constexpr int umax15(int v) {
     return t[v < 0 ? -v : v];
 }
 
-// grid = (ceil(max kp_cap / 8), frames, levels): one warp per key-point slot of one level
-__global__ void __launch_bounds__(256, 6) k_describe(const __grid_constant__ LevelSet L, const DescArgs a) {
-    __shared__ __align__(16) float s_pat[1024];
-    const int frame = blockIdx.y, l = blockIdx.z, lane = threadIdx.x & 31;
-    const int *nkp = a.nkp + frame * ORBFE_MAX_LEVELS;
-    if ((int) blockIdx.x * 8 >= nkp[l]) return;        // whole block beyond this level's key points
-    // pair (lane * 8 + j) is stored at float4 slot j * 32 + lane: the lanes of a warp read consecutive 16-byte slots (no bank conflicts)
-    for (int i = threadIdx.x; i < 1024; i += 256) {
-        const int pair = i >> 2, c = i & 3;
-        s_pat[(((pair & 7) * 32) + (pair >> 3)) * 4 + c] = (float) c_pattern[i];
+// (float) cos((double) a), (float) sin((double) a) for a float angle in [0, 2 pi]: the reference evaluates cos/sin in double
+// (ORBExtractor.cpp:53-54) and rounds to float.  Quadrant reduction with a two-part pi/2 and the fdlibm kernel polynomials
+// (< 1 ulp in double), so the float results agree with glibc's unless the exact value lies within ~1e-16 of a float rounding
+// boundary; the parity tests compare every descriptor bit.
+__device__ __forceinline__ void sincos_to_float(float a, float &c, float &s) {
+    const double x = (double) a;
+    const double n = rint(x * 0.63661977236758134308);                       // 2 / pi
+    double r = fma(-n, 1.57079632679489655800e+00, x);                        // pi/2 head (exact product for n <= 4)
+    r = fma(-n, 6.12323399573676603587e-17, r);                               // pi/2 tail
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06); ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03); ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double sr = fma(z * r, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07); pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03); pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const int q = (int) n & 3;
+    const double sv = (q & 1) ? cr : sr, cv = (q & 1) ? sr : cr;
+    s = (float) ((q & 2) ? -sv : sv);
+    c = (float) (((q + 1) & 2) ? -cv : cv);
+}
+
+// Stage a (box_w x box_h) patch whose top-left pixel is (ax, ay) of frame `frame` into `dst` (pitch box_w); one warp.
+template <bool kTMA>
+__device__ __forceinline__ void stage_patch(uint8_t *dst, uint64_t *bar, const CUtensorMap *map, const uint8_t *frame_base, int pitch,
+                                            int ax, int ay, int frame, int box_w, int box_h, int lane) {
+    if constexpr (kTMA) {
+        if (lane == 0) {
+            mbar_expect_tx(bar, (uint32_t) (box_w * box_h));
+            tma_load_3d(dst, map, bar, ax, ay, frame);
+        }
+    } else {
+        const int wpr = box_w / 4;
+        for (int idx = lane; idx < wpr * box_h; idx += 32) {
+            const int r = idx / wpr, c = idx - r * wpr;
+            const int gx = ax + 4 * c;
+            uint32_t v = 0;
+            if (gx + 4 <= pitch) v = __ldg(reinterpret_cast<const uint32_t *>(frame_base + (size_t) (ay + r) * pitch + gx));
+            reinterpret_cast<uint32_t *>(dst)[idx] = v;
+        }
     }
-    __syncthreads();
-    const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const LevelGeom &G = L.lv[l];
-    if (k >= nkp[l]) return;
-    int out_idx = k;
-    for (int q = 0; q < l; ++q) out_idx += nkp[q];
-    if (out_idx == 0) {                                // first key point of the frame also publishes the total
-        int tot = 0;
-        for (int q = 0; q < L.n_levels; ++q) tot += nkp[q];
-        if (lane == 0) a.out_n[frame] = tot;
+}
+
+// grid = (ceil(kp_per_frame / 8), frames): warp = output slot (levels in order, quadtree order within a level)
+template <bool kTMA>
+__global__ void __launch_bounds__(256, 6) k_describe(const __grid_constant__ LevelSet L, const __grid_constant__ PatchMaps P, const DescArgs a) {
+    __shared__ __align__(128) uint8_t sbuf[8][kPatchBytes + kBPatchBytes];
+    __shared__ __align__(8) uint64_t bars[8][2];
+    const int frame = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int out_idx = blockIdx.x * 8 + wid;
+    const int4 *np = reinterpret_cast<const int4 *>(a.nkp + frame * ORBFE_MAX_LEVELS);
+    static_assert(ORBFE_MAX_LEVELS % 4 == 0, "per-level counts are read as int4");
+    int l = 0, k = out_idx, tot = 0;
+    for (int q4 = 0; 4 * q4 < L.n_levels; ++q4) {                      // level of this output slot: prefix sums of the per-level counts
+        const int4 n4 = __ldg(np + q4);
+        const int cnt[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int q = 4 * q4 + i;
+            if (q < L.n_levels) {
+                if (out_idx >= tot + cnt[i] && q + 1 < L.n_levels) { l = q + 1; k = out_idx - (tot + cnt[i]); }
+                tot += cnt[i];
+            }
+        }
     }
+    if (out_idx == 0 && lane == 0) a.out_n[frame] = tot;            // the first key point of the frame also publishes the total
+    if (out_idx >= tot) return;
     if (out_idx >= a.cap) { if (lane == 0) atomicExch(a.err, 6); return; }
-    const uint32_t v = a.kp[(size_t) frame * a.kp_per_frame + G.kp_off + k];
+    const LevelGeom &G = L.lv[l];
+    const uint32_t v = __ldg(&a.kp[(size_t) frame * a.kp_per_frame + G.kp_off + k]);
     const int x = (int) (v & 0xfffu), y = (int) ((v >> 12) & 0xfffu), score = (int) (v >> 24);
 
-    // IC_Angle (ORBExtractor.cpp:18-42) on the un-blurred level: lane = u + 15, rows v = -15..15 all in flight
-    const int u = lane - kHalfPatch, au = u < 0 ? -u : u;
-    const uint8_t *row = L.img[l] + (size_t) frame * G.frame_stride + (size_t) (y - kHalfPatch) * G.pitch + (x + u);
-    int val[2 * kHalfPatch + 1];
-#pragma unroll
-    for (int vv = -kHalfPatch; vv <= kHalfPatch; ++vv) {
-        val[vv + kHalfPatch] = (au <= umax15(vv)) ? (int) __ldg(row) : 0;      // lane 31: au = 16 > every u_max
-        row += G.pitch;
+    uint8_t *ibuf = sbuf[wid], *bbuf = sbuf[wid] + kPatchBytes;
+    const int ax = (x - kHalfPatch) & ~15, axb = (x - kBPatchR) & ~15;
+    if (kTMA) {
+        if (lane == 0) { mbar_init(&bars[wid][0], 1); mbar_init(&bars[wid][1], 1); fence_barrier_init(); }
+        __syncwarp();
     }
-    int m01 = 0, row_sum = 0;
+    stage_patch<kTMA>(ibuf, &bars[wid][0], &P.img[l], L.img[l] + (size_t) frame * G.frame_stride, G.pitch, ax, y - kHalfPatch, frame, kPatchW, kPatchH, lane);
+    stage_patch<kTMA>(bbuf, &bars[wid][1], &P.blur[l], a.blur + G.img_off + (size_t) frame * G.frame_stride, G.pitch, axb, y - kBPatchR, frame, kBPatchW, kBPatchH, lane);
+    const float4 *pt = a.pattern + lane;
+    if (kTMA) mbar_wait(&bars[wid][0], 0); else __syncwarp();
+
+    // IC_Angle (ORBExtractor.cpp:18-42) on the un-blurred patch: lane = u + 15, rows +v and -v share u_max[v]
+    const int u = lane - kHalfPatch, au = u < 0 ? -u : u;
+    const uint8_t *c = ibuf + kHalfPatch * kPatchW + (x - ax) + u;           // lane 31 (u = 16) stays inside the 48-byte row and is masked
+    int sum = au <= kHalfPatch ? (int) c[0] : 0, m01 = 0;
 #pragma unroll
-    for (int vv = -kHalfPatch; vv <= kHalfPatch; ++vv) { row_sum += val[vv + kHalfPatch]; m01 += vv * val[vv + kHalfPatch]; }
-    int m10 = u * row_sum;
+    for (int vv = 1; vv <= kHalfPatch; ++vv) {
+        const int p = c[vv * kPatchW], m = c[-vv * kPatchW];
+        if (au <= umax15(vv)) { sum += p + m; m01 += vv * (p - m); }
+    }
+    int m10 = u * sum;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         m10 += __shfl_xor_sync(0xffffffffu, m10, o);
@@ -906,30 +986,37 @@ __global__ void __launch_bounds__(256, 6) k_describe(const __grid_constant__ Lev
     }
     const float angle = fast_atan2_deg((float) m01, (float) m10);
 
-    // computeOrbDescriptor (ORBExtractor.cpp:50-97) on the blurred level; cos/sin evaluated in double and rounded
+    // computeOrbDescriptor (ORBExtractor.cpp:50-97) on the blurred patch
     const float factor_pi = (float) (3.1415926535897932384626433832795 / 180.f);
-    const float ang = __fmul_rn(angle, factor_pi);
-    const float ca = (float) cos((double) ang), sb = (float) sin((double) ang);
-    const uint8_t *ctr = a.blur + G.img_off + (size_t) frame * G.frame_stride + (size_t) y * G.pitch + x;
-    const float4 *p = reinterpret_cast<const float4 *>(s_pat) + lane;
+    float ca, sb;
+    sincos_to_float(__fmul_rn(angle, factor_pi), ca, sb);
+    if (kTMA) mbar_wait(&bars[wid][1], 0); else __syncwarp();
+    const uint8_t *ctr = bbuf + kBPatchR * kBPatchW + (x - axb);
     unsigned desc_byte = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float4 q = p[j * 32];                                         // x0, y0, x1, y1
+        const float4 q = __ldg(pt + j * 32);                                 // x0, y0, x1, y1 of pair 8 * lane + j
         const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(q.x, sb), __fmul_rn(q.y, ca)));
         const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(q.x, ca), __fmul_rn(q.y, sb)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(q.z, sb), __fmul_rn(q.w, ca)));
         const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(q.z, ca), __fmul_rn(q.w, sb)));
-        const int t0 = __ldg(ctr + r0 * G.pitch + c0), t1 = __ldg(ctr + r1 * G.pitch + c1);
+        const int t0 = ctr[r0 * kBPatchW + c0], t1 = ctr[r1 * kBPatchW + c1];
         desc_byte |= (unsigned) (t0 < t1) << j;
     }
     a.out_desc[((size_t) frame * a.cap + out_idx) * 32 + lane] = (uint8_t) desc_byte;
-    if (lane == 0) {
-        orbfe_keypoint kp;
-        kp.x = l ? __fmul_rn((float) x, G.scale) : (float) x;             // ORBExtractor.cpp:537-542
-        kp.y = l ? __fmul_rn((float) y, G.scale) : (float) y;
-        kp.size = G.scale; kp.angle = angle; kp.response = (float) score; kp.octave = l; kp.class_id = -1;
-        a.out_kps[(size_t) frame * a.cap + out_idx] = kp;
+    if (lane < 7) {                                                           // cv::KeyPoint, one 32-bit field per lane (ORBExtractor.cpp:537-542)
+        const float fx = l ? __fmul_rn((float) x, G.scale) : (float) x, fy = l ? __fmul_rn((float) y, G.scale) : (float) y;
+        uint32_t w;
+        switch (lane) {
+            case 0: w = __float_as_uint(fx); break;
+            case 1: w = __float_as_uint(fy); break;
+            case 2: w = __float_as_uint(G.scale); break;
+            case 3: w = __float_as_uint(angle); break;
+            case 4: w = __float_as_uint((float) score); break;
+            case 5: w = (uint32_t) l; break;
+            default: w = 0xffffffffu; break;                                  // class_id = -1
+        }
+        reinterpret_cast<uint32_t *>(a.out_kps + (size_t) frame * a.cap + out_idx)[lane] = w;
     }
 }
 
