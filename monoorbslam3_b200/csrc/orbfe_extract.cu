@@ -622,11 +622,25 @@ int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, in
     const bool inplace = width % 16 == 0;
     const LevelGeom &L0 = h->g.lv[0];
     cudaStream_t sc = h->stream, su = h->s_up, sd = h->s_down;
-    // a short first chunk keeps the un-overlapped head of the pipeline (its upload) small; later chunks are full-sized
-    const int first = n_frames > cn ? std::max(1, cn / 4) : cn;
+    // Chunk schedule.  A pass costs about 0.13 ms + 5.9 us per frame and an upload 6.5 us per frame (measured, 752x480 on PCIe 5),
+    // so the pass chain is the critical path: few, large chunks, with a somewhat shorter first one because its upload overlaps
+    // with nothing.  (Ramping the chunk size up and down was measured and is slower: small passes pay the fixed cost too often.)
+    std::vector<int> sizes;
+    for (int left = n_frames; left > 0;) {
+        const int s = std::min(left, sizes.empty() && n_frames > cn ? std::max(1, 3 * cn / 4) : cn);
+        sizes.push_back(s); left -= s;
+    }
+    // ORBFE_TRACE=1: per-chunk completion times of upload / pass / download (ms since the first upload was issued), on stderr
+    static const bool trace = [] { const char *e = getenv("ORBFE_TRACE"); return e && *e == '1'; }();
+    std::vector<cudaEvent_t> tev;
+    if (trace) {
+        tev.resize(3 * sizes.size() + 1);
+        for (auto &e : tev) cudaEventCreate(&e);
+        cudaEventRecord(tev[0], su);
+    }
     int c = 0;
     for (int b0 = 0, nb = 0; b0 < n_frames; b0 += nb, ++c) {
-        nb = std::min(c == 0 ? first : cn, n_frames - b0);
+        nb = sizes[(size_t) c];
         const int slot = c & 1;
         const uint8_t *src = frames + (size_t) b0 * frame_stride;
         uint8_t *stage = h->d_stage[slot];
@@ -637,6 +651,7 @@ int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, in
                 ORBFE_CUDA(h, cudaMemcpy2DAsync(stage + (size_t) b * frame_bytes, width, src + (size_t) b * frame_stride, row_stride, width, height,
                                                 cudaMemcpyHostToDevice, su));
         ORBFE_CUDA(h, cudaEventRecord(h->ev_up[slot], su));
+        if (trace) cudaEventRecord(tev[1 + 3 * c], su);
         ORBFE_CUDA(h, cudaStreamWaitEvent(sc, h->ev_up[slot], 0));
         if (c >= 2) ORBFE_CUDA(h, cudaStreamWaitEvent(sc, h->ev_down[slot], 0));      // the output slot has been downloaded
         orbfe_keypoint *okps = h->d_out_kps + (size_t) slot * cn * cap;
@@ -649,14 +664,24 @@ int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, in
         }
         if (rc) return rc;
         ORBFE_CUDA(h, cudaEventRecord(h->ev_done[slot], sc));
+        if (trace) cudaEventRecord(tev[2 + 3 * c], sc);
         ORBFE_CUDA(h, cudaStreamWaitEvent(sd, h->ev_done[slot], 0));
         ORBFE_CUDA(h, cudaMemcpyAsync(n_per_frame + b0, on, sizeof(int) * nb, cudaMemcpyDeviceToHost, sd));
         ORBFE_CUDA(h, cudaMemcpyAsync(kps + (size_t) b0 * cap, okps, sizeof(orbfe_keypoint) * (size_t) nb * cap, cudaMemcpyDeviceToHost, sd));
         ORBFE_CUDA(h, cudaMemcpyAsync(desc + (size_t) b0 * cap * 32, odesc, (size_t) nb * cap * 32, cudaMemcpyDeviceToHost, sd));
         ORBFE_CUDA(h, cudaEventRecord(h->ev_down[slot], sd));
+        if (trace) cudaEventRecord(tev[3 + 3 * c], sd);
     }
     ORBFE_CUDA(h, cudaStreamSynchronize(sd));
     ORBFE_CUDA(h, cudaStreamSynchronize(su));
+    if (trace) {
+        for (size_t i = 0; i < sizes.size(); ++i) {
+            float a = 0, b = 0, d = 0;
+            cudaEventElapsedTime(&a, tev[0], tev[1 + 3 * i]); cudaEventElapsedTime(&b, tev[0], tev[2 + 3 * i]); cudaEventElapsedTime(&d, tev[0], tev[3 + 3 * i]);
+            fprintf(stderr, "[orbfe trace] chunk %zu (%d frames): uploaded %.3f  pass done %.3f  downloaded %.3f ms\n", i, sizes[i], a, b, d);
+        }
+        for (auto &e : tev) cudaEventDestroy(e);
+    }
     return check_device_error(h, sc);
 }
 

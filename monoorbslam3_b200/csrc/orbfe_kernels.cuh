@@ -521,16 +521,21 @@ __global__ void __launch_bounds__(NT) k_octree(const __grid_constant__ LevelSet 
         nbnd[r] = b; ncnt[r] = 0; nchild[r] = 0;
     }
     __syncthreads();
-    for (int c = wid; c < n_cells; c += NT / 32) {
-        const int cnt = cell_cnt[c], off = cell_off[c];
-        for (int k = lane; k < cnt; k += 32) {
-            const uint32_t v = slots[(size_t) c * kSlotCap + k];
-            cand[off + k] = v;
-            const int r = (int) (v & 0xfffu) / h_x;                         // :673-675
-            cur[off + k] = r;
-            const unsigned act = __activemask();
-            const unsigned same = __match_any_sync(act, r);
-            if (lane == __ffs(same) - 1) atomicAdd(&ncnt[r], __popc(same));
+    {   // 8 lanes per cell (a cell holds ~8 candidates on dense frames, up to kSlotCap), 4 cells per warp step
+        const float inv_hx = 1.0f / (float) h_x;              // root = x / h_x (:673-675); x < 4096, so (x + 0.5) * (1 / h_x) truncates exactly
+        const int sub = lane >> 3, kl = lane & 7;
+        for (int c0 = 4 * wid; c0 < n_cells; c0 += 4 * (NT / 32)) {
+            const int c = c0 + sub;
+            const int cnt = c < n_cells ? cell_cnt[c] : 0, off = c < n_cells ? cell_off[c] : 0;
+            for (int k = kl; k < cnt; k += 8) {
+                const uint32_t v = slots[(size_t) c * kSlotCap + k];
+                cand[off + k] = v;
+                const int r = n_ini > 1 ? (int) (((float) (v & 0xfffu) + 0.5f) * inv_hx) : 0;
+                cur[off + k] = r;
+                const unsigned act = __activemask();
+                const unsigned same = __match_any_sync(act, r);
+                if (lane == __ffs(same) - 1) atomicAdd(&ncnt[r], __popc(same));
+            }
         }
     }
     __syncthreads();
@@ -592,19 +597,27 @@ __global__ void __launch_bounds__(NT) k_octree(const __grid_constant__ LevelSet 
             for (int qd = 0; qd < 4; ++qd) { ncnt[base + qd] = 0; nchild[base + qd] = 0; }
         }
         __syncthreads();
-        // ---- B. every candidate of a split node descends one level (:398-407); careful phase: count only (speculative)
-        for (int i = tid; i < n; i += NT) {
-            const int nd = cur[i];
-            const int base = nchild[nd];
-            if (base > 0) {
-                const NodeBounds b = nbnd[base];           // TL child: x1 = midX, y1 = midY
-                const uint32_t v = cand[i];
-                const int x = (int) (v & 0xfffu), y = (int) ((v >> 12) & 0xfffu);
-                const int ch = base + (x < b.x1 ? 0 : 1) + (y < b.y1 ? 0 : 2);
-                if (!careful) cur[i] = ch;
-                const unsigned act = __activemask();
-                const unsigned same = __match_any_sync(act, ch);
-                if (lane == __ffs(same) - 1) atomicAdd(&ncnt[ch], __popc(same));
+        // ---- B. every candidate of a split node descends one level (:398-407); careful phase: count only (speculative).
+        // Four candidates per thread and step, loads first, so the L2 latency of cur[] / cand[] is paid once per step.
+        for (int i0 = tid; i0 < n; i0 += 4 * NT) {
+            int nd[4]; uint32_t cv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = i0 + q * NT;
+                nd[q] = i < n ? cur[i] : -1; cv[q] = i < n ? cand[i] : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int base = nd[q] >= 0 ? nchild[nd[q]] : 0;
+                if (base > 0) {
+                    const NodeBounds b = nbnd[base];           // TL child: x1 = midX, y1 = midY
+                    const int x = (int) (cv[q] & 0xfffu), y = (int) ((cv[q] >> 12) & 0xfffu);
+                    const int ch = base + (x < b.x1 ? 0 : 1) + (y < b.y1 ? 0 : 2);
+                    if (!careful) cur[i0 + q * NT] = ch;
+                    const unsigned act = __activemask();
+                    const unsigned same = __match_any_sync(act, ch);
+                    if (lane == __ffs(same) - 1) atomicAdd(&ncnt[ch], __popc(same));
+                }
             }
         }
         __syncthreads();
