@@ -3,6 +3,7 @@
 #include "orbfe_kernels.cuh"
 
 #include <cudaTypedefs.h>
+#include <chrono>
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -119,7 +120,10 @@ static int make_tmap(Handle *h, CUtensorMap *m, const uint8_t *base, int w, int 
 // ------------------------------------------------------------------------------------------------
 // geometry + arena
 // ------------------------------------------------------------------------------------------------
+static void drop_graph(Handle *h) { if (h->graph1) { cudaGraphExecDestroy(h->graph1); h->graph1 = nullptr; } }
+
 static void free_arena(Handle *h) {
+    drop_graph(h);
     cudaFree(h->d_img); cudaFree(h->d_blur); cudaFree(h->d_slots); cudaFree(h->d_cell_cnt); cudaFree(h->d_cell_off);
     cudaFree(h->d_cand); cudaFree(h->d_cur); cudaFree(h->d_nodes); cudaFree(h->d_lists); cudaFree(h->d_kp); cudaFree(h->d_nkp);
     cudaFree(h->d_ncand); cudaFree(h->d_tables); cudaFree(h->d_fast_tab); h->d_fast_tab = nullptr; cudaFree(h->d_out_kps); cudaFree(h->d_out_desc); cudaFree(h->d_out_n);
@@ -313,6 +317,7 @@ static int ensure_pipeline(Handle *h, size_t stage_bytes, int chunk, int cap) {
 // the arena (after an H2D / D2D copy) or the caller's device buffer used in place.
 // ------------------------------------------------------------------------------------------------
 // ORBFE_DEBUG_SYNC=1 synchronises after every launch and names the kernel that faulted (debugging aid, off by default)
+static bool no_graph() { static int v = -1; if (v < 0) { const char *e = getenv("ORBFE_NO_GRAPH"); v = e && *e == '1'; } return v == 1; }
 static bool debug_sync() { static int v = -1; if (v < 0) { const char *e = getenv("ORBFE_DEBUG_SYNC"); v = e && *e == '1'; } return v == 1; }
 #define ORBFE_AFTER_LAUNCH(h, st, name)                                                                          \
     do { (h)->launches++;                                                                                        \
@@ -357,6 +362,8 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
             if ((rc = make_tmap(h, &TB.m[0], l0, g.w, g.h, l0_pitch, l0_fstride, nb, kBlurBoxH))) return rc;
             if ((rc = make_tmap(h, &tm_rs0, l0, g.w, g.h, l0_pitch, l0_fstride, nb, kRsBoxH))) return rc;
             if ((rc = make_tmap(h, &PM.img[0], l0, g.w, g.h, l0_pitch, l0_fstride, nb, kPatchH, kPatchW))) return rc;
+            // the blurred level 0 is written with the caller's strides as well (the kernels use one LevelGeom for both arenas)
+            if ((rc = make_tmap(h, &PM.blur[0], h->d_blur + g.lv[0].img_off, g.w, g.h, l0_pitch, l0_fstride, nb, kBPatchH, kBPatchW))) return rc;
         }
     }
     if (h->prof) { int rc = prof_collect(h); if (rc) return rc; }
@@ -404,7 +411,9 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
     oa.cells_per_frame = g.cells_per_frame; oa.cand_per_frame = g.cand_per_frame; oa.nodes_per_frame = g.nodes_per_frame;
     oa.lists_per_frame = g.lists_per_frame; oa.kp_per_frame = g.kp_per_frame;
     oa.sort_cap = g.sort_cap; oa.smem_node_cap = (g.oct_smem_bytes - g.sort_cap * 8) / 16;
-    k_octree<256><<<dim3(nl, nb), 256, g.oct_smem_bytes, st>>>(LS, oa);
+    // few frames: one CTA per (level, frame) leaves most SMs idle and the level-0 CTA is the critical path -> 1024 threads per CTA
+    if (nl * nb <= h->sm_count) k_octree<1024><<<dim3(nl, nb), 1024, g.oct_smem_bytes, st>>>(LS, oa);
+    else k_octree<256><<<dim3(nl, nb), 256, g.oct_smem_bytes, st>>>(LS, oa);
     ORBFE_AFTER_LAUNCH(h, st, "k_octree");
     ORBFE_PROF_MARK(h, st, 3);
     // K6 blur (launched above on the auxiliary stream unless profiling / debugging serialises the stages)
@@ -503,6 +512,7 @@ int orbfe_create(const orbfe_config *cfg, orbfe_handle **out) {
         }
     }
     cudaFuncSetAttribute(k_octree<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_octree<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     *out = h;
     return ORBFE_OK;
 }
@@ -691,25 +701,77 @@ int orbfe_extract(orbfe_handle *h, const uint8_t *gray, int width, int height, s
     *n_out = 0;
     if (!gray || width <= 0 || height <= 0) return ORBFE_OK;                          // image.empty(): outputs untouched
     if (!kps || !desc || cap < 1 || stride < (size_t) width) return set_error(h, ORBFE_E_ARG, "orbfe_extract: invalid argument (kps/desc null, cap < 1 or stride < width)");
+    static const bool trace = [] { const char *e = getenv("ORBFE_TRACE"); return e && *e == '1'; }();
+    const auto t0 = std::chrono::steady_clock::now();
+    auto us = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };
     ORBFE_CUDA(h, cudaSetDevice(h->device));
     int rc = configure(h, width, height, 1);
     if (rc) return rc;
     // device-side capacity is the handle's bound, so a too-small caller capacity is detected on the host without clobbering kps/desc
     const int dcap = h->max_kp;
     if ((rc = ensure_out_staging(h, dcap))) return rc;
+    // pinned mirror of the outputs: [n, err][kps dcap][desc dcap]; one download + one synchronisation per frame
+    const size_t kp_bytes = sizeof(orbfe_keypoint) * (size_t) dcap, desc_bytes = (size_t) dcap * 32;
+    if (h->pinned_bytes < 16 + kp_bytes + desc_bytes) {
+        if (h->h_pinned) cudaFreeHost(h->h_pinned);
+        h->h_pinned = nullptr; h->pinned_bytes = 0;
+        ORBFE_CUDA(h, cudaMallocHost(&h->h_pinned, 16 + kp_bytes + desc_bytes));
+        h->pinned_bytes = 16 + kp_bytes + desc_bytes;
+    }
+    int *p_n = (int *) h->h_pinned;
+    uint8_t *p_kps = (uint8_t *) h->h_pinned + 16, *p_desc = p_kps + kp_bytes;
     cudaStream_t st = h->stream;
     const LevelGeom &L0 = h->g.lv[0];
     ORBFE_CUDA(h, cudaMemcpy2DAsync(h->d_img + L0.img_off, L0.pitch, gray, stride, width, height, cudaMemcpyHostToDevice, st));
-    if ((rc = run_pass(h, 1, h->d_img + L0.img_off, L0.pitch, L0.frame_stride, h->d_out_kps, h->d_out_desc, h->d_out_n, h->out_cap, st))) return rc;
-    int n = 0;
-    ORBFE_CUDA(h, cudaMemcpyAsync(&n, h->d_out_n, sizeof(int), cudaMemcpyDeviceToHost, st));
-    if ((rc = check_device_error(h, st))) return rc;
+    const double t_up = us();
+    // the 13 launches of a one-frame pass are replayed from a CUDA graph (their host-side issue time and the gaps between the
+    // short kernels are a third of the frame's latency); stage profiling and ORBFE_DEBUG_SYNC use the plain launches
+    if (h->prof || debug_sync() || no_graph()) {
+        if ((rc = run_pass(h, 1, h->d_img + L0.img_off, L0.pitch, L0.frame_stride, h->d_out_kps, h->d_out_desc, h->d_out_n, h->out_cap, st))) return rc;
+    } else {
+        const void *key[4] = {h->d_img, h->d_blur, h->d_out_kps, h->d_out_desc};
+        if (h->graph1 && (memcmp(key, h->graph1_key, sizeof key) != 0 || h->graph1_cap != h->out_cap)) drop_graph(h);
+        if (!h->graph1) {
+            const long long l0 = h->launches;
+            cudaGraph_t gr = nullptr;
+            ORBFE_CUDA(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+            rc = run_pass(h, 1, h->d_img + L0.img_off, L0.pitch, L0.frame_stride, h->d_out_kps, h->d_out_desc, h->d_out_n, h->out_cap, st);
+            cudaError_t ce = cudaStreamEndCapture(st, &gr);
+            if (rc) { if (gr) cudaGraphDestroy(gr); return rc; }
+            if (ce != cudaSuccess) return set_error(h, ORBFE_E_CUDA, "graph capture of the one-frame pass failed: %s", cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&h->graph1, gr, 0);
+            cudaGraphDestroy(gr);
+            if (ce != cudaSuccess) { h->graph1 = nullptr; return set_error(h, ORBFE_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce)); }
+            memcpy(h->graph1_key, key, sizeof key); h->graph1_cap = h->out_cap;
+            h->graph1_launches = h->launches - l0; h->launches = l0;
+        }
+        ORBFE_CUDA(h, cudaGraphLaunch(h->graph1, st));
+        h->launches += h->graph1_launches;
+        h->last_batch = 1;
+    }
+    const double t_launch = us();
+    // a frame holds about n_features key points, far fewer than the staging capacity: download the count and the first
+    // `guess` rows in one go, and fetch the rest only if the frame has more
+    const int guess = std::min(dcap, h->cfg.n_features + 4 * h->g.n_levels + 16);
+    ORBFE_CUDA(h, cudaMemcpyAsync(p_n, h->d_out_n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaMemcpyAsync(p_n + 1, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaMemcpyAsync(p_kps, h->d_out_kps, sizeof(orbfe_keypoint) * (size_t) guess, cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaMemcpyAsync(p_desc, h->d_out_desc, (size_t) guess * 32, cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaStreamSynchronize(st));
+    const double t_sync = us();
+    if (p_n[1] != 0) return check_device_error(h, st);                               // reports and clears the device error flag
+    const int n = p_n[0];
     if (n == 0) return ORBFE_OK;                                                       // ORBExtractor.cpp:512
     if (n > cap) return set_error(h, ORBFE_E_CAPACITY, "%d key points but capacity %d", n, cap);
-    ORBFE_CUDA(h, cudaMemcpyAsync(kps, h->d_out_kps, sizeof(orbfe_keypoint) * (size_t) n, cudaMemcpyDeviceToHost, st));
-    ORBFE_CUDA(h, cudaMemcpyAsync(desc, h->d_out_desc, (size_t) n * 32, cudaMemcpyDeviceToHost, st));
-    ORBFE_CUDA(h, cudaStreamSynchronize(st));
+    if (n > guess) {
+        ORBFE_CUDA(h, cudaMemcpyAsync(p_kps + sizeof(orbfe_keypoint) * (size_t) guess, h->d_out_kps + guess, sizeof(orbfe_keypoint) * (size_t) (n - guess), cudaMemcpyDeviceToHost, st));
+        ORBFE_CUDA(h, cudaMemcpyAsync(p_desc + (size_t) guess * 32, h->d_out_desc + (size_t) guess * 32, (size_t) (n - guess) * 32, cudaMemcpyDeviceToHost, st));
+        ORBFE_CUDA(h, cudaStreamSynchronize(st));
+    }
+    memcpy(kps, p_kps, sizeof(orbfe_keypoint) * (size_t) n);
+    memcpy(desc, p_desc, (size_t) n * 32);
     *n_out = n;
+    if (trace) fprintf(stderr, "[orbfe trace] extract: upload issued %.1f us, launches issued %.1f us, results on host %.1f us, done %.1f us\n", t_up, t_launch, t_sync, us());
     return ORBFE_OK;
 }
 

@@ -97,6 +97,11 @@ struct Handle {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_up[2] = {}, ev_done[2] = {}, ev_down[2] = {};
     int last_batch = 0;              // frames of the last pass (for the stage getters)
+    // CUDA graph of the single-frame pass (orbfe_extract): captured once per (arena, output staging), replayed per frame
+    cudaGraphExec_t graph1 = nullptr;
+    const void *graph1_key[4] = {nullptr, nullptr, nullptr, nullptr};
+    int graph1_cap = 0;
+    long long graph1_launches = 0;
     // tensor maps (img arena; level 0 may be rebuilt for an in-place user buffer)
     CUtensorMap tm_fast[ORBFE_MAX_LEVELS], tm_blur[ORBFE_MAX_LEVELS], tm_rs[ORBFE_MAX_LEVELS];
     CUtensorMap tm_pimg[ORBFE_MAX_LEVELS], tm_pblur[ORBFE_MAX_LEVELS];   // per-key-point patch boxes of k_describe (image / blurred arena)
