@@ -77,10 +77,25 @@ def test_against_committed_reference_golden(mods, name):
 def test_other_constructor_arguments(mods, oracle):
     ORBExtractor, synth, _ = mods
     img = synth.frame(480, 640, 77, "dense")
-    for args in [(500, 1.2, 8, 20, 10), (1000, 1.5, 4, 25, 5), (2000, 1.1, 12, 12, 12), (300, 1.3, 6, 7, 20)]:
+    # scale 2.5: a 4-column quad of the resize kernel reads more than 8 source bytes -> the byte-gather variant of k_resize
+    for args in [(500, 1.2, 8, 20, 10), (1000, 1.5, 4, 25, 5), (2000, 1.1, 12, 12, 12), (300, 1.3, 6, 7, 20), (400, 2.5, 3, 20, 7), (600, 2.0, 4, 20, 7)]:
         ex = ORBExtractor(*args)
         kps, desc = ex(img)
         okps, odesc = oracle.Extractor(*args)(img)
+        assert_same_output(kps, desc, okps, odesc)
+        ex.close()
+
+
+def test_high_thresholds_on_binary_image(mods, oracle):
+    """Thresholds >= 128 take the masked compare of FAST stage A; a black/white image makes |p - v| = 255 common, which also
+    exercises the byte-carry case of the unmasked compare (t < 128)."""
+    ORBExtractor, synth, _ = mods
+    img = np.where(synth.frame(480, 752, 11, "dense") > 128, 255, 0).astype(np.uint8)
+    for args in [(800, 1.2, 8, 140, 130), (800, 1.2, 8, 200, 128), (800, 1.2, 8, 20, 7), (800, 1.2, 8, 127, 126)]:
+        ex = ORBExtractor(*args)
+        kps, desc = ex(img)
+        okps, odesc = oracle.Extractor(*args)(img)
+        assert len(okps) > 100
         assert_same_output(kps, desc, okps, odesc)
         ex.close()
 
