@@ -7,6 +7,7 @@
  *   - ORBMatcher::SearchForInitialization modules/ORB/ORBMatcher.h:21-23,   ORBMatcher.cpp:33-116
  *   - ORBMatcher::SearchByProjection      modules/ORB/ORBMatcher.h:28-37,   ORBMatcher.cpp:203-415
  *   - ORBMatcher::SearchForTriangulation  modules/ORB/ORBMatcher.h:40-42,   ORBMatcher.cpp:417-522
+ *   - Frame::Frame post-processing        modules/BasicObject/Frame.cpp:22-51 (size *= uncertainty, undistortKeyPoints, 40-px grid)
  * Plain pointers and sizes only; no C++/torch types cross this boundary.  Every entry point returns an
  * int status (ORBFE_OK or a negative ORBFE_E_*), never throws, and records a message retrievable with
  * orbfe_last_error().  One handle per host thread (a handle owns its CUDA stream, device arena and tensor
@@ -126,6 +127,40 @@ long long orbfe_launch_count(const orbfe_handle *h);
 int orbfe_profile(orbfe_handle *h, int enable);
 /* Accumulated milliseconds per stage and the number of passes since the last reset. */
 int orbfe_profile_read(orbfe_handle *h, float *stage_ms, int *n_passes, int reset);
+
+/* ---------------------------------------------------------------- Frame post-processing (Frame.cpp:22-51)
+ * What Frame::Frame does with the extractor output before any matcher sees it:
+ *   kp.size *= camera->uncertainty(kp.pt)                 Frame.cpp:24-26; Pinhole.cpp:55-57 (1.f), Fisheye.cpp:110-112 (scale_mat lookup)
+ *   camera->undistortKeyPoints(raw, key_points)           Frame.cpp:28; Pinhole.cpp:59-84 = cv::undistortPoints(pts, K, dist, noArray(), K),
+ *                                                         skipped when dist[0] == 0; Fisheye.cpp:114-117 = plain copy
+ *   grid[x/40][y/40].push_back(i) if PosInGrid(kp)        Frame.cpp:31-51, 90-95
+ * The grid comes back as CSR: cell = cx * rows + cy (the reference's grid[cx][cy]), grid_off[cols*rows + 1], grid_idx in
+ * (cell, insertion) order — exactly the order Frame::getFeaturesInArea (Frame.cpp:97-127) enumerates. */
+#define ORBFE_CAMERA_PINHOLE 0   /* DistortionModel "radtan"      (Camera.cpp:43-44) */
+#define ORBFE_CAMERA_FISHEYE 1   /* DistortionModel "equidistant" (Camera.cpp:45-46) */
+typedef struct orbfe_camera {
+    int32_t model;
+    float   fx, fy, cx, cy;            /* CameraMatrix (CV_32F, Camera.cpp:20-21) */
+    float   dist[12];                  /* Distortion, OpenCV order k1 k2 p1 p2 [k3 k4 k5 k6 s1 s2 s3 s4]; the yaml files give 4 */
+    int32_t n_dist;
+    const float *uncertainty_map;      /* Fisheye::scale_mat, row-major height x width floats in HOST memory, or NULL (= 1.f) */
+    int32_t uncertainty_w, uncertainty_h;
+} orbfe_camera;
+
+/* GRID_COLS / GRID_ROWS of an image (Frame.cpp:33-41). */
+int orbfe_grid_size(int img_w, int img_h, int *cols, int *rows);
+
+/* One frame, host memory.  kps_raw (n, in/out): size is multiplied in place; kps_un (n, out): undistorted copy;
+ * grid_off (cols*rows + 1, out), grid_idx (n, out; the first *n_in_grid entries are valid). */
+int orbfe_frame_postprocess(orbfe_handle *h, const orbfe_camera *cam, orbfe_keypoint *kps_raw, int n, int img_w, int img_h,
+                            orbfe_keypoint *kps_un, int32_t *grid_off, int32_t *grid_idx, int *n_in_grid);
+
+/* A batch of frames already in DEVICE memory, laid out like the outputs of orbfe_extract_batch_device (slabs of `cap`
+ * key points per frame, counts in d_n_per_frame): chained after the extractor there is no host round trip between the
+ * extractor and the matcher.  d_grid_off: n_frames x (cols*rows + 1); d_grid_idx: n_frames x cap; d_n_in_grid: n_frames or NULL. */
+int orbfe_frame_postprocess_device(orbfe_handle *h, const orbfe_camera *cam, orbfe_keypoint *d_kps_raw, orbfe_keypoint *d_kps_un,
+                                   const int *d_n_per_frame, int n_frames, int cap, int img_w, int img_h,
+                                   int32_t *d_grid_off, int32_t *d_grid_idx, int32_t *d_n_in_grid, void *stream, int sync);
 
 /* ---------------------------------------------------------------- matcher
  * All descriptor arrays are n x 32 bytes, row-major (cv::Mat N x 32 CV_8U as produced by the extractor).

@@ -23,6 +23,15 @@ class Config(C.Structure):
                 ("min_th_fast", C.c_int32), ("device", C.c_int32), ("max_batch", C.c_int32), ("flags", C.c_uint32)]
 
 
+class Camera(C.Structure):
+    """orbfe_camera (include/orbfe.h): Camera::create's yaml fields (Camera.cpp:27-52)."""
+    _fields_ = [("model", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("dist", C.c_float * 12),
+                ("n_dist", C.c_int32), ("uncertainty_map", C.c_void_p), ("uncertainty_w", C.c_int32), ("uncertainty_h", C.c_int32)]
+
+
+CAMERA_PINHOLE, CAMERA_FISHEYE = 0, 1
+
+
 class OrbfeError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("orbfe error %d: %s" % (code, msg))
@@ -54,6 +63,9 @@ SIGNATURES = {
     "orbfe_launch_count": (C.c_longlong, [_vp]),
     "orbfe_profile": (_i, [_vp, _i]),
     "orbfe_profile_read": (_i, [_vp, _vp, C.POINTER(_i), _i]),
+    "orbfe_grid_size": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "orbfe_frame_postprocess": (_i, [_vp, C.POINTER(Camera), _vp, _i, _i, _i, _vp, _vp, _vp, C.POINTER(_i)]),
+    "orbfe_frame_postprocess_device": (_i, [_vp, C.POINTER(Camera), _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i]),
     "orbfe_popc_peak": (_i, [_vp, C.POINTER(C.c_double)]),
     "orbfe_descriptor_distance": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp]),
     "orbfe_hamming_allpairs": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),

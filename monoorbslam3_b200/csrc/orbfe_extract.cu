@@ -522,7 +522,7 @@ void orbfe_destroy(orbfe_handle *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_arena(h);
-    cudaFree(h->d_err); cudaFree(h->d_match); cudaFree(h->d_pattern);
+    cudaFree(h->d_err); cudaFree(h->d_match); cudaFree(h->d_pattern); cudaFree(h->d_unc);
     for (int i = 0; i <= ORBFE_N_STAGES; ++i) if (h->prof_ev[i]) cudaEventDestroy(h->prof_ev[i]);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->stream) cudaStreamDestroy(h->stream);

@@ -106,6 +106,8 @@ struct Handle {
     CUtensorMap tm_fast[ORBFE_MAX_LEVELS], tm_blur[ORBFE_MAX_LEVELS], tm_rs[ORBFE_MAX_LEVELS];
     CUtensorMap tm_pimg[ORBFE_MAX_LEVELS], tm_pblur[ORBFE_MAX_LEVELS];   // per-key-point patch boxes of k_describe (image / blurred arena)
     float4 *d_pattern = nullptr;     // rotated-BRIEF pattern as floats, lane-major (DescArgs::pattern)
+    // Fisheye uncertainty map (scale_mat) cached on the device by host pointer (orbfe_frame.cu)
+    float *d_unc = nullptr; const float *unc_host = nullptr; size_t unc_bytes = 0;
     // matcher scratch
     void *d_match = nullptr; size_t match_bytes = 0;
     void *h_pinned = nullptr; size_t pinned_bytes = 0;
@@ -121,6 +123,8 @@ struct Handle {
 
 int set_error(Handle *h, int code, const char *fmt, ...);
 int ensure_match_scratch(Handle *h, size_t bytes);
+// Frame grid (CSR) of one device-resident key-point array; d_n holds the count (orbfe_frame.cu)
+int frame_grid_launch(Handle *h, const orbfe_keypoint *d_kps, const int *d_n, int cap, int img_w, int img_h, int *d_grid_off, int *d_grid_idx, cudaStream_t st);
 
 #define ORBFE_CUDA(h, call)                                                                     \
     do { cudaError_t e__ = (call);                                                              \
