@@ -381,22 +381,11 @@ __global__ void k_fill_int(int *p, int v, int n) {
     if (i < n) p[i] = v;
 }
 
-// host mirror of the Frame grid (Frame.cpp:32-51, PosInGrid :90-95): CSR with cell = cx*rows + cy
-static void build_grid(const orbfe_keypoint *kps, int n, int img_w, int img_h, int &cols, int &rows, std::vector<int> &off, std::vector<int> &idx) {
+// GRID_COLS / GRID_ROWS (Frame.cpp:33-41); the grid itself (CSR, cell = cx*rows + cy) is built on the device by
+// frame_grid_launch (orbfe_frame.cu) from the uploaded key points
+static void grid_dims(int img_w, int img_h, int &cols, int &rows) {
     cols = img_w % GRID_SIZE == 0 ? img_w / GRID_SIZE : img_w / GRID_SIZE + 1;
     rows = img_h % GRID_SIZE == 0 ? img_h / GRID_SIZE : img_h / GRID_SIZE + 1;
-    const int nc = cols * rows;
-    off.assign(nc + 1, 0); idx.assign(std::max(n, 1), 0);
-    std::vector<int> cell(std::max(n, 1));
-    for (int i = 0; i < n; ++i) {
-        const int x = (int) floorf(kps[i].x), y = (int) floorf(kps[i].y);
-        if (x < 0 || x >= img_w || y < 0 || y >= img_h) { cell[i] = -1; continue; }
-        cell[i] = (x / GRID_SIZE) * rows + y / GRID_SIZE;
-        off[cell[i] + 1]++;
-    }
-    for (int c = 0; c < nc; ++c) off[c + 1] += off[c];
-    std::vector<int> fill(nc, 0);
-    for (int i = 0; i < n; ++i) if (cell[i] >= 0) idx[off[cell[i]] + fill[cell[i]]++] = i;
 }
 
 static void fill_int(Handle *h, int *p, int v, int n, cudaStream_t st) {
@@ -415,14 +404,15 @@ static int run_window_search(Handle *h, const WindowProblem &p, float nn_ratio, 
     ORBFE_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     const int nq = p.nq, n2 = p.n2;
-    int cols, rows; std::vector<int> goff, gidx;
-    build_grid(p.kps2, n2, p.img_w, p.img_h, cols, rows, goff, gidx);
+    int cols, rows;
+    grid_dims(p.img_w, p.img_h, cols, rows);
+    const size_t n_off = (size_t) cols * rows + 1, n_gidx = (size_t) std::max(n2, 1);
     float *qx, *qy, *qr, *qang, *pre; int *qmin, *qmax, *coff, *cidx, *qcnt, *qoff, *assigned, *m12, *m21, *mdist, *binof, *nmatch, *cand_idx, *cand_dist;
     uint8_t *qvalid, *occ; uint4 *qdesc, *desc2; orbfe_keypoint *kps2;
     auto layout = [&](Bump &b, size_t cand_cap) {
         qx = b.take<float>(nq); qy = b.take<float>(nq); qr = b.take<float>(nq); qmin = b.take<int>(nq); qmax = b.take<int>(nq);
         qvalid = b.take<uint8_t>(nq); qdesc = b.take<uint4>(2 * (size_t) nq); qang = b.take<float>(nq);
-        kps2 = b.take<orbfe_keypoint>(n2); desc2 = b.take<uint4>(2 * (size_t) n2); coff = b.take<int>(goff.size()); cidx = b.take<int>(gidx.size());
+        kps2 = b.take<orbfe_keypoint>(n2); desc2 = b.take<uint4>(2 * (size_t) n2); coff = b.take<int>(n_off); cidx = b.take<int>(n_gidx);
         occ = b.take<uint8_t>(n2); qcnt = b.take<int>(nq); qoff = b.take<int>(nq + 1); assigned = b.take<int>(n2);
         m12 = b.take<int>(nq); m21 = b.take<int>(n2); mdist = b.take<int>(n2); binof = b.take<int>(std::max(nq, n2)); pre = b.take<float>(2 * (size_t) nq);
         nmatch = b.take<int>(4); cand_idx = b.take<int>(cand_cap); cand_dist = b.take<int>(cand_cap);
@@ -439,7 +429,8 @@ static int run_window_search(Handle *h, const WindowProblem &p, float nn_ratio, 
         UP(qmin, p.q_min, sizeof(int) * nq); UP(qmax, p.q_max, sizeof(int) * nq); UP(qvalid, p.q_valid, nq); UP(qdesc, p.q_desc, 32 * (size_t) nq);
         if (p.q_angle) UP(qang, p.q_angle, sizeof(float) * nq);
         UP(kps2, p.kps2, sizeof(orbfe_keypoint) * (size_t) n2); UP(desc2, p.desc2, 32 * (size_t) n2);
-        UP(coff, goff.data(), sizeof(int) * goff.size()); UP(cidx, gidx.data(), sizeof(int) * gidx.size());
+        UP(nmatch + 1, &n2, sizeof(int));                                    // the grid kernel reads the key-point count from device memory
+        if ((rc = frame_grid_launch(h, kps2, nmatch + 1, std::max(n2, 1), p.img_w, p.img_h, coff, cidx, st))) return rc;
         if (p.occupied) UP(occ, p.occupied, n2); else ORBFE_CUDA(h, cudaMemsetAsync(occ, 0, n2, st));
         if (prematched) UP(pre, prematched, sizeof(float) * 2 * (size_t) nq);
         wa.qx = qx; wa.qy = qy; wa.qr = qr; wa.qmin = qmin; wa.qmax = qmax; wa.qvalid = qvalid; wa.qdesc = qdesc; wa.nq = nq;
