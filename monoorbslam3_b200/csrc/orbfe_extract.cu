@@ -525,6 +525,7 @@ void orbfe_destroy(orbfe_handle *h) {
     cudaFree(h->d_err); cudaFree(h->d_match); cudaFree(h->d_pattern); cudaFree(h->d_unc);
     for (int i = 0; i <= ORBFE_N_STAGES; ++i) if (h->prof_ev[i]) cudaEventDestroy(h->prof_ev[i]);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->h_mpin) cudaFreeHost(h->h_mpin);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->s_aux) { cudaStreamDestroy(h->s_aux); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
     if (h->s_up) cudaStreamDestroy(h->s_up);

@@ -111,6 +111,7 @@ struct Handle {
     // matcher scratch
     void *d_match = nullptr; size_t match_bytes = 0;
     void *h_pinned = nullptr; size_t pinned_bytes = 0;
+    void *h_mpin = nullptr; size_t mpin_bytes = 0;      // pinned staging of the matcher's window searches
 
     // optional per-stage timing (orbfe_profile)
     bool prof = false, prof_pending = false;

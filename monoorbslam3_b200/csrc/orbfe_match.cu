@@ -10,6 +10,9 @@
 #define ORBFE_HELPERS_ONLY
 #include "orbfe_kernels.cuh"
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <climits>
 #include <cstring>
@@ -150,49 +153,74 @@ __global__ void __launch_bounds__(256) k_hamming_allpairs(const uint4 *__restric
 struct WinArgs {
     const float *qx, *qy, *qr; const int *qmin, *qmax; const uint8_t *qvalid; const uint4 *qdesc; int nq;
     const orbfe_keypoint *kps2; const uint4 *desc2; const int *cell_off, *cell_idx; int cols, rows;
-    int *q_cnt; const int *q_off; int *c_idx; int *c_dist;
+    int *q_beg, *q_end;              // candidate list of query i = [q_beg[i], q_end[i]) in c_idx / c_dist
+    int *cursor, *overflow; int cand_cap;
+    int *c_idx; int *c_dist;
 };
 
 __device__ __forceinline__ int floor_div_cell(float v) { return (int) floorf(v) / GRID_SIZE; }   // cvFloor(v) / GRID_SIZE, C division
 
-template <bool kFill>
+// Frame::getFeaturesInArea (Frame.cpp:97-127) + DescriptorDistance for every candidate, one warp per query.  The warp walks its
+// window twice: first it counts the candidates, reserves that many slots with one atomicAdd on the global cursor (the lists of
+// different queries may land in any order, each list itself is in the reference's (cx, cy, insertion) order), then it fills them.
+// If the reservation does not fit, the overflow flag is raised and the host retries with the exact total (the cursor).
 __global__ void __launch_bounds__(256) k_window(const WinArgs a) {
     const int qi = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (qi >= a.nq) return;
-    int total = 0;
+    int beg = 0, total = 0;
     if (a.qvalid[qi]) {
         const float x = a.qx[qi], y = a.qy[qi], r = a.qr[qi];
         const int min_l = a.qmin[qi], max_l = a.qmax[qi];
         const int min_cx = max(0, floor_div_cell(__fsub_rn(x, r))), max_cx = min(a.cols - 1, floor_div_cell(__fadd_rn(x, r)));
         const int min_cy = max(0, floor_div_cell(__fsub_rn(y, r))), max_cy = min(a.rows - 1, floor_div_cell(__fadd_rn(y, r)));
         const bool check_level = min_l > 0 || max_l >= 0;
-        uint4 d0, d1; int out0 = 0;
-        if (kFill) { d0 = __ldg(a.qdesc + 2 * (size_t) qi); d1 = __ldg(a.qdesc + 2 * (size_t) qi + 1); out0 = a.q_off[qi]; }
-        if (min_cx <= max_cx && min_cy <= max_cy)
-            for (int cx = min_cx; cx <= max_cx; ++cx) {
-                // cells (cx, min_cy..max_cy) are contiguous in the CSR: walk their members as one run
-                const int beg = a.cell_off[cx * a.rows + min_cy], end = a.cell_off[cx * a.rows + max_cy + 1];
-                for (int k0 = beg; k0 < end; k0 += 32) {
-                    const int k = k0 + lane;
-                    bool ok = false; int idx = -1;
-                    if (k < end) {
-                        idx = a.cell_idx[k];
-                        const orbfe_keypoint kp = a.kps2[idx];
-                        ok = true;
-                        if (check_level) { if (kp.octave < min_l) ok = false; if (max_l >= 0 && kp.octave > max_l) ok = false; }
-                        if (!(fabsf(__fsub_rn(kp.x, x)) <= r && fabsf(__fsub_rn(kp.y, y)) <= r)) ok = false;
+        const uint4 d0 = __ldg(a.qdesc + 2 * (size_t) qi), d1 = __ldg(a.qdesc + 2 * (size_t) qi + 1);
+        if (min_cx <= max_cx && min_cy <= max_cy) {
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                int run = 0;
+                for (int cx = min_cx; cx <= max_cx; ++cx) {
+                    // cells (cx, min_cy..max_cy) are contiguous in the CSR: walk their members as one run
+                    const int cb = a.cell_off[cx * a.rows + min_cy], ce = a.cell_off[cx * a.rows + max_cy + 1];
+                    for (int k0 = cb; k0 < ce; k0 += 32) {
+                        const int k = k0 + lane;
+                        bool ok = false; int idx = -1;
+                        if (k < ce) {
+                            idx = a.cell_idx[k];
+                            const orbfe_keypoint kp = a.kps2[idx];
+                            ok = true;
+                            if (check_level) { if (kp.octave < min_l) ok = false; if (max_l >= 0 && kp.octave > max_l) ok = false; }
+                            if (!(fabsf(__fsub_rn(kp.x, x)) <= r && fabsf(__fsub_rn(kp.y, y)) <= r)) ok = false;
+                        }
+                        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+                        if (pass && ok) {
+                            const int o = beg + run + __popc(bal & ((1u << lane) - 1u));
+                            a.c_idx[o] = idx;
+                            a.c_dist[o] = hamming256(d0, d1, __ldg(a.desc2 + 2 * (size_t) idx), __ldg(a.desc2 + 2 * (size_t) idx + 1));
+                        }
+                        run += __popc(bal);
                     }
-                    const unsigned bal = __ballot_sync(0xffffffffu, ok);
-                    if (kFill && ok) {
-                        const int o = out0 + total + __popc(bal & ((1u << lane) - 1u));
-                        a.c_idx[o] = idx;
-                        a.c_dist[o] = hamming256(d0, d1, __ldg(a.desc2 + 2 * (size_t) idx), __ldg(a.desc2 + 2 * (size_t) idx + 1));
-                    }
-                    total += __popc(bal);
+                }
+                if (pass == 0) {
+                    total = run;
+                    if (total == 0) break;
+                    if (lane == 0) beg = atomicAdd(a.cursor, total);
+                    beg = __shfl_sync(0xffffffffu, beg, 0);
+                    if (beg + total > a.cand_cap) { if (lane == 0) atomicExch(a.overflow, 1); total = 0; break; }
                 }
             }
+        }
     }
-    if (!kFill && lane == 0) a.q_cnt[qi] = total;
+    if (lane == 0) { a.q_beg[qi] = beg; a.q_end[qi] = beg + total; }
+}
+
+// result / state arrays of the resolves in one launch
+__global__ void k_window_init(int *bin_of, int n_bin, int *m12, int nq, int *m21, int *mdist, int *assigned, int n2, int *nmatch) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_bin) bin_of[i] = -1;
+    if (i < nq) m12[i] = -1;
+    if (i < n2) { m21[i] = -1; mdist[i] = INT_MAX; assigned[i] = -1; }
+    if (i < 4) nmatch[i] = 0;
 }
 
 // exclusive scan of n ints by one CTA; out[n] = total
@@ -265,7 +293,7 @@ __device__ void three_maxima(const int *cnt, int &ind1, int &ind2, int &ind3) {
 
 struct ResolveArgs {
     int nq, n2;
-    const int *q_off, *c_idx, *c_dist;
+    const int *q_beg, *q_end, *c_idx, *c_dist;   // candidate list of query i = [q_beg[i], q_end[i])
     const uint8_t *qvalid;
     const float *q_angle;            // angle of query i (kps1 angle / last key point angle)
     const orbfe_keypoint *kps2;
@@ -278,102 +306,162 @@ struct ResolveArgs {
     int *bin_of;                     // rotation bin per entry (-1 = none)
     float *prematched;               // init: n1 x 2
     float nn_ratio; int check_orientation;
+    int n_state;                     // variant 3: key points of frame 2 (n2 carries n1 there)
     int *n_matches;
 };
 
 // variant 0: SearchForInitialization; 1: SearchByProjection (frame/keyframe -> frame); 2: local map points; 3: triangulation
+//
+// The greedy loops of the reference are sequential over the queries (a query's decision depends on matchedDistance / the slots
+// taken by earlier queries), so one warp walks the queries in reference order.  What makes that walk fast is that nothing on
+// its critical path touches global memory: the per-key-point state (matched distance, owner, occupancy, angle / octave) lives in
+// shared memory, and the other seven warps of the CTA stage the candidate lists and per-query fields of the next batch of
+// queries into a double-buffered shared-memory area while warp 0 resolves the current batch.
+constexpr int kResQB = 32;           // queries per batch
+constexpr int kResSC = 128;          // staged candidates per query (longer lists read their tail from global memory)
+
 template <int kVariant>
-__global__ void __launch_bounds__(32) k_resolve(const ResolveArgs a) {
+static size_t resolve_smem_bytes(int n2) {
+    return sizeof(int) * (size_t) n2 * (kVariant == 0 ? 3 : 2) + sizeof(uint32_t) * 2 * kResQB * kResSC + sizeof(int) * 2 * kResQB * 3 + 256;
+}
+
+template <int kVariant>
+__global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
+    extern __shared__ __align__(16) uint8_t rs_dyn[];
     __shared__ int hist[HISTO_LENGTH];
-    const int lane = threadIdx.x;
-    if (lane < HISTO_LENGTH) hist[lane] = 0;
-    __syncwarp();
-    int n_match = 0;
-    for (int qi = 0; qi < a.nq; ++qi) {
-        if (kVariant != 3 && !a.qvalid[qi]) continue;
-        const int s = a.q_off[qi], e = a.q_off[qi + 1];
-        if (s == e) continue;
-        uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
-        for (int k = s + lane; k < e; k += 32) {
-            const int idx2 = a.c_idx[k], d = a.c_dist[k];
-            bool skip;
-            if (kVariant == 0) skip = a.matched_dist[idx2] <= d;
-            else if (kVariant == 3) skip = a.assigned[idx2] != 0 || a.has_mp2[idx2];      // vecBeMatched2 || kf2 map point
-            else skip = a.occupied[idx2] || a.assigned[idx2] >= 0;
-            if (!skip) {
-                const uint32_t key = ((uint32_t) d << 22) | (uint32_t) (k - s);
-                k2 = min(k2, max(key, k1));
-                k1 = min(k1, key);
-            }
-        }
-        warp_two_smallest(k1, k2);
-        if (k1 == 0xffffffffu) continue;                   // every candidate skipped: best stays at its initial value -> no match
-        const int best = (int) (k1 >> 22), best_idx2 = a.c_idx[s + (int) (k1 & 0x3fffffu)];
-        bool accept;
-        if (kVariant == 0) {
-            const int best2 = k2 == 0xffffffffu ? INT_MAX : (int) (k2 >> 22);
-            accept = best <= TH_LOW && best < cv_round_sat(__fmul_rn((float) best2, a.nn_ratio));      // :74
-        } else if (kVariant == 1) {
-            accept = best <= TH_HIGH;                                                                  // :245
-        } else if (kVariant == 2) {
-            accept = best <= TH_HIGH;
-            if (accept && k2 != 0xffffffffu) {
-                const int second = (int) (k2 >> 22);
-                const int lvl1 = a.kps2[best_idx2].octave, lvl2 = a.kps2[a.c_idx[s + (int) (k2 & 0x3fffffu)]].octave;
-                if (lvl1 == lvl2 && (float) best > __fmul_rn(a.nn_ratio, (float) second)) accept = false;   // :401-405
-            }
-        } else {
-            accept = best < TH_LOW && best_idx2 > 0;                                                   // :464-484 (sic: index 0 never accepted)
-        }
-        if (accept) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n2s = kVariant == 3 ? a.n_state : a.n2;                     // key points of frame 2 (variant 3 passes n1 through n2)
+    int *s_a = reinterpret_cast<int *>(rs_dyn);                           // v0: matched distance; v1/v2/v3: slot owner / taken flag
+    int *s_b = s_a + n2s;                                                 // v0: matches21;        v1/v3: angle bits;  v2: octave
+    int *s_c = s_b + n2s;                                                 // v0: angle bits
+    uint32_t *s_pack = reinterpret_cast<uint32_t *>(s_a + (size_t) n2s * (kVariant == 0 ? 3 : 2));     // [2][QB][SC]  dist << 16 | idx2
+    int *s_qs = reinterpret_cast<int *>(s_pack + 2 * kResQB * kResSC);    // [2][QB] list start
+    int *s_qn = s_qs + 2 * kResQB;                                        // [2][QB] list length (0 = skip the query)
+    int *s_qa = s_qn + 2 * kResQB;                                        // [2][QB] query angle bits
+    if (tid < HISTO_LENGTH) hist[tid] = 0;
+    for (int j = tid; j < n2s; j += 256) {
+        const float ang = a.kps2[j].angle;
+        if (kVariant == 0) { s_a[j] = INT_MAX; s_b[j] = -1; s_c[j] = __float_as_int(ang); }
+        else if (kVariant == 1) { s_a[j] = a.occupied[j] ? -2 : -1; s_b[j] = __float_as_int(ang); }
+        else if (kVariant == 2) { s_a[j] = a.occupied[j] ? -2 : -1; s_b[j] = a.kps2[j].octave; }
+        else { s_a[j] = a.has_mp2[j] ? -2 : -1; s_b[j] = __float_as_int(ang); }
+    }
+    const int nb = (a.nq + kResQB - 1) / kResQB;
+    auto stage = [&](int batch, int w, int nw) {                          // warps w, w + nw, ... of the callers copy one query each
+        const int buf = batch & 1;
+        for (int j = w; j < kResQB; j += nw) {
+            const int qi = batch * kResQB + j;
+            int s = 0, n = 0;
+            if (qi < a.nq && (kVariant == 3 || a.qvalid[qi])) { s = a.q_beg[qi]; n = a.q_end[qi] - s; }
+            uint32_t *dst = s_pack + ((size_t) buf * kResQB + j) * kResSC;
+            for (int k = lane; k < min(n, kResSC); k += 32) dst[k] = ((uint32_t) a.c_dist[s + k] << 16) | (uint32_t) a.c_idx[s + k];
             if (lane == 0) {
-                if (kVariant == 0) {
-                    const int old = a.matches21[best_idx2];
-                    if (old >= 0) { a.matches12[old] = -1; n_match--; }
-                    a.matches12[qi] = best_idx2; a.matches21[best_idx2] = qi; a.matched_dist[best_idx2] = best;
-                    n_match++;
-                    if (a.check_orientation) { const int b = rot_bin(a.q_angle[qi], a.kps2[best_idx2].angle); hist[b]++; a.bin_of[qi] = b; }
-                } else if (kVariant == 3) {
-                    const int idx1 = a.q_out_idx[qi];
-                    a.matches12[idx1] = best_idx2; a.assigned[best_idx2] = 1; n_match++;
-                    if (a.check_orientation) { const int b = rot_bin(a.q_angle[qi], a.kps2[best_idx2].angle); hist[b]++; a.bin_of[idx1] = b; }
-                } else {
-                    a.assigned[best_idx2] = qi; n_match++;
-                    if (kVariant == 1 && a.check_orientation) { const int b = rot_bin(a.q_angle[qi], a.kps2[best_idx2].angle); hist[b]++; a.bin_of[best_idx2] = b; }
-                }
-                __threadfence_block();
+                s_qs[buf * kResQB + j] = s; s_qn[buf * kResQB + j] = n;
+                s_qa[buf * kResQB + j] = (n && a.q_angle) ? __float_as_int(a.q_angle[qi]) : 0;
             }
-            __syncwarp();
         }
+    };
+    if (nb > 0) stage(0, wid, 8);
+    __syncthreads();
+    int n_match = 0;
+    for (int b = 0; b < nb; ++b) {
+        if (wid > 0) {
+            if (b + 1 < nb) stage(b + 1, wid - 1, 7);
+        } else {
+            const int buf = b & 1;
+            for (int j = 0; j < kResQB; ++j) {
+                const int n = s_qn[buf * kResQB + j];
+                if (n == 0) continue;
+                const int s = s_qs[buf * kResQB + j], qi = b * kResQB + j;
+                const uint32_t *lst = s_pack + ((size_t) buf * kResQB + j) * kResSC;
+                auto entry = [&](int k) -> uint32_t { return k < kResSC ? lst[k] : (((uint32_t) a.c_dist[s + k] << 16) | (uint32_t) a.c_idx[s + k]); };
+                uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
+                for (int k = lane; k < n; k += 32) {
+                    const uint32_t pk = entry(k);
+                    const int idx2 = (int) (pk & 0xffffu), d = (int) (pk >> 16);
+                    const bool skip = kVariant == 0 ? s_a[idx2] <= d : s_a[idx2] != -1;     // :63 / occupied or already taken
+                    if (!skip) {
+                        const uint32_t key = ((uint32_t) d << 22) | (uint32_t) k;
+                        k2 = min(k2, max(key, k1));
+                        k1 = min(k1, key);
+                    }
+                }
+                warp_two_smallest(k1, k2);
+                if (k1 == 0xffffffffu) continue;               // every candidate skipped: best stays at its initial value -> no match
+                const int best = (int) (k1 >> 22), best_idx2 = (int) (entry((int) (k1 & 0x3fffffu)) & 0xffffu);
+                bool accept;
+                if (kVariant == 0) {
+                    const int best2 = k2 == 0xffffffffu ? INT_MAX : (int) (k2 >> 22);
+                    accept = best <= TH_LOW && best < cv_round_sat(__fmul_rn((float) best2, a.nn_ratio));      // :74
+                } else if (kVariant == 1) {
+                    accept = best <= TH_HIGH;                                                                  // :245
+                } else if (kVariant == 2) {
+                    accept = best <= TH_HIGH;
+                    if (accept && k2 != 0xffffffffu) {
+                        const int second = (int) (k2 >> 22);
+                        const int lvl1 = s_b[best_idx2], lvl2 = s_b[entry((int) (k2 & 0x3fffffu)) & 0xffffu];
+                        if (lvl1 == lvl2 && (float) best > __fmul_rn(a.nn_ratio, (float) second)) accept = false;   // :401-405
+                    }
+                } else {
+                    accept = best < TH_LOW && best_idx2 > 0;                                                   // :464-484 (sic: index 0 never accepted)
+                }
+                if (accept) {
+                    if (lane == 0) {
+                        const float qang = __int_as_float(s_qa[buf * kResQB + j]);
+                        if (kVariant == 0) {
+                            const int old = s_b[best_idx2];
+                            if (old >= 0) { a.matches12[old] = -1; n_match--; }
+                            a.matches12[qi] = best_idx2; s_b[best_idx2] = qi; s_a[best_idx2] = best;
+                            n_match++;
+                            if (a.check_orientation) { const int bn = rot_bin(qang, __int_as_float(s_c[best_idx2])); hist[bn]++; a.bin_of[qi] = bn; }
+                        } else if (kVariant == 3) {
+                            const int idx1 = a.q_out_idx[qi];
+                            a.matches12[idx1] = best_idx2; s_a[best_idx2] = 1; n_match++;
+                            if (a.check_orientation) { const int bn = rot_bin(qang, __int_as_float(s_b[best_idx2])); hist[bn]++; a.bin_of[idx1] = bn; }
+                        } else {
+                            s_a[best_idx2] = qi; n_match++;
+                            if (kVariant == 1 && a.check_orientation) { const int bn = rot_bin(qang, __int_as_float(s_b[best_idx2])); hist[bn]++; a.bin_of[best_idx2] = bn; }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        __syncthreads();
     }
-    // rotation consistency: keep the three dominant bins (ORBMatcher.cpp:95-108 and copies)
-    n_match = __shfl_sync(0xffffffffu, n_match, 0);
-    if (a.check_orientation && kVariant != 2) {
-        __syncwarp();
-        int i1, i2, i3;
-        three_maxima(hist, i1, i2, i3);
-        const int n_entries = (kVariant == 0 || kVariant == 3) ? a.nq : a.n2;
-        // variant 3 indexes bin_of by frame-1 key point; its caller passes nq = n1-sized arrays through n2 when needed
-        const int limit = kVariant == 3 ? a.n2 : n_entries;
-        int removed = 0;
-        for (int i = lane; i < limit; i += 32) {
-            const int b = a.bin_of[i];
-            if (b < 0 || b == i1 || b == i2 || b == i3) continue;
-            if (kVariant == 0 || kVariant == 3) { if (a.matches12[i] >= 0) { a.matches12[i] = -1; removed++; } }
-            else { a.assigned[i] = -1; removed++; }
-        }
+    // rotation consistency: keep the three dominant bins (ORBMatcher.cpp:95-108 and copies); warp 0 owns the counters
+    __threadfence_block();
+    __syncthreads();
+    if (wid == 0) {
+        n_match = __shfl_sync(0xffffffffu, n_match, 0);
+        if (a.check_orientation && kVariant != 2) {
+            int i1, i2, i3;
+            three_maxima(hist, i1, i2, i3);
+            // bin_of / matches12 are indexed by frame-1 key points for variants 0 and 3 (a.n2 carries n1 for variant 3)
+            const int limit = kVariant == 0 ? a.nq : a.n2;
+            int removed = 0;
+            for (int i = lane; i < limit; i += 32) {
+                const int bn = a.bin_of[i];
+                if (bn < 0 || bn == i1 || bn == i2 || bn == i3) continue;
+                if (kVariant == 0 || kVariant == 3) { if (a.matches12[i] >= 0) { a.matches12[i] = -1; removed++; } }
+                else { s_a[i] = -1; removed++; }
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
-        n_match -= removed;
+            for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+            n_match -= removed;
+        }
+        if (lane == 0) *a.n_matches = n_match;
     }
+    __threadfence_block();
+    __syncthreads();
     if (kVariant == 0) {                                    // update previous match (:111-113)
-        __syncwarp();
-        for (int i = lane; i < a.nq; i += 32) {
+        for (int i = tid; i < a.nq; i += 256) {
             const int m = a.matches12[i];
             if (m >= 0) { a.prematched[2 * i] = a.kps2[m].x; a.prematched[2 * i + 1] = a.kps2[m].y; }
         }
+    } else if (kVariant == 1 || kVariant == 2) {            // slot owners back to global memory (occupied slots report -1)
+        for (int j = tid; j < a.n2; j += 256) a.assigned[j] = s_a[j] < -1 ? -1 : s_a[j];
     }
-    if (lane == 0) *a.n_matches = n_match;
 }
 
 __global__ void k_fill_int(int *p, int v, int n) {
@@ -399,6 +487,29 @@ struct WindowProblem {
 };
 
 template <int kVariant>
+static int launch_resolve(Handle *h, const ResolveArgs &ra, int n2, cudaStream_t st) {
+    const size_t smem = resolve_smem_bytes<kVariant>(n2);
+    if (n2 >= 65536 || smem > 200 * 1024)
+        return set_error(h, ORBFE_E_ARG, "matcher: %d key points in the searched frame exceed the resolve kernel's shared-memory state (limit about %d)", n2,
+                         kVariant == 0 ? 13000 : 20000);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_resolve<kVariant>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+    k_resolve<kVariant><<<1, 256, smem, st>>>(ra);
+    return ORBFE_OK;
+}
+
+// pinned host staging of the matcher (one upload and one download per search instead of a dozen small copies)
+static int ensure_match_pinned(Handle *h, size_t bytes) {
+    if (h->mpin_bytes >= bytes) return ORBFE_OK;
+    if (h->h_mpin) cudaFreeHost(h->h_mpin);
+    h->h_mpin = nullptr; h->mpin_bytes = 0;
+    bytes = bytes + bytes / 4 + 4096;
+    ORBFE_CUDA(h, cudaMallocHost(&h->h_mpin, bytes));
+    h->mpin_bytes = bytes;
+    return ORBFE_OK;
+}
+
+template <int kVariant>
 static int run_window_search(Handle *h, const WindowProblem &p, float nn_ratio, int check_orientation,
                              int *out_n2 /*assigned*/, int *matches12 /*init*/, float *prematched, int *n_matches) {
     ORBFE_CUDA(h, cudaSetDevice(h->device));
@@ -407,67 +518,84 @@ static int run_window_search(Handle *h, const WindowProblem &p, float nn_ratio, 
     int cols, rows;
     grid_dims(p.img_w, p.img_h, cols, rows);
     const size_t n_off = (size_t) cols * rows + 1, n_gidx = (size_t) std::max(n2, 1);
-    float *qx, *qy, *qr, *qang, *pre; int *qmin, *qmax, *coff, *cidx, *qcnt, *qoff, *assigned, *m12, *m21, *mdist, *binof, *nmatch, *cand_idx, *cand_dist;
+    static const bool trace = [] { const char *e = getenv("ORBFE_TRACE"); return e && *e == '1'; }();
+    const auto t0 = std::chrono::steady_clock::now();
+    auto us = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };
+    // device layout: [upload block: hdr, queries, frame-2 key points and descriptors, prematched][download block: nmatch, result]
+    // [device-only state].  The upload block is mirrored in pinned host memory at the same offsets.
+    int *hdr; float *qx, *qy, *qr, *qang, *pre; int *qmin, *qmax, *coff, *cidx, *qbeg, *qend, *assigned, *m12, *m21, *mdist, *binof, *nmatch, *cand_idx, *cand_dist;
     uint8_t *qvalid, *occ; uint4 *qdesc, *desc2; orbfe_keypoint *kps2;
+    size_t up_end = 0, down_beg = 0, down_end = 0;
     auto layout = [&](Bump &b, size_t cand_cap) {
+        hdr = b.take<int>(4);
         qx = b.take<float>(nq); qy = b.take<float>(nq); qr = b.take<float>(nq); qmin = b.take<int>(nq); qmax = b.take<int>(nq);
-        qvalid = b.take<uint8_t>(nq); qdesc = b.take<uint4>(2 * (size_t) nq); qang = b.take<float>(nq);
-        kps2 = b.take<orbfe_keypoint>(n2); desc2 = b.take<uint4>(2 * (size_t) n2); coff = b.take<int>(n_off); cidx = b.take<int>(n_gidx);
-        occ = b.take<uint8_t>(n2); qcnt = b.take<int>(nq); qoff = b.take<int>(nq + 1); assigned = b.take<int>(n2);
-        m12 = b.take<int>(nq); m21 = b.take<int>(n2); mdist = b.take<int>(n2); binof = b.take<int>(std::max(nq, n2)); pre = b.take<float>(2 * (size_t) nq);
-        nmatch = b.take<int>(4); cand_idx = b.take<int>(cand_cap); cand_dist = b.take<int>(cand_cap);
+        qvalid = b.take<uint8_t>(nq); qang = b.take<float>(nq); occ = b.take<uint8_t>(n2); qdesc = b.take<uint4>(2 * (size_t) nq);
+        kps2 = b.take<orbfe_keypoint>(n2); desc2 = b.take<uint4>(2 * (size_t) n2);
+        const size_t pre_off = (b.off + 255) & ~(size_t) 255;
+        pre = b.take<float>(2 * (size_t) nq);
+        up_end = b.off;
+        down_beg = kVariant == 0 ? pre_off : ((b.off + 255) & ~(size_t) 255);
+        nmatch = b.take<int>(4);
+        if (kVariant == 0) { m12 = b.take<int>(nq); down_end = b.off; assigned = b.take<int>(n2); }
+        else { assigned = b.take<int>(n2); down_end = b.off; m12 = b.take<int>(nq); }
+        coff = b.take<int>(n_off); cidx = b.take<int>(n_gidx); qbeg = b.take<int>(nq); qend = b.take<int>(nq);
+        m21 = b.take<int>(n2); mdist = b.take<int>(n2); binof = b.take<int>(std::max(nq, n2));
+        cand_idx = b.take<int>(cand_cap); cand_dist = b.take<int>(cand_cap);
     };
-#define UP(dst, src, bytes) ORBFE_CUDA(h, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, st))
-    WinArgs wa;
-    size_t cand_cap = (size_t) nq * 64 + 1024;      // first guess; the count pass tells the truth and the (rare) retry resizes
+    size_t cand_cap = (size_t) nq * 64 + 1024;      // first guess; an overflowing pass reports the exact total and is repeated
     for (int attempt = 0;; ++attempt) {
         Bump probe{nullptr}; layout(probe, cand_cap);
         int rc = ensure_match_scratch(h, probe.off + 1024);
         if (rc) return rc;
+        if ((rc = ensure_match_pinned(h, std::max(up_end, down_end) + 1024))) return rc;
         Bump b{(uint8_t *) h->d_match}; layout(b, cand_cap);
-        UP(qx, p.q_u, sizeof(float) * nq); UP(qy, p.q_v, sizeof(float) * nq); UP(qr, p.q_r, sizeof(float) * nq);
-        UP(qmin, p.q_min, sizeof(int) * nq); UP(qmax, p.q_max, sizeof(int) * nq); UP(qvalid, p.q_valid, nq); UP(qdesc, p.q_desc, 32 * (size_t) nq);
-        if (p.q_angle) UP(qang, p.q_angle, sizeof(float) * nq);
-        UP(kps2, p.kps2, sizeof(orbfe_keypoint) * (size_t) n2); UP(desc2, p.desc2, 32 * (size_t) n2);
-        UP(nmatch + 1, &n2, sizeof(int));                                    // the grid kernel reads the key-point count from device memory
-        if ((rc = frame_grid_launch(h, kps2, nmatch + 1, std::max(n2, 1), p.img_w, p.img_h, coff, cidx, st))) return rc;
-        if (p.occupied) UP(occ, p.occupied, n2); else ORBFE_CUDA(h, cudaMemsetAsync(occ, 0, n2, st));
-        if (prematched) UP(pre, prematched, sizeof(float) * 2 * (size_t) nq);
+        uint8_t *hp = (uint8_t *) h->h_mpin, *db = (uint8_t *) h->d_match;
+        auto H = [&](const void *dev) { return hp + ((const uint8_t *) dev - db); };
+        int hdr_h[4] = {n2, 0, 0, 0};
+        memcpy(H(hdr), hdr_h, sizeof hdr_h);
+        memcpy(H(qx), p.q_u, sizeof(float) * nq); memcpy(H(qy), p.q_v, sizeof(float) * nq); memcpy(H(qr), p.q_r, sizeof(float) * nq);
+        memcpy(H(qmin), p.q_min, sizeof(int) * nq); memcpy(H(qmax), p.q_max, sizeof(int) * nq); memcpy(H(qvalid), p.q_valid, nq);
+        if (p.q_angle) memcpy(H(qang), p.q_angle, sizeof(float) * nq); else memset(H(qang), 0, sizeof(float) * nq);
+        if (p.occupied) memcpy(H(occ), p.occupied, n2); else memset(H(occ), 0, n2);
+        memcpy(H(qdesc), p.q_desc, 32 * (size_t) nq);
+        memcpy(H(kps2), p.kps2, sizeof(orbfe_keypoint) * (size_t) n2); memcpy(H(desc2), p.desc2, 32 * (size_t) n2);
+        if (prematched) memcpy(H(pre), prematched, sizeof(float) * 2 * (size_t) nq);
+        ORBFE_CUDA(h, cudaMemcpyAsync(db, hp, up_end, cudaMemcpyHostToDevice, st));
+        if ((rc = frame_grid_launch(h, kps2, hdr, std::max(n2, 1), p.img_w, p.img_h, coff, cidx, st))) return rc;
+        const int n_init = std::max(std::max(nq, n2), 4);
+        k_window_init<<<(n_init + 255) / 256, 256, 0, st>>>(binof, std::max(nq, n2), m12, nq, m21, mdist, assigned, n2, nmatch);
+        WinArgs wa;
         wa.qx = qx; wa.qy = qy; wa.qr = qr; wa.qmin = qmin; wa.qmax = qmax; wa.qvalid = qvalid; wa.qdesc = qdesc; wa.nq = nq;
         wa.kps2 = kps2; wa.desc2 = desc2; wa.cell_off = coff; wa.cell_idx = cidx; wa.cols = cols; wa.rows = rows;
-        wa.q_cnt = qcnt; wa.q_off = qoff; wa.c_idx = cand_idx; wa.c_dist = cand_dist;
-        k_window<false><<<(nq + 7) / 8, 256, 0, st>>>(wa);
-        k_scan<<<1, 1024, 0, st>>>(qcnt, qoff, nq);
-        h->launches += 2;
-        int total = 0;
-        ORBFE_CUDA(h, cudaMemcpyAsync(&total, qoff + nq, sizeof(int), cudaMemcpyDeviceToHost, st));
+        wa.q_beg = qbeg; wa.q_end = qend; wa.cursor = nmatch + 1; wa.overflow = nmatch + 2; wa.cand_cap = (int) std::min<size_t>(cand_cap, INT_MAX);
+        wa.c_idx = cand_idx; wa.c_dist = cand_dist;
+        k_window<<<(nq + 7) / 8, 256, 0, st>>>(wa);
+        ResolveArgs ra; memset(&ra, 0, sizeof ra);
+        ra.nq = nq; ra.n2 = n2; ra.q_beg = qbeg; ra.q_end = qend; ra.c_idx = cand_idx; ra.c_dist = cand_dist; ra.qvalid = qvalid; ra.q_angle = qang; ra.kps2 = kps2;
+        ra.occupied = occ; ra.matches12 = m12; ra.matches21 = m21; ra.matched_dist = mdist; ra.assigned = assigned; ra.bin_of = binof;
+        ra.prematched = pre; ra.nn_ratio = nn_ratio; ra.check_orientation = check_orientation; ra.n_matches = nmatch;
+        if ((rc = launch_resolve<kVariant>(h, ra, n2, st))) return rc;
+        h->launches += 3;
+        ORBFE_CUDA(h, cudaGetLastError());
+        const double t_issue = us();
+        ORBFE_CUDA(h, cudaMemcpyAsync(hp + down_beg, db + down_beg, down_end - down_beg, cudaMemcpyDeviceToHost, st));
         ORBFE_CUDA(h, cudaStreamSynchronize(st));
-        if ((size_t) total <= cand_cap) break;
-        if (attempt) return set_error(h, ORBFE_E_INTERNAL, "candidate count changed between passes");
-        cand_cap = (size_t) total;
+        if (trace) fprintf(stderr, "[orbfe trace] window search variant %d: nq %d n2 %d, issued %.1f us, results on host %.1f us\n", kVariant, nq, n2, t_issue, us());
+        const int *nm_h = (const int *) H(nmatch);
+        if (nm_h[2]) {                                    // candidate lists did not fit: nm_h[1] is the exact total
+            if (attempt) return set_error(h, ORBFE_E_INTERNAL, "candidate count changed between passes");
+            cand_cap = (size_t) nm_h[1] + 1024;
+            continue;
+        }
+        *n_matches = nm_h[0];
+        if (kVariant == 0) {
+            memcpy(matches12, H(m12), sizeof(int) * nq);
+            memcpy(prematched, H(pre), sizeof(float) * 2 * (size_t) nq);
+        } else {
+            memcpy(out_n2, H(assigned), sizeof(int) * n2);
+        }
+        return ORBFE_OK;
     }
-    k_window<true><<<(nq + 7) / 8, 256, 0, st>>>(wa);
-    h->launches++;
-    ResolveArgs ra; memset(&ra, 0, sizeof ra);
-    ra.nq = nq; ra.n2 = n2; ra.q_off = qoff; ra.c_idx = cand_idx; ra.c_dist = cand_dist; ra.qvalid = qvalid; ra.q_angle = qang; ra.kps2 = kps2;
-    ra.occupied = occ; ra.matches12 = m12; ra.matches21 = m21; ra.matched_dist = mdist; ra.assigned = assigned; ra.bin_of = binof;
-    ra.prematched = pre; ra.nn_ratio = nn_ratio; ra.check_orientation = check_orientation; ra.n_matches = nmatch;
-    fill_int(h, binof, -1, std::max(nq, n2), st);
-    if (kVariant == 0) { fill_int(h, m12, -1, nq, st); fill_int(h, m21, -1, n2, st); fill_int(h, mdist, INT_MAX, n2, st); }
-    else fill_int(h, assigned, -1, n2, st);
-    k_resolve<kVariant><<<1, 32, 0, st>>>(ra);
-    h->launches++;
-    ORBFE_CUDA(h, cudaGetLastError());
-    if (kVariant == 0) {
-        ORBFE_CUDA(h, cudaMemcpyAsync(matches12, m12, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
-        ORBFE_CUDA(h, cudaMemcpyAsync(prematched, pre, sizeof(float) * 2 * (size_t) nq, cudaMemcpyDeviceToHost, st));
-    } else {
-        ORBFE_CUDA(h, cudaMemcpyAsync(out_n2, assigned, sizeof(int) * n2, cudaMemcpyDeviceToHost, st));
-    }
-    ORBFE_CUDA(h, cudaMemcpyAsync(n_matches, nmatch, sizeof(int), cudaMemcpyDeviceToHost, st));
-    ORBFE_CUDA(h, cudaStreamSynchronize(st));
-#undef UP
-    return ORBFE_OK;
 }
 
 }  // namespace orbfe
@@ -676,9 +804,10 @@ int orbfe_search_for_triangulation(orbfe_handle *h, const uint8_t *desc1, const 
     fill_int(h, m12, -1, n1, st); fill_int(h, asg, 0, n2, st); fill_int(h, binof, -1, n1, st);
     k_csr_distance<<<(nq + 7) / 8, 256, 0, st>>>(d1, qi, qo, nq, ci, d2, cd);
     ResolveArgs ra; memset(&ra, 0, sizeof ra);
-    ra.nq = nq; ra.n2 = n1 /* bin_of / matches12 are indexed by frame-1 key points */; ra.q_off = qo; ra.c_idx = ci; ra.c_dist = cd; ra.q_angle = qa; ra.kps2 = k2;
+    ra.nq = nq; ra.n2 = n1 /* bin_of / matches12 are indexed by frame-1 key points */; ra.q_beg = qo; ra.q_end = qo + 1; ra.c_idx = ci; ra.c_dist = cd; ra.q_angle = qa; ra.kps2 = k2;
     ra.q_out_idx = qi; ra.has_mp2 = mp2; ra.matches12 = m12; ra.assigned = asg; ra.bin_of = binof; ra.check_orientation = check_orientation; ra.n_matches = nm;
-    k_resolve<3><<<1, 32, 0, st>>>(ra);
+    ra.n_state = n2;
+    if ((rc = launch_resolve<3>(h, ra, n2, st))) return rc;
     h->launches += 2;
     ORBFE_CUDA(h, cudaGetLastError());
     ORBFE_CUDA(h, cudaMemcpyAsync(matches12, m12, sizeof(int) * n1, cudaMemcpyDeviceToHost, st));
