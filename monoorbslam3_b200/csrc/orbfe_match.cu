@@ -317,13 +317,15 @@ struct ResolveArgs {
 // its critical path touches global memory: the per-key-point state (matched distance, owner, occupancy, angle / octave) lives in
 // shared memory, and the other seven warps of the CTA stage the candidate lists and per-query fields of the next batch of
 // queries into a double-buffered shared-memory area while warp 0 resolves the current batch.
-constexpr int kResQB = 32;           // queries per batch
-constexpr int kResSC = 128;          // staged candidates per query (longer lists read their tail from global memory)
+constexpr int kResQB = 128;          // queries per batch (at most)
+constexpr int kResE = 6144;          // staged candidate entries per batch (a single longer list reads its tail from global memory)
 
 template <int kVariant>
 static size_t resolve_smem_bytes(int n2) {
-    return sizeof(int) * (size_t) n2 * (kVariant == 0 ? 3 : 2) + sizeof(uint32_t) * 2 * kResQB * kResSC + sizeof(int) * 2 * kResQB * 3 + 256;
+    return sizeof(int) * (size_t) n2 * (kVariant == 0 ? 3 : 2) + 2 * (sizeof(uint32_t) * kResE + sizeof(int) * (4 * kResQB + 4)) + 256;
 }
+
+__device__ __forceinline__ void loaders_sync() { asm volatile("bar.sync 1, 224;" ::: "memory"); }     // warps 1..7
 
 template <int kVariant>
 __global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
@@ -334,10 +336,9 @@ __global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
     int *s_a = reinterpret_cast<int *>(rs_dyn);                           // v0: matched distance; v1/v2/v3: slot owner / taken flag
     int *s_b = s_a + n2s;                                                 // v0: matches21;        v1/v3: angle bits;  v2: octave
     int *s_c = s_b + n2s;                                                 // v0: angle bits
-    uint32_t *s_pack = reinterpret_cast<uint32_t *>(s_a + (size_t) n2s * (kVariant == 0 ? 3 : 2));     // [2][QB][SC]  dist << 16 | idx2
-    int *s_qs = reinterpret_cast<int *>(s_pack + 2 * kResQB * kResSC);    // [2][QB] list start
-    int *s_qn = s_qs + 2 * kResQB;                                        // [2][QB] list length (0 = skip the query)
-    int *s_qa = s_qn + 2 * kResQB;                                        // [2][QB] query angle bits
+    // two batch buffers: [entries E][off QB+1][global start QB][length QB][angle QB][first query, query count]
+    constexpr int kBufInts = kResE + 4 * kResQB + 4;
+    int *s_buf = s_a + (size_t) n2s * (kVariant == 0 ? 3 : 2);
     if (tid < HISTO_LENGTH) hist[tid] = 0;
     for (int j = tid; j < n2s; j += 256) {
         const float ang = a.kps2[j].angle;
@@ -346,47 +347,88 @@ __global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
         else if (kVariant == 2) { s_a[j] = a.occupied[j] ? -2 : -1; s_b[j] = a.kps2[j].octave; }
         else { s_a[j] = a.has_mp2[j] ? -2 : -1; s_b[j] = __float_as_int(ang); }
     }
-    const int nb = (a.nq + kResQB - 1) / kResQB;
-    auto stage = [&](int batch, int w, int nw) {                          // warps w, w + nw, ... of the callers copy one query each
-        const int buf = batch & 1;
-        for (int j = w; j < kResQB; j += nw) {
-            const int qi = batch * kResQB + j;
-            int s = 0, n = 0;
-            if (qi < a.nq && (kVariant == 3 || a.qvalid[qi])) { s = a.q_beg[qi]; n = a.q_end[qi] - s; }
-            uint32_t *dst = s_pack + ((size_t) buf * kResQB + j) * kResSC;
-            for (int k = lane; k < min(n, kResSC); k += 32) dst[k] = ((uint32_t) a.c_dist[s + k] << 16) | (uint32_t) a.c_idx[s + k];
-            if (lane == 0) {
-                s_qs[buf * kResQB + j] = s; s_qn[buf * kResQB + j] = n;
-                s_qa[buf * kResQB + j] = (n && a.q_angle) ? __float_as_int(a.q_angle[qi]) : 0;
-            }
+    // Stage the batch that starts at query q0 into buffer `buf` (called by warps 1..7 together; lt = 0..223).  A batch takes
+    // consecutive queries until kResQB queries or kResE entries; all its global reads are two dependent round trips
+    // (query fields, then the candidate entries), however many queries it holds.
+    auto stage = [&](int q0, int buf) {
+        int *bp = s_buf + (size_t) buf * kBufInts;
+        uint32_t *pack = reinterpret_cast<uint32_t *>(bp);
+        int *off = bp + kResE, *gs = off + kResQB + 1, *ln = gs + kResQB, *qa = ln + kResQB, *hdr = qa + kResQB;
+        const int lt = tid - 32;
+        for (int j = lt; j < kResQB; j += 224) {
+            const int qi = q0 + j;
+            int st = 0, n = 0;
+            if (qi < a.nq && (kVariant == 3 || a.qvalid[qi])) { st = a.q_beg[qi]; n = a.q_end[qi] - st; }
+            gs[j] = st; ln[j] = n;
+            qa[j] = (n && a.q_angle) ? __float_as_int(a.q_angle[qi]) : 0;
+        }
+        loaders_sync();
+        if (wid == 1) {                                        // prefix of min(length, E) over the 128 slots, 4 per lane
+            int c[4], run = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { c[i] = min(ln[4 * lane + i], kResE); run += c[i]; }
+            int inc = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            int ex = inc - run;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { off[4 * lane + i] = ex; ex += c[i]; }
+            if (lane == 31) off[kResQB] = ex;
+            __syncwarp();
+            // queries in the batch: the longest prefix whose entries fit (at least one query), not past the last query
+            int m = 0;
+            for (int j = lane; j < kResQB; j += 32) if (off[j + 1] <= kResE) m = max(m, j + 1);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+            m = max(1, min(m, a.nq - q0));
+            if (lane == 0) { hdr[0] = q0; hdr[1] = m; }
+        }
+        loaders_sync();
+        const int m = hdr[1], total = min(off[m], kResE);
+        for (int e = lt; e < total; e += 224) {
+            int lo = 0, hi = m - 1;                            // last j with off[j] <= e
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (off[mid] <= e) lo = mid; else hi = mid - 1; }
+            const int src = gs[lo] + (e - off[lo]);
+            pack[e] = ((uint32_t) a.c_dist[src] << 16) | (uint32_t) a.c_idx[src];
         }
     };
-    if (nb > 0) stage(0, wid, 8);
     __syncthreads();
-    int n_match = 0;
-    for (int b = 0; b < nb; ++b) {
+    if (wid > 0 && a.nq > 0) stage(0, 0);
+    __syncthreads();
+    int n_match = 0, q0 = 0;
+    for (int b = 0; q0 < a.nq; ++b) {
+        const int *bp = s_buf + (size_t) (b & 1) * kBufInts;
+        const uint32_t *pack = reinterpret_cast<const uint32_t *>(bp);
+        const int *off = bp + kResE, *gs = off + kResQB + 1, *ln = gs + kResQB, *qa = ln + kResQB, *hdr = qa + kResQB;
+        const int m = hdr[1];
         if (wid > 0) {
-            if (b + 1 < nb) stage(b + 1, wid - 1, 7);
+            if (q0 + m < a.nq) stage(q0 + m, (b + 1) & 1);
         } else {
-            const int buf = b & 1;
-            for (int j = 0; j < kResQB; ++j) {
-                const int n = s_qn[buf * kResQB + j];
-                if (n == 0) continue;
-                const int s = s_qs[buf * kResQB + j], qi = b * kResQB + j;
-                const uint32_t *lst = s_pack + ((size_t) buf * kResQB + j) * kResSC;
-                auto entry = [&](int k) -> uint32_t { return k < kResSC ? lst[k] : (((uint32_t) a.c_dist[s + k] << 16) | (uint32_t) a.c_idx[s + k]); };
+            for (int j0 = 0; j0 < m; j0 += 32) {
+              // queries with candidates in this group of 32 (a single warp pays every latency in full: skip the empty ones in bulk)
+              unsigned live = __ballot_sync(0xffffffffu, j0 + lane < m && ln[j0 + lane] != 0);
+              while (live) {
+                const int j = j0 + __ffs(live) - 1;
+                live &= live - 1;
+                const int n = ln[j];
+                const int s = gs[j], qi = q0 + j, o = off[j], staged = min(n, kResE - o);
+                auto entry = [&](int k) -> uint32_t { return k < staged ? pack[o + k] : (((uint32_t) a.c_dist[s + k] << 16) | (uint32_t) a.c_idx[s + k]); };
                 uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
-                for (int k = lane; k < n; k += 32) {
-                    const uint32_t pk = entry(k);
-                    const int idx2 = (int) (pk & 0xffffu), d = (int) (pk >> 16);
-                    const bool skip = kVariant == 0 ? s_a[idx2] <= d : s_a[idx2] != -1;     // :63 / occupied or already taken
-                    if (!skip) {
-                        const uint32_t key = ((uint32_t) d << 22) | (uint32_t) k;
-                        k2 = min(k2, max(key, k1));
-                        k1 = min(k1, key);
-                    }
+                for (int k = lane; k < n; k += 64) {           // two entries per step: their loads and state look-ups overlap
+                    const bool has2 = k + 32 < n;
+                    const uint32_t pa = entry(k), pb = has2 ? entry(k + 32) : 0u;
+                    const int ia = (int) (pa & 0xffffu), da = (int) (pa >> 16), ib = (int) (pb & 0xffffu), db = (int) (pb >> 16);
+                    const int sa = s_a[ia], sb = s_a[ib];
+                    const bool skip_a = kVariant == 0 ? sa <= da : sa != -1;                 // :63 / occupied or already taken
+                    const bool skip_b = !has2 || (kVariant == 0 ? sb <= db : sb != -1);
+                    if (!skip_a) { const uint32_t key = ((uint32_t) da << 22) | (uint32_t) k; k2 = min(k2, max(key, k1)); k1 = min(k1, key); }
+                    if (!skip_b) { const uint32_t key = ((uint32_t) db << 22) | (uint32_t) (k + 32); k2 = min(k2, max(key, k1)); k1 = min(k1, key); }
                 }
-                warp_two_smallest(k1, k2);
+                {   // two smallest keys of the warp with the hardware reductions (keys are unique: they carry the position)
+                    const uint32_t g1 = __reduce_min_sync(0xffffffffu, k1);
+                    const uint32_t g2 = __reduce_min_sync(0xffffffffu, k1 == g1 ? k2 : k1);
+                    k1 = g1; k2 = g2;
+                }
                 if (k1 == 0xffffffffu) continue;               // every candidate skipped: best stays at its initial value -> no match
                 const int best = (int) (k1 >> 22), best_idx2 = (int) (entry((int) (k1 & 0x3fffffu)) & 0xffffu);
                 bool accept;
@@ -407,7 +449,7 @@ __global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
                 }
                 if (accept) {
                     if (lane == 0) {
-                        const float qang = __int_as_float(s_qa[buf * kResQB + j]);
+                        const float qang = __int_as_float(qa[j]);
                         if (kVariant == 0) {
                             const int old = s_b[best_idx2];
                             if (old >= 0) { a.matches12[old] = -1; n_match--; }
@@ -425,8 +467,10 @@ __global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
                     }
                     __syncwarp();
                 }
+              }
             }
         }
+        q0 += m;
         __syncthreads();
     }
     // rotation consistency: keep the three dominant bins (ORBMatcher.cpp:95-108 and copies); warp 0 owns the counters
