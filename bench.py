@@ -325,10 +325,22 @@ def run_ours(args):
                             "frac_of_hbm_peak": (ab[k] * B / (per_launch_ms[k] * 1e-3) / 1e9 / peak_gbs) if per_launch_ms[k] > 0 and ab[k] else None}
                         for k in stage_ms}
         traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
+        issue = None            # why the HBM fraction is low: the stage kernels are bound by instruction issue, not by bytes
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
             if tj.get("batch") == B:
                 traffic = tj["stages"][dom]["dram_read_bytes"] + tj["stages"][dom]["dram_write_bytes"]
+                clk = (sampler.summary().get("sm_mhz") or 1965.0) * 1e6
+                slots_per_s = 148 * 4 * clk                       # warp instructions the SM sub-partitions can issue per second
+                issue = {}
+                for k, d in tj["stages"].items():
+                    if "warp_instructions" not in d or per_launch_ms.get(k, 0) <= 0:
+                        continue
+                    floor_ms = d["warp_instructions"] / slots_per_s * 1e3
+                    issue[k] = {"warp_instructions_per_step": d["warp_instructions"], "issue_floor_ms": floor_ms,
+                                "issue_frac": floor_ms / per_launch_ms[k], "ncu_issue_active_pct": d.get("issue_active_pct"),
+                                "ncu_alu_pipe_pct": d.get("alu_pipe_pct"),
+                                "thread_instructions_per_pixel": (d["warp_instructions"] * 32 / (ab["fast"] * B)) if k in ("fast", "blur") else None}
         except Exception:
             pass
         line = {
@@ -344,6 +356,8 @@ def run_ours(args):
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab[dom] * B,
                          "whole_step_algorithmic_GBps": ab["frame_total"] * B / (ms_dev / K * 1e-3) / 1e9},
             "stages": stage_report, "ms_per_step_serialised_with_stage_events": ms_prof / K,
+            "issue_roofline": {"note": "warp instructions per step (committed ncu capture) / (148 SMs x 4 schedulers x SM clock): the time the stage would "
+                                       "take at one instruction per scheduler per cycle; issue_frac = that / measured stage time", "stages": issue},
             "match": {"metric": "Hamming GMatch/s (all-pairs 40000 x 40000, best/second-best)", "value": gmatch, "unit": "GMatch/s", "ms": ms_match,
                       "roofline": {"bound": "integer pipe (popc)", "achieved": gmatch, "peak": popc_peak / 8, "unit": "GMatch/s", "frac": gmatch / (popc_peak / 8),
                                    "peak_source": "measured popc micro-benchmark (orbfe_popc_peak), 8 popc per 256-bit match"}},

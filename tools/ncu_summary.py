@@ -20,7 +20,7 @@ def rows_of(rep):
     return res, {hdr[i]: units[i] for i in idx}
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and sys.argv[1] != "--traffic":
     out_csv = sys.argv[1]
     allrows, units = [], {}
     for rep in sys.argv[2:]:
@@ -33,3 +33,41 @@ if __name__ == "__main__":
         for r in allrows:
             w.writerow([r[k] for k in keys])
     print("wrote", out_csv, len(allrows), "kernels")
+
+
+def traffic_json(rep, out_json, batch, note=""):
+    """profiles/rNN_traffic.json: per stage of the LAST pass in `rep` (tools/profile_run.py runs the pass twice) the kernel time,
+    DRAM bytes, executed warp instructions and issue / pipe utilisation — what bench.py's roofline.traffic and issue figures read."""
+    import json
+    rows, _ = rows_of(rep)
+    stage_of = {"k_resize": "pyramid", "k_fast": "fast", "k_octree": "quadtree", "k_blur": "blur", "k_describe": "describe"}
+    seq = [(next((v for k, v in stage_of.items() if k in r["Kernel Name"]), None), r) for r in rows]
+    seq = [(s, r) for s, r in seq if s]
+    n_desc = sum(1 for s, _ in seq if s == "describe")
+    # keep the kernels after the second-to-last describe launch (= the last pass)
+    if n_desc > 1:
+        seen = 0
+        for i, (s, _) in enumerate(seq):
+            if s == "describe":
+                seen += 1
+                if seen == n_desc - 1:
+                    seq = seq[i + 1:]
+                    break
+    stages = {}
+    for s, r in seq:
+        d = stages.setdefault(s, {"duration_ns": 0.0, "dram_read_bytes": 0.0, "dram_write_bytes": 0.0, "warp_instructions": 0.0, "launches": 0,
+                                  "issue_active_pct": 0.0, "alu_pipe_pct": 0.0})
+        t = float(r["gpu__time_duration.sum"])
+        d["duration_ns"] += t; d["dram_read_bytes"] += float(r["dram__bytes_read.sum"]); d["dram_write_bytes"] += float(r["dram__bytes_write.sum"])
+        d["warp_instructions"] += float(r["smsp__inst_executed.sum"]); d["launches"] += 1
+        d["issue_active_pct"] += t * float(r["smsp__issue_active.avg.pct_of_peak_sustained_active"])
+        d["alu_pipe_pct"] += t * float(r["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"])
+    for d in stages.values():
+        d["issue_active_pct"] /= d["duration_ns"]; d["alu_pipe_pct"] /= d["duration_ns"]
+    json.dump({"source": "ncu --set full --clock-control none --import-source on, tools/profile_run.py %d 2 (C1 frames), last pass; %s" % (batch, note),
+               "batch": batch, "stages": stages}, open(out_json, "w"), indent=1)
+    print("wrote", out_json)
+
+
+if __name__ == "__main__" and sys.argv[1] == "--traffic":
+    traffic_json(sys.argv[2], sys.argv[3], int(sys.argv[4]), " ".join(sys.argv[5:]))
