@@ -7,6 +7,7 @@
  *   - ORBMatcher::SearchForInitialization modules/ORB/ORBMatcher.h:21-23,   ORBMatcher.cpp:33-116
  *   - ORBMatcher::SearchByProjection      modules/ORB/ORBMatcher.h:28-37,   ORBMatcher.cpp:203-415
  *   - ORBMatcher::SearchForTriangulation  modules/ORB/ORBMatcher.h:40-42,   ORBMatcher.cpp:417-522
+ *   - ORBMatcher::SearchByBow             modules/ORB/ORBMatcher.h:26,      ORBMatcher.cpp:118-201
  *   - Frame::Frame post-processing        modules/BasicObject/Frame.cpp:22-51 (size *= uncertainty, undistortKeyPoints, 40-px grid)
  * Plain pointers and sizes only; no C++/torch types cross this boundary.  Every entry point returns an
  * int status (ORBFE_OK or a negative ORBFE_E_*), never throws, and records a message retrievable with
@@ -218,6 +219,17 @@ int orbfe_search_for_triangulation(orbfe_handle *h,
                                    const uint8_t *desc2, const float *angle2, const uint8_t *has_mp2, int n2,
                                    const int32_t *node_id2, const int32_t *node_off2, const int32_t *node_idx2, int n_nodes2,
                                    int32_t *matches12, int check_orientation, int *n_matches);
+
+/* ORBMatcher::SearchByBow(KeyFrame, Frame) (ORBMatcher.cpp:118-201), SURVEY.md 8f rank 3.  Feature vectors as CSR like above.
+ * valid1[i] != 0: key-frame key point i has a map point that is not bad (:143-144); occupied2[j] != 0: frame->map_points[j] is
+ * already set (:151).  assigned[j] (n2, out) = key-frame key-point index whose map point the call puts into frame slot j, or -1.
+ * Best / second-best with the float ratio test bestDist < nn_ratio * secondDist (:164), rotation histogram as in the reference. */
+int orbfe_search_by_bow(orbfe_handle *h,
+                        const uint8_t *desc1, const float *angle1, const uint8_t *valid1, int n1,
+                        const int32_t *node_id1, const int32_t *node_off1, const int32_t *node_idx1, int n_nodes1,
+                        const uint8_t *desc2, const float *angle2, const uint8_t *occupied2, int n2,
+                        const int32_t *node_id2, const int32_t *node_off2, const int32_t *node_idx2, int n_nodes2,
+                        int32_t *assigned, float nn_ratio, int check_orientation, int *n_matches);
 
 #ifdef __cplusplus
 }

@@ -310,7 +310,8 @@ struct ResolveArgs {
     int *n_matches;
 };
 
-// variant 0: SearchForInitialization; 1: SearchByProjection (frame/keyframe -> frame); 2: local map points; 3: triangulation
+// variant 0: SearchForInitialization; 1: SearchByProjection (frame/keyframe -> frame); 2: local map points; 3: triangulation;
+// 4: SearchByBow
 //
 // The greedy loops of the reference are sequential over the queries (a query's decision depends on matchedDistance / the slots
 // taken by earlier queries), so one warp walks the queries in reference order.  What makes that walk fast is that nothing on
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
     for (int j = tid; j < n2s; j += 256) {
         const float ang = a.kps2[j].angle;
         if (kVariant == 0) { s_a[j] = INT_MAX; s_b[j] = -1; s_c[j] = __float_as_int(ang); }
-        else if (kVariant == 1) { s_a[j] = a.occupied[j] ? -2 : -1; s_b[j] = __float_as_int(ang); }
+        else if (kVariant == 1 || kVariant == 4) { s_a[j] = a.occupied[j] ? -2 : -1; s_b[j] = __float_as_int(ang); }
         else if (kVariant == 2) { s_a[j] = a.occupied[j] ? -2 : -1; s_b[j] = a.kps2[j].octave; }
         else { s_a[j] = a.has_mp2[j] ? -2 : -1; s_b[j] = __float_as_int(ang); }
     }
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
         for (int j = lt; j < kResQB; j += 224) {
             const int qi = q0 + j;
             int st = 0, n = 0;
-            if (qi < a.nq && (kVariant == 3 || a.qvalid[qi])) { st = a.q_beg[qi]; n = a.q_end[qi] - st; }
+            if (qi < a.nq && (kVariant == 3 || kVariant == 4 || a.qvalid[qi])) { st = a.q_beg[qi]; n = a.q_end[qi] - st; }
             gs[j] = st; ln[j] = n;
             qa[j] = (n && a.q_angle) ? __float_as_int(a.q_angle[qi]) : 0;
         }
@@ -444,8 +445,11 @@ __global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
                         const int lvl1 = s_b[best_idx2], lvl2 = s_b[entry((int) (k2 & 0x3fffffu)) & 0xffffu];
                         if (lvl1 == lvl2 && (float) best > __fmul_rn(a.nn_ratio, (float) second)) accept = false;   // :401-405
                     }
-                } else {
+                } else if (kVariant == 3) {
                     accept = best < TH_LOW && best_idx2 > 0;                                                   // :464-484 (sic: index 0 never accepted)
+                } else {
+                    const int second = k2 == 0xffffffffu ? 256 : (int) (k2 >> 22);                             // :149 initial 256
+                    accept = best <= TH_LOW && (float) best < __fmul_rn(a.nn_ratio, (float) second);           // :164
                 }
                 if (accept) {
                     if (lane == 0) {
@@ -461,8 +465,8 @@ __global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
                             a.matches12[idx1] = best_idx2; s_a[best_idx2] = 1; n_match++;
                             if (a.check_orientation) { const int bn = rot_bin(qang, __int_as_float(s_b[best_idx2])); hist[bn]++; a.bin_of[idx1] = bn; }
                         } else {
-                            s_a[best_idx2] = qi; n_match++;
-                            if (kVariant == 1 && a.check_orientation) { const int bn = rot_bin(qang, __int_as_float(s_b[best_idx2])); hist[bn]++; a.bin_of[best_idx2] = bn; }
+                            s_a[best_idx2] = kVariant == 4 ? a.q_out_idx[qi] : qi; n_match++;
+                            if ((kVariant == 1 || kVariant == 4) && a.check_orientation) { const int bn = rot_bin(qang, __int_as_float(s_b[best_idx2])); hist[bn]++; a.bin_of[best_idx2] = bn; }
                         }
                     }
                     __syncwarp();
@@ -503,7 +507,7 @@ __global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
             const int m = a.matches12[i];
             if (m >= 0) { a.prematched[2 * i] = a.kps2[m].x; a.prematched[2 * i + 1] = a.kps2[m].y; }
         }
-    } else if (kVariant == 1 || kVariant == 2) {            // slot owners back to global memory (occupied slots report -1)
+    } else if (kVariant == 1 || kVariant == 2 || kVariant == 4) {   // slot owners back to global memory (occupied slots report -1)
         for (int j = tid; j < a.n2; j += 256) a.assigned[j] = s_a[j] < -1 ? -1 : s_a[j];
     }
 }
@@ -645,6 +649,75 @@ static int run_window_search(Handle *h, const WindowProblem &p, float nn_ratio, 
 }  // namespace orbfe
 
 using namespace orbfe;
+
+// Shared driver of the two vocabulary-node searches (SearchForTriangulation = variant 3, SearchByBow = variant 4): merge-join of
+// the two DBoW2 feature vectors on the host (std::map order, lower_bound skips: ORBMatcher.cpp:131-187, 443-512) into the query
+// list in reference order with the node members of frame 2 as candidate lists; distances and the greedy resolve on the device.
+template <int kVariant>
+static int run_node_search(orbfe_handle *h, const uint8_t *desc1, const float *angle1, const uint8_t *flag1, int n1, const int32_t *node_id1,
+                           const int32_t *node_off1, const int32_t *node_idx1, int n_nodes1, const uint8_t *desc2, const float *angle2,
+                           const uint8_t *flag2, int n2, const int32_t *node_id2, const int32_t *node_off2, const int32_t *node_idx2, int n_nodes2,
+                           int32_t *out, float nn_ratio, int check_orientation, int *n_matches) {
+    std::vector<int> q_idx1, q_off(1, 0), c_idx; std::vector<float> q_ang;
+    int a = 0, b = 0;
+    while (a < n_nodes1 && b < n_nodes2) {
+        if (node_id1[a] == node_id2[b]) {
+            for (int i = node_off1[a]; i < node_off1[a + 1]; ++i) {
+                const int idx1 = node_idx1[i];
+                if (idx1 < 0 || idx1 >= n1) return set_error(h, ORBFE_E_ARG, "feature vector 1 index out of range");
+                if (kVariant == 3 ? flag1[idx1] != 0 : flag1[idx1] == 0) continue;      // :452 has a map point / :143-144 no good map point
+                q_idx1.push_back(idx1); q_ang.push_back(angle1[idx1]);
+                for (int k = node_off2[b]; k < node_off2[b + 1]; ++k) {
+                    if (node_idx2[k] < 0 || node_idx2[k] >= n2) return set_error(h, ORBFE_E_ARG, "feature vector 2 index out of range");
+                    c_idx.push_back(node_idx2[k]);
+                }
+                q_off.push_back((int) c_idx.size());
+            }
+            ++a; ++b;
+        } else if (node_id1[a] < node_id2[b]) { while (a < n_nodes1 && node_id1[a] < node_id2[b]) ++a; }
+        else { while (b < n_nodes2 && node_id2[b] < node_id1[a]) ++b; }
+    }
+    const int nq = (int) q_idx1.size(), total = (int) c_idx.size();
+    if (nq == 0) return ORBFE_OK;
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    std::vector<orbfe_keypoint> kps2(n2);
+    for (int j = 0; j < n2; ++j) { memset(&kps2[j], 0, sizeof(orbfe_keypoint)); kps2[j].angle = angle2[j]; }
+    const int n_bin = kVariant == 3 ? n1 : n2;                 // bin_of is indexed by frame-1 key points (3) / frame-2 slots (4)
+    auto layout = [&](Bump &bp, uint4 *&d1, uint4 *&d2, int *&qi, int *&qo, int *&ci, int *&cd, float *&qa, orbfe_keypoint *&k2, uint8_t *&f2, int *&m12,
+                      int *&asg, int *&binof, int *&nm) {
+        d1 = bp.take<uint4>(2 * (size_t) n1); d2 = bp.take<uint4>(2 * (size_t) n2); qi = bp.take<int>(nq); qo = bp.take<int>(nq + 1);
+        ci = bp.take<int>(std::max(total, 1)); cd = bp.take<int>(std::max(total, 1)); qa = bp.take<float>(nq); k2 = bp.take<orbfe_keypoint>(n2);
+        f2 = bp.take<uint8_t>(n2); m12 = bp.take<int>(n1); asg = bp.take<int>(n2); binof = bp.take<int>(n_bin); nm = bp.take<int>(4);
+    };
+    uint4 *d1, *d2; int *qi, *qo, *ci, *cd, *m12, *asg, *binof, *nm; float *qa; orbfe_keypoint *k2; uint8_t *f2;
+    Bump probe{nullptr}; layout(probe, d1, d2, qi, qo, ci, cd, qa, k2, f2, m12, asg, binof, nm);
+    int rc = ensure_match_scratch(h, probe.off + 1024);
+    if (rc) return rc;
+    Bump bp{(uint8_t *) h->d_match}; layout(bp, d1, d2, qi, qo, ci, cd, qa, k2, f2, m12, asg, binof, nm);
+#define UP(dst, src, bytes) ORBFE_CUDA(h, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, st))
+    UP(d1, desc1, 32 * (size_t) n1); UP(d2, desc2, 32 * (size_t) n2); UP(qi, q_idx1.data(), sizeof(int) * nq); UP(qo, q_off.data(), sizeof(int) * (nq + 1));
+    if (total) UP(ci, c_idx.data(), sizeof(int) * total);
+    UP(qa, q_ang.data(), sizeof(float) * nq); UP(k2, kps2.data(), sizeof(orbfe_keypoint) * (size_t) n2);
+    if (flag2) UP(f2, flag2, n2); else ORBFE_CUDA(h, cudaMemsetAsync(f2, 0, n2, st));
+#undef UP
+    fill_int(h, m12, -1, n1, st); fill_int(h, asg, -1, n2, st); fill_int(h, binof, -1, n_bin, st);
+    k_csr_distance<<<(nq + 7) / 8, 256, 0, st>>>(d1, qi, qo, nq, ci, d2, cd);
+    ResolveArgs ra; memset(&ra, 0, sizeof ra);
+    ra.nq = nq; ra.q_beg = qo; ra.q_end = qo + 1; ra.c_idx = ci; ra.c_dist = cd; ra.q_angle = qa; ra.kps2 = k2;
+    ra.q_out_idx = qi; ra.matches12 = m12; ra.assigned = asg; ra.bin_of = binof; ra.check_orientation = check_orientation; ra.n_matches = nm;
+    ra.nn_ratio = nn_ratio; ra.n_state = n2;
+    if (kVariant == 3) { ra.n2 = n1 /* bin_of / matches12 are indexed by frame-1 key points */; ra.has_mp2 = f2; }
+    else { ra.n2 = n2; ra.occupied = f2; }
+    if ((rc = launch_resolve<kVariant>(h, ra, n2, st))) return rc;
+    h->launches += 2;
+    ORBFE_CUDA(h, cudaGetLastError());
+    if (kVariant == 3) ORBFE_CUDA(h, cudaMemcpyAsync(out, m12, sizeof(int) * n1, cudaMemcpyDeviceToHost, st));
+    else ORBFE_CUDA(h, cudaMemcpyAsync(out, asg, sizeof(int) * n2, cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaMemcpyAsync(n_matches, nm, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaStreamSynchronize(st));
+    return ORBFE_OK;
+}
 
 extern "C" {
 
@@ -803,61 +876,23 @@ int orbfe_search_for_triangulation(orbfe_handle *h, const uint8_t *desc1, const 
     *n_matches = 0;
     for (int i = 0; i < n1; ++i) matches12[i] = -1;
     if (n1 == 0 || n2 == 0 || n_nodes1 == 0 || n_nodes2 == 0) return ORBFE_OK;
-    // merge-join of the two feature vectors (ORBMatcher.cpp:443-512): the query list in reference order, candidates = node members of kf2
-    std::vector<int> q_idx1, q_off(1, 0), c_idx; std::vector<float> q_ang;
-    int a = 0, b = 0;
-    while (a < n_nodes1 && b < n_nodes2) {
-        if (node_id1[a] == node_id2[b]) {
-            for (int i = node_off1[a]; i < node_off1[a + 1]; ++i) {
-                const int idx1 = node_idx1[i];
-                if (idx1 < 0 || idx1 >= n1) return set_error(h, ORBFE_E_ARG, "feature vector 1 index out of range");
-                if (has_mp1[idx1]) continue;                                     // :452
-                q_idx1.push_back(idx1); q_ang.push_back(angle1[idx1]);
-                for (int k = node_off2[b]; k < node_off2[b + 1]; ++k) {
-                    if (node_idx2[k] < 0 || node_idx2[k] >= n2) return set_error(h, ORBFE_E_ARG, "feature vector 2 index out of range");
-                    c_idx.push_back(node_idx2[k]);
-                }
-                q_off.push_back((int) c_idx.size());
-            }
-            ++a; ++b;
-        } else if (node_id1[a] < node_id2[b]) { while (a < n_nodes1 && node_id1[a] < node_id2[b]) ++a; }
-        else { while (b < n_nodes2 && node_id2[b] < node_id1[a]) ++b; }
-    }
-    const int nq = (int) q_idx1.size(), total = (int) c_idx.size();
-    if (nq == 0) return ORBFE_OK;
-    ORBFE_CUDA(h, cudaSetDevice(h->device));
-    cudaStream_t st = h->stream;
-    std::vector<orbfe_keypoint> kps2(n2);
-    for (int j = 0; j < n2; ++j) { memset(&kps2[j], 0, sizeof(orbfe_keypoint)); kps2[j].angle = angle2[j]; }
-    auto layout = [&](Bump &bp, uint4 *&d1, uint4 *&d2, int *&qi, int *&qo, int *&ci, int *&cd, float *&qa, orbfe_keypoint *&k2, uint8_t *&mp2, int *&m12,
-                      int *&asg, int *&binof, int *&nm) {
-        d1 = bp.take<uint4>(2 * (size_t) n1); d2 = bp.take<uint4>(2 * (size_t) n2); qi = bp.take<int>(nq); qo = bp.take<int>(nq + 1);
-        ci = bp.take<int>(std::max(total, 1)); cd = bp.take<int>(std::max(total, 1)); qa = bp.take<float>(nq); k2 = bp.take<orbfe_keypoint>(n2);
-        mp2 = bp.take<uint8_t>(n2); m12 = bp.take<int>(n1); asg = bp.take<int>(n2); binof = bp.take<int>(n1); nm = bp.take<int>(4);
-    };
-    uint4 *d1, *d2; int *qi, *qo, *ci, *cd, *m12, *asg, *binof, *nm; float *qa; orbfe_keypoint *k2; uint8_t *mp2;
-    Bump probe{nullptr}; layout(probe, d1, d2, qi, qo, ci, cd, qa, k2, mp2, m12, asg, binof, nm);
-    int rc = ensure_match_scratch(h, probe.off + 1024);
-    if (rc) return rc;
-    Bump bp{(uint8_t *) h->d_match}; layout(bp, d1, d2, qi, qo, ci, cd, qa, k2, mp2, m12, asg, binof, nm);
-#define UP(dst, src, bytes) ORBFE_CUDA(h, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, st))
-    UP(d1, desc1, 32 * (size_t) n1); UP(d2, desc2, 32 * (size_t) n2); UP(qi, q_idx1.data(), sizeof(int) * nq); UP(qo, q_off.data(), sizeof(int) * (nq + 1));
-    if (total) UP(ci, c_idx.data(), sizeof(int) * total);
-    UP(qa, q_ang.data(), sizeof(float) * nq); UP(k2, kps2.data(), sizeof(orbfe_keypoint) * (size_t) n2); UP(mp2, has_mp2, n2);
-#undef UP
-    fill_int(h, m12, -1, n1, st); fill_int(h, asg, 0, n2, st); fill_int(h, binof, -1, n1, st);
-    k_csr_distance<<<(nq + 7) / 8, 256, 0, st>>>(d1, qi, qo, nq, ci, d2, cd);
-    ResolveArgs ra; memset(&ra, 0, sizeof ra);
-    ra.nq = nq; ra.n2 = n1 /* bin_of / matches12 are indexed by frame-1 key points */; ra.q_beg = qo; ra.q_end = qo + 1; ra.c_idx = ci; ra.c_dist = cd; ra.q_angle = qa; ra.kps2 = k2;
-    ra.q_out_idx = qi; ra.has_mp2 = mp2; ra.matches12 = m12; ra.assigned = asg; ra.bin_of = binof; ra.check_orientation = check_orientation; ra.n_matches = nm;
-    ra.n_state = n2;
-    if ((rc = launch_resolve<3>(h, ra, n2, st))) return rc;
-    h->launches += 2;
-    ORBFE_CUDA(h, cudaGetLastError());
-    ORBFE_CUDA(h, cudaMemcpyAsync(matches12, m12, sizeof(int) * n1, cudaMemcpyDeviceToHost, st));
-    ORBFE_CUDA(h, cudaMemcpyAsync(n_matches, nm, sizeof(int), cudaMemcpyDeviceToHost, st));
-    ORBFE_CUDA(h, cudaStreamSynchronize(st));
-    return ORBFE_OK;
+    return run_node_search<3>(h, desc1, angle1, has_mp1, n1, node_id1, node_off1, node_idx1, n_nodes1, desc2, angle2, has_mp2, n2, node_id2, node_off2,
+                              node_idx2, n_nodes2, matches12, 0.f, check_orientation, n_matches);
+}
+
+int orbfe_search_by_bow(orbfe_handle *h, const uint8_t *desc1, const float *angle1, const uint8_t *valid1, int n1, const int32_t *node_id1,
+                        const int32_t *node_off1, const int32_t *node_idx1, int n_nodes1, const uint8_t *desc2, const float *angle2,
+                        const uint8_t *occupied2, int n2, const int32_t *node_id2, const int32_t *node_off2, const int32_t *node_idx2, int n_nodes2,
+                        int32_t *assigned, float nn_ratio, int check_orientation, int *n_matches) {
+    if (!h) return ORBFE_E_ARG;
+    if (!n_matches || n1 < 0 || n2 < 0 || n_nodes1 < 0 || n_nodes2 < 0 || (n1 && (!desc1 || !angle1 || !valid1)) ||
+        (n2 && (!desc2 || !angle2 || !assigned)) || (n_nodes1 && (!node_id1 || !node_off1 || !node_idx1)) || (n_nodes2 && (!node_id2 || !node_off2 || !node_idx2)))
+        return set_error(h, ORBFE_E_ARG, "invalid argument");
+    *n_matches = 0;
+    for (int j = 0; j < n2; ++j) assigned[j] = -1;
+    if (n1 == 0 || n2 == 0 || n_nodes1 == 0 || n_nodes2 == 0) return ORBFE_OK;
+    return run_node_search<4>(h, desc1, angle1, valid1, n1, node_id1, node_off1, node_idx1, n_nodes1, desc2, angle2, occupied2, n2, node_id2, node_off2,
+                              node_idx2, n_nodes2, assigned, nn_ratio, check_orientation, n_matches);
 }
 
 }  // extern "C"

@@ -122,6 +122,20 @@ class ORBMatcher:
         return n.value, assigned[:len(k2)]
 
     # ---- int SearchForTriangulation(keyFrame1, keyFrame2, matches12) — ORBMatcher.cpp:417-522
+    def SearchByBow(self, desc1, angle1, valid1, fv1, desc2, angle2, occupied2, fv2):
+        """ORBMatcher::SearchByBow(KeyFrame, Frame) (ORBMatcher.cpp:118-201).  valid1[i]: key-frame key point i has a good map point;
+        occupied2[j]: frame slot j already holds a map point.  -> (numMatch, assigned[n2]: key-frame index placed in slot j or -1)."""
+        d1 = _c(desc1, np.uint8); d2 = _c(desc2, np.uint8)
+        a1 = _c(angle1, np.float32); a2 = _c(angle2, np.float32); v1 = _c(valid1, np.uint8); o2 = _c(occupied2, np.uint8)
+        f1 = [_c(x, np.int32) for x in fv1]; f2 = [_c(x, np.int32) for x in fv2]
+        asg = np.full(max(len(d2), 1), -1, np.int32)
+        n = C.c_int()
+        _capi.check(self._h, self._lib.orbfe_search_by_bow(self._h, _capi.ptr(d1), _capi.ptr(a1), _capi.ptr(v1), len(d1), _capi.ptr(f1[0]), _capi.ptr(f1[1]),
+                                                           _capi.ptr(f1[2]), len(f1[0]), _capi.ptr(d2), _capi.ptr(a2), _capi.ptr(o2), len(d2), _capi.ptr(f2[0]),
+                                                           _capi.ptr(f2[1]), _capi.ptr(f2[2]), len(f2[0]), _capi.ptr(asg), float(self.nn_ratio),
+                                                           int(self.be_check_orientation), C.byref(n)))
+        return n.value, asg[:len(d2)]
+
     def SearchForTriangulation(self, desc1, angle1, has_mp1, fv1, desc2, angle2, has_mp2, fv2):
         """fv = (node ids ascending, CSR offsets, key-point indices): the DBoW2 FeatureVector of a key frame."""
         d1 = _c(desc1, np.uint8); d2 = _c(desc2, np.uint8)

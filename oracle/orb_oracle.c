@@ -857,6 +857,53 @@ int orc_search_for_triangulation(const uint8_t *desc1, const float *angle1, cons
     return n_match;
 }
 
+int orc_search_by_bow(const uint8_t *desc1, const float *angle1, const uint8_t *valid1, int n1,
+                      const int *node_id1, const int *node_off1, const int *node_idx1, int n_nodes1,
+                      const uint8_t *desc2, const float *angle2, const uint8_t *occupied2, int n2,
+                      const int *node_id2, const int *node_off2, const int *node_idx2, int n_nodes2,
+                      int *assigned, float nn_ratio, int check_orientation) {                          /* ORBMatcher.cpp:118-201 */
+    /* valid1[i]: key frame key point i has a map point that is not bad (:143-144); occupied2[j]: frame->map_points[j] != nullptr;
+       assigned[j] = key-frame index whose map point the call writes into frame->map_points[j], or -1 */
+    int n_match = 0;
+    uint8_t *taken = (uint8_t *) calloc((size_t) (n2 > 0 ? n2 : 1), 1);
+    for (int j = 0; j < n2; ++j) { assigned[j] = -1; taken[j] = occupied2 ? occupied2[j] : 0; }
+    rot_hist rh; memset(&rh, 0, sizeof(rh));
+    int a = 0, b = 0;
+    while (a < n_nodes1 && b < n_nodes2) {
+        if (node_id1[a] == node_id2[b]) {
+            for (int i = node_off1[a]; i < node_off1[a + 1]; ++i) {
+                const int idx1 = node_idx1[i];
+                if (!valid1[idx1]) continue;
+                int best = 256, second = 256, best_idx2 = -1;                                     /* :149 */
+                for (int k = node_off2[b]; k < node_off2[b + 1]; ++k) {
+                    const int idx2 = node_idx2[k];
+                    if (taken[idx2]) continue;                                                    /* :151 */
+                    const int dist = orc_descriptor_distance(desc1 + 32 * (size_t) idx1, desc2 + 32 * (size_t) idx2);
+                    if (dist < best) { second = best; best = dist; best_idx2 = idx2; }
+                    else if (dist < second) second = dist;
+                }
+                if (best <= TH_LOW && (float) best < nn_ratio * (float) second) {                 /* :164 */
+                    taken[best_idx2] = 1; assigned[best_idx2] = idx1; n_match++;
+                    if (check_orientation) rh_push(&rh, rot_bin(angle1[idx1], angle2[best_idx2]), best_idx2);
+                }
+            }
+            ++a; ++b;
+        } else if (node_id1[a] < node_id2[b]) { while (a < n_nodes1 && node_id1[a] < node_id2[b]) ++a; }   /* lower_bound */
+        else { while (b < n_nodes2 && node_id2[b] < node_id1[a]) ++b; }
+    }
+    if (check_orientation) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        orc_compute_three_maxima(rh.n, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == i1 || i == i2 || i == i3) continue;
+            for (int k = 0; k < rh.n[i]; ++k) { assigned[rh.v[i][k]] = -1; n_match--; }
+        }
+    }
+    rh_free(&rh); free(taken);
+    (void) n1;
+    return n_match;
+}
+
 void orc_hamming_allpairs(const uint8_t *q, int nq, const uint8_t *t, int nt,
                           int *best_idx, int *best_dist, int *second_dist) {
     for (int i = 0; i < nq; ++i) {

@@ -65,6 +65,8 @@ def lib():
                                                C.c_int, u8p, i32p, C.c_int]
         L.orc_search_local_points.argtypes = [f32p, f32p, f32p, i32p, u8p, u8p, C.c_int, vp, u8p, C.c_int, C.c_int, C.c_int,
                                               u8p, i32p, C.c_float]
+        L.orc_search_by_bow.argtypes = [u8p, f32p, u8p, C.c_int, i32p, i32p, i32p, C.c_int, u8p, f32p, u8p, C.c_int, i32p, i32p, i32p, C.c_int,
+                                        i32p, C.c_float, C.c_int]
         L.orc_search_for_triangulation.argtypes = [u8p, f32p, u8p, C.c_int, i32p, i32p, i32p, C.c_int,
                                                    u8p, f32p, u8p, C.c_int, i32p, i32p, i32p, C.c_int, i32p, C.c_int]
         L.orc_compute_three_maxima.argtypes = [i32p, C.c_int, i32p, i32p, i32p]
@@ -243,6 +245,19 @@ def search_for_triangulation(desc1, angle1, has_mp1, fv1, desc2, angle2, has_mp2
                                            _p(desc2), _p(angle2), _p(has_mp2), len(desc2), _p(b[0]), _p(b[1]), _p(b[2]), len(b[0]),
                                            _p(m12), int(check_orientation))
     return n, m12[:len(desc1)].copy()
+
+
+def search_by_bow(desc1, angle1, valid1, fv1, desc2, angle2, occupied2, fv2, nn_ratio=0.7, check_orientation=True):
+    """ORBMatcher::SearchByBow (ORBMatcher.cpp:118-201) on flat arrays; fv = (node_ids ascending, offsets, indices)."""
+    desc1 = _c(desc1, np.uint8); desc2 = _c(desc2, np.uint8)
+    angle1 = _c(angle1, np.float32); angle2 = _c(angle2, np.float32)
+    valid1 = _c(valid1, np.uint8); occupied2 = _c(occupied2, np.uint8)
+    a = [_c(x, np.int32) for x in fv1]; b = [_c(x, np.int32) for x in fv2]
+    asg = np.empty(max(len(desc2), 1), np.int32)
+    n = lib().orc_search_by_bow(_p(desc1), _p(angle1), _p(valid1), len(desc1), _p(a[0]), _p(a[1]), _p(a[2]), len(a[0]),
+                                _p(desc2), _p(angle2), _p(occupied2), len(desc2), _p(b[0]), _p(b[1]), _p(b[2]), len(b[0]),
+                                _p(asg), float(nn_ratio), int(check_orientation))
+    return n, asg[:len(desc2)].copy()
 
 
 def compute_three_maxima(counts):

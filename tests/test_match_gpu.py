@@ -120,3 +120,22 @@ def test_search_for_triangulation(ctx, oracle, bits, orient):
     on, om12 = oracle.search_for_triangulation(da, ctx["ka"]["angle"], has1, fv1, db, ctx["kb"]["angle"], has2, fv2, orient)
     assert n == on and n > 20 and np.array_equal(m12, om12)
     assert not (m12 == 0).any()                       # ORBMatcher.cpp:484: index 0 is never accepted (sic)
+
+
+@pytest.mark.parametrize("bits,ratio,orient", [(3, 0.7, True), (5, 0.7, True), (4, 0.9, False), (2, 0.6, True)])
+def test_search_by_bow(ctx, oracle, bits, ratio, orient):
+    """ORBMatcher::SearchByBow (ORBMatcher.cpp:118-201): key-frame key points with a good map point against the frame's free
+    slots of the same vocabulary node, float ratio test, rotation histogram."""
+    rng = np.random.default_rng(100 + bits)
+    da, db = ctx["da"], ctx["db"]
+    valid1 = (rng.random(len(da)) < 0.7).astype(np.uint8); occ2 = (rng.random(len(db)) < 0.2).astype(np.uint8)
+    fv1, fv2 = _feature_vector(da, bits), _feature_vector(db, bits)
+    m = ctx["ORBMatcher"](ratio, orient)
+    n, asg = m.SearchByBow(da, ctx["ka"]["angle"], valid1, fv1, db, ctx["kb"]["angle"], occ2, fv2)
+    on, oasg = oracle.search_by_bow(da, ctx["ka"]["angle"], valid1, fv1, db, ctx["kb"]["angle"], occ2, fv2, ratio, orient)
+    assert n == on and n > 20 and np.array_equal(asg, oasg)
+    assert not (asg[occ2 != 0] >= 0).any() and valid1[asg[asg >= 0]].all()
+    # identical descriptors on both sides: distance-0 ties (second == best == 0 fails the ratio test, :164)
+    n2, asg2 = m.SearchByBow(da, ctx["ka"]["angle"], valid1, fv1, da, ctx["ka"]["angle"], np.zeros(len(da), np.uint8), fv1)
+    on2, oasg2 = oracle.search_by_bow(da, ctx["ka"]["angle"], valid1, fv1, da, ctx["ka"]["angle"], np.zeros(len(da), np.uint8), fv1, ratio, orient)
+    assert n2 == on2 and np.array_equal(asg2, oasg2)
