@@ -38,6 +38,19 @@ namespace mono_orb_slam3 {
         return n;
     }
 
+    int ORBMatcher::SearchByBow(const cv::Mat &desc1, const std::vector<float> &angle1, const std::vector<uint8_t> &validMapPoint1, const FeatureVector &fv1,
+                                const cv::Mat &desc2, const std::vector<float> &angle2, const std::vector<uint8_t> &occupied2, const FeatureVector &fv2,
+                                std::vector<int> &assigned) const {
+        std::vector<int> id1, off1, idx1, id2, off2, idx2;
+        flatten(fv1, id1, off1, idx1); flatten(fv2, id2, off2, idx2);
+        assigned.assign((size_t) desc2.rows, -1);
+        int n = 0;
+        check(orbfe_search_by_bow(handle(), desc1.data, angle1.data(), validMapPoint1.data(), desc1.rows, id1.data(), off1.data(), idx1.data(), (int) id1.size(),
+                                  desc2.data, angle2.data(), occupied2.data(), desc2.rows, id2.data(), off2.data(), idx2.data(), (int) id2.size(),
+                                  assigned.data(), nn_ratio, be_check_orientation ? 1 : 0, &n));
+        return n;
+    }
+
     int ORBMatcher::HammingAllPairs(const cv::Mat &q, const cv::Mat &t, std::vector<int> &bestIdx, std::vector<int> &bestDist, std::vector<int> &secondDist) {
         bestIdx.assign((size_t) q.rows, -1); bestDist.assign((size_t) q.rows, 257); secondDist.assign((size_t) q.rows, 257);
         check(orbfe_hamming_allpairs(handle(), q.data, q.rows, t.data, t.rows, bestIdx.data(), bestDist.data(), secondDist.data()));

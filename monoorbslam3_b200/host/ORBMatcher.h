@@ -78,6 +78,13 @@ namespace mono_orb_slam3 {
                                    const cv::Mat &desc2, const std::vector<float> &angle2, const std::vector<uint8_t> &hasMapPoint2, const FeatureVector &fv2,
                                    std::vector<int> &matches12) const;
 
+        /// Relocalisation / reference-key-frame tracking: SearchByBow(keyFrame, frame) (ORBMatcher.cpp:118-201).
+        /// validMapPoint1[i]: key-frame key point i has a map point that is not bad; occupied2[j]: frame->map_points[j] is set.
+        /// assigned[j] = key-frame key-point index whose map point goes into frame->map_points[j], or -1.
+        int SearchByBow(const cv::Mat &desc1, const std::vector<float> &angle1, const std::vector<uint8_t> &validMapPoint1, const FeatureVector &fv1,
+                        const cv::Mat &desc2, const std::vector<float> &angle2, const std::vector<uint8_t> &occupied2, const FeatureVector &fv2,
+                        std::vector<int> &assigned) const;
+
         /// Offline: brute-force best / second best of every row of `q` against `t`
         static int HammingAllPairs(const cv::Mat &q, const cv::Mat &t, std::vector<int> &bestIdx, std::vector<int> &bestDist, std::vector<int> &secondDist);
 
