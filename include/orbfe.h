@@ -8,6 +8,8 @@
  *   - ORBMatcher::SearchByProjection      modules/ORB/ORBMatcher.h:28-37,   ORBMatcher.cpp:203-415
  *   - ORBMatcher::SearchForTriangulation  modules/ORB/ORBMatcher.h:40-42,   ORBMatcher.cpp:417-522
  *   - ORBMatcher::SearchByBow             modules/ORB/ORBMatcher.h:26,      ORBMatcher.cpp:118-201
+ *   - ORBMatcher::SearchByProjection(KeyFrame, mapPoints) search half   ORBMatcher.h:44-45, ORBMatcher.cpp:524-571
+ *   - MapPoint::computeDescriptor         modules/BasicObject/MapPoint.cpp:103-152
  *   - Frame::Frame post-processing        modules/BasicObject/Frame.cpp:22-51 (size *= uncertainty, undistortKeyPoints, 40-px grid)
  * Plain pointers and sizes only; no C++/torch types cross this boundary.  Every entry point returns an
  * int status (ORBFE_OK or a negative ORBFE_E_*), never throws, and records a message retrievable with
@@ -230,6 +232,21 @@ int orbfe_search_by_bow(orbfe_handle *h,
                         const uint8_t *desc2, const float *angle2, const uint8_t *occupied2, int n2,
                         const int32_t *node_id2, const int32_t *node_off2, const int32_t *node_idx2, int n_nodes2,
                         int32_t *assigned, float nn_ratio, int check_orientation, int *n_matches);
+
+/* Search half of the fuse ORBMatcher::SearchByProjection(KeyFrame, mapPoints, Map*, th) (ORBMatcher.cpp:524-571), SURVEY.md 8f rank 3:
+ * for every map point the adapter projected into the key frame (q_valid, u, v, radius = th * scale[predictLevel], predictLevel) the best
+ * key point within KeyFrame::getFeaturesInArea (strict "< r", KeyFrame.cpp:181-211; levels [predict-1, predict]) that passes the
+ * chi-square gate (:563-564, square_sigmas of the handle's scale table) with dist <= TH_LOW.  best_idx1[i] = -1 if none; best_dist may
+ * be NULL.  The observation / replace bookkeeping of :573-586 is the adapter's. */
+int orbfe_search_fuse(orbfe_handle *h, const float *q_u, const float *q_v, const float *q_radius, const int32_t *q_level,
+                      const uint8_t *q_desc, const uint8_t *q_valid, int nq,
+                      const orbfe_keypoint *kps1, const uint8_t *desc1, int n1, int img_w, int img_h,
+                      int32_t *best_idx1, int32_t *best_dist, int *n_matches);
+
+/* MapPoint::computeDescriptor (BasicObject/MapPoint.cpp:103-152) for a batch of map points: group g owns the descriptor rows
+ * [group_off[g], group_off[g+1]) (its observations in std::map order); best[g] = index within the group of the descriptor with the
+ * least median Hamming distance to the others (first minimum wins), -1 for an empty group.  At most 512 observations per point. */
+int orbfe_compute_descriptors(orbfe_handle *h, const uint8_t *desc, const int32_t *group_off, int n_groups, int32_t *best);
 
 #ifdef __cplusplus
 }

@@ -214,6 +214,97 @@ __global__ void __launch_bounds__(256) k_window(const WinArgs a) {
     if (lane == 0) { a.q_beg[qi] = beg; a.q_end[qi] = beg + total; }
 }
 
+// Search half of the fuse SearchByProjection(KeyFrame, mapPoints) (ORBMatcher.cpp:524-571): the queries are independent (the
+// map-point bookkeeping that makes the reference loop sequential stays on the host), so one warp per projected map point walks
+// KeyFrame::getFeaturesInArea's window (strict "< r", KeyFrame.cpp:204), applies the chi-square gate and keeps the first minimum.
+struct FuseArgs {
+    const float *qx, *qy, *qr; const int *qlevel; const uint8_t *qvalid; const uint4 *qdesc; int nq;
+    const orbfe_keypoint *kps1; const uint4 *desc1; const int *cell_off, *cell_idx; int cols, rows;
+    float sigma2[ORBFE_MAX_LEVELS]; int n_levels;
+    int *best_idx, *best_dist, *n_matches;
+};
+
+__global__ void __launch_bounds__(256) k_fuse(const FuseArgs a) {
+    const int qi = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (qi >= a.nq) return;
+    uint32_t key = 0xffffffffu; int my_idx = -1;
+    if (a.qvalid[qi]) {
+        const float x = a.qx[qi], y = a.qy[qi], r = a.qr[qi];
+        const int min_l = a.qlevel[qi] - 1, max_l = a.qlevel[qi];                         // :553-554
+        const int min_cx = max(0, floor_div_cell(__fsub_rn(x, r))), max_cx = min(a.cols - 1, floor_div_cell(__fadd_rn(x, r)));
+        const int min_cy = max(0, floor_div_cell(__fsub_rn(y, r))), max_cy = min(a.rows - 1, floor_div_cell(__fadd_rn(y, r)));
+        const bool check_level = min_l > 0 || max_l >= 0;
+        const uint4 d0 = __ldg(a.qdesc + 2 * (size_t) qi), d1 = __ldg(a.qdesc + 2 * (size_t) qi + 1);
+        int run = 0;
+        if (min_cx <= max_cx && min_cy <= max_cy)
+            for (int cx = min_cx; cx <= max_cx; ++cx) {
+                const int cb = a.cell_off[cx * a.rows + min_cy], ce = a.cell_off[cx * a.rows + max_cy + 1];
+                for (int k0 = cb; k0 < ce; k0 += 32) {
+                    const int k = k0 + lane;
+                    if (k < ce) {
+                        const int idx = a.cell_idx[k];
+                        const orbfe_keypoint kp = a.kps1[idx];
+                        bool ok = true;
+                        if (check_level) { if (kp.octave < min_l) ok = false; if (max_l >= 0 && kp.octave > max_l) ok = false; }
+                        if (!(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) ok = false;
+                        if (ok) {
+                            const float ex = __fsub_rn(x, kp.x), ey = __fsub_rn(y, kp.y);
+                            const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                            const float s2 = a.sigma2[min(max(kp.octave, 0), a.n_levels - 1)];
+                            if ((double) e2 > __dmul_rn(5.991, (double) s2)) ok = false;                          // :564
+                        }
+                        if (ok) {
+                            const int d = hamming256(d0, d1, __ldg(a.desc1 + 2 * (size_t) idx), __ldg(a.desc1 + 2 * (size_t) idx + 1));
+                            const uint32_t kk = ((uint32_t) d << 22) | (uint32_t) (run + k - k0);                 // position in enumeration order
+                            if (kk < key) { key = kk; my_idx = idx; }
+                        }
+                    }
+                    run += min(32, ce - k0);
+                }
+            }
+    }
+    const uint32_t best = __reduce_min_sync(0xffffffffu, key);
+    const unsigned who = __ballot_sync(0xffffffffu, key == best && key != 0xffffffffu);
+    int idx = -1, dist = TH_LOW + 1;
+    if (who && (int) (best >> 22) < TH_LOW + 1) { idx = __shfl_sync(0xffffffffu, my_idx, __ffs(who) - 1); dist = (int) (best >> 22); }   // :560, 568
+    if (lane == 0) {
+        a.best_idx[qi] = idx; a.best_dist[qi] = dist;
+        if (idx >= 0) atomicAdd(a.n_matches, 1);
+    }
+}
+
+// MapPoint::computeDescriptor (MapPoint.cpp:103-152) for a batch of map points, one warp per map point: row i of the distance
+// matrix goes to shared memory, its median (sorted row [(N-1)/2]) is found by bisection on the value with ballot counts, and the
+// first row with the smallest median wins.
+constexpr int kCdMaxObs = 512;
+__global__ void __launch_bounds__(256) k_compute_descriptors(const uint4 *desc, const int *off, int n_groups, int *best, int *err) {
+    __shared__ int s_row[8][kCdMaxObs];
+    const int g = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (g >= n_groups) return;
+    const int o = off[g], n = off[g + 1] - o;
+    if (n <= 0) { if (lane == 0) best[g] = -1; return; }
+    if (n > kCdMaxObs) { if (lane == 0) { best[g] = -1; atomicExch(err, 7); } return; }
+    const int kth = (n - 1) / 2;
+    int best_median = 256, best_idx = 0;
+    for (int i = 0; i < n; ++i) {
+        const uint4 a0 = __ldg(desc + 2 * (size_t) (o + i)), a1 = __ldg(desc + 2 * (size_t) (o + i) + 1);
+        for (int j = lane; j < n; j += 32)
+            s_row[w][j] = i == j ? 0 : hamming256(a0, a1, __ldg(desc + 2 * (size_t) (o + j)), __ldg(desc + 2 * (size_t) (o + j) + 1));
+        __syncwarp();
+        int lo = 0, hi = 256;                                   // smallest v with #{d <= v} >= kth + 1
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            int c = 0;
+            for (int j = lane; j < n; j += 32) c += s_row[w][j] <= mid;
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (c >= kth + 1) hi = mid; else lo = mid + 1;
+        }
+        if (lo < best_median) { best_median = lo; best_idx = i; }
+        __syncwarp();
+    }
+    if (lane == 0) best[g] = best_idx;
+}
+
 // result / state arrays of the resolves in one launch
 __global__ void k_window_init(int *bin_of, int n_bin, int *m12, int nq, int *m21, int *mdist, int *assigned, int n2, int *nmatch) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -863,6 +954,80 @@ int orbfe_search_local_points(orbfe_handle *h, const float *q_u, const float *q_
     for (int i = 0; i < nq; ++i) { qmin[i] = q_level[i] - 1; qmax[i] = q_level[i]; }                  // ORBMatcher.cpp:367-369
     WindowProblem p{q_u, q_v, q_radius, qmin.data(), qmax.data(), q_valid, q_desc, nullptr, nq, kps2, desc2, n2, img_w, img_h, occupied};
     return run_window_search<2>(h, p, nn_ratio, 0, assigned, nullptr, nullptr, n_matches);
+}
+
+int orbfe_search_fuse(orbfe_handle *h, const float *q_u, const float *q_v, const float *q_radius, const int32_t *q_level, const uint8_t *q_desc,
+                      const uint8_t *q_valid, int nq, const orbfe_keypoint *kps1, const uint8_t *desc1, int n1, int img_w, int img_h,
+                      int32_t *best_idx1, int32_t *best_dist, int *n_matches) {
+    if (!h) return ORBFE_E_ARG;
+    if (!n_matches || nq < 0 || n1 < 0 || (nq && (!q_u || !q_v || !q_radius || !q_level || !q_desc || !q_valid || !best_idx1)) || (n1 && (!kps1 || !desc1)) ||
+        img_w <= 0 || img_h <= 0)
+        return set_error(h, ORBFE_E_ARG, "invalid argument");
+    *n_matches = 0;
+    for (int i = 0; i < nq; ++i) { best_idx1[i] = -1; if (best_dist) best_dist[i] = TH_LOW + 1; }
+    if (nq == 0 || n1 == 0) return ORBFE_OK;
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    int cols, rows; grid_dims(img_w, img_h, cols, rows);
+    const size_t n_off = (size_t) cols * rows + 1;
+    float *qx, *qy, *qr; int *ql, *coff, *cidx, *bi, *bd, *nm; uint8_t *qv; uint4 *qd, *d1; orbfe_keypoint *k1;
+    auto layout = [&](Bump &b) {
+        nm = b.take<int>(4); qx = b.take<float>(nq); qy = b.take<float>(nq); qr = b.take<float>(nq); ql = b.take<int>(nq); qv = b.take<uint8_t>(nq);
+        qd = b.take<uint4>(2 * (size_t) nq); k1 = b.take<orbfe_keypoint>(n1); d1 = b.take<uint4>(2 * (size_t) n1);
+        coff = b.take<int>(n_off); cidx = b.take<int>(n1); bi = b.take<int>(nq); bd = b.take<int>(nq);
+    };
+    Bump probe{nullptr}; layout(probe);
+    int rc = ensure_match_scratch(h, probe.off + 1024);
+    if (rc) return rc;
+    Bump b{(uint8_t *) h->d_match}; layout(b);
+    const int hdr[4] = {0, n1, 0, 0};                            // nm[0] = match counter, nm[1] = key-point count for the grid kernel
+#define UP(dst, src, bytes) ORBFE_CUDA(h, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, st))
+    UP(nm, hdr, sizeof hdr); UP(qx, q_u, sizeof(float) * nq); UP(qy, q_v, sizeof(float) * nq); UP(qr, q_radius, sizeof(float) * nq);
+    UP(ql, q_level, sizeof(int) * nq); UP(qv, q_valid, nq); UP(qd, q_desc, 32 * (size_t) nq);
+    UP(k1, kps1, sizeof(orbfe_keypoint) * (size_t) n1); UP(d1, desc1, 32 * (size_t) n1);
+#undef UP
+    if ((rc = frame_grid_launch(h, k1, nm + 1, n1, img_w, img_h, coff, cidx, st))) return rc;
+    FuseArgs fa; memset(&fa, 0, sizeof fa);
+    fa.qx = qx; fa.qy = qy; fa.qr = qr; fa.qlevel = ql; fa.qvalid = qv; fa.qdesc = qd; fa.nq = nq; fa.kps1 = k1; fa.desc1 = d1;
+    fa.cell_off = coff; fa.cell_idx = cidx; fa.cols = cols; fa.rows = rows; fa.n_levels = h->cfg.n_levels;
+    for (int l = 0; l < h->cfg.n_levels; ++l) fa.sigma2[l] = h->scale[l] * h->scale[l];          // square_sigmas (ORBExtractor.cpp:432-436)
+    fa.best_idx = bi; fa.best_dist = bd; fa.n_matches = nm;
+    k_fuse<<<(nq + 7) / 8, 256, 0, st>>>(fa);
+    h->launches++;
+    ORBFE_CUDA(h, cudaGetLastError());
+    ORBFE_CUDA(h, cudaMemcpyAsync(best_idx1, bi, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
+    if (best_dist) ORBFE_CUDA(h, cudaMemcpyAsync(best_dist, bd, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaMemcpyAsync(n_matches, nm, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaStreamSynchronize(st));
+    return ORBFE_OK;
+}
+
+int orbfe_compute_descriptors(orbfe_handle *h, const uint8_t *desc, const int32_t *group_off, int n_groups, int32_t *best) {
+    if (!h) return ORBFE_E_ARG;
+    if (n_groups < 0 || (n_groups && (!group_off || !best))) return set_error(h, ORBFE_E_ARG, "invalid argument");
+    if (n_groups == 0) return ORBFE_OK;
+    const int total = group_off[n_groups];
+    if (group_off[0] != 0 || total < 0 || (total && !desc)) return set_error(h, ORBFE_E_ARG, "group offsets must start at 0 and be non-decreasing");
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    uint4 *dd; int *doff, *dbest, *derr;
+    auto layout = [&](Bump &b) { dd = b.take<uint4>(2 * (size_t) std::max(total, 1)); doff = b.take<int>(n_groups + 1); dbest = b.take<int>(n_groups); derr = b.take<int>(4); };
+    Bump probe{nullptr}; layout(probe);
+    int rc = ensure_match_scratch(h, probe.off + 1024);
+    if (rc) return rc;
+    Bump b{(uint8_t *) h->d_match}; layout(b);
+    if (total) ORBFE_CUDA(h, cudaMemcpyAsync(dd, desc, 32 * (size_t) total, cudaMemcpyHostToDevice, st));
+    ORBFE_CUDA(h, cudaMemcpyAsync(doff, group_off, sizeof(int) * (n_groups + 1), cudaMemcpyHostToDevice, st));
+    ORBFE_CUDA(h, cudaMemsetAsync(derr, 0, sizeof(int), st));
+    k_compute_descriptors<<<(n_groups + 7) / 8, 256, 0, st>>>(dd, doff, n_groups, dbest, derr);
+    h->launches++;
+    ORBFE_CUDA(h, cudaGetLastError());
+    int e = 0;
+    ORBFE_CUDA(h, cudaMemcpyAsync(best, dbest, sizeof(int) * n_groups, cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaMemcpyAsync(&e, derr, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaStreamSynchronize(st));
+    if (e) return set_error(h, ORBFE_E_ARG, "orbfe_compute_descriptors: a map point has more than %d observations", kCdMaxObs);
+    return ORBFE_OK;
 }
 
 int orbfe_search_for_triangulation(orbfe_handle *h, const uint8_t *desc1, const float *angle1, const uint8_t *has_mp1, int n1, const int32_t *node_id1,

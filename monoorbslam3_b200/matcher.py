@@ -136,6 +136,26 @@ class ORBMatcher:
                                                            int(self.be_check_orientation), C.byref(n)))
         return n.value, asg[:len(d2)]
 
+    def SearchFuse(self, keyframe, q_u, q_v, q_radius, q_level, q_desc, q_valid):
+        """Search half of the fuse SearchByProjection(KeyFrame, mapPoints, Map*, th) (ORBMatcher.cpp:524-571): per projected map point the
+        best key-frame key point (or -1) and its distance.  `keyframe` is a FrameView of the key frame (undistorted key points)."""
+        u = _c(q_u, np.float32); v = _c(q_v, np.float32); r = _c(q_radius, np.float32); lv = _c(q_level, np.int32)
+        qd = _c(q_desc, np.uint8); qv = _c(q_valid, np.uint8)
+        bi = np.full(max(len(u), 1), -1, np.int32); bd = np.zeros(max(len(u), 1), np.int32)
+        n = C.c_int()
+        _capi.check(self._h, self._lib.orbfe_search_fuse(self._h, _capi.ptr(u), _capi.ptr(v), _capi.ptr(r), _capi.ptr(lv), _capi.ptr(qd), _capi.ptr(qv), len(u),
+                                                         _capi.ptr(_c(keyframe.key_points, KP_DTYPE)), _capi.ptr(_c(keyframe.descriptors, np.uint8)), keyframe.num_kps, keyframe.width, keyframe.height,
+                                                         _capi.ptr(bi), _capi.ptr(bd), C.byref(n)))
+        return n.value, bi[:len(u)], bd[:len(u)]
+
+    def compute_descriptors(self, desc, group_off):
+        """MapPoint::computeDescriptor (MapPoint.cpp:103-152) for a batch of map points: index (within each group of observation
+        descriptors) of the descriptor with the least median distance to the rest."""
+        d = _c(desc, np.uint8); off = _c(group_off, np.int32)
+        best = np.full(max(len(off) - 1, 1), -1, np.int32)
+        _capi.check(self._h, self._lib.orbfe_compute_descriptors(self._h, _capi.ptr(d), _capi.ptr(off), len(off) - 1, _capi.ptr(best)))
+        return best[:len(off) - 1]
+
     def SearchForTriangulation(self, desc1, angle1, has_mp1, fv1, desc2, angle2, has_mp2, fv2):
         """fv = (node ids ascending, CSR offsets, key-point indices): the DBoW2 FeatureVector of a key frame."""
         d1 = _c(desc1, np.uint8); d2 = _c(desc2, np.uint8)

@@ -904,6 +904,57 @@ int orc_search_by_bow(const uint8_t *desc1, const float *angle1, const uint8_t *
     return n_match;
 }
 
+/* The search half of the fuse ORBMatcher::SearchByProjection(KeyFrame, mapPoints, Map*, th) (ORBMatcher.cpp:524-592): for every map
+   point the adapter projected into the key frame (u, v, radius = th * scale[predictLevel], level window [predict-1, predict]) the best
+   key point of KeyFrame::getFeaturesInArea (strict "< r", KeyFrame.cpp:181-211) that passes the chi-square gate (:563-564) with
+   dist < TH_LOW + 1 (:560, 568).  best_idx1[i] = -1 if none.  The map-point bookkeeping that follows (:573-586) stays on the host. */
+int orc_search_fuse(const float *q_u, const float *q_v, const float *q_radius, const int *q_level, const uint8_t *q_desc, const uint8_t *q_valid, int nq,
+                    const orc_keypoint *kps1, const uint8_t *desc1, int n1, int img_w, int img_h, const float *square_sigmas,
+                    int *best_idx1, int *best_dist) {
+    orc_grid *g = orc_grid_build(kps1, n1, img_w, img_h);
+    int *cand = (int *) malloc(sizeof(int) * (size_t) (n1 > 0 ? n1 : 1));
+    int n_match = 0;
+    for (int i = 0; i < nq; ++i) {
+        best_idx1[i] = -1; best_dist[i] = TH_LOW + 1;
+        if (!q_valid[i]) continue;
+        const int nc = orc_features_in_area(g, kps1, q_u[i], q_v[i], q_radius[i], q_level[i] - 1, q_level[i], 1, cand, n1);
+        int best = TH_LOW + 1, bi = -1;
+        for (int k = 0; k < nc; ++k) {
+            const orc_keypoint *kp = &kps1[cand[k]];
+            const float e2 = (q_u[i] - kp->x) * (q_u[i] - kp->x) + (q_v[i] - kp->y) * (q_v[i] - kp->y);
+            if ((double) e2 > 5.991 * (double) square_sigmas[kp->octave]) continue;                    /* :564 */
+            const int dist = orc_descriptor_distance(desc1 + 32 * (size_t) cand[k], q_desc + 32 * (size_t) i);
+            if (dist < best) { best = dist; bi = cand[k]; }
+        }
+        best_idx1[i] = bi; best_dist[i] = best;
+        if (bi != -1) n_match++;
+    }
+    free(cand); orc_grid_destroy(g);
+    return n_match;
+}
+
+/* MapPoint::computeDescriptor (BasicObject/MapPoint.cpp:103-152) for a batch of map points: group g owns the descriptor rows
+   [off[g], off[g+1]); best[g] = index within the group of the descriptor with the least median distance to the others
+   (median = sorted row [(N-1)/2], first minimum wins, bestMedian starts at 256); -1 for an empty group. */
+static int cmp_int(const void *a, const void *b) { return *(const int *) a - *(const int *) b; }
+void orc_compute_descriptors(const uint8_t *desc, const int *off, int n_groups, int *best) {
+    for (int g = 0; g < n_groups; ++g) {
+        const int n = off[g + 1] - off[g];
+        best[g] = -1;
+        if (n <= 0) continue;
+        int *row = (int *) malloc(sizeof(int) * (size_t) n);
+        int best_median = 256, best_idx = 0;
+        for (int i = 0; i < n; ++i) {
+            for (int j = 0; j < n; ++j) row[j] = i == j ? 0 : orc_descriptor_distance(desc + 32 * (size_t) (off[g] + i), desc + 32 * (size_t) (off[g] + j));
+            qsort(row, (size_t) n, sizeof(int), cmp_int);
+            const int median = row[(n - 1) / 2];
+            if (median < best_median) { best_median = median; best_idx = i; }
+        }
+        best[g] = best_idx;
+        free(row);
+    }
+}
+
 void orc_hamming_allpairs(const uint8_t *q, int nq, const uint8_t *t, int nt,
                           int *best_idx, int *best_dist, int *second_dist) {
     for (int i = 0; i < nq; ++i) {

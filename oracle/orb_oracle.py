@@ -65,6 +65,8 @@ def lib():
                                                C.c_int, u8p, i32p, C.c_int]
         L.orc_search_local_points.argtypes = [f32p, f32p, f32p, i32p, u8p, u8p, C.c_int, vp, u8p, C.c_int, C.c_int, C.c_int,
                                               u8p, i32p, C.c_float]
+        L.orc_search_fuse.argtypes = [f32p, f32p, f32p, i32p, u8p, u8p, C.c_int, vp, u8p, C.c_int, C.c_int, C.c_int, f32p, i32p, i32p]
+        L.orc_compute_descriptors.argtypes = [u8p, i32p, C.c_int, i32p]
         L.orc_search_by_bow.argtypes = [u8p, f32p, u8p, C.c_int, i32p, i32p, i32p, C.c_int, u8p, f32p, u8p, C.c_int, i32p, i32p, i32p, C.c_int,
                                         i32p, C.c_float, C.c_int]
         L.orc_search_for_triangulation.argtypes = [u8p, f32p, u8p, C.c_int, i32p, i32p, i32p, C.c_int,
@@ -258,6 +260,25 @@ def search_by_bow(desc1, angle1, valid1, fv1, desc2, angle2, occupied2, fv2, nn_
                                 _p(desc2), _p(angle2), _p(occupied2), len(desc2), _p(b[0]), _p(b[1]), _p(b[2]), len(b[0]),
                                 _p(asg), float(nn_ratio), int(check_orientation))
     return n, asg[:len(desc2)].copy()
+
+
+def search_fuse(q_u, q_v, q_radius, q_level, q_desc, q_valid, kps1, desc1, img_w, img_h, square_sigmas):
+    """Search half of the fuse SearchByProjection(KeyFrame, mapPoints) (ORBMatcher.cpp:524-571) -> (numMatch, best_idx1[nq], best_dist[nq])."""
+    q_u = _c(q_u, np.float32); q_v = _c(q_v, np.float32); q_radius = _c(q_radius, np.float32); q_level = _c(q_level, np.int32)
+    q_desc = _c(q_desc, np.uint8); q_valid = _c(q_valid, np.uint8); kps1 = _c(kps1, KP_DTYPE); desc1 = _c(desc1, np.uint8)
+    ss = _c(square_sigmas, np.float32)
+    bi = np.empty(max(len(q_u), 1), np.int32); bd = np.empty(max(len(q_u), 1), np.int32)
+    n = lib().orc_search_fuse(_p(q_u), _p(q_v), _p(q_radius), _p(q_level), _p(q_desc), _p(q_valid), len(q_u), _p(kps1), _p(desc1), len(kps1),
+                              int(img_w), int(img_h), _p(ss), _p(bi), _p(bd))
+    return n, bi[:len(q_u)].copy(), bd[:len(q_u)].copy()
+
+
+def compute_descriptors(desc, off):
+    """MapPoint::computeDescriptor (MapPoint.cpp:103-152) for groups of descriptor rows [off[g], off[g+1]) -> best index within each group."""
+    desc = _c(desc, np.uint8); off = _c(off, np.int32)
+    best = np.empty(max(len(off) - 1, 1), np.int32)
+    lib().orc_compute_descriptors(_p(desc), _p(off), len(off) - 1, _p(best))
+    return best[:len(off) - 1].copy()
 
 
 def compute_three_maxima(counts):

@@ -139,3 +139,39 @@ def test_search_by_bow(ctx, oracle, bits, ratio, orient):
     n2, asg2 = m.SearchByBow(da, ctx["ka"]["angle"], valid1, fv1, da, ctx["ka"]["angle"], np.zeros(len(da), np.uint8), fv1)
     on2, oasg2 = oracle.search_by_bow(da, ctx["ka"]["angle"], valid1, fv1, da, ctx["ka"]["angle"], np.zeros(len(da), np.uint8), fv1, ratio, orient)
     assert n2 == on2 and np.array_equal(asg2, oasg2)
+
+
+@pytest.mark.parametrize("th", [3.0, 6.0])
+def test_search_fuse(ctx, oracle, th):
+    """Search half of the fuse SearchByProjection(KeyFrame, mapPoints) (ORBMatcher.cpp:524-571): strict window, chi-square gate, first minimum."""
+    rng = np.random.default_rng(int(th))
+    ka, da, kb, db = ctx["ka"], ctx["da"], ctx["kb"], ctx["db"]
+    nq = 1500
+    src = rng.integers(0, len(kb), nq)                            # map points observed around frame-b key points, projected into frame a
+    u = (kb["x"][src] + 7 + rng.normal(0, 1.0, nq)).astype(np.float32); v = (kb["y"][src] + 3 + rng.normal(0, 1.0, nq)).astype(np.float32)
+    level = np.clip(kb["octave"][src] + rng.integers(-1, 2, nq), 0, 7).astype(np.int32)
+    sf = np.array([ctx["ex"].getScaleFactor(l) for l in range(8)], np.float32)
+    radius = (np.float32(th) * sf[level]).astype(np.float32)
+    valid = (rng.random(nq) < 0.9).astype(np.uint8)
+    qd = db[src].copy()
+    m = ctx["ORBMatcher"](handle=ctx["ex"]._h)
+    n, bi, bd = m.SearchFuse(ctx["FrameView"](ka, da, ctx["w"], ctx["h"]), u, v, radius, level, qd, valid)
+    on, obi, obd = oracle.search_fuse(u, v, radius, level, qd, valid, ka, da, ctx["w"], ctx["h"], sf * sf)
+    assert n == on and n > 100 and np.array_equal(bi, obi) and np.array_equal(bd, obd)
+    assert (bi[valid == 0] == -1).all()
+
+
+def test_compute_descriptors(ctx, oracle):
+    """MapPoint::computeDescriptor (MapPoint.cpp:103-152): least median distance, first minimum wins; group sizes 0..70."""
+    rng = np.random.default_rng(9)
+    sizes = [1, 2, 3, 0, 7, 32, 33, 70, 5, 2, 2, 40] + rng.integers(1, 25, 300).tolist()
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    base = ctx["da"][rng.integers(0, len(ctx["da"]), len(sizes))]
+    desc = np.repeat(base, sizes, axis=0).copy()
+    noise = (rng.random((len(desc), 32, 8)) < 0.06)
+    desc ^= np.packbits(noise, axis=2).reshape(len(desc), 32)
+    desc[off[4]:off[4] + 3] = desc[off[4]]                        # exact duplicates: median ties, the first row must win
+    m = ctx["ORBMatcher"](handle=ctx["ex"]._h)
+    got = m.compute_descriptors(desc, off)
+    assert np.array_equal(got, oracle.compute_descriptors(desc, off))
+    assert got[3] == -1
