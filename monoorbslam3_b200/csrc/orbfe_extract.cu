@@ -519,6 +519,7 @@ int orbfe_create(const orbfe_config *cfg, orbfe_handle **out) {
 
 void orbfe_destroy(orbfe_handle *h) {
     if (!h) return;
+    if (h->peer) { orbfe_destroy(h->peer); h->peer = nullptr; }
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_arena(h);
@@ -549,7 +550,7 @@ int orbfe_max_keypoints(const orbfe_handle *h) {
     for (int l = 0; l < h->cfg.n_levels; ++l) s += h->quota[l] + 40;
     return s;
 }
-long long orbfe_launch_count(const orbfe_handle *h) { return h ? h->launches : 0; }
+long long orbfe_launch_count(const orbfe_handle *h) { return h ? h->launches + (h->peer ? h->peer->launches : 0) : 0; }
 
 int orbfe_profile(orbfe_handle *h, int enable) {
     if (!h) return ORBFE_E_ARG;
@@ -632,14 +633,41 @@ int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, in
     const bool dense_rows = row_stride == (size_t) width, dense_frames = dense_rows && frame_stride == frame_bytes;
     const bool inplace = width % 16 == 0;
     const LevelGeom &L0 = h->g.lv[0];
-    cudaStream_t sc = h->stream, su = h->s_up, sd = h->s_down;
-    // Chunk schedule.  A pass costs about 0.13 ms + 5.9 us per frame and an upload 6.5 us per frame (measured, 752x480 on PCIe 5),
-    // so the pass chain is the critical path: few, large chunks, with a somewhat shorter first one because its upload overlaps
-    // with nothing.  (Ramping the chunk size up and down was measured and is slower: small passes pay the fixed cost too often.)
+    cudaStream_t su = h->s_up, sd = h->s_down;
+    // Two passes in flight: even chunks run on this handle's arena and stream, odd chunks on the peer's (ORBFE_NO_PEER=1 disables)
+    static const bool no_peer = [] { const char *e = getenv("ORBFE_NO_PEER"); return e && *e == '1'; }();
+    if (!no_peer && n_frames > cn) {
+        if (!h->peer) {
+            orbfe_config pc = h->cfg; pc.max_batch = cn;
+            if ((rc = orbfe_create(&pc, &h->peer))) return set_error(h, rc, "pipeline peer: %s", orbfe_last_error(nullptr));
+        }
+        if ((rc = configure(h->peer, width, height, cn))) return set_error(h, rc, "pipeline peer: %s", orbfe_last_error(h->peer));
+        h->peer->use_tma = h->use_tma;
+    }
+    Handle *const hp[2] = {h, (!no_peer && n_frames > cn) ? (Handle *) h->peer : h};
+    // Chunk schedule.  A pass costs about 0.13 ms + 5.9 us per frame and an upload 6.5 us per frame (measured, 752x480 on PCIe 5):
+    // uploads and passes are balanced, so the call takes about the upload time of the batch plus the first upload and the last pass.
     std::vector<int> sizes;
-    for (int left = n_frames; left > 0;) {
-        const int s = std::min(left, sizes.empty() && n_frames > cn ? std::max(1, 3 * cn / 4) : cn);
-        sizes.push_back(s); left -= s;
+    if (const char *e = getenv("ORBFE_SCHED")) {              // explicit chunk sizes "a,b,c,..." (tuning aid; the rest is filled with cn)
+        int left = n_frames;
+        for (const char *p = e; *p && left > 0;) {
+            const int v = std::min(std::min(atoi(p), cn), left);
+            if (v > 0) { sizes.push_back(v); left -= v; }
+            while (*p && *p != ',') ++p;
+            if (*p == ',') ++p;
+        }
+        while (left > 0) { const int v = std::min(cn, left); sizes.push_back(v); left -= v; }
+    } else {
+        // short chunks at both ends (the first upload and the last pass + download overlap with nothing), full ones in between;
+        // measured on 512 frames with 128-frame chunks: 32,64,128,128,96,64 (two passes in flight) is the best of the variants tried
+        const int head[2] = {std::max(1, cn / 4), std::max(1, cn / 2)}, tail[2] = {std::max(1, 3 * cn / 4), std::max(1, cn / 2)};
+        int left = n_frames;
+        if (n_frames >= 3 * cn) {
+            for (int v : head) { sizes.push_back(v); left -= v; }
+            left -= tail[0] + tail[1];
+        }
+        while (left > 0) { const int v = std::min(cn, left); sizes.push_back(v); left -= v; }
+        if (n_frames >= 3 * cn) for (int v : tail) sizes.push_back(v);
     }
     // ORBFE_TRACE=1: per-chunk completion times of upload / pass / download (ms since the first upload was issued), on stderr
     static const bool trace = [] { const char *e = getenv("ORBFE_TRACE"); return e && *e == '1'; }();
@@ -653,6 +681,8 @@ int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, in
     for (int b0 = 0, nb = 0; b0 < n_frames; b0 += nb, ++c) {
         nb = sizes[(size_t) c];
         const int slot = c & 1;
+        Handle *const hc = hp[slot];
+        cudaStream_t sc = hc->stream;
         const uint8_t *src = frames + (size_t) b0 * frame_stride;
         uint8_t *stage = h->d_stage[slot];
         if (c >= 2) ORBFE_CUDA(h, cudaStreamWaitEvent(su, h->ev_done[slot], 0));      // the pass that read this slot has finished
@@ -668,12 +698,12 @@ int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, in
         orbfe_keypoint *okps = h->d_out_kps + (size_t) slot * cn * cap;
         uint8_t *odesc = h->d_out_desc + (size_t) slot * cn * cap * 32;
         int *on = h->d_out_n + (size_t) slot * cn;
-        if (inplace) rc = run_pass(h, nb, stage, width, frame_bytes, okps, odesc, on, cap, sc);
+        if (inplace) rc = run_pass(hc, nb, stage, width, frame_bytes, okps, odesc, on, cap, sc);
         else {
-            ORBFE_CUDA(h, cudaMemcpy2DAsync(h->d_img + L0.img_off, L0.pitch, stage, width, width, (size_t) height * nb, cudaMemcpyDeviceToDevice, sc));
-            rc = run_pass(h, nb, h->d_img + L0.img_off, L0.pitch, L0.frame_stride, okps, odesc, on, cap, sc);
+            ORBFE_CUDA(h, cudaMemcpy2DAsync(hc->d_img + L0.img_off, L0.pitch, stage, width, width, (size_t) height * nb, cudaMemcpyDeviceToDevice, sc));
+            rc = run_pass(hc, nb, hc->d_img + L0.img_off, L0.pitch, L0.frame_stride, okps, odesc, on, cap, sc);
         }
-        if (rc) return rc;
+        if (rc) return hc == h ? rc : set_error(h, rc, "pipeline peer: %s", orbfe_last_error(static_cast<orbfe_handle *>(hc)));
         ORBFE_CUDA(h, cudaEventRecord(h->ev_done[slot], sc));
         if (trace) cudaEventRecord(tev[2 + 3 * c], sc);
         ORBFE_CUDA(h, cudaStreamWaitEvent(sd, h->ev_done[slot], 0));
@@ -693,7 +723,9 @@ int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, in
         }
         for (auto &e : tev) cudaEventDestroy(e);
     }
-    return check_device_error(h, sc);
+    rc = check_device_error(h, h->stream);
+    if (!rc && hp[1] != h && (rc = check_device_error(hp[1], hp[1]->stream))) return set_error(h, rc, "pipeline peer: %s", orbfe_last_error(static_cast<orbfe_handle *>(hp[1])));
+    return rc;
 }
 
 int orbfe_extract(orbfe_handle *h, const uint8_t *gray, int width, int height, size_t stride, orbfe_keypoint *kps, uint8_t *desc, int cap, int *n_out) {

@@ -97,6 +97,9 @@ struct Handle {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_up[2] = {}, ev_done[2] = {}, ev_down[2] = {};
     int last_batch = 0;              // frames of the last pass (for the stage getters)
+    // Second arena + stream for the pipelined host path: odd chunks run their pass on the peer so that the tail of one pass
+    // (quadtree, descriptors) overlaps with the head of the next (pyramid, FAST).  A complete handle, created lazily.
+    orbfe_handle *peer = nullptr;
     // CUDA graph of the single-frame pass (orbfe_extract): captured once per (arena, output staging), replayed per frame
     cudaGraphExec_t graph1 = nullptr;
     const void *graph1_key[4] = {nullptr, nullptr, nullptr, nullptr};
