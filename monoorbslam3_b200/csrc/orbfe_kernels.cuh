@@ -949,21 +949,23 @@ __global__ void __launch_bounds__(256, 6) k_describe(const __grid_constant__ Lev
     __shared__ __align__(8) uint64_t bars[8][2];
     const int frame = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int out_idx = blockIdx.x * 8 + wid;
-    const int4 *np = reinterpret_cast<const int4 *>(a.nkp + frame * ORBFE_MAX_LEVELS);
-    static_assert(ORBFE_MAX_LEVELS % 4 == 0, "per-level counts are read as int4");
-    int l = 0, k = out_idx, tot = 0;
-    for (int q4 = 0; 4 * q4 < L.n_levels; ++q4) {                      // level of this output slot: prefix sums of the per-level counts
-        const int4 n4 = __ldg(np + q4);
-        const int cnt[4] = {n4.x, n4.y, n4.z, n4.w};
+    // level of this output slot: the block's warps share the frame, so warp 0 turns the per-level counts into prefix sums once
+    // (lane q = level q) and every warp finds its level with one compare + ballot
+    static_assert(ORBFE_MAX_LEVELS <= 32, "one lane per level");
+    __shared__ int s_pre[ORBFE_MAX_LEVELS + 1];
+    if (wid == 0) {
+        const int c = lane < L.n_levels ? __ldg(a.nkp + frame * ORBFE_MAX_LEVELS + lane) : 0;
+        int inc = c;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int q = 4 * q4 + i;
-            if (q < L.n_levels) {
-                if (out_idx >= tot + cnt[i] && q + 1 < L.n_levels) { l = q + 1; k = out_idx - (tot + cnt[i]); }
-                tot += cnt[i];
-            }
-        }
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane < ORBFE_MAX_LEVELS) s_pre[lane] = inc - c;                                      // exclusive prefix: first slot of level `lane`
+        if (lane == 31) s_pre[ORBFE_MAX_LEVELS] = inc;                                           // total
     }
+    __syncthreads();
+    const int tot = s_pre[ORBFE_MAX_LEVELS];
+    const unsigned below = __ballot_sync(0xffffffffu, lane > 0 && lane < L.n_levels && out_idx >= s_pre[min(lane, ORBFE_MAX_LEVELS - 1)]);
+    const int l = __popc(below);                                       // levels whose first slot is <= out_idx (empty levels included), minus level 0
+    const int k = out_idx - s_pre[l];
     if (out_idx == 0 && lane == 0) a.out_n[frame] = tot;            // the first key point of the frame also publishes the total
     if (out_idx >= tot) return;
     if (out_idx >= a.cap) { if (lane == 0) atomicExch(a.err, 6); return; }
