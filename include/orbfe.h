@@ -248,6 +248,23 @@ int orbfe_search_fuse(orbfe_handle *h, const float *q_u, const float *q_v, const
  * least median Hamming distance to the others (first minimum wins), -1 for an empty group.  At most 512 observations per point. */
 int orbfe_compute_descriptors(orbfe_handle *h, const uint8_t *desc, const int32_t *group_off, int n_groups, int32_t *best);
 
+/* ---------------------------------------------------------------- DBoW2 vocabulary descent
+ * Frame::computeBow / KeyFrame::computeBow (BasicObject/Frame.cpp:168-178, KeyFrame.cpp:213-223) call
+ * ORBVocabulary::transform(descriptors, bow_vector, feature_vector, 4) of the vendored DBoW2
+ * (thirdParty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1172, 1217-1259).  The vocabulary is handed over the way loadFromTextFile
+ * (:1338-1420) reads ORBvoc.txt: node i = 1..n_nodes-1 in file order with its parent id, leaf flag, 32-byte descriptor and
+ * weight (index 0 = root, ignored).  orbfe_vocab_transform returns, per feature, the word id, the node reached at level
+ * L - levelsup and the word weight, and (if the fv_* pointers are given) the FeatureVector as CSR in std::map order with
+ * stopped words (weight 0) left out; the BowVector is the adapter's sum of `weight` per `word_id` in feature order followed by
+ * the scoring object's normalisation (:1150-1166). */
+typedef struct orbfe_vocab orbfe_vocab;
+int  orbfe_vocab_create(orbfe_handle *h, int k, int L, int n_nodes, const int32_t *parent, const uint8_t *is_leaf, const uint8_t *desc,
+                        const double *weight, orbfe_vocab **out);
+void orbfe_vocab_destroy(orbfe_vocab *v);
+int  orbfe_vocab_words(const orbfe_vocab *v);
+int  orbfe_vocab_transform(orbfe_vocab *v, const uint8_t *desc, int n, int levelsup, int32_t *word_id, int32_t *node_id, double *weight,
+                           int32_t *fv_node_id, int32_t *fv_off /* n + 1 */, int32_t *fv_idx /* n */, int *fv_n_nodes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,10 @@ SIGNATURES = {
     "orbfe_search_for_initialization": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _f, _i, C.POINTER(_i)]),
     "orbfe_search_by_projection": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, C.POINTER(_i)]),
     "orbfe_search_local_points": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _f, C.POINTER(_i)]),
+    "orbfe_vocab_create": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "orbfe_vocab_destroy": (None, [_vp]),
+    "orbfe_vocab_words": (_i, [_vp]),
+    "orbfe_vocab_transform": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i)]),
     "orbfe_search_fuse": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, C.POINTER(_i)]),
     "orbfe_compute_descriptors": (_i, [_vp, _vp, _vp, _i, _vp]),
     "orbfe_search_by_bow": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _f, _i, C.POINTER(_i)]),
