@@ -265,6 +265,17 @@ int  orbfe_vocab_words(const orbfe_vocab *v);
 int  orbfe_vocab_transform(orbfe_vocab *v, const uint8_t *desc, int n, int levelsup, int32_t *word_id, int32_t *node_id, double *weight,
                            int32_t *fv_node_id, int32_t *fv_off /* n + 1 */, int32_t *fv_idx /* n */, int *fv_n_nodes);
 
+/* ---------------------------------------------------------------- RANSAC hypothesis scoring
+ * TwoViewReconstruction::CheckHomography / CheckFundamental (Frontend/TwoViewReconstruction.cpp:226-288, 290-345) for all
+ * hypotheses of FindHomography / FindFundamental (:86-160) at once.  Matrices are 3x3 row-major floats, n_hyp of them; H12 is the
+ * caller's H21.inverse() (:227); pts1 / pts2 are the matched key points' (x, y) in match order; sigma as in the constructor
+ * (TwoViewReconstruction.h:18-20).  scores[n_hyp] and inliers[n_hyp x n_matches] (may be NULL) are bit-identical to the
+ * reference's float results: same operation order, no FMA, scores summed in match order. */
+int orbfe_check_homography(orbfe_handle *h, const float *H21, const float *H12, int n_hyp, const float *pts1, const float *pts2, int n_matches,
+                           float sigma, float *scores, uint8_t *inliers);
+int orbfe_check_fundamental(orbfe_handle *h, const float *F21, int n_hyp, const float *pts1, const float *pts2, int n_matches,
+                            float sigma, float *scores, uint8_t *inliers);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,8 @@ SIGNATURES = {
     "orbfe_search_for_initialization": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _f, _i, C.POINTER(_i)]),
     "orbfe_search_by_projection": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, C.POINTER(_i)]),
     "orbfe_search_local_points": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _f, C.POINTER(_i)]),
+    "orbfe_check_homography": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _f, _vp, _vp]),
+    "orbfe_check_fundamental": (_i, [_vp, _vp, _i, _vp, _vp, _i, _f, _vp, _vp]),
     "orbfe_vocab_create": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "orbfe_vocab_destroy": (None, [_vp]),
     "orbfe_vocab_words": (_i, [_vp]),
