@@ -179,3 +179,38 @@ def test_full_size_batch_properties(mods):
         sc = np.array([ex.getScaleFactor(int(o)) for o in k["octave"]], np.float32)
         assert (k["x"] >= 19 * sc).all() and (k["x"] <= 752 + sc).all() and (k["angle"] >= 0).all() and (k["angle"] < 360).all()
     ex.close()
+
+
+def test_bench_sized_batch_properties(mods):
+    """Size-independent properties at the bench batch (512 C1 frames, device-resident): replicas of a scene give identical slabs
+    (the pass is a pure function of the frame, T5), every frame equals the single-frame call, key points lie inside the 19-px border
+    of their level, per-level counts stay within quota + 2 (ORBExtractor.cpp:750-808)."""
+    torch = pytest.importorskip("torch")
+    ORBExtractor, synth, KP = mods
+    H, W, NF, B, D = 480, 752, 1000, 512, 16
+    base = synth.frames(D, H, W, 7000, "dense")
+    base[5] = synth.frame(H, W, 7005, "natural")
+    fr = torch.from_numpy(np.concatenate([base] * (B // D))).cuda()
+    cap = NF + 64
+    ex = ORBExtractor(NF, 1.2, 8, 20, 7, max_batch=B)
+    d_kps = torch.zeros((B, cap, 7), dtype=torch.float32, device="cuda"); d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
+    d_n = torch.zeros(B, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ex.extract_batch_device(fr, B, H, W, d_kps, d_desc, cap, d_n, sync=True)
+    n = d_n.cpu().numpy(); kps = d_kps.cpu().numpy().view(KP).reshape(B, cap); desc = d_desc.cpu().numpy()
+    assert (n >= NF).all() and (n <= NF + 16).all()
+    for b in range(D, B):
+        assert n[b] == n[b % D]
+        assert kps[b, :n[b]].tobytes() == kps[b % D, :n[b]].tobytes() and np.array_equal(desc[b, :n[b]], desc[b % D, :n[b]])
+    ex1 = ORBExtractor(NF, 1.2, 8, 20, 7)
+    quota = [ex1.getFeaturesPerLevel(l) for l in range(8)]
+    for b in range(D):
+        k1, d1 = ex1(base[b])
+        assert len(k1) == n[b] and kps[b, :n[b]].tobytes() == k1.tobytes() and np.array_equal(desc[b, :n[b]], d1)
+        for l in range(8):
+            sel = k1[k1["octave"] == l]
+            assert len(sel) <= quota[l] + 2
+            s = np.float32(ex1.getScaleFactor(l)); lw, lh = ex1.level_size(l) if hasattr(ex1, "level_size") else (None, None)
+            x = np.rint(sel["x"] / s); y = np.rint(sel["y"] / s)
+            assert (x >= 19).all() and (y >= 19).all() and (x < lw - 19).all() and (y < lh - 19).all()
+    ex.close(); ex1.close()
