@@ -119,17 +119,20 @@ struct ResizeArgs {
     const int2 *xtab, *ytab;
 };
 
-// A thread owns 4 destination columns (their coefficient-table entries stay in registers) and walks down a run of destination
-// rows, re-using the horizontal interpolation of a source row when consecutive destination rows share it (5 times out of 6 at
-// scale 1.2).  192 threads = 48 column quads x 4 row runs.
-// kPacked (every quad's source span fits 8 bytes, true for scale factors up to 2): a source row costs three aligned word loads,
-// two funnel shifts, and per column one PRMT (byte pair s0, s1) + one DP2A (s0 * a0 + s1 * a1); otherwise bytes are gathered.
+// A thread owns 8 destination columns (two quads; their coefficient-table entries stay in registers) and walks down a run of
+// destination rows, re-using the horizontal interpolation of a source row when consecutive destination rows share it (5 times out
+// of 6 at scale 1.2).  96 threads = 24 column octets x 4 row runs; the per-row bookkeeping (row table entry, loop, reuse test) is
+// paid once per 8 pixels.
+// kPacked (every quad's source span fits 8 bytes, true for scale factors up to 2): a source row costs per quad three aligned word
+// loads, two funnel shifts, and per column one PRMT (byte pair s0, s1) + one DP2A (s0 * a0 + s1 * a1); otherwise bytes are gathered.
 // The horizontal results are kept pre-shifted (H >> 4), the vertical blend is two IMAD.HI with the row weights pre-shifted by 16.
-constexpr int kRsThreads = 192;
+constexpr int kRsQuads = 1;
+constexpr int kRsThreads = (kRsMaxTW / (4 * kRsQuads)) * 4;
 
 template <bool kTMA, bool kPacked>
 __global__ void __launch_bounds__(kRsThreads) k_resize(const __grid_constant__ CUtensorMap tm_src, const ResizeArgs a) {
     constexpr int SP = TilePitch<kTMA>::value;
+    constexpr int NC = 4 * kRsQuads;
     __shared__ __align__(128) uint8_t tile[kRsBoxH * SP + 16];                // + 16: the packed path may read one word past a row
     __shared__ __align__(8) uint64_t bar;
     const int frame = blockIdx.y;
@@ -137,33 +140,40 @@ __global__ void __launch_bounds__(kRsThreads) k_resize(const __grid_constant__ C
     const int dx0 = tx * a.tw, dy0 = ty * a.th;
     const int ox = __ldg(&a.xtab[dx0]).x & 0xffff, oy = __ldg(&a.ytab[dy0]).x & 0xffff;
     const int xo = stage_box<kTMA, kRsThreads>(tile, &bar, &tm_src, a.src + (size_t) frame * a.sframe, a.spitch, a.sh, ox, oy, frame, kRsBoxH);
-    const int qx = threadIdx.x % (kRsMaxTW / 4), grp = threadIdx.x / (kRsMaxTW / 4);
-    const int dxb = dx0 + 4 * qx;
-    if (4 * qx >= a.tw || dxb >= a.dw) return;
-    int c0[4], c1[4];
-    uint32_t wq[4];                                       // a0 | a1 << 16
+    const int qx = threadIdx.x % (kRsMaxTW / NC), grp = threadIdx.x / (kRsMaxTW / NC);
+    const int dxb = dx0 + NC * qx;
+    if (NC * qx >= a.tw || dxb >= a.dw) return;
+    int c0[NC], c1[NC];
+    uint32_t wq[NC];                                      // a0 | a1 << 16
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NC; ++i) {
         const int2 xe = __ldg(&a.xtab[min(dxb + i, a.dw - 1)]);
         c0[i] = (xe.x & 0xffff) - ox + xo; c1[i] = (xe.x >> 16) - ox + xo;
         wq[i] = (uint32_t) xe.y;
     }
-    const int cw = c0[0] >> 2, sh = (c0[0] & 3) * 8;
-    uint32_t sel[4];
+    int cw[kRsQuads], sh[kRsQuads];
+    uint32_t sel[NC];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) sel[i] = (uint32_t) (c0[i] - c0[0]) | ((uint32_t) (c1[i] - c0[0]) << 4);
+    for (int q = 0; q < kRsQuads; ++q) {
+        cw[q] = c0[4 * q] >> 2; sh[q] = (c0[4 * q] & 3) * 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sel[4 * q + i] = (uint32_t) (c0[4 * q + i] - c0[4 * q]) | ((uint32_t) (c1[4 * q + i] - c0[4 * q]) << 4);
+    }
     // horizontal interpolation of one staged source row, >> 4
-    auto hrow = [&](int r, uint32_t (&hs)[4]) {
+    auto hrow = [&](int r, uint32_t (&hs)[NC]) {
         if constexpr (kPacked) {
-            const uint32_t *wp = reinterpret_cast<const uint32_t *>(tile + r * SP) + cw;
-            const uint32_t wa = wp[0], wb = wp[1], wc = wp[2];
-            const uint32_t lo = __funnelshift_r(wa, wb, sh), hi = __funnelshift_r(wb, wc, sh);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) hs[i] = __dp2a_lo(wq[i], __byte_perm(lo, hi, sel[i]), 0u) >> 4;
+            for (int q = 0; q < kRsQuads; ++q) {
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(tile + r * SP) + cw[q];
+                const uint32_t wa = wp[0], wb = wp[1], wc = wp[2];
+                const uint32_t lo = __funnelshift_r(wa, wb, sh[q]), hi = __funnelshift_r(wb, wc, sh[q]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) hs[4 * q + i] = __dp2a_lo(wq[4 * q + i], __byte_perm(lo, hi, sel[4 * q + i]), 0u) >> 4;
+            }
         } else {
             const uint8_t *t = tile + r * SP;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) hs[i] = (t[c0[i]] * (wq[i] & 0xffffu) + t[c1[i]] * (wq[i] >> 16)) >> 4;
+            for (int i = 0; i < NC; ++i) hs[i] = (t[c0[i]] * (wq[i] & 0xffffu) + t[c1[i]] * (wq[i] >> 16)) >> 4;
         }
     };
     const int rows_per = (a.th + 3) >> 2;
@@ -173,28 +183,35 @@ __global__ void __launch_bounds__(kRsThreads) k_resize(const __grid_constant__ C
     uint8_t *dst = a.dst + (size_t) frame * a.dframe + (size_t) (dy0 + ry0) * a.dpitch + dxb;
     const int2 *yt = a.ytab + dy0;
     int prev_r = -1;
-    uint32_t hp[4] = {0, 0, 0, 0};
+    uint32_t hp[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) hp[i] = 0;
     for (int ry = ry0; ry < ry_end; ++ry) {
         const int2 ye = __ldg(&yt[ry]);
         const int r0 = (ye.x & 0xffff) - oy, r1 = (ye.x >> 16) - oy;
         const uint32_t b0 = (uint32_t) ye.y << 16, b1 = (uint32_t) ye.y & 0xffff0000u;        // row weights << 16
-        uint32_t h0[4], h1[4];
+        uint32_t h0[NC], h1[NC];
         if (r0 == prev_r) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) h0[i] = hp[i];
+            for (int i = 0; i < NC; ++i) h0[i] = hp[i];
         } else hrow(r0, h0);
         if (r1 == r0) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) h1[i] = h0[i];
+            for (int i = 0; i < NC; ++i) h1[i] = h0[i];
         } else hrow(r1, h1);
-        uint32_t v[4];
+        uint32_t v[NC];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < NC; ++i) {
             v[i] = (__umulhi(b0, h0[i]) + __umulhi(b1, h1[i]) + 2u) >> 2;           // ((b0 * (H0 >> 4)) >> 16) + ...
             hp[i] = h1[i];
         }
         prev_r = r1;
-        *reinterpret_cast<uint32_t *>(dst) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+        uint32_t out[kRsQuads];
+#pragma unroll
+        for (int q = 0; q < kRsQuads; ++q)          // v <= 255: byte 0 of each
+            out[q] = __byte_perm(__byte_perm(v[4 * q], v[4 * q + 1], 0x0040), __byte_perm(v[4 * q + 2], v[4 * q + 3], 0x0040), 0x5410);
+        if (kRsQuads == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(out[0], out[kRsQuads - 1]);
+        else *reinterpret_cast<uint32_t *>(dst) = out[0];
         dst += a.dpitch;
     }
 }
