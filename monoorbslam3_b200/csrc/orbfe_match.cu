@@ -3,10 +3,13 @@
 //   K8  k_pair_distance      ORBMatcher::DescriptorDistance (ORBMatcher.cpp:17-31) over explicit pairs
 //   K11 k_hamming_allpairs   brute-force best / second-best (BASELINE configs 4/5): train tiles staged with TMA bulk copies
 //                            (cp.async.bulk + mbarrier, double buffered), uint4-packed descriptors, __popc, keyed min / second-min
-//   K9  k_win_count/fill     Frame::getFeaturesInArea windows (Frame.cpp:97-127) + distances, one warp per query
-//   K10 k_resolve_*          the order-preserving greedy resolves of SearchForInitialization (:33-116),
-//                            SearchByProjection (:203-348), SearchByProjection/local points (:350-415),
-//                            SearchForTriangulation (:417-522): one warp walks the queries in reference order
+//   K9  k_window             Frame::getFeaturesInArea windows (Frame.cpp:97-127) + distances, one warp per query (count, reserve, fill)
+//   K10 k_resolve<variant>   the order-preserving greedy resolves of SearchForInitialization (:33-116), SearchByProjection
+//                            (:203-348), SearchByProjection/local points (:350-415), SearchForTriangulation (:417-522) and
+//                            SearchByBow (:118-201): warp 0 walks the queries in reference order on shared-memory state while
+//                            the other warps stage the next batch of candidate lists
+//       k_fuse               search half of the fuse SearchByProjection(KeyFrame, mapPoints) (:524-571), independent queries
+//       k_compute_descriptors  MapPoint::computeDescriptor (MapPoint.cpp:103-152), one warp per map point
 #define ORBFE_HELPERS_ONLY
 #include "orbfe_kernels.cuh"
 
@@ -312,21 +315,6 @@ __global__ void k_window_init(int *bin_of, int n_bin, int *m12, int nq, int *m21
     if (i < nq) m12[i] = -1;
     if (i < n2) { m21[i] = -1; mdist[i] = INT_MAX; assigned[i] = -1; }
     if (i < 4) nmatch[i] = 0;
-}
-
-// exclusive scan of n ints by one CTA; out[n] = total
-__global__ void __launch_bounds__(1024) k_scan(const int *in, int *out, int n) {
-    __shared__ int s_warp[32];
-    int run = 0;
-    for (int base = 0; base < n; base += 1024) {
-        const int i = base + threadIdx.x;
-        const int v = i < n ? in[i] : 0;
-        int tot;
-        const int ex = block_scan_excl<1024>(v, tot, s_warp);
-        if (i < n) out[i] = run + ex;
-        run += tot;
-    }
-    if (threadIdx.x == 0) out[n] = run;
 }
 
 // distances of CSR candidate lists given explicitly (SearchForTriangulation): one warp per query
