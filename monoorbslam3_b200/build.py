@@ -38,7 +38,8 @@ def build_cpp_adapter_test(out=None):
     root = os.path.dirname(HERE)
     out = out or os.path.join(HERE, "lib", "adapter_test")
     srcs = [os.path.join(HERE, "host", "ORBExtractor.cpp"), os.path.join(HERE, "host", "ORBMatcher.cpp"), os.path.join(root, "tests", "cpp", "adapter_test.cpp")]
-    if os.path.exists(out) and all(os.path.getmtime(s) < os.path.getmtime(out) for s in srcs + [LIB]):
+    deps = srcs + [LIB] + [os.path.join(HERE, "host", f) for f in ("ORBExtractor.h", "ORBMatcher.h", "FramePost.h", "cv_compat.h")]
+    if os.path.exists(out) and all(os.path.getmtime(s) < os.path.getmtime(out) for s in deps):
         return out
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", out] + srcs + ["-L" + os.path.dirname(LIB), "-lorbfe", "-Wl,-rpath," + os.path.dirname(LIB)])
     return out

@@ -8,6 +8,7 @@
 #include <vector>
 #include "../../monoorbslam3_b200/host/ORBExtractor.h"
 #include "../../monoorbslam3_b200/host/ORBMatcher.h"
+#include "../../monoorbslam3_b200/host/FramePost.h"
 
 using namespace mono_orb_slam3;
 
@@ -56,6 +57,20 @@ int main(int argc, char **argv) {
     const int n3 = (int) k3.size();
     fwrite(&n3, 4, 1, o);
     fwrite(k3.data(), sizeof(cv::KeyPoint), k3.size(), o);
+    // Frame::Frame post-processing (Frame.cpp:22-51) with the euroc camera: undistorted key points + grid cell sizes
+    CameraParams cam; cam.fx = 458.654f; cam.fy = 457.296f; cam.cx = 367.215f; cam.cy = 248.375f;
+    cam.dist = {-0.28340811f, 0.07395907f, 0.00019359f, 1.76187114e-05f};
+    std::vector<cv::KeyPoint> un; std::vector<std::vector<std::vector<size_t>>> grid;
+    postprocessFrame(cam, w, h, k3, un, grid);
+    fwrite(un.data(), sizeof(cv::KeyPoint), un.size(), o);
+    const int gc = (int) grid.size(), gr = (int) grid[0].size();
+    fwrite(&gc, 4, 1, o); fwrite(&gr, 4, 1, o);
+    for (int cx = 0; cx < gc; ++cx)
+        for (int cy = 0; cy < gr; ++cy) {
+            const int m = (int) grid[cx][cy].size();
+            fwrite(&m, 4, 1, o);
+            for (size_t v : grid[cx][cy]) { const int vi = (int) v; fwrite(&vi, 4, 1, o); }
+        }
     fclose(o);
     printf("adapter ok: %d / %d key points, %d matches, %d (1000-feature extractor)\n", f1->num_kps, f2->num_kps, nm, n3);
     return 0;

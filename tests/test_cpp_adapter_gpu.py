@@ -45,3 +45,13 @@ def test_cpp_adapters_match_python_mirror(tmp_path):
     ppre = np.stack([frames[0][0]["x"], frames[0][0]["y"]], 1).astype(np.float32)
     pn, pm12 = ORBMatcher(0.9, True).SearchForInitialization(f1, f2, ppre, 100)
     assert pn == nm and np.array_equal(pm12, m12) and np.array_equal(ppre, pre)
+    # Frame post-processing through the C++ helper == the Python mirror (which the frame suite pins to cv2 and the oracle)
+    from monoorbslam3_b200 import Camera, frame_postprocess
+    un = take(KP_DTYPE, n3)
+    gc, gr = (int(v) for v in take(np.int32, 2))
+    post = frame_postprocess(ex2, k3, Camera(458.654, 457.296, 367.215, 248.375, [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05]), 752, 480)
+    assert un.tobytes() == post.key_points.tobytes() and (gc, gr) == (post.cols, post.rows)
+    for cx in range(gc):
+        for cy in range(gr):
+            m = int(take(np.int32, 1)[0])
+            assert take(np.int32, m).tolist() == post.cell(cx, cy).tolist()
