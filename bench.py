@@ -332,6 +332,36 @@ def run_ours(args):
         ms_init = (time.perf_counter() - t0) * 1e3 / 20
         init = {"matches": int(n_init), "gpu_ms_per_call": ms_init, "queries": int((ka["octave"] == 0).sum())}
 
+    # ---- tracking-loop matchers on the same frame pair: SearchByProjection (frame -> frame, th 15) and the local-map search (th 2)
+    track = None
+    if rank == 0:
+        rng = np.random.default_rng(0)
+        nq = len(ka)
+        q_u = (ka["x"] - 7 + rng.normal(0, 1.0, nq)).astype(np.float32); q_v = (ka["y"] - 3 + rng.normal(0, 1.0, nq)).astype(np.float32)
+        q_l = ka["octave"].astype(np.int32); q_a = ka["angle"].astype(np.float32); q_ok = (rng.random(nq) < 0.9).astype(np.uint8)
+        occ = np.zeros(len(kb), np.uint8)
+        sfac = np.array([ex2.getScaleFactor(int(l)) for l in q_l], np.float32)
+        r_proj = (np.float32(15) * ka["size"]).astype(np.float32); r_loc = (np.float32(2) * np.float32(4.0) * sfac).astype(np.float32)
+        mt1 = ORBMatcher(0.9, True, handle=ex2._h); mt2 = ORBMatcher(0.8, True, handle=ex2._h)
+
+        def _ms(f, reps):
+            for _ in range(3):
+                f()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                r = f()
+            return (time.perf_counter() - t0) * 1e3 / reps, r
+        g1, (n1_, _) = _ms(lambda: mt1.SearchByProjection(q_u, q_v, r_proj, q_l, q_a, da, q_ok, f2, occ), 20)
+        g2, (n2_, _) = _ms(lambda: mt2.SearchLocalPoints(q_u, q_v, r_loc, q_l, da, q_ok, f2, occ), 20)
+        track = {"queries": int(nq), "search_by_projection_th15": {"gpu_ms_per_call": g1, "matches": int(n1_)},
+                 "search_local_points_th2": {"gpu_ms_per_call": g2, "matches": int(n2_)}}
+        if world == 1 and not args.no_cpu:
+            from oracle import orb_oracle as orc
+            c1, (cn1, _) = _ms(lambda: orc.search_by_projection(q_u, q_v, r_proj, q_l, q_a, da, q_ok, kb, db, W, H, occ, True), 5)
+            c2, (cn2, _) = _ms(lambda: orc.search_local_points(q_u, q_v, r_loc, q_l, da, q_ok, kb, db, W, H, occ, 0.8), 5)
+            track["search_by_projection_th15"].update(cpu_port_ms_per_call=c1, cpu_matches=int(cn1))
+            track["search_local_points_th2"].update(cpu_port_ms_per_call=c2, cpu_matches=int(cn2))
+
     if rank == 0:
         peaks = {}
         try:
@@ -386,6 +416,7 @@ def run_ours(args):
                                    "peak_source": "measured popc micro-benchmark (orbfe_popc_peak), 8 popc per 256-bit match"}},
             "single_frame": {"ms_per_call": ms_single, "frames_per_s": 1e3 / ms_single, "api": "ORBExtractor.__call__ -> orbfe_extract (host image in, host key points out)"},
             "search_for_initialization": init,
+            "tracking_matchers": track,
             "clocks": sampler.summary(),
         }
         if world == 1 and not args.no_cpu:

@@ -386,6 +386,7 @@ struct ResolveArgs {
     float *prematched;               // init: n1 x 2
     float nn_ratio; int check_orientation;
     int n_state;                     // variant 3: key points of frame 2 (n2 carries n1 there)
+    int *dbg;                        // optional: undecided queries after rounds 2 and 8, number of rounds (parallel resolve)
     int *n_matches;
 };
 
@@ -613,10 +614,139 @@ struct WindowProblem {
     const orbfe_keypoint *kps2; const uint8_t *desc2; int n2; int img_w, img_h; const uint8_t *occupied;
 };
 
+// ------------------------------------------------------------------------------------------------
+// Parallel resolve of the searches whose frame-2 slots are exclusive (variants 1, 2, 3, 4: a slot that holds a match is skipped by
+// every later query).  The reference's loop is sequential, but query i's decision only depends on earlier queries through the
+// slots they take, and only its best (and, where a ratio test looks at it, second-best) available slot matters.  Rounds:
+//   1. every undecided query marks all its still-free candidate slots with its index (atomicMin) and finds its best / second-best
+//      free candidate (first minimum in list order, as the sequential loop would);
+//   2. a query is decided when it is the smallest undecided index on its best slot (and on its second-best slot if the variant's
+//      acceptance looks at it): no earlier undecided query can take or change them, and every earlier decided query already has.
+//      It then accepts or rejects exactly as the sequential loop, taking the slot if it accepts.
+// The smallest undecided index is always decided, so the rounds terminate, and by induction over the query index the result is the
+// sequential one (tests compare bit-exactly with the oracle's sequential restatement).  One CTA of 1024 threads, thread per query.
+// ------------------------------------------------------------------------------------------------
+template <int kVariant>
+__global__ void __launch_bounds__(1024) k_resolve_par(const ResolveArgs a) {
+    extern __shared__ __align__(16) uint8_t rp_dyn[];
+    __shared__ int hist[HISTO_LENGTH];
+    __shared__ int s_left, s_nmatch;
+    const int tid = threadIdx.x;
+    const int n2s = kVariant == 3 ? a.n_state : a.n2;
+    int *taken = reinterpret_cast<int *>(rp_dyn);            // -1 free, -2 occupied before the call, else the owner (query / key point)
+    int *minq = taken + n2s;
+    uint32_t *done = reinterpret_cast<uint32_t *>(minq + n2s);   // bit per query
+    const int n_words = (a.nq + 31) / 32;
+    if (tid < HISTO_LENGTH) hist[tid] = 0;
+    if (tid == 0) s_nmatch = 0;
+    for (int j = tid; j < n2s; j += 1024) taken[j] = (kVariant == 3 ? a.has_mp2[j] : a.occupied[j]) ? -2 : -1;
+    for (int w = tid; w < n_words; w += 1024) done[w] = 0;
+    __syncthreads();
+    // queries without candidates (or invalid) are decided from the start
+    for (int qi = tid; qi < a.nq; qi += 1024) {
+        const bool live = (kVariant >= 3 || a.qvalid[qi]) && a.q_end[qi] > a.q_beg[qi];
+        if (!live) atomicOr(&done[qi >> 5], 1u << (qi & 31));
+    }
+    __syncthreads();
+    int round = 0;
+    while (true) {
+        if (tid == 0) s_left = 0;
+        for (int j = tid; j < n2s; j += 1024) minq[j] = INT_MAX;
+        __syncthreads();
+        for (int qi = tid; qi < a.nq; qi += 1024) {
+            if ((done[qi >> 5] >> (qi & 31)) & 1u) continue;
+            for (int k = a.q_beg[qi]; k < a.q_end[qi]; ++k) {
+                const int s = a.c_idx[k];
+                if (taken[s] == -1) atomicMin(&minq[s], qi);
+            }
+        }
+        __syncthreads();
+        for (int qi = tid; qi < a.nq; qi += 1024) {
+            if ((done[qi >> 5] >> (qi & 31)) & 1u) continue;
+            const int beg = a.q_beg[qi], end = a.q_end[qi];
+            uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
+            for (int k = beg; k < end; ++k) {
+                if (taken[a.c_idx[k]] != -1) continue;
+                const uint32_t key = ((uint32_t) a.c_dist[k] << 22) | (uint32_t) (k - beg);
+                k2 = min(k2, max(key, k1));
+                k1 = min(k1, key);
+            }
+            bool decided, accept = false;
+            int best_idx2 = -1;
+            if (k1 == 0xffffffffu) decided = true;                               // nothing free: bestDist stays at its initial value
+            else {
+                const int best = (int) (k1 >> 22);
+                best_idx2 = a.c_idx[beg + (int) (k1 & 0x3fffffu)];
+                const int s2 = k2 == 0xffffffffu ? -1 : a.c_idx[beg + (int) (k2 & 0x3fffffu)];
+                const bool uses_second = kVariant == 2 || kVariant == 4;
+                decided = minq[best_idx2] == qi && (!uses_second || s2 < 0 || minq[s2] == qi);
+                if (decided) {
+                    if (kVariant == 1) accept = best <= TH_HIGH;                                              // :245
+                    else if (kVariant == 2) {
+                        accept = best <= TH_HIGH;
+                        if (accept && s2 >= 0) {
+                            const int second = (int) (k2 >> 22);
+                            if (a.kps2[best_idx2].octave == a.kps2[s2].octave && (float) best > __fmul_rn(a.nn_ratio, (float) second)) accept = false;   // :401-405
+                        }
+                    } else if (kVariant == 3) accept = best < TH_LOW && best_idx2 > 0;                        // :464-484 (sic)
+                    else {
+                        const int second = s2 < 0 ? 256 : (int) (k2 >> 22);
+                        accept = best <= TH_LOW && (float) best < __fmul_rn(a.nn_ratio, (float) second);      // :164
+                    }
+                }
+            }
+            if (!decided) { atomicAdd(&s_left, 1); continue; }
+            atomicOr(&done[qi >> 5], 1u << (qi & 31));
+            if (accept) {
+                const int owner = (kVariant == 3 || kVariant == 4) ? a.q_out_idx[qi] : qi;
+                taken[best_idx2] = kVariant == 3 ? 1 : owner;
+                if (kVariant == 3) a.matches12[owner] = best_idx2;
+                atomicAdd(&s_nmatch, 1);
+                if (a.check_orientation && kVariant != 2) {
+                    const int bn = rot_bin(a.q_angle[qi], a.kps2[best_idx2].angle);
+                    atomicAdd(&hist[bn], 1);
+                    a.bin_of[kVariant == 3 ? owner : best_idx2] = bn;
+                }
+            }
+        }
+        __syncthreads();
+        ++round;
+        if (tid == 0 && a.dbg) { if (round == 2) a.dbg[0] = s_left; if (round == 8) a.dbg[1] = s_left; a.dbg[2] = round; }
+        if (s_left == 0) break;
+        __syncthreads();
+    }
+    // rotation consistency (ORBMatcher.cpp:95-108 and copies), then the slot owners go back to global memory
+    if (a.check_orientation && kVariant != 2) {
+        int i1, i2, i3;
+        three_maxima(hist, i1, i2, i3);
+        const int limit = a.n2;                               // variant 3: n2 carries n1 (bin_of / matches12 per frame-1 key point)
+        for (int i = tid; i < limit; i += 1024) {
+            const int bn = a.bin_of[i];
+            if (bn < 0 || bn == i1 || bn == i2 || bn == i3) continue;
+            if (kVariant == 3) { if (a.matches12[i] >= 0) { a.matches12[i] = -1; atomicSub(&s_nmatch, 1); } }
+            else { taken[i] = -1; atomicSub(&s_nmatch, 1); }
+        }
+    }
+    __syncthreads();
+    if (kVariant != 3) for (int j = tid; j < a.n2; j += 1024) a.assigned[j] = taken[j] < -1 ? -1 : taken[j];
+    if (tid == 0) *a.n_matches = s_nmatch;
+}
+
 template <int kVariant>
 static int launch_resolve(Handle *h, const ResolveArgs &ra, int n2, cudaStream_t st) {
+    static const bool serial = [] { const char *e = getenv("ORBFE_SERIAL_RESOLVE"); return e && *e == '1'; }();      // A/B aid
+    if (n2 >= 65536) return set_error(h, ORBFE_E_ARG, "matcher: %d key points in the searched frame (limit 65535)", n2);
+    if (kVariant != 0 && !serial) {
+        const size_t smem = sizeof(int) * 2 * (size_t) n2 + sizeof(uint32_t) * (((size_t) ra.nq + 31) / 32) + 64;
+        if (smem <= 200 * 1024) {
+            static bool attr_par = false;
+            if (!attr_par) { cudaFuncSetAttribute(k_resolve_par<kVariant>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_par = true; }
+            k_resolve_par<kVariant><<<1, 1024, smem, st>>>(ra);
+            return ORBFE_OK;
+        }
+    }
     const size_t smem = resolve_smem_bytes<kVariant>(n2);
-    if (n2 >= 65536 || smem > 200 * 1024)
+    if (smem > 200 * 1024)
         return set_error(h, ORBFE_E_ARG, "matcher: %d key points in the searched frame exceed the resolve kernel's shared-memory state (limit about %d)", n2,
                          kVariant == 0 ? 13000 : 20000);
     static bool attr_set = false;
@@ -700,14 +830,19 @@ static int run_window_search(Handle *h, const WindowProblem &p, float nn_ratio, 
         ResolveArgs ra; memset(&ra, 0, sizeof ra);
         ra.nq = nq; ra.n2 = n2; ra.q_beg = qbeg; ra.q_end = qend; ra.c_idx = cand_idx; ra.c_dist = cand_dist; ra.qvalid = qvalid; ra.q_angle = qang; ra.kps2 = kps2;
         ra.occupied = occ; ra.matches12 = m12; ra.matches21 = m21; ra.matched_dist = mdist; ra.assigned = assigned; ra.bin_of = binof;
-        ra.prematched = pre; ra.nn_ratio = nn_ratio; ra.check_orientation = check_orientation; ra.n_matches = nmatch;
+        ra.prematched = pre; ra.nn_ratio = nn_ratio; ra.check_orientation = check_orientation; ra.n_matches = nmatch; ra.dbg = trace ? hdr + 1 : nullptr;
         if ((rc = launch_resolve<kVariant>(h, ra, n2, st))) return rc;
         h->launches += 3;
         ORBFE_CUDA(h, cudaGetLastError());
         const double t_issue = us();
         ORBFE_CUDA(h, cudaMemcpyAsync(hp + down_beg, db + down_beg, down_end - down_beg, cudaMemcpyDeviceToHost, st));
         ORBFE_CUDA(h, cudaStreamSynchronize(st));
-        if (trace) fprintf(stderr, "[orbfe trace] window search variant %d: nq %d n2 %d, issued %.1f us, results on host %.1f us\n", kVariant, nq, n2, t_issue, us());
+        if (trace) {
+            int dbg[4] = {0, 0, 0, 0};
+            cudaMemcpy(dbg, hdr, sizeof dbg, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[orbfe trace] window search variant %d: nq %d n2 %d, issued %.1f us, results on host %.1f us; resolve rounds %d (undecided after 2: %d, after 8: %d)\n",
+                    kVariant, nq, n2, t_issue, us(), dbg[3], dbg[1], dbg[2]);
+        }
         const int *nm_h = (const int *) H(nmatch);
         if (nm_h[2]) {                                    // candidate lists did not fit: nm_h[1] is the exact total
             if (attempt) return set_error(h, ORBFE_E_INTERNAL, "candidate count changed between passes");
