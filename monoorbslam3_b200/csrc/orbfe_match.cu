@@ -386,6 +386,8 @@ struct ResolveArgs {
     float *prematched;               // init: n1 x 2
     float nn_ratio; int check_orientation;
     int n_state;                     // variant 3: key points of frame 2 (n2 carries n1 there)
+    const int *n_cand;               // device: total candidate entries in c_idx / c_dist (parallel resolve stages them in shared memory if they fit)
+    int smem_entries;                // capacity of that staging area
     int *dbg;                        // optional: undecided queries after rounds 2 and 8, number of rounds (parallel resolve)
     int *n_matches;
 };
@@ -637,6 +639,13 @@ __global__ void __launch_bounds__(1024) k_resolve_par(const ResolveArgs a) {
     int *minq = taken + n2s;
     uint32_t *done = reinterpret_cast<uint32_t *>(minq + n2s);   // bit per query
     const int n_words = (a.nq + 31) / 32;
+    // candidate lists (dist << 16 | idx) staged once when they fit: the rounds then never touch global memory for them
+    uint32_t *s_pack = done + n_words;
+    const int total = a.n_cand ? *a.n_cand : 0;
+    const bool staged = a.n_cand && total <= a.smem_entries;
+    if (staged) for (int k = tid; k < total; k += 1024) s_pack[k] = ((uint32_t) a.c_dist[k] << 16) | (uint32_t) a.c_idx[k];
+    auto cand_idx = [&](int k) -> int { return staged ? (int) (s_pack[k] & 0xffffu) : a.c_idx[k]; };
+    auto cand_dist = [&](int k) -> int { return staged ? (int) (s_pack[k] >> 16) : a.c_dist[k]; };
     if (tid < HISTO_LENGTH) hist[tid] = 0;
     if (tid == 0) s_nmatch = 0;
     for (int j = tid; j < n2s; j += 1024) taken[j] = (kVariant == 3 ? a.has_mp2[j] : a.occupied[j]) ? -2 : -1;
@@ -656,7 +665,7 @@ __global__ void __launch_bounds__(1024) k_resolve_par(const ResolveArgs a) {
         for (int qi = tid; qi < a.nq; qi += 1024) {
             if ((done[qi >> 5] >> (qi & 31)) & 1u) continue;
             for (int k = a.q_beg[qi]; k < a.q_end[qi]; ++k) {
-                const int s = a.c_idx[k];
+                const int s = cand_idx(k);
                 if (taken[s] == -1) atomicMin(&minq[s], qi);
             }
         }
@@ -666,8 +675,8 @@ __global__ void __launch_bounds__(1024) k_resolve_par(const ResolveArgs a) {
             const int beg = a.q_beg[qi], end = a.q_end[qi];
             uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
             for (int k = beg; k < end; ++k) {
-                if (taken[a.c_idx[k]] != -1) continue;
-                const uint32_t key = ((uint32_t) a.c_dist[k] << 22) | (uint32_t) (k - beg);
+                if (taken[cand_idx(k)] != -1) continue;
+                const uint32_t key = ((uint32_t) cand_dist(k) << 22) | (uint32_t) (k - beg);
                 k2 = min(k2, max(key, k1));
                 k1 = min(k1, key);
             }
@@ -676,8 +685,8 @@ __global__ void __launch_bounds__(1024) k_resolve_par(const ResolveArgs a) {
             if (k1 == 0xffffffffu) decided = true;                               // nothing free: bestDist stays at its initial value
             else {
                 const int best = (int) (k1 >> 22);
-                best_idx2 = a.c_idx[beg + (int) (k1 & 0x3fffffu)];
-                const int s2 = k2 == 0xffffffffu ? -1 : a.c_idx[beg + (int) (k2 & 0x3fffffu)];
+                best_idx2 = cand_idx(beg + (int) (k1 & 0x3fffffu));
+                const int s2 = k2 == 0xffffffffu ? -1 : cand_idx(beg + (int) (k2 & 0x3fffffu));
                 const bool uses_second = kVariant == 2 || kVariant == 4;
                 decided = minq[best_idx2] == qi && (!uses_second || s2 < 0 || minq[s2] == qi);
                 if (decided) {
@@ -737,11 +746,13 @@ static int launch_resolve(Handle *h, const ResolveArgs &ra, int n2, cudaStream_t
     static const bool serial = [] { const char *e = getenv("ORBFE_SERIAL_RESOLVE"); return e && *e == '1'; }();      // A/B aid
     if (n2 >= 65536) return set_error(h, ORBFE_E_ARG, "matcher: %d key points in the searched frame (limit 65535)", n2);
     if (kVariant != 0 && !serial) {
-        const size_t smem = sizeof(int) * 2 * (size_t) n2 + sizeof(uint32_t) * (((size_t) ra.nq + 31) / 32) + 64;
-        if (smem <= 200 * 1024) {
+        const size_t state = sizeof(int) * 2 * (size_t) n2 + sizeof(uint32_t) * (((size_t) ra.nq + 31) / 32) + 64;
+        if (state <= 200 * 1024) {
             static bool attr_par = false;
             if (!attr_par) { cudaFuncSetAttribute(k_resolve_par<kVariant>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_par = true; }
-            k_resolve_par<kVariant><<<1, 1024, smem, st>>>(ra);
+            ResolveArgs rb = ra;
+            rb.smem_entries = (int) ((200 * 1024 - state) / sizeof(uint32_t));
+            k_resolve_par<kVariant><<<1, 1024, 200 * 1024, st>>>(rb);
             return ORBFE_OK;
         }
     }
@@ -830,7 +841,7 @@ static int run_window_search(Handle *h, const WindowProblem &p, float nn_ratio, 
         ResolveArgs ra; memset(&ra, 0, sizeof ra);
         ra.nq = nq; ra.n2 = n2; ra.q_beg = qbeg; ra.q_end = qend; ra.c_idx = cand_idx; ra.c_dist = cand_dist; ra.qvalid = qvalid; ra.q_angle = qang; ra.kps2 = kps2;
         ra.occupied = occ; ra.matches12 = m12; ra.matches21 = m21; ra.matched_dist = mdist; ra.assigned = assigned; ra.bin_of = binof;
-        ra.prematched = pre; ra.nn_ratio = nn_ratio; ra.check_orientation = check_orientation; ra.n_matches = nmatch; ra.dbg = trace ? hdr + 1 : nullptr;
+        ra.prematched = pre; ra.nn_ratio = nn_ratio; ra.check_orientation = check_orientation; ra.n_matches = nmatch; ra.dbg = trace ? hdr + 1 : nullptr; ra.n_cand = nmatch + 1;
         if ((rc = launch_resolve<kVariant>(h, ra, n2, st))) return rc;
         h->launches += 3;
         ORBFE_CUDA(h, cudaGetLastError());
@@ -916,11 +927,12 @@ static int run_node_search(orbfe_handle *h, const uint8_t *desc1, const float *a
     if (flag2) UP(f2, flag2, n2); else ORBFE_CUDA(h, cudaMemsetAsync(f2, 0, n2, st));
 #undef UP
     fill_int(h, m12, -1, n1, st); fill_int(h, asg, -1, n2, st); fill_int(h, binof, -1, n_bin, st);
+    ORBFE_CUDA(h, cudaMemcpyAsync(nm + 1, &total, sizeof(int), cudaMemcpyHostToDevice, st));     // candidate count for the resolve's staging
     k_csr_distance<<<(nq + 7) / 8, 256, 0, st>>>(d1, qi, qo, nq, ci, d2, cd);
     ResolveArgs ra; memset(&ra, 0, sizeof ra);
     ra.nq = nq; ra.q_beg = qo; ra.q_end = qo + 1; ra.c_idx = ci; ra.c_dist = cd; ra.q_angle = qa; ra.kps2 = k2;
     ra.q_out_idx = qi; ra.matches12 = m12; ra.assigned = asg; ra.bin_of = binof; ra.check_orientation = check_orientation; ra.n_matches = nm;
-    ra.nn_ratio = nn_ratio; ra.n_state = n2;
+    ra.nn_ratio = nn_ratio; ra.n_state = n2; ra.n_cand = nm + 1;
     if (kVariant == 3) { ra.n2 = n1 /* bin_of / matches12 are indexed by frame-1 key points */; ra.has_mp2 = f2; }
     else { ra.n2 = n2; ra.occupied = f2; }
     if ((rc = launch_resolve<kVariant>(h, ra, n2, st))) return rc;
