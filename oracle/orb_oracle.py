@@ -140,7 +140,7 @@ class Extractor:
 
     def __call__(self, img):
         img = _c(img, np.uint8)
-        cap = self.n_features + 4 * self.n_levels + 64
+        cap = self.n_features + 64 * self.n_levels + 256        # a level may return more than its quota when its root nodes alone exceed it
         kps = np.zeros(cap, KP_DTYPE)
         desc = np.zeros((cap, 32), np.uint8)
         n = lib().orc_extract(self._h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps), _p(desc), cap)
