@@ -626,7 +626,7 @@ struct WindowProblem {
 //      acceptance looks at it): no earlier undecided query can take or change them, and every earlier decided query already has.
 //      It then accepts or rejects exactly as the sequential loop, taking the slot if it accepts.
 // The smallest undecided index is always decided, so the rounds terminate, and by induction over the query index the result is the
-// sequential one (tests compare bit-exactly with the oracle's sequential restatement).  One CTA of 1024 threads, thread per query.
+// sequential one (the parity tests compare bit-exactly with a sequential CPU restatement of the reference loops).  One CTA of 1024 threads, thread per query.
 // ------------------------------------------------------------------------------------------------
 template <int kVariant>
 __global__ void __launch_bounds__(1024) k_resolve_par(const ResolveArgs a) {
