@@ -20,9 +20,9 @@ constexpr int kFastBoxH   = 36;   // 30 + 2*3
 constexpr int kBlurTileW  = 224;  // outputs per blur tile row (+6 halo +13 alignment slack <= 256)
 constexpr int kBlurTileH  = 32;
 constexpr int kBlurBoxH   = kBlurTileH + 6;
-constexpr int kRsBoxH     = 40;   // source rows staged per resize tile
+constexpr int kRsBoxH     = 80;   // source rows staged per resize tile
 constexpr int kRsMaxTW    = 192;  // destination tile (chosen per level so the source span fits the box)
-constexpr int kRsMaxTH    = 32;
+constexpr int kRsMaxTH    = 64;
 
 // Per-level geometry, passed to kernels inside __grid_constant__ parameter blocks.
 struct LevelGeom {
