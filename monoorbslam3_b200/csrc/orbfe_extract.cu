@@ -130,7 +130,7 @@ static void free_arena(Handle *h) {
     h->d_img = h->d_blur = nullptr; h->d_slots = nullptr; h->d_cell_cnt = h->d_cell_off = nullptr; h->d_cand = nullptr; h->d_cur = nullptr;
     h->d_nodes = nullptr; h->d_lists = nullptr; h->d_kp = nullptr; h->d_nkp = h->d_ncand = nullptr; h->d_tables = nullptr;
     h->d_out_kps = nullptr; h->d_out_desc = nullptr; h->d_out_n = nullptr; h->out_cap = 0; h->out_frames = 0;
-    for (int i = 0; i < 2; ++i) { cudaFree(h->d_stage[i]); h->d_stage[i] = nullptr; }
+    for (int i = 0; i < Handle::kStageSlots; ++i) { cudaFree(h->d_stage[i]); h->d_stage[i] = nullptr; }
     h->stage_bytes = 0;
     h->batch_cap = 0; h->g.w = h->g.h = 0;
 }
@@ -282,12 +282,12 @@ static int ensure_out_staging(Handle *h, int cap) {
     return ORBFE_OK;
 }
 
-// staging of the pipelined host entry point: two dense input slots, two output slots, copy streams and events
+// staging of the pipelined host entry point: kStageSlots dense input slots and output slots, copy streams and events
 static int ensure_pipeline(Handle *h, size_t stage_bytes, int chunk, int cap) {
     if (!h->s_up) {
         ORBFE_CUDA(h, cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
         ORBFE_CUDA(h, cudaStreamCreateWithFlags(&h->s_down, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < Handle::kStageSlots; ++i) {
             ORBFE_CUDA(h, cudaEventCreateWithFlags(&h->ev_up[i], cudaEventDisableTiming));
             ORBFE_CUDA(h, cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
             ORBFE_CUDA(h, cudaEventCreateWithFlags(&h->ev_down[i], cudaEventDisableTiming));
@@ -295,15 +295,15 @@ static int ensure_pipeline(Handle *h, size_t stage_bytes, int chunk, int cap) {
     }
     if (h->stage_bytes < stage_bytes) {
         ORBFE_CUDA(h, cudaDeviceSynchronize());
-        for (int i = 0; i < 2; ++i) { cudaFree(h->d_stage[i]); h->d_stage[i] = nullptr; }
-        for (int i = 0; i < 2; ++i) ORBFE_CUDA(h, cudaMalloc(&h->d_stage[i], stage_bytes + 256));
+        for (int i = 0; i < Handle::kStageSlots; ++i) { cudaFree(h->d_stage[i]); h->d_stage[i] = nullptr; }
+        for (int i = 0; i < Handle::kStageSlots; ++i) ORBFE_CUDA(h, cudaMalloc(&h->d_stage[i], stage_bytes + 256));
         h->stage_bytes = stage_bytes;
     }
-    if (!h->d_out_kps || h->out_cap < cap || h->out_frames < 2 * chunk) {
+    if (!h->d_out_kps || h->out_cap < cap || h->out_frames < Handle::kStageSlots * chunk) {
         ORBFE_CUDA(h, cudaDeviceSynchronize());
         cudaFree(h->d_out_kps); cudaFree(h->d_out_desc); cudaFree(h->d_out_n);
         h->d_out_kps = nullptr; h->d_out_desc = nullptr; h->d_out_n = nullptr;
-        const size_t B = (size_t) std::max(2 * chunk, h->batch_cap);
+        const size_t B = (size_t) std::max(Handle::kStageSlots * chunk, h->batch_cap);
         ORBFE_CUDA(h, cudaMalloc(&h->d_out_kps, B * cap * sizeof(orbfe_keypoint)));
         ORBFE_CUDA(h, cudaMalloc(&h->d_out_desc, B * cap * 32));
         ORBFE_CUDA(h, cudaMalloc(&h->d_out_n, B * sizeof(int)));
@@ -537,7 +537,7 @@ void orbfe_destroy(orbfe_handle *h) {
     if (h->s_aux) { cudaStreamDestroy(h->s_aux); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
     if (h->s_up) cudaStreamDestroy(h->s_up);
     if (h->s_down) cudaStreamDestroy(h->s_down);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < Handle::kStageSlots; ++i) {
         if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
         if (h->ev_down[i]) cudaEventDestroy(h->ev_down[i]);
@@ -665,12 +665,13 @@ int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, in
         while (left > 0) { const int v = std::min(cn, left); sizes.push_back(v); left -= v; }
     } else {
         // short chunks at both ends (the first upload and the last pass + download overlap with nothing), full ones in between;
-        // measured on 512 frames with 128-frame chunks: 32,64,128,128,96,64 (two passes in flight) is the best of the variants tried
-        const int head[2] = {std::max(1, cn / 4), std::max(1, cn / 2)}, tail[2] = {std::max(1, 3 * cn / 4), std::max(1, cn / 2)};
+        // measured on 512 frames with 128-frame chunks: 64,128,128,96,64,32 (two passes in flight, three staging slots) is the
+        // best of the variants tried (tools/e2e_probe.py with ORBFE_SCHED)
+        const int head[1] = {std::max(1, cn / 2)}, tail[3] = {std::max(1, 3 * cn / 4), std::max(1, cn / 2), std::max(1, cn / 4)};
         int left = n_frames;
         if (n_frames >= 3 * cn) {
             for (int v : head) { sizes.push_back(v); left -= v; }
-            left -= tail[0] + tail[1];
+            left -= tail[0] + tail[1] + tail[2];
         }
         while (left > 0) { const int v = std::min(cn, left); sizes.push_back(v); left -= v; }
         if (n_frames >= 3 * cn) for (int v : tail) sizes.push_back(v);
@@ -686,12 +687,12 @@ int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, in
     int c = 0;
     for (int b0 = 0, nb = 0; b0 < n_frames; b0 += nb, ++c) {
         nb = sizes[(size_t) c];
-        const int slot = c & 1;
-        Handle *const hc = hp[slot];
+        const int slot = c % Handle::kStageSlots;              // staging + output slot; the arena / stream alternates with the chunk parity
+        Handle *const hc = hp[c & 1];
         cudaStream_t sc = hc->stream;
         const uint8_t *src = frames + (size_t) b0 * frame_stride;
         uint8_t *stage = h->d_stage[slot];
-        if (c >= 2) ORBFE_CUDA(h, cudaStreamWaitEvent(su, h->ev_done[slot], 0));      // the pass that read this slot has finished
+        if (c >= Handle::kStageSlots) ORBFE_CUDA(h, cudaStreamWaitEvent(su, h->ev_done[slot], 0));      // the pass that read this slot has finished
         if (dense_frames) ORBFE_CUDA(h, cudaMemcpyAsync(stage, src, frame_bytes * nb, cudaMemcpyHostToDevice, su));
         else
             for (int b = 0; b < nb; ++b)
@@ -700,7 +701,7 @@ int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, in
         ORBFE_CUDA(h, cudaEventRecord(h->ev_up[slot], su));
         if (trace) cudaEventRecord(tev[1 + 3 * c], su);
         ORBFE_CUDA(h, cudaStreamWaitEvent(sc, h->ev_up[slot], 0));
-        if (c >= 2) ORBFE_CUDA(h, cudaStreamWaitEvent(sc, h->ev_down[slot], 0));      // the output slot has been downloaded
+        if (c >= Handle::kStageSlots) ORBFE_CUDA(h, cudaStreamWaitEvent(sc, h->ev_down[slot], 0));      // the output slot has been downloaded
         orbfe_keypoint *okps = h->d_out_kps + (size_t) slot * cn * cap;
         uint8_t *odesc = h->d_out_desc + (size_t) slot * cn * cap * 32;
         int *on = h->d_out_n + (size_t) slot * cn;

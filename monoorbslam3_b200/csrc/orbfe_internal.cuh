@@ -92,10 +92,11 @@ struct Handle {
     // staging for the host entry points
     orbfe_keypoint *d_out_kps = nullptr; uint8_t *d_out_desc = nullptr; int *d_out_n = nullptr; int out_cap = 0;
     int out_frames = 0;              // frames the output staging holds
-    uint8_t *d_stage[2] = {nullptr, nullptr}; size_t stage_bytes = 0;          // dense H2D staging of the pipelined host path
+    static constexpr int kStageSlots = 3;   // staging / output slots of the host pipeline (uploads run up to two chunks ahead of the passes)
+    uint8_t *d_stage[kStageSlots] = {}; size_t stage_bytes = 0;          // dense H2D staging of the pipelined host path
     cudaStream_t s_up = nullptr, s_down = nullptr, s_aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    cudaEvent_t ev_up[2] = {}, ev_done[2] = {}, ev_down[2] = {};
+    cudaEvent_t ev_up[kStageSlots] = {}, ev_done[kStageSlots] = {}, ev_down[kStageSlots] = {};
     int last_batch = 0;              // frames of the last pass (for the stage getters)
     // Second arena + stream for the pipelined host path: odd chunks run their pass on the peer so that the tail of one pass
     // (quadtree, descriptors) overlaps with the head of the next (pyramid, FAST).  A complete handle, created lazily.
