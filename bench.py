@@ -332,6 +332,29 @@ def run_ours(args):
         ms_init = (time.perf_counter() - t0) * 1e3 / 20
         init = {"matches": int(n_init), "gpu_ms_per_call": ms_init, "queries": int((ka["octave"] == 0).sum())}
 
+    # ---- the other single-GPU BASELINE configs, frames resident in HBM (reported next to the headline, not the headline)
+    other = None
+    if rank == 0:
+        other = {}
+        for name, (ow, oh, onf, ob) in {"C2: 1241x376, 2000 features (kitti-shaped)": (1241, 376, 2000, 256),
+                                         "C3: 1920x1080, 4000 features (phone-shaped)": (1920, 1080, 4000, 128)}.items():
+            ob_frames = torch.from_numpy(synth.frames(8, oh, ow, 1000, "dense")).to(dev)[torch.arange(ob, device=dev) % 8].contiguous()
+            oex = ORBExtractor(device=local, max_batch=ob, **dict(ORB, nFeatures=onf))
+            ocap = onf + 128
+            okps = torch.zeros((ob, ocap, 7), dtype=torch.float32, device=dev); odesc = torch.zeros((ob, ocap, 32), dtype=torch.uint8, device=dev)
+            on_ = torch.zeros(ob, dtype=torch.int32, device=dev)
+            for _ in range(3):
+                oex.extract_batch_device(ob_frames, ob, oh, ow, okps, odesc, ocap, on_, stream=stream, sync=False)
+            torch.cuda.synchronize()
+            o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            o0.record()
+            for _ in range(5):
+                oex.extract_batch_device(ob_frames, ob, oh, ow, okps, odesc, ocap, on_, stream=stream, sync=False)
+            o1.record(); torch.cuda.synchronize()
+            oms = o0.elapsed_time(o1) / 5
+            other[name] = {"frames_per_s": ob / oms * 1e3, "ms_per_pass": oms, "frames_per_pass": ob, "mean_keypoints_per_frame": float(on_.float().mean().item())}
+            oex.close(); del ob_frames, okps, odesc, on_
+
     # ---- tracking-loop matchers on the same frame pair: SearchByProjection (frame -> frame, th 15) and the local-map search (th 2)
     track = None
     if rank == 0:
@@ -417,6 +440,7 @@ def run_ours(args):
             "single_frame": {"ms_per_call": ms_single, "frames_per_s": 1e3 / ms_single, "api": "ORBExtractor.__call__ -> orbfe_extract (host image in, host key points out)"},
             "search_for_initialization": init,
             "tracking_matchers": track,
+            "other_configs": other,
             "clocks": sampler.summary(),
         }
         if world == 1 and not args.no_cpu:
