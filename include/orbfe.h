@@ -138,7 +138,8 @@ int orbfe_profile_read(orbfe_handle *h, float *stage_ms, int *n_passes, int rese
  *                                                         skipped when dist[0] == 0; Fisheye.cpp:114-117 = plain copy
  *   grid[x/40][y/40].push_back(i) if PosInGrid(kp)        Frame.cpp:31-51, 90-95
  * The grid comes back as CSR: cell = cx * rows + cy (the reference's grid[cx][cy]), grid_off[cols*rows + 1], grid_idx in
- * (cell, insertion) order — exactly the order Frame::getFeaturesInArea (Frame.cpp:97-127) enumerates. */
+ * (cell, insertion) order — exactly the order Frame::getFeaturesInArea (Frame.cpp:97-127) enumerates.
+ * Limits: at most 16384 key points per frame (the reference's extractors return 1000-8000). */
 #define ORBFE_CAMERA_PINHOLE 0   /* DistortionModel "radtan"      (Camera.cpp:43-44) */
 #define ORBFE_CAMERA_FISHEYE 1   /* DistortionModel "equidistant" (Camera.cpp:45-46) */
 typedef struct orbfe_camera {
@@ -167,6 +168,8 @@ int orbfe_frame_postprocess_device(orbfe_handle *h, const orbfe_camera *cam, orb
 
 /* ---------------------------------------------------------------- matcher
  * All descriptor arrays are n x 32 bytes, row-major (cv::Mat N x 32 CV_8U as produced by the extractor).
+ * Limits of the window / node searches: fewer than 65536 key points in the searched frame (the greedy state of a search lives in
+ * the shared memory of one CTA); SearchForInitialization about 13000.  Larger inputs return ORBFE_E_ARG, never a wrong result.
  */
 
 /* Measured popc throughput of the device (10^9 32-bit popc per second; 8 popc = one 256-bit match): the roofline
