@@ -410,15 +410,23 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
     oa.nodes = h->d_nodes; oa.lists = h->d_lists; oa.kp = h->d_kp; oa.nkp = h->d_nkp; oa.ncand = h->d_ncand; oa.err = h->d_err;
     oa.cells_per_frame = g.cells_per_frame; oa.cand_per_frame = g.cand_per_frame; oa.nodes_per_frame = g.nodes_per_frame;
     oa.lists_per_frame = g.lists_per_frame; oa.kp_per_frame = g.kp_per_frame;
-    oa.sort_cap = g.sort_cap; oa.smem_node_cap = (g.oct_smem_bytes - g.sort_cap * 8) / 16;
-    // few frames: one CTA per (level, frame) leaves most SMs idle and the level-0 CTA is the critical path -> 1024 threads per CTA
-    // one CTA per (level, frame).  Few frames: the level-0 CTA is the critical path and most SMs are idle -> 1024 threads;
-    // batches: 512 threads (measured 0.286 ms vs 0.312 ms with 256 and 0.53 ms with 1024 per 512 C1 frames).  ORBFE_OCT_NT overrides.
+    // one CTA per (level, frame).  Few frames: the level-0 CTA is the critical path and most SMs are idle -> 1024 threads and a node
+    // pool of up to 200 KB in shared memory (1 CTA per SM; measured 0.161 -> 0.129 ms for one 1920x1080 / 4000-feature frame);
+    // batches: 512 threads and the 100 KB budget (measured 0.286 ms vs 0.312 ms with 256 and 0.53 ms with 1024 threads per 512 C1
+    // frames; the large pool would cost occupancy there).  ORBFE_OCT_NT overrides the thread count.
     static const int oct_nt = [] { const char *e = getenv("ORBFE_OCT_NT"); return e ? atoi(e) : 0; }();
-    const int nt = oct_nt ? oct_nt : (nl * nb <= h->sm_count ? 1024 : 512);
-    if (nt == 1024) k_octree<1024><<<dim3(nl, nb), 1024, g.oct_smem_bytes, st>>>(LS, oa);
-    else if (nt == 512) k_octree<512><<<dim3(nl, nb), 512, g.oct_smem_bytes, st>>>(LS, oa);
-    else k_octree<256><<<dim3(nl, nb), 256, g.oct_smem_bytes, st>>>(LS, oa);
+    const bool few = nl * nb <= h->sm_count;
+    const int nt = oct_nt ? oct_nt : (few ? 1024 : 512);
+    int oct_smem = g.oct_smem_bytes;
+    if (few) {
+        int max_node_cap = 1;
+        for (int l = 0; l < nl; ++l) max_node_cap = std::max(max_node_cap, g.lv[l].node_cap);
+        oct_smem = std::max(oct_smem, std::min(200 * 1024, g.sort_cap * 8 + max_node_cap * 16));
+    }
+    oa.sort_cap = g.sort_cap; oa.smem_node_cap = (oct_smem - g.sort_cap * 8) / 16;
+    if (nt == 1024) k_octree<1024><<<dim3(nl, nb), 1024, oct_smem, st>>>(LS, oa);
+    else if (nt == 512) k_octree<512><<<dim3(nl, nb), 512, oct_smem, st>>>(LS, oa);
+    else k_octree<256><<<dim3(nl, nb), 256, oct_smem, st>>>(LS, oa);
     ORBFE_AFTER_LAUNCH(h, st, "k_octree");
     ORBFE_PROF_MARK(h, st, 3);
     // K6 blur (launched above on the auxiliary stream unless profiling / debugging serialises the stages)
@@ -516,9 +524,9 @@ int orbfe_create(const orbfe_config *cfg, orbfe_handle **out) {
             orbfe_destroy(h); return ORBFE_E_CUDA;
         }
     }
-    cudaFuncSetAttribute(k_octree<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(k_octree<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(k_octree<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_octree<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_octree<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_octree<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     *out = h;
     return ORBFE_OK;
 }
