@@ -760,17 +760,29 @@ int orbfe_extract(orbfe_handle *h, const uint8_t *gray, int width, int height, s
     if ((rc = ensure_out_staging(h, dcap))) return rc;
     // pinned mirror of the outputs: [n, err][kps dcap][desc dcap]; one download + one synchronisation per frame
     const size_t kp_bytes = sizeof(orbfe_keypoint) * (size_t) dcap, desc_bytes = (size_t) dcap * 32;
-    if (h->pinned_bytes < 16 + kp_bytes + desc_bytes) {
+    // ... followed by a pinned copy of a small input frame: the driver's pageable 2-D upload costs 0.1 ms more than a host
+    // memcpy into pinned memory plus one DMA when the rows are not 16-byte multiples (1241x376: 0.37 -> 0.26 ms per call);
+    // above 512 KB the driver's pipelined staging wins (1920x1080: 0.47 vs 0.54 ms) and is kept
+    static const bool pageable_upload = [] { const char *e = getenv("ORBFE_PAGEABLE_UPLOAD"); return e && *e == '1'; }();
+    const bool stage_in = !pageable_upload && (size_t) width * height <= 512 * 1024;
+    const size_t in_bytes = stage_in ? (size_t) width * height : 0;
+    if (h->pinned_bytes < 16 + kp_bytes + desc_bytes + in_bytes) {
         if (h->h_pinned) cudaFreeHost(h->h_pinned);
         h->h_pinned = nullptr; h->pinned_bytes = 0;
-        ORBFE_CUDA(h, cudaMallocHost(&h->h_pinned, 16 + kp_bytes + desc_bytes));
-        h->pinned_bytes = 16 + kp_bytes + desc_bytes;
+        ORBFE_CUDA(h, cudaMallocHost(&h->h_pinned, 16 + kp_bytes + desc_bytes + in_bytes));
+        h->pinned_bytes = 16 + kp_bytes + desc_bytes + in_bytes;
     }
     int *p_n = (int *) h->h_pinned;
-    uint8_t *p_kps = (uint8_t *) h->h_pinned + 16, *p_desc = p_kps + kp_bytes;
+    uint8_t *p_kps = (uint8_t *) h->h_pinned + 16, *p_desc = p_kps + kp_bytes, *p_in = p_desc + desc_bytes;
     cudaStream_t st = h->stream;
     const LevelGeom &L0 = h->g.lv[0];
-    ORBFE_CUDA(h, cudaMemcpy2DAsync(h->d_img + L0.img_off, L0.pitch, gray, stride, width, height, cudaMemcpyHostToDevice, st));
+    if (stage_in) {
+        if (stride == (size_t) width) memcpy(p_in, gray, in_bytes);
+        else for (int y = 0; y < height; ++y) memcpy(p_in + (size_t) y * width, gray + (size_t) y * stride, width);
+        ORBFE_CUDA(h, cudaMemcpy2DAsync(h->d_img + L0.img_off, L0.pitch, p_in, width, width, height, cudaMemcpyHostToDevice, st));
+    } else {
+        ORBFE_CUDA(h, cudaMemcpy2DAsync(h->d_img + L0.img_off, L0.pitch, gray, stride, width, height, cudaMemcpyHostToDevice, st));
+    }
     const double t_up = us();
     // the 13 launches of a one-frame pass are replayed from a CUDA graph (their host-side issue time and the gaps between the
     // short kernels are a third of the frame's latency); stage profiling and ORBFE_DEBUG_SYNC use the plain launches
