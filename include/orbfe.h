@@ -189,6 +189,14 @@ int orbfe_hamming_allpairs_device(orbfe_handle *h, const uint8_t *d_q, int nq, c
                                   int32_t *d_best_idx, int32_t *d_best_dist, int32_t *d_second_dist,
                                   void *stream, int sync);
 
+/* Best / second-best over caller-supplied candidate lists (SURVEY.md section 8b `orbfe_hamming_window`): the candidates of
+ * query i are t[cand_idx[cand_offsets[i] .. cand_offsets[i+1])], scanned in list order like the `if (dist < bestDist)` loops of
+ * ORBMatcher.cpp:60-72 / :237-248 (first minimum wins).  best_idx is the train index of the minimum (-1 and 257 for an
+ * empty list), second_dist the second-smallest distance of the list (257 if fewer than two).  Host memory. */
+int orbfe_hamming_window(orbfe_handle *h, const uint8_t *q, int nq, const uint8_t *t, int nt,
+                         const int32_t *cand_offsets, const int32_t *cand_idx,
+                         int32_t *best_idx, int32_t *best_dist, int32_t *second_dist);
+
 /* ORBMatcher::SearchForInitialization (ORBMatcher.cpp:33-116).  kps are the Frames' (undistorted) key points,
  * prematched_xy (n1 x 2, in/out) is vecPreMatched, matches12 (n1, out) the result; returns the match count in
  * *n_matches.  The candidate windows follow Frame::getFeaturesInArea on the 40-px grid (Frame.cpp:97-127). */

@@ -150,6 +150,40 @@ __global__ void __launch_bounds__(256) k_hamming_allpairs(const uint4 *__restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// K10 caller-supplied candidate lists (CSR): 8 lanes per query, lane l takes positions l, l+8, ... of the query's list.
+// key = dist << 22 | position in the list, so the first minimum of the sequential `if (d < best)` scan wins.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_hamming_window(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, const int *__restrict__ off,
+                                                        const int *__restrict__ idx, int *best_idx, int *best_dist, int *second_dist) {
+    const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, sub = threadIdx.x & 7;
+    const bool live = qi < nq;
+    uint32_t k1 = kApNone, k2 = kApNone;
+    int beg = 0;
+    if (live) {
+        const uint4 a0 = __ldg(q + 2 * (size_t) qi), a1 = __ldg(q + 2 * (size_t) qi + 1);
+        beg = __ldg(off + qi);
+        const int n = __ldg(off + qi + 1) - beg;
+        for (int j = sub; j < n; j += 8) {
+            const int ti = __ldg(idx + beg + j);
+            const uint32_t key = ((uint32_t) hamming256(a0, a1, __ldg(t + 2 * (size_t) ti), __ldg(t + 2 * (size_t) ti + 1)) << 22) | (uint32_t) j;
+            k2 = min(k2, max(key, k1));
+            k1 = min(k1, key);
+        }
+    }
+#pragma unroll
+    for (int m = 1; m < 8; m <<= 1) {
+        const uint32_t b1 = __shfl_xor_sync(0xffffffffu, k1, m), b2 = __shfl_xor_sync(0xffffffffu, k2, m);
+        const uint32_t n2 = min(max(k1, b1), min(k2, b2));
+        k1 = min(k1, b1); k2 = n2;
+    }
+    if (live && sub == 0) {
+        const int d1 = (int) (k1 >> 22);
+        best_idx[qi] = d1 >= 257 ? -1 : __ldg(idx + beg + (int) (k1 & 0x3fffffu));
+        best_dist[qi] = d1; second_dist[qi] = (int) (k2 >> 22);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K9 windows.  Grid of frame 2 as CSR (cell = cx*rows + cy, members in key-point index order) built by the host mirror of
 // Frame::Frame (Frame.cpp:32-51).  One warp per query; candidates come out in (cx, cy, insertion) order.
 // ------------------------------------------------------------------------------------------------
@@ -1035,6 +1069,42 @@ int orbfe_hamming_allpairs(orbfe_handle *h, const uint8_t *q, int nq, const uint
     ORBFE_CUDA(h, cudaMemcpyAsync(best_idx, bi, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
     ORBFE_CUDA(h, cudaMemcpyAsync(best_dist, bd, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
     ORBFE_CUDA(h, cudaMemcpyAsync(second_dist, sd, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaStreamSynchronize(st));
+    return ORBFE_OK;
+}
+
+int orbfe_hamming_window(orbfe_handle *h, const uint8_t *q, int nq, const uint8_t *t, int nt, const int32_t *cand_offsets, const int32_t *cand_idx,
+                         int32_t *best_idx, int32_t *best_dist, int32_t *second_dist) {
+    if (!h) return ORBFE_E_ARG;
+    if (nq < 0 || nt < 0 || (nq && (!q || !cand_offsets || !best_idx || !best_dist || !second_dist)) || (nt && !t)) return set_error(h, ORBFE_E_ARG, "invalid argument");
+    if (nq == 0) return ORBFE_OK;
+    const int total = cand_offsets[nq];
+    if (cand_offsets[0] != 0 || total < 0 || (total && !cand_idx)) return set_error(h, ORBFE_E_ARG, "cand_offsets must start at 0 and be non-decreasing");
+    for (int i = 0; i < nq; ++i) {
+        if (cand_offsets[i + 1] < cand_offsets[i]) return set_error(h, ORBFE_E_ARG, "cand_offsets must start at 0 and be non-decreasing");
+        if (cand_offsets[i + 1] - cand_offsets[i] >= (1 << 22)) return set_error(h, ORBFE_E_ARG, "query %d has 2^22 or more candidates", i);
+    }
+    for (int i = 0; i < total; ++i) if (cand_idx[i] < 0 || cand_idx[i] >= nt) return set_error(h, ORBFE_E_ARG, "candidate %d out of range", i);
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    Bump probe{nullptr};
+    probe.take<uint4>(2 * (size_t) nq); probe.take<uint4>(2 * (size_t) std::max(nt, 1)); probe.take<int>(nq + 1); probe.take<int>(std::max(total, 1));
+    probe.take<int>(3 * (size_t) nq);
+    int rc = ensure_match_scratch(h, probe.off + 1024);
+    if (rc) return rc;
+    Bump bp{(uint8_t *) h->d_match};
+    uint4 *dq = bp.take<uint4>(2 * (size_t) nq), *dt = bp.take<uint4>(2 * (size_t) std::max(nt, 1));
+    int *doff = bp.take<int>(nq + 1), *didx = bp.take<int>(std::max(total, 1)), *res = bp.take<int>(3 * (size_t) nq);
+    ORBFE_CUDA(h, cudaMemcpyAsync(dq, q, 32 * (size_t) nq, cudaMemcpyHostToDevice, st));
+    if (nt) ORBFE_CUDA(h, cudaMemcpyAsync(dt, t, 32 * (size_t) nt, cudaMemcpyHostToDevice, st));
+    ORBFE_CUDA(h, cudaMemcpyAsync(doff, cand_offsets, sizeof(int) * ((size_t) nq + 1), cudaMemcpyHostToDevice, st));
+    if (total) ORBFE_CUDA(h, cudaMemcpyAsync(didx, cand_idx, sizeof(int) * (size_t) total, cudaMemcpyHostToDevice, st));
+    k_hamming_window<<<(nq * 8 + 255) / 256, 256, 0, st>>>(dq, nq, dt, doff, didx, res, res + nq, res + 2 * (size_t) nq);
+    h->launches++;
+    ORBFE_CUDA(h, cudaGetLastError());
+    ORBFE_CUDA(h, cudaMemcpyAsync(best_idx, res, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaMemcpyAsync(best_dist, res + nq, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
+    ORBFE_CUDA(h, cudaMemcpyAsync(second_dist, res + 2 * (size_t) nq, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
     ORBFE_CUDA(h, cudaStreamSynchronize(st));
     return ORBFE_OK;
 }

@@ -78,6 +78,19 @@ class ORBMatcher:
                                                               _capi.ptr(sd)))
         return bi, bd, sd
 
+    # ---- best / second best over caller-supplied candidate lists (CSR)
+    def hamming_window(self, q, t, cand_offsets, cand_idx):
+        q = _c(q, np.uint8); t = _c(t, np.uint8)
+        off = _c(cand_offsets, np.int32); idx = _c(cand_idx, np.int32)
+        if len(off) != len(q) + 1:
+            raise ValueError("cand_offsets must have len(q) + 1 entries")
+        if len(q) and len(idx) < off[-1]:
+            raise ValueError("cand_idx shorter than cand_offsets[-1]")
+        bi = np.zeros(len(q), np.int32); bd = np.zeros(len(q), np.int32); sd = np.zeros(len(q), np.int32)
+        _capi.check(self._h, self._lib.orbfe_hamming_window(self._h, _capi.ptr(q), len(q), _capi.ptr(t), len(t), _capi.ptr(off), _capi.ptr(idx),
+                                                            _capi.ptr(bi), _capi.ptr(bd), _capi.ptr(sd)))
+        return bi, bd, sd
+
     def hamming_allpairs_device(self, d_q, nq, d_t, nt, d_bi, d_bd, d_sd, stream=None, sync=True):
         _capi.check(self._h, self._lib.orbfe_hamming_allpairs_device(self._h, _capi.ptr(d_q), nq, _capi.ptr(d_t), nt, _capi.ptr(d_bi), _capi.ptr(d_bd),
                                                                      _capi.ptr(d_sd), C.c_void_p(stream) if stream else None, int(sync)))

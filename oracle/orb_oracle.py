@@ -295,6 +295,21 @@ def hamming_allpairs(q, t):
     return bi, bd, sd
 
 
+def hamming_window(q, t, cand_offsets, cand_idx):
+    """Best / second best of each query over its own candidate list, scanned in list order the way ORBMatcher.cpp:60-72 does
+    (`if (dist < bestDist) {second = best; best = dist} else if (dist < second) second = dist`); 257 where there is none."""
+    q = _c(q, np.uint8); t = _c(t, np.uint8)
+    bi = np.full(len(q), -1, np.int32); bd = np.full(len(q), 257, np.int32); sd = np.full(len(q), 257, np.int32)
+    for i in range(len(q)):
+        for j in cand_idx[cand_offsets[i]:cand_offsets[i + 1]]:
+            d = int(np.unpackbits(q[i] ^ t[j]).sum())
+            if d < bd[i]:
+                sd[i] = bd[i]; bd[i] = d; bi[i] = j
+            elif d < sd[i]:
+                sd[i] = d
+    return bi, bd, sd
+
+
 # ---------------------------------------------------------------- verbatim reference build (oracle/_ref)
 class ReferenceExtractor:
     """The reference's own ORBExtractor.cpp compiled verbatim against oracle/cvshim (see oracle/ref_harness.cpp).

@@ -46,6 +46,26 @@ def test_allpairs_real_descriptors_and_empty(ctx, oracle):
     assert bi.tolist() == [-1] * 5 and bd.tolist() == [257] * 5 and sd.tolist() == [257] * 5
 
 
+@pytest.mark.parametrize("nq,nt,max_len", [(1, 1, 1), (9, 40, 3), (500, 700, 40), (257, 3000, 300)])
+def test_hamming_window(ctx, oracle, nq, nt, max_len):
+    """orbfe_hamming_window: ragged candidate lists (empty, single, long, repeated candidates, exact duplicates)."""
+    m = ctx["ORBMatcher"]()
+    rng = np.random.default_rng(nq * 31 + nt)
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8); t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    t[rng.integers(0, nt, max(nt // 8, 1))] = q[rng.integers(0, nq, max(nt // 8, 1))]
+    lens = rng.integers(0, max_len + 1, nq); lens[0] = max_len; lens[-1] = 0 if nq > 1 else lens[-1]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    idx = rng.integers(0, nt, off[-1]).astype(np.int32)
+    bi, bd, sd = m.hamming_window(q, t, off, idx)
+    obi, obd, osd = oracle.hamming_window(q, t, off, idx)
+    assert np.array_equal(bi, obi) and np.array_equal(bd, obd) and np.array_equal(sd, osd)
+    # the full list 0..nt-1 for every query is the all-pairs search
+    full_off = (np.arange(nq + 1) * nt).astype(np.int32); full_idx = np.tile(np.arange(nt, dtype=np.int32), nq)
+    assert all(np.array_equal(a, b) for a, b in zip(m.hamming_window(q, t, full_off, full_idx), m.hamming_allpairs(q, t)))
+    with pytest.raises(Exception):
+        m.hamming_window(q, t, off, np.where(np.arange(len(idx)) == 0, nt, idx).astype(np.int32))     # candidate out of range
+
+
 @pytest.mark.parametrize("window,ratio,orient", [(100, 0.9, True), (100, 0.9, False), (30, 0.7, True), (200, 1.0, True)])
 def test_search_for_initialization(ctx, oracle, window, ratio, orient):
     m = ctx["ORBMatcher"](ratio, orient)
