@@ -102,6 +102,18 @@ int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, in
                         size_t row_stride, size_t frame_stride,
                         orbfe_keypoint *kps, uint8_t *desc, int cap, int *n_per_frame);
 
+/* Asynchronous form for streams of batches: orbfe_extract_batch_submit enqueues the uploads, passes and downloads of one batch
+ * and returns a ticket; orbfe_extract_batch_wait(ticket) blocks until that batch's outputs are in the caller's buffers and reports
+ * its device errors (ticket < 0 waits for everything submitted).  A batch submitted while the previous one is in flight continues
+ * the pipeline: its first uploads run under the previous batch's last passes, so a stream of batches runs at the PCIe rate without
+ * the fill / drain cost each synchronous call pays.  Input and output buffers must be pinned (orbfe_host_alloc) for the copies to
+ * be asynchronous and must stay valid until the batch has been waited for; at most 8 tickets are outstanding (submit blocks on
+ * the oldest).  orbfe_extract_batch == submit + wait. */
+int orbfe_extract_batch_submit(orbfe_handle *h, const uint8_t *frames, int n_frames, int width, int height,
+                               size_t row_stride, size_t frame_stride,
+                               orbfe_keypoint *kps, uint8_t *desc, int cap, int *n_per_frame, long long *ticket);
+int orbfe_extract_batch_wait(orbfe_handle *h, long long ticket);
+
 /* The same with frames and outputs already resident in DEVICE memory (what bench.py's `value` times).
  * `stream` is a cudaStream_t (NULL = the handle's own stream); the call is asynchronous on that stream
  * unless `sync` != 0.  n_frames may exceed max_batch (processed in passes). */

@@ -54,6 +54,8 @@ SIGNATURES = {
     "orbfe_host_free": (None, [_vp]),
     "orbfe_extract": (_i, [_vp, _vp, _i, _i, _sz, _vp, _vp, _i, C.POINTER(_i)]),
     "orbfe_extract_batch": (_i, [_vp, _vp, _i, _i, _i, _sz, _sz, _vp, _vp, _i, _vp]),
+    "orbfe_extract_batch_submit": (_i, [_vp, _vp, _i, _i, _i, _sz, _sz, _vp, _vp, _i, _vp, C.POINTER(C.c_longlong)]),
+    "orbfe_extract_batch_wait": (_i, [_vp, C.c_longlong]),
     "orbfe_extract_batch_device": (_i, [_vp, _vp, _i, _i, _i, _sz, _sz, _vp, _vp, _i, _vp, _vp, _i]),
     "orbfe_level_size": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i)]),
     "orbfe_get_level_image": (_i, [_vp, _i, _i, _vp]),

@@ -477,6 +477,21 @@ static int check_device_error(Handle *h, cudaStream_t st) {
     return ORBFE_OK;
 }
 
+// Waits for every batch submitted to the host pipeline and reports (and clears) the overflow flags of both arenas.
+static int pipeline_drain(Handle *h) {
+    if (!h->pipe_pending) return ORBFE_OK;
+    h->pipe_pending = false;
+    ORBFE_CUDA(h, cudaStreamSynchronize(h->s_down));
+    ORBFE_CUDA(h, cudaStreamSynchronize(h->s_up));
+    int rc = check_device_error(h, h->stream);
+    if (h->peer && h->pipe_peer_used) {
+        h->pipe_peer_used = false;
+        const int rp = check_device_error(h->peer, h->peer->stream);
+        if (!rc && rp) rc = set_error(h, rp, "pipeline peer: %s", orbfe_last_error(static_cast<orbfe_handle *>(h->peer)));
+    }
+    return rc;
+}
+
 }  // namespace orbfe
 
 using namespace orbfe;
@@ -533,14 +548,18 @@ int orbfe_create(const orbfe_config *cfg, orbfe_handle **out) {
 
 void orbfe_destroy(orbfe_handle *h) {
     if (!h) return;
-    if (h->peer) { orbfe_destroy(h->peer); h->peer = nullptr; }
     cudaSetDevice(h->device);
+    if (h->s_up) cudaStreamSynchronize(h->s_up);                 // batches still in flight (orbfe_extract_batch_submit)
+    if (h->s_down) cudaStreamSynchronize(h->s_down);
+    if (h->peer) { orbfe_destroy(h->peer); h->peer = nullptr; }
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_arena(h);
     cudaFree(h->d_err); cudaFree(h->d_match); cudaFree(h->d_pattern); cudaFree(h->d_unc);
     for (int i = 0; i <= ORBFE_N_STAGES; ++i) if (h->prof_ev[i]) cudaEventDestroy(h->prof_ev[i]);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->h_mpin) cudaFreeHost(h->h_mpin);
+    if (h->h_ticket_err) cudaFreeHost(h->h_ticket_err);
+    for (int i = 0; i < Handle::kTickets; ++i) if (h->ev_ticket[i]) cudaEventDestroy(h->ev_ticket[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->s_aux) { cudaStreamDestroy(h->s_aux); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
     if (h->s_up) cudaStreamDestroy(h->s_up);
@@ -599,8 +618,9 @@ int orbfe_extract_batch_device(orbfe_handle *h, const uint8_t *d_frames, int n_f
     if (n_frames == 0 || width <= 0 || height <= 0) return ORBFE_OK;
     ORBFE_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t) stream : h->stream;
-    int rc = configure(h, width, height, std::min(n_frames, h->cfg.max_batch));
+    int rc = pipeline_drain(h);                                  // submitted host batches share the arena
     if (rc) return rc;
+    if ((rc = configure(h, width, height, std::min(n_frames, h->cfg.max_batch)))) return rc;
     const bool inplace = ((uintptr_t) d_frames % 16 == 0) && row_stride % 16 == 0 && frame_stride % 16 == 0;
     for (int b0 = 0; b0 < n_frames; b0 += h->batch_cap) {
         const int nb = std::min(h->batch_cap, n_frames - b0);
@@ -627,9 +647,11 @@ int orbfe_extract_batch_device(orbfe_handle *h, const uint8_t *d_frames, int n_f
 // Host batch entry point: a 3-stream software pipeline over chunks of frames.  Chunk c is copied host->device into one of two
 // dense staging buffers on the copy stream while chunk c-1 runs on the compute stream and the results of chunk c-2 go back to the
 // host on the download stream; level 0 is read in place from the staging buffer when the row size allows TMA (multiple of 16).
-int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, int width, int height, size_t row_stride, size_t frame_stride,
-                        orbfe_keypoint *kps, uint8_t *desc, int cap, int *n_per_frame) {
-    if (!h) return ORBFE_E_ARG;
+//
+// The pipeline state (slot rotation, arena parity, slot events) lives in the handle, so a batch submitted while the previous one is
+// still in flight continues the rotation: its first uploads run under the last passes of the previous batch.
+static int batch_enqueue(Handle *h, const uint8_t *frames, int n_frames, int width, int height, size_t row_stride, size_t frame_stride,
+                         orbfe_keypoint *kps, uint8_t *desc, int cap, int *n_per_frame, bool blocking) {
     if (!frames || !kps || !desc || !n_per_frame || n_frames < 0 || cap < 1 || row_stride < (size_t) width)
         return set_error(h, ORBFE_E_ARG, "orbfe_extract_batch: invalid argument (frames=%p kps=%p desc=%p n=%p n_frames=%d cap=%d row_stride=%zu width=%d)",
                          (const void *) frames, (void *) kps, (void *) desc, (void *) n_per_frame, n_frames, cap, row_stride, width);
@@ -639,10 +661,17 @@ int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, in
     int chunk_target = 128;                               // frames per pipeline stage (ORBFE_CHUNK overrides, for tuning)
     if (const char *e = getenv("ORBFE_CHUNK")) chunk_target = std::max(1, atoi(e));
     const int chunk = std::min(h->cfg.max_batch, std::max(std::min(16, chunk_target), std::min(chunk_target, (n_frames + 3) / 4)));
+    // batches in flight share the output slots: a change of frame size, chunk size or capacity drains the pipeline first
+    if (h->pipe_pending && (h->pipe_w != width || h->pipe_h != height || h->pipe_cap != cap || h->pipe_chunk != chunk)) {
+        int rcw = pipeline_drain(h);
+        if (rcw) return rcw;
+    }
     int rc = configure(h, width, height, std::min(n_frames, chunk));
     if (rc) return rc;
     const int cn = std::min(h->batch_cap, chunk);                                   // frames per pipeline stage
     if ((rc = ensure_pipeline(h, (size_t) cn * width * height, cn, cap))) return rc;
+    if (h->pipe_pending && h->pipe_cn != cn) { if ((rc = pipeline_drain(h))) return rc; }
+    h->pipe_w = width; h->pipe_h = height; h->pipe_cap = cap; h->pipe_chunk = chunk; h->pipe_cn = cn;
     const size_t frame_bytes = (size_t) width * height;
     const bool dense_rows = row_stride == (size_t) width, dense_frames = dense_rows && frame_stride == frame_bytes;
     const bool inplace = width % 16 == 0;
@@ -676,31 +705,38 @@ int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, in
         // measured on 512 frames with 128-frame chunks: 64,128,128,96,64,32 (two passes in flight, three staging slots) is the
         // best of the variants tried (tools/e2e_probe.py with ORBFE_SCHED)
         const int head[1] = {std::max(1, cn / 2)}, tail[3] = {std::max(1, 3 * cn / 4), std::max(1, cn / 2), std::max(1, cn / 4)};
+        // A submitted batch (orbfe_extract_batch_submit) is one of a stream: its ends overlap with its neighbours, and full chunks
+        // throughout are best (512 frames, two batches in flight: 147.7 k frames/s against 137.9 k with the short ends)
+        const bool short_ends = blocking && n_frames >= 3 * cn;
         int left = n_frames;
-        if (n_frames >= 3 * cn) {
+        if (short_ends) {
             for (int v : head) { sizes.push_back(v); left -= v; }
             left -= tail[0] + tail[1] + tail[2];
         }
         while (left > 0) { const int v = std::min(cn, left); sizes.push_back(v); left -= v; }
-        if (n_frames >= 3 * cn) for (int v : tail) sizes.push_back(v);
+        if (short_ends) for (int v : tail) sizes.push_back(v);
     }
     // ORBFE_TRACE=1: per-chunk completion times of upload / pass / download (ms since the first upload was issued), on stderr
-    static const bool trace = [] { const char *e = getenv("ORBFE_TRACE"); return e && *e == '1'; }();
+    static const bool trace_env = [] { const char *e = getenv("ORBFE_TRACE"); return e && *e == '1'; }();
+    const bool trace = trace_env && blocking;
     std::vector<cudaEvent_t> tev;
     if (trace) {
         tev.resize(3 * sizes.size() + 1);
         for (auto &e : tev) cudaEventCreate(&e);
         cudaEventRecord(tev[0], su);
     }
+    h->pipe_pending = true;
+    h->pipe_peer_used = h->pipe_peer_used || hp[1] != h;
     int c = 0;
     for (int b0 = 0, nb = 0; b0 < n_frames; b0 += nb, ++c) {
         nb = sizes[(size_t) c];
-        const int slot = c % Handle::kStageSlots;              // staging + output slot; the arena / stream alternates with the chunk parity
-        Handle *const hc = hp[c & 1];
+        const long long seq = h->pipe_seq++;                   // chunk number since the handle was created
+        const int slot = (int) (seq % Handle::kStageSlots);    // staging + output slot; the arena / stream alternates with the chunk parity
+        Handle *const hc = hp[seq & 1];
         cudaStream_t sc = hc->stream;
         const uint8_t *src = frames + (size_t) b0 * frame_stride;
         uint8_t *stage = h->d_stage[slot];
-        if (c >= Handle::kStageSlots) ORBFE_CUDA(h, cudaStreamWaitEvent(su, h->ev_done[slot], 0));      // the pass that read this slot has finished
+        if (seq >= Handle::kStageSlots) ORBFE_CUDA(h, cudaStreamWaitEvent(su, h->ev_done[slot], 0));    // the pass that read this slot has finished
         if (dense_frames) ORBFE_CUDA(h, cudaMemcpyAsync(stage, src, frame_bytes * nb, cudaMemcpyHostToDevice, su));
         else
             for (int b = 0; b < nb; ++b)
@@ -709,7 +745,7 @@ int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, in
         ORBFE_CUDA(h, cudaEventRecord(h->ev_up[slot], su));
         if (trace) cudaEventRecord(tev[1 + 3 * c], su);
         ORBFE_CUDA(h, cudaStreamWaitEvent(sc, h->ev_up[slot], 0));
-        if (c >= Handle::kStageSlots) ORBFE_CUDA(h, cudaStreamWaitEvent(sc, h->ev_down[slot], 0));      // the output slot has been downloaded
+        if (seq >= Handle::kStageSlots) ORBFE_CUDA(h, cudaStreamWaitEvent(sc, h->ev_down[slot], 0));    // the output slot has been downloaded
         orbfe_keypoint *okps = h->d_out_kps + (size_t) slot * cn * cap;
         uint8_t *odesc = h->d_out_desc + (size_t) slot * cn * cap * 32;
         int *on = h->d_out_n + (size_t) slot * cn;
@@ -728,9 +764,9 @@ int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, in
         ORBFE_CUDA(h, cudaEventRecord(h->ev_down[slot], sd));
         if (trace) cudaEventRecord(tev[3 + 3 * c], sd);
     }
-    ORBFE_CUDA(h, cudaStreamSynchronize(sd));
-    ORBFE_CUDA(h, cudaStreamSynchronize(su));
     if (trace) {
+        ORBFE_CUDA(h, cudaStreamSynchronize(sd));
+        ORBFE_CUDA(h, cudaStreamSynchronize(su));
         for (size_t i = 0; i < sizes.size(); ++i) {
             float a = 0, b = 0, d = 0;
             cudaEventElapsedTime(&a, tev[0], tev[1 + 3 * i]); cudaEventElapsedTime(&b, tev[0], tev[2 + 3 * i]); cudaEventElapsedTime(&d, tev[0], tev[3 + 3 * i]);
@@ -738,9 +774,56 @@ int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, in
         }
         for (auto &e : tev) cudaEventDestroy(e);
     }
-    rc = check_device_error(h, h->stream);
-    if (!rc && hp[1] != h && (rc = check_device_error(hp[1], hp[1]->stream))) return set_error(h, rc, "pipeline peer: %s", orbfe_last_error(static_cast<orbfe_handle *>(hp[1])));
-    return rc;
+    return ORBFE_OK;
+}
+
+int orbfe_extract_batch_submit(orbfe_handle *h, const uint8_t *frames, int n_frames, int width, int height, size_t row_stride, size_t frame_stride,
+                               orbfe_keypoint *kps, uint8_t *desc, int cap, int *n_per_frame, long long *ticket) {
+    if (!h) return ORBFE_E_ARG;
+    if (!ticket) return set_error(h, ORBFE_E_ARG, "orbfe_extract_batch_submit: ticket is null");
+    *ticket = -1;
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    int rc = batch_enqueue(h, frames, n_frames, width, height, row_stride, frame_stride, kps, desc, cap, n_per_frame, false);
+    if (rc) return rc;
+    if (!h->s_down) { *ticket = h->pipe_ticket; return ORBFE_OK; }                    // nothing was enqueued (empty batch / empty image)
+    // the ticket's event follows the batch's last download on the download stream; the overflow flags of both arenas ride along
+    const long long t = ++h->pipe_ticket;
+    const int r = (int) (t % Handle::kTickets);
+    if (!h->ev_ticket[r]) {
+        ORBFE_CUDA(h, cudaEventCreateWithFlags(&h->ev_ticket[r], cudaEventDisableTiming));
+        if (!h->h_ticket_err) ORBFE_CUDA(h, cudaMallocHost(&h->h_ticket_err, sizeof(int) * 2 * Handle::kTickets));
+    } else {
+        ORBFE_CUDA(h, cudaEventSynchronize(h->ev_ticket[r]));                         // ring slot of a batch submitted kTickets ago
+    }
+    int *flags = h->h_ticket_err + 2 * r;
+    flags[0] = flags[1] = 0;
+    ORBFE_CUDA(h, cudaMemcpyAsync(flags, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->s_down));
+    if (h->peer && h->pipe_peer_used)                                                 // (every pass is ahead of its chunk's download on s_down)
+        ORBFE_CUDA(h, cudaMemcpyAsync(flags + 1, h->peer->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->s_down));
+    ORBFE_CUDA(h, cudaEventRecord(h->ev_ticket[r], h->s_down));
+    *ticket = t;
+    return ORBFE_OK;
+}
+
+int orbfe_extract_batch_wait(orbfe_handle *h, long long ticket) {
+    if (!h) return ORBFE_E_ARG;
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    if (ticket < 0 || ticket >= h->pipe_ticket) return pipeline_drain(h);            // the newest batch (or "everything"): drain
+    if (ticket + Handle::kTickets <= h->pipe_ticket) return ORBFE_OK;                // its ring slot was synchronised when it was reused
+    const int r = (int) (ticket % Handle::kTickets);
+    if (!h->ev_ticket[r]) return ORBFE_OK;
+    ORBFE_CUDA(h, cudaEventSynchronize(h->ev_ticket[r]));
+    if (h->h_ticket_err[2 * r] || h->h_ticket_err[2 * r + 1]) return pipeline_drain(h);   // reports and clears the device flag
+    return ORBFE_OK;
+}
+
+int orbfe_extract_batch(orbfe_handle *h, const uint8_t *frames, int n_frames, int width, int height, size_t row_stride, size_t frame_stride,
+                        orbfe_keypoint *kps, uint8_t *desc, int cap, int *n_per_frame) {
+    if (!h) return ORBFE_E_ARG;
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    int rc = batch_enqueue(h, frames, n_frames, width, height, row_stride, frame_stride, kps, desc, cap, n_per_frame, true);
+    if (rc) return rc;
+    return pipeline_drain(h);
 }
 
 int orbfe_extract(orbfe_handle *h, const uint8_t *gray, int width, int height, size_t stride, orbfe_keypoint *kps, uint8_t *desc, int cap, int *n_out) {
@@ -753,8 +836,9 @@ int orbfe_extract(orbfe_handle *h, const uint8_t *gray, int width, int height, s
     const auto t0 = std::chrono::steady_clock::now();
     auto us = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };
     ORBFE_CUDA(h, cudaSetDevice(h->device));
-    int rc = configure(h, width, height, 1);
+    int rc = pipeline_drain(h);                                  // submitted host batches share the arena and the output staging
     if (rc) return rc;
+    if ((rc = configure(h, width, height, 1))) return rc;
     // device-side capacity is the handle's bound, so a too-small caller capacity is detected on the host without clobbering kps/desc
     const int dcap = h->max_kp;
     if ((rc = ensure_out_staging(h, dcap))) return rc;

@@ -98,6 +98,14 @@ struct Handle {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_up[kStageSlots] = {}, ev_done[kStageSlots] = {}, ev_down[kStageSlots] = {};
     int last_batch = 0;              // frames of the last pass (for the stage getters)
+    // state of the host pipeline across calls (orbfe_extract_batch_submit keeps batches in flight)
+    long long pipe_seq = 0;          // chunks enqueued since creation: slot = seq % kStageSlots, arena = seq & 1
+    bool pipe_pending = false, pipe_peer_used = false;
+    int pipe_w = 0, pipe_h = 0, pipe_cap = 0, pipe_chunk = 0, pipe_cn = 0;
+    static constexpr int kTickets = 8;
+    long long pipe_ticket = 0;       // last ticket handed out
+    cudaEvent_t ev_ticket[kTickets] = {};
+    int *h_ticket_err = nullptr;     // pinned [kTickets][2]: overflow flags of both arenas as of the ticket's last download
     // Second arena + stream for the pipelined host path: odd chunks run their pass on the peer so that the tail of one pass
     // (quadtree, descriptors) overlaps with the head of the next (pyramid, FAST).  A complete handle, created lazily.
     orbfe_handle *peer = nullptr;

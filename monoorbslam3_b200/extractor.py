@@ -100,6 +100,27 @@ class ORBExtractor:
         _capi.check(self._h, rc)
         return n, kps, desc
 
+    def extract_batch_submit(self, frames, out, cap=None):
+        """Asynchronous extract_batch for streams of batches: enqueues the batch and returns a ticket; `frames` and the arrays of
+        `out` = (n[B], kps[B,cap], desc[B,cap,32]) must be pinned host arrays that stay alive until extract_batch_wait(ticket)."""
+        if frames.dtype != np.uint8 or frames.ndim != 3 or frames.strides[2] != 1 or frames.strides[1] < frames.shape[2]:
+            raise TypeError("frames must be a [B,H,W] uint8 array with unit pixel stride")
+        B, H, W = frames.shape
+        n, kps, desc = out
+        if cap is None:
+            cap = kps.shape[1]
+        if kps.shape[0] < B or kps.shape[1] != cap or desc.shape[:2] != kps.shape[:2] or len(n) < B:
+            raise ValueError("output arrays do not match the batch")
+        t = C.c_longlong(-1)
+        rc = self._lib.orbfe_extract_batch_submit(self._h, _capi.ptr(frames), B, W, H, frames.strides[1], frames.strides[0], _capi.ptr(kps),
+                                                  _capi.ptr(desc), cap, _capi.ptr(n), C.byref(t))
+        _capi.check(self._h, rc)
+        return t.value
+
+    def extract_batch_wait(self, ticket=-1):
+        """Blocks until the batch of `ticket` (default: every submitted batch) has its results in the caller's arrays."""
+        _capi.check(self._h, self._lib.orbfe_extract_batch_wait(self._h, ticket))
+
     def extract_batch_device(self, d_frames, B, H, W, d_kps, d_desc, cap, d_n, row_stride=None, frame_stride=None, stream=None, sync=True):
         """Device-resident variant: arguments are torch CUDA tensors (or raw device pointers as ints)."""
         row_stride = W if row_stride is None else row_stride

@@ -118,6 +118,47 @@ def test_deterministic_and_batch_equals_single(mods, oracle):
     ex.close()
 
 
+def test_submitted_batches_in_flight_equal_blocking_calls(mods):
+    """orbfe_extract_batch_submit / _wait: several batches in flight (different scenes, sizes that change the chunk schedule, a
+    frame-size change in the middle, a capacity error) give what the blocking call gives, whatever order they are waited in."""
+    torch = pytest.importorskip("torch")
+    ORBExtractor, synth, KP = mods
+    ex = ORBExtractor(1000, 1.2, 8, 20, 7, max_batch=8)
+    ref = ORBExtractor(1000, 1.2, 8, 20, 7, max_batch=8)
+    cap = 1100
+
+    def pinned(B, h, w, seed):
+        fr = torch.from_numpy(synth.frames(B, h, w, seed, "dense")).pin_memory()
+        n = torch.zeros(B, dtype=torch.int32).pin_memory(); k = torch.zeros((B, cap, 7), dtype=torch.float32).pin_memory()
+        d = torch.zeros((B, cap, 32), dtype=torch.uint8).pin_memory()
+        return fr, (n.numpy(), k.numpy().view(KP).reshape(B, cap), d.numpy()), (fr, n, k, d)
+
+    jobs = [pinned(B, h, w, seed) for (B, h, w, seed) in [(40, 480, 752, 10), (5, 480, 752, 60), (33, 480, 752, 70), (12, 376, 1241, 90), (26, 480, 752, 120)]]
+    tickets = [ex.extract_batch_submit(fr.numpy(), out, cap=cap) for fr, out, _ in jobs]
+    assert tickets == sorted(tickets) and len(set(tickets)) == len(tickets)
+    for i in (2, 0, 4, 1, 3):
+        ex.extract_batch_wait(tickets[i])
+    for fr, (n, kps, desc), _ in jobs:
+        rn, rk, rd = ref.extract_batch(fr.numpy(), cap=cap)
+        assert np.array_equal(n, rn) and n.min() > 900
+        for b in range(len(n)):
+            assert kps[b, :n[b]].tobytes() == rk[b, :n[b]].tobytes() and np.array_equal(desc[b, :n[b]], rd[b, :n[b]])
+    # wait-all, then the handle is usable by the blocking entry points again
+    t = ex.extract_batch_submit(jobs[0][0].numpy(), jobs[0][1], cap=cap)
+    ex.extract_batch_wait()
+    ex.extract_batch_wait(t)                                     # waiting twice is harmless
+    k1, d1 = ex(jobs[0][0].numpy()[0])
+    assert len(k1) == jobs[0][1][0][0]
+    # a capacity overflow inside a submitted batch surfaces at the wait
+    small = (np.zeros(5, np.int32), np.zeros((5, 100), KP), np.zeros((5, 100, 32), np.uint8))
+    t = ex.extract_batch_submit(jobs[1][0].numpy(), small, cap=100)
+    with pytest.raises(Exception):
+        ex.extract_batch_wait(t)
+    n, kps, desc = ex.extract_batch(jobs[1][0].numpy(), cap=cap)       # and the handle recovers
+    assert np.array_equal(n, jobs[1][1][0])
+    ex.close(); ref.close()
+
+
 def test_device_entry_point_equals_host_entry_point(mods):
     torch = pytest.importorskip("torch")
     ORBExtractor, synth, KP = mods
