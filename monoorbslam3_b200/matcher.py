@@ -4,6 +4,7 @@ The reference's methods take Frame/KeyFrame objects; here a frame is anything wi
 `descriptors` ([N,32] uint8) and `width`/`height` — see FrameView.  The adapters do what the C++ adapters of INTEGRATION.md do:
 flatten the objects, call the C-ABI, write the results back in the reference's order."""
 import ctypes as C
+import threading
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -29,14 +30,18 @@ class FrameView:
         return len(self.key_points)
 
 
-_shared_handle = None
+_tls = threading.local()
 
 
 def _handle(device=0):
-    global _shared_handle
-    if _shared_handle is None:
-        _shared_handle = _capi.create(1000, 1.2, 8, 20, 7, device, 1, 0)
-    return _shared_handle
+    """One handle (= one CUDA stream + scratch) per host thread and device, like the C++ adapter's thread_local holder: the
+    reference runs ORBMatcher on the tracking and the local-mapping thread concurrently (System.cpp:55)."""
+    handles = getattr(_tls, "handles", None)
+    if handles is None:
+        handles = _tls.handles = {}
+    if device not in handles:
+        handles[device] = _capi.create(1000, 1.2, 8, 20, 7, device, 1, 0)
+    return handles[device]
 
 
 def _c(a, dt):

@@ -195,3 +195,59 @@ def test_compute_descriptors(ctx, oracle):
     got = m.compute_descriptors(desc, off)
     assert np.array_equal(got, oracle.compute_descriptors(desc, off))
     assert got[3] == -1
+
+
+def test_tracking_and_local_mapping_threads_run_concurrently(ctx, oracle):
+    """SURVEY section 8b, threading: the reference runs ORBMatcher on the tracking thread and on the local-mapping thread at the same
+    time (System.cpp:55) while the tracking thread also extracts.  One handle per host thread, no shared mutable state: every
+    result of the concurrent runs equals the single-threaded one."""
+    import threading
+    from monoorbslam3_b200 import ORBExtractor, matcher as matcher_mod
+    FV = ctx["FrameView"]
+    a, b = ctx["synth"].shifted_pair(480, 752, 1000)
+    da, db, ka, kb = ctx["da"], ctx["db"], ctx["ka"], ctx["kb"]
+    rng = np.random.default_rng(3)
+    has1 = (rng.random(len(da)) < 0.3).astype(np.uint8); has2 = (rng.random(len(db)) < 0.3).astype(np.uint8)
+    fv1, fv2 = _feature_vector(da, 4), _feature_vector(db, 4)
+    exp_tri = oracle.search_for_triangulation(da, ka["angle"], has1, fv1, db, kb["angle"], has2, fv2, True)
+    pre0 = np.stack([ka["x"], ka["y"]], 1).astype(np.float32)
+    exp_init = oracle.search_for_initialization(ka, da, kb, db, 752, 480, pre0.copy(), 100, 0.9, True)
+    exp_ap = oracle.hamming_allpairs(da, db)
+    exp_kps, exp_desc = ctx["ex"](a)
+    errors, handles = [], {}
+
+    def tracking():
+        try:
+            ex = ORBExtractor(2000, 1.2, 8, 20, 7)
+            m = ctx["ORBMatcher"](0.9, True)
+            handles["tracking"] = m._h
+            for _ in range(25):
+                k, d = ex(a)
+                assert k.tobytes() == exp_kps.tobytes() and np.array_equal(d, exp_desc)
+                pre = pre0.copy()
+                n, m12 = m.SearchForInitialization(FV(ka, da, 752, 480), FV(kb, db, 752, 480), pre, 100)
+                assert n == exp_init[0] and np.array_equal(m12, exp_init[1]) and np.array_equal(pre, exp_init[2])
+            ex.close()
+        except BaseException as e:       # noqa: BLE001 - reported by the main thread
+            errors.append(("tracking", repr(e)))
+
+    def local_mapping():
+        try:
+            m = ctx["ORBMatcher"](0.6, True)
+            handles["mapping"] = m._h
+            for _ in range(25):
+                n, m12 = m.SearchForTriangulation(da, ka["angle"], has1, fv1, db, kb["angle"], has2, fv2)
+                assert n == exp_tri[0] and np.array_equal(m12, exp_tri[1])
+                got = m.hamming_allpairs(da, db)
+                assert all(np.array_equal(x, y) for x, y in zip(got, exp_ap))
+        except BaseException as e:       # noqa: BLE001
+            errors.append(("local mapping", repr(e)))
+
+    threads = [threading.Thread(target=tracking), threading.Thread(target=local_mapping)]
+    for t in threads: t.start()
+    for t in threads: t.join(timeout=300)
+    assert not errors, errors
+    assert not any(t.is_alive() for t in threads)
+    main = matcher_mod._handle()
+    addr = lambda h: h.value if hasattr(h, "value") else int(h)
+    assert len({addr(handles["tracking"]), addr(handles["mapping"]), addr(main)}) == 3       # every thread got its own handle
