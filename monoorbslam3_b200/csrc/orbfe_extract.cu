@@ -560,6 +560,7 @@ void orbfe_destroy(orbfe_handle *h) {
     if (h->h_mpin) cudaFreeHost(h->h_mpin);
     if (h->h_ticket_err) cudaFreeHost(h->h_ticket_err);
     for (int i = 0; i < Handle::kTickets; ++i) if (h->ev_ticket[i]) cudaEventDestroy(h->ev_ticket[i]);
+    for (auto &e : h->ev_split) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->s_aux) { cudaStreamDestroy(h->s_aux); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
     if (h->s_up) cudaStreamDestroy(h->s_up);
@@ -620,27 +621,62 @@ int orbfe_extract_batch_device(orbfe_handle *h, const uint8_t *d_frames, int n_f
     cudaStream_t st = stream ? (cudaStream_t) stream : h->stream;
     int rc = pipeline_drain(h);                                  // submitted host batches share the arena
     if (rc) return rc;
-    if ((rc = configure(h, width, height, std::min(n_frames, h->cfg.max_batch)))) return rc;
+    // A batch of 64 frames or more runs as two half-size passes on two arenas / streams (this handle's and the peer's, forked from
+    // and joined back into `st`): the latency-bound tail of one half (quadtree, descriptors) fills the issue slots the other half's
+    // FAST leaves idle.  512 C1 frames: 2.99 -> 2.89 ms (tools/split_probe.py).  Stage profiling keeps the single pass.
+    static const bool no_peer = [] { const char *e = getenv("ORBFE_NO_PEER"); return e && *e == '1'; }();
+    const int whole = std::min(n_frames, h->cfg.max_batch);
+    const bool split = !no_peer && !h->prof && !debug_sync() && n_frames >= 64;
+    const int pass = split ? (whole + 1) / 2 : whole;
+    if ((rc = configure(h, width, height, pass))) return rc;
+    Handle *hp = h;
+    if (split) {
+        if (!h->peer) {
+            orbfe_config pc = h->cfg; pc.max_batch = pass;
+            if ((rc = orbfe_create(&pc, &h->peer))) return set_error(h, rc, "peer arena: %s", orbfe_last_error(nullptr));
+        }
+        if ((rc = configure(h->peer, width, height, pass))) return set_error(h, rc, "peer arena: %s", orbfe_last_error(h->peer));
+        h->peer->use_tma = h->use_tma;
+        hp = h->peer;
+        if (!h->ev_split[0]) for (auto &e : h->ev_split) ORBFE_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ORBFE_CUDA(h, cudaEventRecord(h->ev_split[0], st));
+        ORBFE_CUDA(h, cudaStreamWaitEvent(hp->stream, h->ev_split[0], 0));
+    }
+    const int step = std::min(pass, std::min(h->batch_cap, hp->batch_cap));
     const bool inplace = ((uintptr_t) d_frames % 16 == 0) && row_stride % 16 == 0 && frame_stride % 16 == 0;
-    for (int b0 = 0; b0 < n_frames; b0 += h->batch_cap) {
-        const int nb = std::min(h->batch_cap, n_frames - b0);
+    int i = 0;
+    for (int b0 = 0; b0 < n_frames; b0 += step, ++i) {
+        const int nb = std::min(step, n_frames - b0);
+        Handle *hc = (i & 1) ? hp : h;
+        cudaStream_t sc = hc == h ? st : hc->stream;
         const uint8_t *src = d_frames + (size_t) b0 * frame_stride;
-        const LevelGeom &L0 = h->g.lv[0];
+        const LevelGeom &L0 = hc->g.lv[0];
         if (inplace) {
-            rc = run_pass(h, nb, src, row_stride, frame_stride, d_kps + (size_t) b0 * cap, d_desc + (size_t) b0 * cap * 32, d_n + b0, cap, st);
+            rc = run_pass(hc, nb, src, row_stride, frame_stride, d_kps + (size_t) b0 * cap, d_desc + (size_t) b0 * cap * 32, d_n + b0, cap, sc);
         } else {
             // image.clone() into the pitched arena (ORBExtractor.cpp:567)
             if (frame_stride == row_stride * (size_t) height)
-                ORBFE_CUDA(h, cudaMemcpy2DAsync(h->d_img + L0.img_off, L0.pitch, src, row_stride, width, (size_t) height * nb, cudaMemcpyDeviceToDevice, st));
+                ORBFE_CUDA(h, cudaMemcpy2DAsync(hc->d_img + L0.img_off, L0.pitch, src, row_stride, width, (size_t) height * nb, cudaMemcpyDeviceToDevice, sc));
             else
                 for (int b = 0; b < nb; ++b)
-                    ORBFE_CUDA(h, cudaMemcpy2DAsync(h->d_img + L0.img_off + (size_t) b * L0.frame_stride, L0.pitch, src + (size_t) b * frame_stride,
-                                                    row_stride, width, height, cudaMemcpyDeviceToDevice, st));
-            rc = run_pass(h, nb, h->d_img + L0.img_off, L0.pitch, L0.frame_stride, d_kps + (size_t) b0 * cap, d_desc + (size_t) b0 * cap * 32, d_n + b0, cap, st);
+                    ORBFE_CUDA(h, cudaMemcpy2DAsync(hc->d_img + L0.img_off + (size_t) b * L0.frame_stride, L0.pitch, src + (size_t) b * frame_stride,
+                                                    row_stride, width, height, cudaMemcpyDeviceToDevice, sc));
+            rc = run_pass(hc, nb, hc->d_img + L0.img_off, L0.pitch, L0.frame_stride, d_kps + (size_t) b0 * cap, d_desc + (size_t) b0 * cap * 32, d_n + b0, cap, sc);
         }
-        if (rc) return rc;
+        if (rc) return hc == h ? rc : set_error(h, rc, "peer arena: %s", orbfe_last_error(static_cast<orbfe_handle *>(hc)));
     }
-    if (sync) return check_device_error(h, st);
+    if (split) {
+        ORBFE_CUDA(h, cudaEventRecord(h->ev_split[1], hp->stream));
+        ORBFE_CUDA(h, cudaStreamWaitEvent(st, h->ev_split[1], 0));
+    }
+    if (sync) {
+        rc = check_device_error(h, st);
+        if (split) {
+            const int rp = check_device_error(hp, hp->stream);
+            if (!rc && rp) rc = set_error(h, rp, "peer arena: %s", orbfe_last_error(static_cast<orbfe_handle *>(hp)));
+        }
+        return rc;
+    }
     return ORBFE_OK;
 }
 

@@ -109,6 +109,7 @@ struct Handle {
     // Second arena + stream for the pipelined host path: odd chunks run their pass on the peer so that the tail of one pass
     // (quadtree, descriptors) overlaps with the head of the next (pyramid, FAST).  A complete handle, created lazily.
     orbfe_handle *peer = nullptr;
+    cudaEvent_t ev_split[2] = {};    // fork / join of the two half-batch passes of orbfe_extract_batch_device
     // CUDA graph of the single-frame pass (orbfe_extract): captured once per (arena, output staging), replayed per frame
     cudaGraphExec_t graph1 = nullptr;
     const void *graph1_key[4] = {nullptr, nullptr, nullptr, nullptr};
