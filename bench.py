@@ -164,7 +164,20 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created; stdout carries exactly one JSON line, so the
+        # banner is sent to stderr (fd-level, NCCL writes from C)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            t = torch.zeros(1, device=dev)
+            dist.all_reduce(t)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
 
     # synthetic frames: `distinct` different scenes, repeated to fill the batch (B*H*W = 185 MB at B=512 > the 126 MB L2)
