@@ -47,3 +47,19 @@ class ORBVocabulary:
                                                                  _capi.ptr(fid), _capi.ptr(foff), _capi.ptr(fidx), C.byref(nn)))
         k = nn.value
         return wid[:n], nid[:n], w[:n], (fid[:k].copy(), foff[:k + 1].copy(), fidx[:foff[k]].copy())
+
+    @staticmethod
+    def bow_vector(word_id, weight):
+        """The adapter's half of transform(features, BowVector, FeatureVector, levelsup) (:1150-1166) for ORBvoc.txt's TF_IDF /
+        L1_NORM header: BowVector::addWeight in feature order (stopped words, weight 0, left out), then BowVector::normalize(L1)
+        in std::map order.  -> (word ids ascending, values)."""
+        acc = {}
+        for w, v in zip(np.asarray(word_id).tolist(), np.asarray(weight, np.float64).tolist()):
+            if v > 0:
+                acc[w] = acc.get(w, 0.0) + v
+        ids = sorted(acc)
+        norm = 0.0
+        for w in ids:
+            norm += abs(acc[w])
+        vals = [acc[w] / norm for w in ids] if norm > 0.0 else [acc[w] for w in ids]
+        return np.array(ids, np.int32), np.array(vals, np.float64)

@@ -3,11 +3,14 @@
 // (resize, GaussianBlur, FAST, fastAtan2) forward to oracle/orb_oracle.c, which is pinned bit-exact to
 // cv2 4.13.0 by tests/test_oracle_primitives.py.
 #pragma once
+#include <algorithm>
 #include <cassert>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <sstream>       // the real opencv2/core pulls these in; the vendored DBoW2 headers rely on that
+#include <string>
 #include <vector>
 #include "orb_oracle.h"
 
@@ -15,6 +18,7 @@ typedef unsigned char uchar;
 #define CV_PI 3.1415926535897932384626433832795
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32F 5
 
 static inline int cvRound(double v) { return orc_round(v); }
 static inline int cvRound(float v) { return orc_roundf(v); }
@@ -60,11 +64,13 @@ namespace cv {
         int rows, cols; uchar *data; MatStep step;
         Mat() : rows(0), cols(0), data(nullptr), step(0) {}
         Mat(int r, int c, int /*type*/) : Mat() { create(r, c, CV_8U); }
-        void create(int r, int c, int /*type*/) {
-            if (data && r == rows && c == cols && isContinuous()) return;
-            buf_ = std::shared_ptr<uchar>(new uchar[(size_t) r * c > 0 ? (size_t) r * c : 1], std::default_delete<uchar[]>());
-            data = buf_.get(); rows = r; cols = c; step = (size_t) c;
+        void create(int r, int c, int type) {
+            if (data && r == rows && c == cols && isContinuous() && type == CV_8U) return;
+            const size_t es = type == CV_32F ? 4 : 1;           // (DBoW2's FORB::toMat32F; cols then counts elements, step bytes)
+            buf_ = std::shared_ptr<uchar>(new uchar[(size_t) r * c * es > 0 ? (size_t) r * c * es : 1], std::default_delete<uchar[]>());
+            data = buf_.get(); rows = r; cols = c; step = (size_t) c * es;
         }
+        void release() { buf_.reset(); data = nullptr; rows = cols = 0; step = 0; }
         bool isContinuous() const { return (size_t) step == (size_t) cols || rows == 1; }
         bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
         int type() const { return CV_8UC1; }
@@ -81,6 +87,7 @@ namespace cv {
             for (int y = 0; y < rows; ++y) std::memcpy(m.ptr(y), ptr(y), (size_t) cols);
             return m;
         }
+        Mat row(int y) const { return rowRange(y, y + 1); }
         Mat rowRange(int a, int b) const { Mat m = *this; m.data = data + (size_t) a * step; m.rows = b - a; return m; }
         Mat colRange(int a, int b) const { Mat m = *this; m.data = data + a; m.cols = b - a; return m; }
         static MatZeros zeros(int r, int c, int /*type*/) { return MatZeros{r, c}; }
@@ -95,4 +102,24 @@ namespace cv {
     };
 
     static inline float fastAtan2(float y, float x) { return orc_fast_atan2(y, x); }
+
+    // Name-only stand-ins for the YAML storage classes that the vendored DBoW2's TemplatedVocabulary.h mentions in its virtual
+    // save / load members (instantiated with the class, never called by the oracle harness, which loads text files)
+    struct FileNode {
+        FileNode operator[](const std::string &) const { return FileNode(); }
+        FileNode operator[](const char *) const { return FileNode(); }
+        FileNode operator[](int) const { return FileNode(); }
+        size_t size() const { return 0; }
+        operator int() const { return 0; }
+        operator double() const { return 0; }
+        operator std::string() const { return std::string(); }
+    };
+    struct FileStorage {
+        enum { READ = 0, WRITE = 1 };
+        FileStorage() {}
+        FileStorage(const std::string &, int) {}
+        bool isOpened() const { return false; }
+        FileNode operator[](const std::string &) const { return FileNode(); }
+        template <class T> FileStorage &operator<<(const T &) { return *this; }
+    };
 }

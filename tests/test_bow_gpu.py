@@ -1,6 +1,9 @@
-"""GPU: DBoW2 vocabulary descent (csrc/orbfe_bow.cu) through the C-ABI against the restatement of
-TemplatedVocabulary::transform (oracle/bow.py) on synthetic vocabulary trees — word ids, node ids, weights and the
-FeatureVector bit-exact; then SearchByBow on feature vectors produced by the device."""
+"""GPU: DBoW2 vocabulary descent (csrc/orbfe_bow.cu) through the C-ABI against golden vectors of the reference's own vendored
+DBoW2 (tests/golden/dbow_ref.npz, thirdParty/DBoW2 compiled verbatim) and against the restatement of
+TemplatedVocabulary::transform (oracle/bow.py) on further synthetic vocabulary trees — word ids, node ids, weights, the
+FeatureVector and the BowVector bit-exact; then SearchByBow on feature vectors produced by the device."""
+import os
+
 import numpy as np
 import pytest
 
@@ -16,6 +19,21 @@ def env():
     ka, da = ex(a); kb, db = ex(b)
     yield ex, ORBVocabulary, ORBMatcher, bow, ka, da, kb, db
     ex.close()
+
+
+@pytest.mark.parametrize("name", ["k10L3", "k6L4", "k3L6", "k10L2_root"])
+def test_transform_matches_reference_dbow2_golden(env, name):
+    ex, ORBVocabulary = env[0], env[1]
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "dbow_ref.npz"))
+    c = {k.split("/", 1)[1]: g[k] for k in g.files if k.startswith(name + "/")}
+    gv = ORBVocabulary(ex, int(c["k"]), int(c["L"]), c["parent"], c["leaf"], c["desc"], c["weight"])
+    assert gv.n_words == int(c["n_words"])
+    wid, nid, w, (fnode, foff, fidx) = gv.transform(c["feats"], int(c["levelsup"]))
+    assert np.array_equal(wid, c["word_id"]) and np.array_equal(nid, c["node_id"]) and np.array_equal(w, c["word_weight"])
+    assert np.array_equal(fnode, c["fv_node"]) and np.array_equal(foff, c["fv_off"]) and np.array_equal(fidx, c["fv_idx"])
+    bid, bval = gv.bow_vector(wid, w)
+    assert np.array_equal(bid, c["bow_id"]) and np.array_equal(bval, c["bow_val"])
+    gv.close()
 
 
 @pytest.mark.parametrize("k,L,levelsup", [(10, 3, 1), (6, 4, 2), (3, 6, 4), (20, 2, 4), (33, 2, 1)])

@@ -251,3 +251,33 @@ def test_tracking_and_local_mapping_threads_run_concurrently(ctx, oracle):
     main = matcher_mod._handle()
     addr = lambda h: h.value if hasattr(h, "value") else int(h)
     assert len({addr(handles["tracking"]), addr(handles["mapping"]), addr(main)}) == 3       # every thread got its own handle
+
+
+def test_matchers_reproduce_the_reference_matcher_golden(ctx):
+    """Every matcher entry point of the C-ABI against tests/golden/matcher_ref.npz: outputs of the reference's own
+    modules/ORB/ORBMatcher.cpp compiled verbatim (tools/gen_golden_matcher.py) — match counts, assignments, matches12 and the
+    updated vecPreMatched bit for bit."""
+    from golden_matcher import replay
+    M, FV = ctx["ORBMatcher"], ctx["FrameView"]
+
+    def init(ka, da, kb, db, w, h, pre, window, ratio, orient):
+        n, m12 = M(ratio, orient).SearchForInitialization(FV(ka, da, w, h), FV(kb, db, w, h), pre, window)
+        return n, m12, pre
+
+    def proj(q_u, q_v, q_r, q_l, q_a, q_d, q_valid, kb, db, w, h, occ, orient):
+        return M(0.6, orient).SearchByProjection(q_u, q_v, q_r, q_l, q_a, q_d, q_valid, FV(kb, db, w, h), occ)
+
+    def local(q_u, q_v, q_r, q_l, q_d, q_valid, kb, db, w, h, occ, ratio):
+        return M(ratio, True).SearchLocalPoints(q_u, q_v, q_r, q_l, q_d, q_valid, FV(kb, db, w, h), occ)
+
+    def tri(d1, a1, has1, fv1, d2, a2, has2, fv2, orient):
+        return M(0.6, orient).SearchForTriangulation(d1, a1, has1, fv1, d2, a2, has2, fv2)
+
+    def bow(d1, a1, valid1, fv1, d2, a2, occ2, fv2, ratio, orient):
+        return M(ratio, orient).SearchByBow(d1, a1, valid1, fv1, d2, a2, occ2, fv2)
+
+    def fuse(u, v, radius, level, qd, valid, ka, da, w, h, square_sigmas):
+        return M().SearchFuse(FV(ka, da, w, h), u, v, radius, level, qd, valid)
+
+    assert replay(dict(search_for_initialization=init, search_by_projection=proj, search_local_points=local, search_for_triangulation=tri,
+                       search_by_bow=bow, search_fuse=fuse)) == 13
