@@ -4,6 +4,7 @@
 // Python mirror (which is parity-tested against the oracle).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <memory>
 #include <vector>
 #include "../../monoorbslam3_b200/host/ORBExtractor.h"
@@ -39,6 +40,31 @@ int main(int argc, char **argv) {
     std::vector<std::vector<cv::KeyPoint>> bk; std::vector<cv::Mat> bd;
     extractor.extractBatch({f1->img, f2->img, f1->img}, bk, bd);
     if (bk[0].size() != k3.size() || bk[2].size() != k3.size() || memcmp(bk[0].data(), k3.data(), k3.size() * sizeof(cv::KeyPoint)) != 0) return 4;
+    {   // the streaming form through the plain C-ABI: two batches in flight on pinned buffers, waited in
+        // submission order; both must hold what the blocking adapter call returned
+        const int B = 3, cap = 1400;
+        const size_t fb = (size_t) w * h;
+        uint8_t *fr = nullptr; orbfe_keypoint *kp[2] = {}; uint8_t *ds[2] = {}; int *cnt[2] = {};
+        if (orbfe_host_alloc((void **) &fr, B * fb)) return 6;
+        for (int s = 0; s < 2; ++s)
+            if (orbfe_host_alloc((void **) &kp[s], sizeof(orbfe_keypoint) * B * cap) || orbfe_host_alloc((void **) &ds[s], (size_t) B * cap * 32) ||
+                orbfe_host_alloc((void **) &cnt[s], sizeof(int) * B)) return 6;
+        const cv::Mat *src[3] = {&f1->img, &f2->img, &f1->img};
+        for (int b = 0; b < B; ++b) memcpy(fr + b * fb, src[b]->data, fb);
+        long long t[2] = {-1, -1};
+        for (int s = 0; s < 2; ++s)
+            if (orbfe_extract_batch_submit(extractor.handle(), fr, B, w, h, (size_t) w, fb, kp[s], ds[s], cap, cnt[s], &t[s])) return 7;
+        if (t[0] < 0 || t[1] <= t[0]) return 7;
+        for (int s = 0; s < 2; ++s) {
+            if (orbfe_extract_batch_wait(extractor.handle(), t[s])) return 8;
+            for (int b = 0; b < B; ++b) {
+                if (cnt[s][b] != (int) bk[b].size() || memcmp(kp[s] + (size_t) b * cap, bk[b].data(), bk[b].size() * sizeof(cv::KeyPoint)) != 0 ||
+                    memcmp(ds[s] + (size_t) b * cap * 32, bd[b].data, bk[b].size() * 32) != 0) return 9;
+            }
+        }
+        orbfe_host_free(fr);
+        for (int s = 0; s < 2; ++s) { orbfe_host_free(kp[s]); orbfe_host_free(ds[s]); orbfe_host_free(cnt[s]); }
+    }
     std::vector<cv::Point2f> pre(f1->key_points.size());
     for (size_t i = 0; i < pre.size(); ++i) pre[i] = f1->key_points[i].pt;      // Tracking.cpp:598-600
     std::vector<int> m12;
