@@ -4,7 +4,9 @@
 
 A step = one pass of the hot path (pyramid, FAST, quadtree, blur, descriptors) over one batch of B synthetic frames per GPU.
   value : frames/s with the frames already resident in HBM (device API), CUDA events on the launching stream, max over ranks
-  e2e   : frames/s through the host C-ABI call (orbfe_extract_batch) with pinned HOST buffers — H2D and D2H inside the timed region
+  e2e   : frames/s through the host C-ABI with pinned HOST buffers — H2D and D2H of every step inside the timed region; the streaming
+          form orbfe_extract_batch_submit / _wait with two batches in flight (e2e.value) and one blocking orbfe_extract_batch call
+          per step (e2e.sync_call_value)
   roofline : the dominant stage, algorithmic bytes per launch / its CUDA-event duration, against MEASURED_PEAKS.json
   cpu_baseline : the reference's own ORBExtractor.cpp (oracle/_ref, compiled verbatim) on the host cores, bounded sample
 `--impl reference` runs only that CPU arm.  N > 1: frames are sharded by rank (weak scaling), results gathered with NCCL."""
