@@ -188,12 +188,18 @@ int orbfe_frame_postprocess_device(orbfe_handle *h, const orbfe_camera *cam, orb
  * denominator bench.py quotes the matching kernels against. */
 int orbfe_popc_peak(orbfe_handle *h, double *gpopc_per_s);
 
+/* Measured throughput of the int8 tensor-core instruction the large all-pairs searches run on (mma.sync m16n8k32.s8), expressed in
+ * 10^9 descriptor pairs per second (256 int8 multiply-adds = one pair): the roofline denominator of that path. */
+int orbfe_imma_peak(orbfe_handle *h, double *gmatch_per_s);
+
 /* ORBMatcher::DescriptorDistance over explicit pairs: dist[i] = hamming(a[ia[i]], b[ib[i]]). */
 int orbfe_descriptor_distance(orbfe_handle *h, const uint8_t *a, int na, const uint8_t *b, int nb,
                               const int32_t *ia, const int32_t *ib, int n_pairs, int32_t *dist);
 
 /* Brute-force best / second-best over all pairs (BASELINE configs 4/5): for each query row the train index of the
- * minimum distance (first minimum wins), that distance and the second-smallest distance (257 if none). Host memory. */
+ * minimum distance (first minimum wins), that distance and the second-smallest distance (257 if none). Host memory.
+ * Problems of at least 256 x 256 run as an int8 GEMM on the tensor cores (hamming = (256 - <a, b>) / 2 over +-1 vectors, exact),
+ * smaller ones on the popc kernel; the results are identical (ORBFE_ALLPAIRS_POPC=1 forces the popc kernel). */
 int orbfe_hamming_allpairs(orbfe_handle *h, const uint8_t *q, int nq, const uint8_t *t, int nt,
                            int32_t *best_idx, int32_t *best_dist, int32_t *second_dist);
 /* Device-resident variant (asynchronous on `stream` unless sync). */

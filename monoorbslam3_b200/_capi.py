@@ -69,6 +69,7 @@ SIGNATURES = {
     "orbfe_frame_postprocess": (_i, [_vp, C.POINTER(Camera), _vp, _i, _i, _i, _vp, _vp, _vp, C.POINTER(_i)]),
     "orbfe_frame_postprocess_device": (_i, [_vp, C.POINTER(Camera), _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i]),
     "orbfe_popc_peak": (_i, [_vp, C.POINTER(C.c_double)]),
+    "orbfe_imma_peak": (_i, [_vp, C.POINTER(C.c_double)]),
     "orbfe_descriptor_distance": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp]),
     "orbfe_hamming_allpairs": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "orbfe_hamming_window": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),

@@ -554,7 +554,7 @@ void orbfe_destroy(orbfe_handle *h) {
     if (h->peer) { orbfe_destroy(h->peer); h->peer = nullptr; }
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_arena(h);
-    cudaFree(h->d_err); cudaFree(h->d_match); cudaFree(h->d_pattern); cudaFree(h->d_unc);
+    cudaFree(h->d_err); cudaFree(h->d_match); cudaFree(h->d_ap); cudaFree(h->d_pattern); cudaFree(h->d_unc);
     for (int i = 0; i <= ORBFE_N_STAGES; ++i) if (h->prof_ev[i]) cudaEventDestroy(h->prof_ev[i]);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->h_mpin) cudaFreeHost(h->h_mpin);

@@ -123,6 +123,7 @@ struct Handle {
     float *d_unc = nullptr; const float *unc_host = nullptr; size_t unc_bytes = 0;
     // matcher scratch
     void *d_match = nullptr; size_t match_bytes = 0;
+    void *d_ap = nullptr; size_t ap_bytes = 0;        // all-pairs on the tensor cores: +-1 int8 rows of both sides + partial results
     void *h_pinned = nullptr; size_t pinned_bytes = 0;
     void *h_mpin = nullptr; size_t mpin_bytes = 0;      // pinned staging of the matcher's window searches
 

@@ -150,6 +150,154 @@ __global__ void __launch_bounds__(256) k_hamming_allpairs(const uint4 *__restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// K11b all-pairs on the tensor cores.  hamming(a, b) = (256 - <a', b'>) / 2 with a', b' the descriptors as +-1 int8 vectors, so the
+// N x M distance matrix is an int8 GEMM with K = 256 (exact in s32) followed by the same (min, second-min) key reduction as above.
+// Descriptors are expanded once per call to 288-byte rows (256 of +-1, 32 of padding that makes the 64-bit fragment loads
+// bank-conflict free).  CTA = 4 warps x 32 query rows; the A fragments of a warp's rows stay in registers for the whole kernel,
+// train rows stream through shared memory in tiles of 64 (cp.async.bulk, double-buffered), the train range is split over
+// blockIdx.y to fill the machine and the partial (min, second-min) pairs are merged by k_allpairs_merge.
+// A thread loads 8 contiguous bytes of a row per k-step for both operands: the k order inside a 32-byte step is permuted the same
+// way on both sides, which a dot product does not see.
+// Legacy warp-level IMMA (mma.sync.m16n8k32.s8): measured 1.13 POPS = 2 200 GMatch/s equivalent on B200 (tools/micro/mma_b1.cu).
+// ------------------------------------------------------------------------------------------------
+constexpr int kImStride = 288;
+constexpr int kImN = 64;
+constexpr int kImM = 128;
+
+__global__ void k_expand_pm1(const uint8_t *__restrict__ bits, int n, uint8_t *__restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * 36) return;
+    const int row = idx / 36, g = idx - row * 36;
+    uint2 v = make_uint2(0u, 0u);
+    if (g < 32) {
+        const uint32_t b = bits[(size_t) row * 32 + g];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v.x |= (((b >> j) & 1u) ? 0x01u : 0xffu) << (8 * j);
+            v.y |= (((b >> (j + 4)) & 1u) ? 0x01u : 0xffu) << (8 * j);
+        }
+    }
+    *reinterpret_cast<uint2 *>(out + (size_t) row * kImStride + g * 8) = v;
+}
+
+__device__ __forceinline__ void imma16832(int (&c)[4], const uint32_t (&a)[4], const uint2 b) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+
+__global__ void __launch_bounds__(128) k_allpairs_imma(const uint8_t *__restrict__ qe, int nq, const uint8_t *__restrict__ te, int nt, int tiles_per_split,
+                                                        uint2 *__restrict__ partial) {
+    __shared__ __align__(128) uint8_t tile[2][kImN * kImStride];
+    __shared__ __align__(8) uint64_t bar[2];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, q = lane & 3;
+    const int row0 = blockIdx.x * kImM + wid * 32;
+    uint32_t a[2][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        const int r0 = min(row0 + mt * 16 + g, nq - 1), r1 = min(row0 + mt * 16 + g + 8, nq - 1);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            const uint2 v0 = __ldg(reinterpret_cast<const uint2 *>(qe + (size_t) r0 * kImStride + ks * 32 + q * 8));
+            const uint2 v1 = __ldg(reinterpret_cast<const uint2 *>(qe + (size_t) r1 * kImStride + ks * 32 + q * 8));
+            a[mt][ks][0] = v0.x; a[mt][ks][1] = v1.x; a[mt][ks][2] = v0.y; a[mt][ks][3] = v1.y;
+        }
+    }
+    uint32_t k1[4] = {kApNone, kApNone, kApNone, kApNone}, k2[4] = {kApNone, kApNone, kApNone, kApNone};
+    const int n_tiles = (nt + kImN - 1) / kImN;
+    const int t_begin = blockIdx.y * tiles_per_split, t_end = min(n_tiles, t_begin + tiles_per_split);
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_barrier_init(); }
+    __syncthreads();
+    if (tid == 0 && t_begin < t_end) {
+        const uint32_t bytes = (uint32_t) min(kImN, nt - t_begin * kImN) * kImStride;
+        mbar_expect_tx(&bar[0], bytes);
+        bulk_g2s(tile[0], te + (size_t) t_begin * kImN * kImStride, bytes, &bar[0]);
+    }
+    for (int it = t_begin; it < t_end; ++it) {
+        const int li = it - t_begin, buf = li & 1;
+        if (tid == 0 && it + 1 < t_end) {
+            const uint32_t bytes = (uint32_t) min(kImN, nt - (it + 1) * kImN) * kImStride;
+            mbar_expect_tx(&bar[buf ^ 1], bytes);
+            bulk_g2s(tile[buf ^ 1], te + (size_t) (it + 1) * kImN * kImStride, bytes, &bar[buf ^ 1]);
+        }
+        mbar_wait(&bar[buf], (uint32_t) ((li >> 1) & 1));
+        int acc[2][8][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int n8 = 0; n8 < 8; ++n8)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[mt][n8][c] = 0;
+        const uint8_t *tb = tile[buf] + g * kImStride + q * 8;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+            for (int n8 = 0; n8 < 8; ++n8) {
+                const uint2 b = *reinterpret_cast<const uint2 *>(tb + n8 * 8 * kImStride + ks * 32);
+                imma16832(acc[0][n8], a[0][ks], b);
+                imma16832(acc[1][n8], a[1][ks], b);
+            }
+        }
+        const int j0 = it * kImN;
+        const bool ragged = nt - j0 < kImN;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int n8 = 0; n8 < 8; ++n8)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int col = j0 + n8 * 8 + q * 2 + (c & 1);
+                    uint32_t key = ((uint32_t) (256 - acc[mt][n8][c]) << 21) | (uint32_t) col;      // (256 - dot) = 2 * distance
+                    if (ragged && col >= nt) key = kApNone;
+                    const int r = mt * 2 + (c >> 1);
+                    k2[r] = min(k2[r], max(key, k1[r]));
+                    k1[r] = min(k1[r], key);
+                }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int m = 1; m < 4; m <<= 1) {
+            const uint32_t b1 = __shfl_xor_sync(0xffffffffu, k1[r], m), b2 = __shfl_xor_sync(0xffffffffu, k2[r], m);
+            const uint32_t n2 = min(max(k1[r], b1), min(k2[r], b2));
+            k1[r] = min(k1[r], b1); k2[r] = n2;
+        }
+        const int row = row0 + (r >> 1) * 16 + g + (r & 1) * 8;
+        if (q == 0 && row < nq) partial[(size_t) blockIdx.y * nq + row] = make_uint2(k1[r], k2[r]);
+    }
+}
+
+__global__ void k_allpairs_merge(const uint2 *__restrict__ partial, int n_split, int nq, int *best_idx, int *best_dist, int *second_dist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    uint32_t a1 = kApNone, a2 = kApNone;
+    for (int s = 0; s < n_split; ++s) {
+        const uint2 p = __ldg(partial + (size_t) s * nq + i);
+        const uint32_t n2 = min(max(a1, p.x), min(a2, p.y));
+        a1 = min(a1, p.x); a2 = n2;
+    }
+    const int d1 = (int) (a1 >> 22);
+    best_idx[i] = d1 >= 257 ? -1 : (int) (a1 & 0x3fffffu);
+    best_dist[i] = d1; second_dist[i] = (int) (a2 >> 22);
+}
+
+// IMMA micro-benchmark: the roofline denominator of k_allpairs_imma.  Register operands only, four independent accumulator chains
+// per warp; one m16n8k32 instruction = 16 x 8 x 32 int8 multiply-adds = 1/8 of 128 descriptor pairs.
+__global__ void __launch_bounds__(256) k_imma_peak(int *out, int iters) {
+    uint32_t a[4] = {threadIdx.x * 2654435761u, threadIdx.x * 40503u + 1u, threadIdx.x ^ 0x9e3779b9u, threadIdx.x + 77u};
+    const uint2 b = make_uint2(threadIdx.x * 2246822519u, threadIdx.x * 3266489917u);
+    int c[4][4] = {};
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) imma16832(c[u], a, b);
+    }
+    int s = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s += c[u][0] + c[u][1] + c[u][2] + c[u][3];
+    if (s == 0x7fffffff) out[0] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K10 caller-supplied candidate lists (CSR): 8 lanes per query, lane l takes positions l, l+8, ... of the query's list.
 // key = dist << 22 | position in the list, so the first minimum of the sequential `if (d < best)` scan wins.
 // ------------------------------------------------------------------------------------------------
@@ -1007,6 +1155,33 @@ int orbfe_popc_peak(orbfe_handle *h, double *gpopc_per_s) {
     return ORBFE_OK;
 }
 
+int orbfe_imma_peak(orbfe_handle *h, double *gmatch_per_s) {
+    if (!h || !gmatch_per_s) return ORBFE_E_ARG;
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_match_scratch(h, 4096);
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    cudaEvent_t e0, e1;
+    ORBFE_CUDA(h, cudaEventCreate(&e0)); ORBFE_CUDA(h, cudaEventCreate(&e1));
+    const int blocks = h->sm_count * 8, iters = 4096;
+    k_imma_peak<<<blocks, 256, 0, st>>>((int *) h->d_match, 64);                     // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        ORBFE_CUDA(h, cudaEventRecord(e0, st));
+        k_imma_peak<<<blocks, 256, 0, st>>>((int *) h->d_match, iters);
+        ORBFE_CUDA(h, cudaEventRecord(e1, st));
+        ORBFE_CUDA(h, cudaEventSynchronize(e1));
+        float ms = 0;
+        ORBFE_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+        // warps x iterations x 4 instructions, each 1/8 of a 16 x 8 tile of 256-bit pairs
+        best = std::max(best, (double) blocks * 8 * iters * 4 * (128.0 / 8.0) / (ms * 1e-3) / 1e9);
+    }
+    h->launches += 6;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *gmatch_per_s = best;
+    return ORBFE_OK;
+}
+
 int orbfe_descriptor_distance(orbfe_handle *h, const uint8_t *a, int na, const uint8_t *b, int nb, const int32_t *ia, const int32_t *ib, int n_pairs, int32_t *dist) {
     if (!h) return ORBFE_E_ARG;
     if (!a || !b || !ia || !ib || !dist || na < 0 || nb < 0 || n_pairs < 0) return set_error(h, ORBFE_E_ARG, "invalid argument");
@@ -1042,8 +1217,40 @@ int orbfe_hamming_allpairs_device(orbfe_handle *h, const uint8_t *d_q, int nq, c
     if (nq == 0) return ORBFE_OK;
     ORBFE_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t) stream : h->stream;
-    k_hamming_allpairs<<<(nq + kApQ - 1) / kApQ, 256, 0, st>>>((const uint4 *) d_q, nq, (const uint4 *) d_t, nt, d_best_idx, d_best_dist, d_second_dist);
-    h->launches++;
+    // large problems go to the tensor-core formulation (ORBFE_ALLPAIRS_POPC=1 keeps the popc kernel, for A/B runs)
+    const char *popc_env = getenv("ORBFE_ALLPAIRS_POPC");             // read per call: bench.py times both kernels in one process
+    const bool force_popc = popc_env && *popc_env == '1';
+    if (!force_popc && nq >= 2 * kImM && nt >= 4 * kImN) {
+        const int n_mt = (nq + kImM - 1) / kImM, n_tiles = (nt + kImN - 1) / kImN;
+        const int slots = std::max(h->sm_count, 1) * 3;                      // resident CTAs (about 160 registers x 128 threads, 37 KB)
+        int n_split = 1; double best_eff = 0;
+        for (int s = 1; s <= 32; s *= 2) {
+            if (s > 1 && (n_tiles + s - 1) / s < 4) break;
+            const long long total = (long long) n_mt * s;
+            const double eff = (double) total / (double) (((total + slots - 1) / slots) * slots);
+            if (eff > best_eff + 0.02) { best_eff = eff; n_split = s; }
+        }
+        const int tiles_per_split = (n_tiles + n_split - 1) / n_split;
+        n_split = (n_tiles + tiles_per_split - 1) / tiles_per_split;
+        const size_t qe_bytes = ((size_t) nq * kImStride + 255) & ~(size_t) 255, te_bytes = ((size_t) nt * kImStride + 255) & ~(size_t) 255;
+        const size_t need = qe_bytes + te_bytes + (size_t) n_split * nq * sizeof(uint2) + 256;
+        if (h->ap_bytes < need) {
+            ORBFE_CUDA(h, cudaDeviceSynchronize());
+            cudaFree(h->d_ap); h->d_ap = nullptr; h->ap_bytes = 0;
+            ORBFE_CUDA(h, cudaMalloc(&h->d_ap, need));
+            h->ap_bytes = need;
+        }
+        uint8_t *qe = (uint8_t *) h->d_ap, *te = qe + qe_bytes;
+        uint2 *partial = reinterpret_cast<uint2 *>(te + te_bytes);
+        k_expand_pm1<<<(nq * 36 + 255) / 256, 256, 0, st>>>(d_q, nq, qe);
+        k_expand_pm1<<<(nt * 36 + 255) / 256, 256, 0, st>>>(d_t, nt, te);
+        k_allpairs_imma<<<dim3(n_mt, n_split), 128, 0, st>>>(qe, nq, te, nt, tiles_per_split, partial);
+        k_allpairs_merge<<<(nq + 255) / 256, 256, 0, st>>>(partial, n_split, nq, d_best_idx, d_best_dist, d_second_dist);
+        h->launches += 4;
+    } else {
+        k_hamming_allpairs<<<(nq + kApQ - 1) / kApQ, 256, 0, st>>>((const uint4 *) d_q, nq, (const uint4 *) d_t, nt, d_best_idx, d_best_dist, d_second_dist);
+        h->launches++;
+    }
     ORBFE_CUDA(h, cudaGetLastError());
     if (sync) ORBFE_CUDA(h, cudaStreamSynchronize(st));
     return ORBFE_OK;

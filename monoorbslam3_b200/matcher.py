@@ -75,6 +75,13 @@ class ORBMatcher:
         _capi.check(self._h, self._lib.orbfe_popc_peak(self._h, C.byref(v)))
         return v.value
 
+    def imma_peak(self):
+        """Measured int8 tensor-core (mma.sync m16n8k32) throughput in 10^9 descriptor pairs/s: the roofline denominator of the
+        large all-pairs searches."""
+        v = C.c_double()
+        _capi.check(self._h, self._lib.orbfe_imma_peak(self._h, C.byref(v)))
+        return v.value
+
     # ---- brute force best / second best (BASELINE configs 4/5)
     def hamming_allpairs(self, q, t):
         q = _c(q, np.uint8); t = _c(t, np.uint8)
