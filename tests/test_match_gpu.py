@@ -26,7 +26,10 @@ def test_descriptor_distance(ctx, oracle):
     assert m.DescriptorDistance(np.zeros(32, np.uint8), np.full(32, 255, np.uint8)) == 256
 
 
-@pytest.mark.parametrize("nq,nt", [(1, 1), (7, 513), (64, 512), (65, 1025), (2012, 2009), (300, 5000)])
+# problems of at least 256 x 256 run on the tensor cores (k_allpairs_imma), smaller ones on the popc kernel: shapes on both sides of
+# the switch, ragged last tiles (nt % 64, nq % 128), one train split and several
+@pytest.mark.parametrize("nq,nt", [(1, 1), (7, 513), (64, 512), (65, 1025), (2012, 2009), (300, 5000), (256, 256), (257, 319), (1153, 4097), (129, 300),
+                                   (5000, 257)])
 def test_allpairs(ctx, oracle, nq, nt):
     m = ctx["ORBMatcher"]()
     rng = np.random.default_rng(nq * 7 + nt)
@@ -35,6 +38,23 @@ def test_allpairs(ctx, oracle, nq, nt):
     bi, bd, sd = m.hamming_allpairs(q, t)
     obi, obd, osd = oracle.hamming_allpairs(q, t)
     assert np.array_equal(bi, obi) and np.array_equal(bd, obd) and np.array_equal(sd, osd)
+
+
+def test_allpairs_tensor_core_and_popc_kernels_agree(ctx, monkeypatch):
+    """The +-1 int8 GEMM formulation and the popc kernel give identical (index, best, second) on real descriptors and on
+    adversarial ones (all-equal rows: every distance 0, the first index must win; complementary rows: distance 256)."""
+    m = ctx["ORBMatcher"]()
+    rng = np.random.default_rng(11)
+    q = np.concatenate([ctx["da"], ctx["db"]])[:3000].copy(); t = np.concatenate([ctx["db"], ctx["da"]])[:2900].copy()
+    t[100:400] = t[100]                                   # 300 identical train rows
+    q[5] = t[100]; q[6] = ~t[100]                         # distance 0 against all of them / distance 256
+    t[rng.integers(0, len(t), 200)] = q[rng.integers(0, len(q), 200)]
+    got = m.hamming_allpairs(q, t)
+    monkeypatch.setenv("ORBFE_ALLPAIRS_POPC", "1")
+    ref = m.hamming_allpairs(q, t)
+    monkeypatch.delenv("ORBFE_ALLPAIRS_POPC")
+    assert all(np.array_equal(a, b) for a, b in zip(got, ref))
+    assert got[1][5] == 0 and got[0][5] <= 100 and got[2][5] == 0
 
 
 def test_allpairs_real_descriptors_and_empty(ctx, oracle):
