@@ -17,7 +17,7 @@ def build(force=False):
     """(Re)build the oracle and, when /root/reference exists, the verbatim reference libraries."""
     so = os.path.join(HERE, "liborb_oracle.so")
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(HERE, "orb_oracle.c")):
-        subprocess.check_call(["make", "-s", "-C", HERE, "all"])
+        subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "all"])
     return so
 
 
