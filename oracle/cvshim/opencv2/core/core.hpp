@@ -41,6 +41,13 @@ namespace cv {
     typedef Point_<int> Point2i;
     typedef Point_<float> Point2f;
 
+    template<typename T> struct Point3_ { T x, y, z; Point3_() : x(0), y(0), z(0) {} Point3_(T x_, T y_, T z_) : x(x_), y(y_), z(z_) {} };
+    typedef Point3_<float> Point3f;
+    struct RNG {            // name-only (TwoViewReconstruction draws its RANSAC sets with it; the oracle harness supplies its own hypotheses)
+        unsigned long long state = 0xffffffffu;
+        int uniform(int a, int b) { state = state * 4164903690ULL + (state >> 32); return a + (int) ((unsigned) state % (unsigned) (b - a)); }
+    };
+
     struct Size { int width, height; Size() : width(0), height(0) {} Size(int w, int h) : width(w), height(h) {} };
 
     struct KeyPoint {     // same 28-byte layout as the real class

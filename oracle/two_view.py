@@ -2,7 +2,8 @@
 TwoViewReconstruction::CheckHomography / CheckFundamental (Frontend/TwoViewReconstruction.cpp:226-288, 290-345) restated with
 numpy float32 arrays — every operation is a separate IEEE single operation in the reference's order (the reference is compiled
 without FMA), and the score is the sequential float32 sum over the matches (np.cumsum accumulates in order).
-The class itself needs Eigen + OpenCV and is not compilable in this image: pinned to this restatement only."""
+PINNED to the reference's own TwoViewReconstruction.cpp compiled verbatim against a name-level Eigen stand-in (oracle/twoview_harness.cpp,
+oracle/_ref/libref_twoview.so): tests/test_oracle_two_view_ref.py compares scores (bit for bit) and inlier flags."""
 import numpy as np
 
 F = np.float32
