@@ -46,6 +46,32 @@ def features_in_area(kps, img_w, img_h, qx, qy, qr, qmin, qmax):
     return off, idx[:total].copy(), (cols.value, rows.value)
 
 
+KF_PATH = os.path.join(HERE, "_ref", "libref_keyframe.so")
+_kf = None
+
+
+def keyframe_available():
+    return os.path.exists(KF_PATH)
+
+
+def keyframe_features_in_area(kps, img_w, img_h, qx, qy, qr, qmin, qmax):
+    """KeyFrame::getFeaturesInArea (KeyFrame.cpp:181-211, strict `<`) of the reference's own KeyFrame.cpp compiled verbatim
+    (oracle/keyframe_harness.cpp): -> (offsets[nq + 1], indices)."""
+    global _kf
+    if _kf is None:
+        _kf = C.CDLL(KF_PATH)
+        _kf.ref_keyframe_features_in_area.restype = C.c_int
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    qx = np.ascontiguousarray(qx, np.float32); qy = np.ascontiguousarray(qy, np.float32); qr = np.ascontiguousarray(qr, np.float32)
+    qmin = np.ascontiguousarray(qmin, np.int32); qmax = np.ascontiguousarray(qmax, np.int32)
+    nq = len(qx)
+    idx = np.empty(min(max(len(kps) * max(nq, 1), 1), 1 << 26), np.int32); off = np.zeros(nq + 1, np.int32)
+    total = _kf.ref_keyframe_features_in_area(_p(kps), len(kps), int(img_w), int(img_h), _p(qx), _p(qy), _p(qr), _p(qmin), _p(qmax), nq,
+                                              _p(idx), len(idx), _p(off))
+    assert total >= 0
+    return off, idx[:total].copy()
+
+
 def grid(kps, img_w, img_h):
     """-> (grid_off[cols * rows + 1], grid_idx, (cols, rows)): Frame::grid flattened with cell = cx * rows + cy."""
     kps = np.ascontiguousarray(kps, KP_DTYPE)

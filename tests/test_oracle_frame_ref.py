@@ -2,7 +2,8 @@
 grid_dims / build_grid) to the reference's own BasicObject/Frame.cpp compiled verbatim (oracle/_ref/libref_frame.so, see
 oracle/frame_harness.cpp): Frame::Frame's 40-px grid (Frame.cpp:32-51) and Frame::getFeaturesInArea (:97-127) on random key points —
 fractional and out-of-image coordinates, image sizes that are and are not multiples of 40, windows that leave the image, level
-filters on and off.  KeyFrame::getFeaturesInArea (KeyFrame.cpp:181-211) differs from it by `<` for `<=` only and stays a restatement."""
+filters on and off.  KeyFrame::getFeaturesInArea (KeyFrame.cpp:181-211, `<` for `<=`) is pinned the same way against the reference's
+own KeyFrame.cpp (oracle/_ref/libref_keyframe.so)."""
 import numpy as np
 import pytest
 
@@ -49,10 +50,17 @@ def test_grid_and_window_queries_match_the_reference_frame(w, h, n, seed):
     qmax = np.where(mode == 0, -1, np.where(mode == 1, -1, qmin + rng.integers(0, 3, nq))).astype(np.int32)
     qmin[mode == 3] = 0                                               # minLevel 0 with maxLevel >= 0: filter on through maxLevel alone
     roff, ridx, _ = ref.features_in_area(kps, w, h, qx, qy, qr, qmin, qmax)
-    n_nonempty = 0
+    koff, kidx = ref.keyframe_features_in_area(kps, w, h, qx, qy, qr, qmin, qmax) if ref.keyframe_available() else (None, None)
+    n_nonempty = n_edge = 0
     for i in range(nq):
         got = orc.features_in_area(kps, w, h, float(qx[i]), float(qy[i]), float(qr[i]), int(qmin[i]), int(qmax[i]), strict=False)
         exp = ridx[roff[i]:roff[i + 1]]
         assert np.array_equal(got, exp), (i, qx[i], qy[i], qr[i], qmin[i], qmax[i])
         n_nonempty += len(exp) > 0
+        if koff is not None:                                          # the strict variant against the reference's KeyFrame
+            got_s = orc.features_in_area(kps, w, h, float(qx[i]), float(qy[i]), float(qr[i]), int(qmin[i]), int(qmax[i]), strict=True)
+            exp_s = kidx[koff[i]:koff[i + 1]]
+            assert np.array_equal(got_s, exp_s), ("strict", i, qx[i], qy[i], qr[i], qmin[i], qmax[i])
+            n_edge += len(exp_s) < len(exp)
     assert n == 0 or n_nonempty > nq // 4
+    assert koff is None or n < 300 or n_edge > 10                     # windows whose border passes through a key point: `<` and `<=` differ
