@@ -185,6 +185,25 @@ __device__ __forceinline__ void imma16832(int (&c)[4], const uint32_t (&a)[4], c
                  : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
 }
 
+// (min, second-min) update of a warp's 2 x 8 accumulator tiles; kRagged masks the columns beyond the last train row (their
+// key base, which carries the column, is compared with `limit` = nt + (256 << 21))
+template <bool kRagged>
+__device__ __forceinline__ void imma_epilogue(const int (&acc)[2][8][4], uint32_t kbase, uint32_t limit, uint32_t (&k1)[4], uint32_t (&k2)[4]) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int n8 = 0; n8 < 8; ++n8)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t cb = kbase + (uint32_t) (n8 * 8 + (c & 1));
+                uint32_t key = (uint32_t) acc[mt][n8][c] * 0xFFE00000u + cb;
+                if (kRagged && cb >= limit) key = kApNone;
+                const int r = mt * 2 + (c >> 1);
+                k2[r] = min(k2[r], max(key, k1[r]));
+                k1[r] = min(k1[r], key);
+            }
+}
+
 __global__ void __launch_bounds__(128) k_allpairs_imma(const uint8_t *__restrict__ qe, int nq, const uint8_t *__restrict__ te, int nt, int tiles_per_split,
                                                         uint2 *__restrict__ partial) {
     __shared__ __align__(128) uint8_t tile[2][kImN * kImStride];
@@ -238,20 +257,10 @@ __global__ void __launch_bounds__(128) k_allpairs_imma(const uint8_t *__restrict
             }
         }
         const int j0 = it * kImN;
-        const bool ragged = nt - j0 < kImN;
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int n8 = 0; n8 < 8; ++n8)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int col = j0 + n8 * 8 + q * 2 + (c & 1);
-                    uint32_t key = ((uint32_t) (256 - acc[mt][n8][c]) << 21) | (uint32_t) col;      // (256 - dot) = 2 * distance
-                    if (ragged && col >= nt) key = kApNone;
-                    const int r = mt * 2 + (c >> 1);
-                    k2[r] = min(k2[r], max(key, k1[r]));
-                    k1[r] = min(k1[r], key);
-                }
+        // key = distance << 22 | column with (256 - dot) = 2 * distance: one multiply-add per pair, dot * -2^21 + ((256 << 21) + column)
+        const uint32_t kbase = (256u << 21) + (uint32_t) (j0 + q * 2);
+        if (nt - j0 < kImN) imma_epilogue<true>(acc, kbase, (uint32_t) nt + (256u << 21), k1, k2);
+        else imma_epilogue<false>(acc, kbase, 0u, k1, k2);
         __syncthreads();
     }
 #pragma unroll
