@@ -6,46 +6,47 @@
 namespace mono_orb_slam3 {
     static_assert(sizeof(cv::KeyPoint) == sizeof(orbfe_keypoint), "cv::KeyPoint must be 7 x 4 bytes");
 
-    float ORBExtractor::scale_factor = 1.f;
-    float ORBExtractor::log_sale_factor = 1.f;
-    int ORBExtractor::n_levels = 1;
-    std::vector<float> ORBExtractor::scale_factors;
-    std::vector<float> ORBExtractor::inv_scale_factors;
-    std::vector<float> ORBExtractor::square_sigmas;
-    std::vector<float> ORBExtractor::inv_square_sigmas;
+    namespace detail {
+        PyramidTable &pyramid() { static PyramidTable table; return table; }
 
-    void ORBExtractor::createHandle(float scaleFactor, int nLevels) {
-        orbfe_config cfg{};
-        cfg.n_features = n_features; cfg.scale_factor = scaleFactor; cfg.n_levels = nLevels;
-        cfg.ini_th_fast = ini_th_fast; cfg.min_th_fast = min_th_fast; cfg.device = 0; cfg.max_batch = 64; cfg.flags = 0;
-        if (orbfe_create(&cfg, &handle_) != ORBFE_OK) throw std::runtime_error(std::string("orbfe_create: ") + orbfe_last_error(nullptr));
-        n_features_per_level.resize(nLevels);
-        for (int l = 0; l < nLevels; ++l) n_features_per_level[l] = orbfe_features_per_level(handle_, l);
+        // values come from the handle so that host and device agree bit for bit
+        void PyramidTable::fill(orbfe_handle *h, float scaleFactor, int nLevels) {
+            levels = nLevels; factor = scaleFactor; log_factor = std::log(scaleFactor);
+            scale.assign((size_t) nLevels, 1.f); inv_scale = scale; sigma2 = scale; inv_sigma2 = scale;
+            for (int l = 0; l < nLevels; ++l) {
+                const float s = orbfe_scale_factor(h, l);
+                scale[(size_t) l] = s; inv_scale[(size_t) l] = 1.f / s;
+                sigma2[(size_t) l] = s * s; inv_sigma2[(size_t) l] = 1.f / (s * s);
+            }
+        }
     }
 
+    void ORBExtractor::open(float scaleFactor, int nLevels) {
+        orbfe_config cfg{};
+        cfg.n_features = budget_; cfg.scale_factor = scaleFactor; cfg.n_levels = nLevels;
+        cfg.ini_th_fast = fast_ini_; cfg.min_th_fast = fast_min_; cfg.device = 0; cfg.max_batch = 64; cfg.flags = 0;
+        if (orbfe_create(&cfg, &handle_) != ORBFE_OK) throw std::runtime_error(std::string("orbfe_create: ") + orbfe_last_error(nullptr));
+        quota_.resize((size_t) nLevels);
+        for (int l = 0; l < nLevels; ++l) quota_[(size_t) l] = orbfe_features_per_level(handle_, l);
+        image_pyramid.resize((size_t) nLevels);
+    }
+
+    int ORBExtractor::capacity() const {
+        int cap = 0;
+        for (int q : quota_) cap += q + 40;
+        return cap;
+    }
+
+    // the primary constructor (re)initialises the process-wide pyramid table, like the reference's (ORBExtractor.cpp:427-439)
     ORBExtractor::ORBExtractor(int nFeatures, float scaleFactor, int nLevels, int iniThFast, int minThFast)
-            : n_features(nFeatures), ini_th_fast(iniThFast), min_th_fast(minThFast) {
-        createHandle(scaleFactor, nLevels);
-        // the static pyramid tables are (re)initialised by the primary constructor, like the reference (ORBExtractor.cpp:427-439);
-        // the values come from the handle so that host and device agree bit for bit
-        scale_factor = scaleFactor;
-        log_sale_factor = std::log(scaleFactor);
-        n_levels = nLevels;
-        scale_factors.resize(n_levels); inv_scale_factors.resize(n_levels);
-        square_sigmas.resize(n_levels); inv_square_sigmas.resize(n_levels);
-        for (int i = 0; i < n_levels; i++) {
-            scale_factors[i] = orbfe_scale_factor(handle_, i);
-            inv_scale_factors[i] = 1.f / scale_factors[i];
-            square_sigmas[i] = scale_factors[i] * scale_factors[i];
-            inv_square_sigmas[i] = 1.f / square_sigmas[i];
-        }
-        image_pyramid.resize(n_levels);
+            : budget_(nFeatures), fast_ini_(iniThFast), fast_min_(minThFast) {
+        open(scaleFactor, nLevels);
+        detail::pyramid().fill(handle_, scaleFactor, nLevels);
     }
 
     ORBExtractor::ORBExtractor(int nFeatures, const ORBExtractor &orbExtractor)
-            : n_features(nFeatures), ini_th_fast(orbExtractor.ini_th_fast), min_th_fast(orbExtractor.min_th_fast) {
-        createHandle(scale_factor, n_levels);
-        image_pyramid.resize(n_levels);
+            : budget_(nFeatures), fast_ini_(orbExtractor.fast_ini_), fast_min_(orbExtractor.fast_min_) {
+        open(detail::pyramid().factor, detail::pyramid().levels);
     }
 
     ORBExtractor::~ORBExtractor() { orbfe_destroy(handle_); }
@@ -53,8 +54,7 @@ namespace mono_orb_slam3 {
     void ORBExtractor::operator()(const cv::Mat &image, std::vector<cv::KeyPoint> &_keyPoints, cv::Mat &descriptors) {
         if (image.empty()) return;
         assert(image.type() == CV_8UC1);
-        int cap = 0;
-        for (int l = 0; l < n_levels; ++l) cap += n_features_per_level[l] + 40;
+        const int cap = capacity();
         std::vector<cv::KeyPoint> kps((size_t) cap);
         cv::Mat desc(cap, 32, CV_8U);
         int n = 0;
@@ -62,7 +62,7 @@ namespace mono_orb_slam3 {
                                      desc.data, cap, &n);
         if (rc != ORBFE_OK) throw std::runtime_error(std::string("orbfe_extract: ") + orbfe_last_error(handle_));
         if (keep_image_pyramid) {
-            for (int l = 0; l < n_levels; ++l) {
+            for (int l = 0; l < detail::pyramid().levels; ++l) {
                 int w = 0, h = 0;
                 orbfe_level_size(handle_, l, &w, &h);
                 image_pyramid[l].create(h, w, CV_8U);
@@ -85,8 +85,7 @@ namespace mono_orb_slam3 {
             if (frames[b].cols != w || frames[b].rows != h) throw std::invalid_argument("extractBatch: frames must have equal size");
             for (int r = 0; r < h; ++r) std::memcpy(&packed[((size_t) b * h + r) * w], frames[b].ptr(r), (size_t) w);
         }
-        int cap = 0;
-        for (int l = 0; l < n_levels; ++l) cap += n_features_per_level[l] + 40;
+        const int cap = capacity();
         std::vector<cv::KeyPoint> kps((size_t) B * cap);
         std::vector<unsigned char> desc((size_t) B * cap * 32);
         std::vector<int> n((size_t) B);
@@ -101,12 +100,8 @@ namespace mono_orb_slam3 {
     }
 
     void ORBExtractor::print() const {
-        std::cout << std::endl << "ORB Pyramid Information: " << std::endl;
-        std::cout << " - Features: " << n_features << "(at initial stage)" << std::endl;
-        std::cout << " - ScaleFactor: " << scale_factor << std::endl;
-        std::cout << " - Levels: " << n_levels << std::endl;
-        std::cout << " - IniThFAST: " << ini_th_fast << std::endl;
-        std::cout << " - MinThFAST: " << min_th_fast << std::endl;
-        std::cout << std::endl;
+        const detail::PyramidTable &p = detail::pyramid();
+        std::cout << "\nORB extractor (B200): " << budget_ << " features, scale factor " << p.factor << ", " << p.levels << " levels, FAST thresholds "
+                  << fast_ini_ << " / " << fast_min_ << "\n" << std::endl;
     }
 } // mono_orb_slam3
