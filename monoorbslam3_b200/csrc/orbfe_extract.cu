@@ -169,11 +169,19 @@ static int configure(Handle *h, int w, int ht, int batch) {
         L.quota = h->quota[l];
         const int n_ini = ceil_f((float) bw / (float) bh);
         L.cand_off = g.cand_per_frame; L.cand_cap = L.n_cols * L.n_rows * kSlotCap; g.cand_per_frame += L.cand_cap;
-        L.node_cap = 8 * (L.quota + 4) + 5 * n_ini + 64; L.node_off = g.nodes_per_frame; g.nodes_per_frame += L.node_cap;
         L.kp_cap = std::max(L.quota + 4, 4 * n_ini + 4); L.kp_off = g.kp_per_frame; g.kp_per_frame += L.kp_cap;
+        // Quadtree node pool.  A split takes 4 slots and slots are never reclaimed.  Every pass that does not end the loop splits
+        // all expandable nodes, so after p passes they all sit at depth p and are at most ceil(size / 2^p) wide; key points have
+        // distinct pixel coordinates, so a 1 x 1 node is never expandable: at most ceil(log2(max(W, H))) + 1 passes, each over at
+        // most max(quota, n_ini) nodes (the loop only continues while the list is within the quota).  That is the size of the
+        // global pool; the shared-memory pool keeps the size frames need in practice (typ_node_cap) and k_octree moves to the
+        // global one when a pass would overflow it.
+        int depth = 1; while ((1 << depth) < std::max(bw, bh)) ++depth;
+        L.node_cap = 4 * L.kp_cap * (depth + 2) + 5 * n_ini + 64; L.node_off = g.nodes_per_frame; g.nodes_per_frame += L.node_cap;
+        const int typ_node_cap = 8 * (L.quota + 4) + 5 * n_ini + 64;
         L.list_off = g.lists_per_frame; g.lists_per_frame += 2 * L.kp_cap;
         L.scale = h->scale[l];
-        max_kp_cap = std::max(max_kp_cap, L.kp_cap); max_node_cap = std::max(max_node_cap, L.node_cap);
+        max_kp_cap = std::max(max_kp_cap, L.kp_cap); max_node_cap = std::max(max_node_cap, typ_node_cap);
         if (l) {
             build_axis_table(L.w, g.lv[l - 1].w, true, xt[l]);
             build_axis_table(L.h, g.lv[l - 1].h, false, yt[l]);
@@ -210,6 +218,7 @@ static int configure(Handle *h, int w, int ht, int batch) {
         const int budget = 100 * 1024 - g.sort_cap * 8;
         int cap = std::min(max_node_cap, budget / 16);
         g.oct_smem_bytes = g.sort_cap * 8 + cap * 16;
+        g.typ_node_cap = max_node_cap;
         // stored in Geometry via oct_smem_bytes; smem_node_cap is recomputed at launch
     }
     h->max_kp = g.kp_per_frame;
@@ -419,11 +428,11 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
     const int nt = oct_nt ? oct_nt : (few ? 1024 : 512);
     int oct_smem = g.oct_smem_bytes;
     if (few) {
-        int max_node_cap = 1;
-        for (int l = 0; l < nl; ++l) max_node_cap = std::max(max_node_cap, g.lv[l].node_cap);
-        oct_smem = std::max(oct_smem, std::min(200 * 1024, g.sort_cap * 8 + max_node_cap * 16));
+        oct_smem = std::max(oct_smem, std::min(200 * 1024, g.sort_cap * 8 + g.typ_node_cap * 16));
     }
     oa.sort_cap = g.sort_cap; oa.smem_node_cap = (oct_smem - g.sort_cap * 8) / 16;
+    // ORBFE_OCT_SMEM_NODES=n shrinks the shared-memory pool so that the tests can drive the move to the global pool
+    if (const char *e = getenv("ORBFE_OCT_SMEM_NODES")) { const int v = atoi(e); if (v > 0) oa.smem_node_cap = std::min(oa.smem_node_cap, v); }
     if (nt == 1024) k_octree<1024><<<dim3(nl, nb), 1024, oct_smem, st>>>(LS, oa);
     else if (nt == 512) k_octree<512><<<dim3(nl, nb), 512, oct_smem, st>>>(LS, oa);
     else k_octree<256><<<dim3(nl, nb), 256, oct_smem, st>>>(LS, oa);
@@ -539,9 +548,17 @@ int orbfe_create(const orbfe_config *cfg, orbfe_handle **out) {
             orbfe_destroy(h); return ORBFE_E_CUDA;
         }
     }
-    cudaFuncSetAttribute(k_octree<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_octree<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_octree<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    // dynamic shared-memory opt-ins are per device: set them for this handle's device (current after cudaSetDevice above)
+    if ((e = cudaFuncSetAttribute(k_octree<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_octree<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_octree<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) {
+        set_error(nullptr, ORBFE_E_CUDA, "kernel attributes: %s", cudaGetErrorString(e));
+        orbfe_destroy(h); return ORBFE_E_CUDA;
+    }
+    if (match_device_setup(h) != ORBFE_OK || frame_device_setup(h) != ORBFE_OK) {
+        set_error(nullptr, ORBFE_E_CUDA, "kernel attributes: %s", h->err.c_str());
+        orbfe_destroy(h); return ORBFE_E_CUDA;
+    }
     *out = h;
     return ORBFE_OK;
 }

@@ -154,8 +154,6 @@ int frame_post_launch(Handle *h, const CamDev &c, orbfe_keypoint *d_raw, orbfe_k
     if ((long long) cols * rows >= (1ll << (32 - kGridIdxBits)) - 1) return set_error(h, ORBFE_E_ARG, "frame grid: image too large");
     k_frame_post<<<dim3((cap + 255) / 256, n_frames), 256, 0, st>>>(c, d_raw, d_un, d_n, cap);
     int sort_cap = 32; while (sort_cap < cap) sort_cap <<= 1;
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_frame_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, kGridMaxKp * 4); attr_set = true; }
     k_frame_grid<<<n_frames, 1024, (size_t) sort_cap * 4, st>>>(d_un, d_n, cap, img_w, img_h, cols, rows, sort_cap, d_grid_off, d_grid_idx, d_n_in_grid);
     h->launches += 2;
     ORBFE_CUDA(h, cudaGetLastError());
@@ -163,12 +161,15 @@ int frame_post_launch(Handle *h, const CamDev &c, orbfe_keypoint *d_raw, orbfe_k
 }
 
 // grid of one device-resident key-point array (used by the window searches of orbfe_match.cu): d_n holds the count
+int frame_device_setup(Handle *h) {        // per-device opt-in of k_frame_grid's sort buffer (called by orbfe_create)
+    ORBFE_CUDA(h, cudaFuncSetAttribute(k_frame_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, kGridMaxKp * 4));
+    return ORBFE_OK;
+}
+
 int frame_grid_launch(Handle *h, const orbfe_keypoint *d_kps, const int *d_n, int cap, int img_w, int img_h, int *d_grid_off, int *d_grid_idx, cudaStream_t st) {
     if (cap > kGridMaxKp) return set_error(h, ORBFE_E_ARG, "frame grid: at most %d key points per frame (got %d)", kGridMaxKp, cap);
     int cols, rows; grid_dims(img_w, img_h, cols, rows);
     int sort_cap = 32; while (sort_cap < cap) sort_cap <<= 1;
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_frame_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, kGridMaxKp * 4); attr_set = true; }
     k_frame_grid<<<1, 1024, (size_t) sort_cap * 4, st>>>(d_kps, d_n, cap, img_w, img_h, cols, rows, sort_cap, d_grid_off, d_grid_idx, nullptr);
     h->launches++;
     ORBFE_CUDA(h, cudaGetLastError());

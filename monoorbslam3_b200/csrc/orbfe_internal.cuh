@@ -56,6 +56,7 @@ struct Geometry {
     int cand_per_frame = 0, nodes_per_frame = 0, kp_per_frame = 0, lists_per_frame = 0;
     size_t img_bytes_per_frame = 0;  // sum over levels of pitch*h (levels 0..n-1)
     int oct_smem_bytes = 0;          // dynamic smem of the quadtree kernel
+    int typ_node_cap = 0;            // largest per-level node count frames need in practice (sizes the shared-memory pool)
     int sort_cap = 0;                // power of two >= max kp_cap
 };
 
@@ -138,6 +139,9 @@ struct Handle {
 
 int set_error(Handle *h, int code, const char *fmt, ...);
 int ensure_match_scratch(Handle *h, size_t bytes);
+// per-device kernel attributes (dynamic shared-memory opt-ins) of the matcher and frame kernels; called by orbfe_create
+int match_device_setup(Handle *h);
+int frame_device_setup(Handle *h);
 // Frame grid (CSR) of one device-resident key-point array; d_n holds the count (orbfe_frame.cu)
 int frame_grid_launch(Handle *h, const orbfe_keypoint *d_kps, const int *d_n, int cap, int img_w, int img_h, int *d_grid_off, int *d_grid_idx, cudaStream_t st);
 

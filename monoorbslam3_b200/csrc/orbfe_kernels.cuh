@@ -507,13 +507,23 @@ __global__ void __launch_bounds__(NT) k_octree(const __grid_constant__ LevelSet 
     int *S = E + G.kp_cap;                                                  // split list of the current pass
     uint32_t *kp_out = a.kp + (size_t) frame * a.kp_per_frame + G.kp_off;
 
-    // dynamic smem: [sort keys: sort_cap u64][node pool: smem_node_cap * 16 B]
+    // dynamic smem: [sort keys: sort_cap u64][node pool: smem_node_cap * 16 B].  The pool starts in shared memory (sized for the
+    // slot counts frames produce in practice) and moves to the level's global pool — sized by the proven bound, see configure() —
+    // the first time a pass would not fit, so a valid image can never exhaust it.
     unsigned long long *skey = reinterpret_cast<unsigned long long *>(dyn);
+    uint8_t *gpool = a.nodes + ((size_t) frame * a.nodes_per_frame + G.node_off) * 16;
+    int cap_cur = min(a.smem_node_cap, G.node_cap);
     uint8_t *pool = dyn + (size_t) a.sort_cap * 8;
-    if (G.node_cap > a.smem_node_cap) pool = a.nodes + ((size_t) frame * a.nodes_per_frame + G.node_off) * 16;
     NodeBounds *nbnd = reinterpret_cast<NodeBounds *>(pool);
-    int *ncnt = reinterpret_cast<int *>(pool + (size_t) G.node_cap * 8);
-    int *nchild = ncnt + G.node_cap;
+    int *ncnt = reinterpret_cast<int *>(pool + (size_t) cap_cur * 8);
+    int *nchild = ncnt + cap_cur;
+    auto use_global_pool = [&](int n_live) {            // block-uniform; copies the n_live slots in use
+        NodeBounds *gb = reinterpret_cast<NodeBounds *>(gpool);
+        int *gc = reinterpret_cast<int *>(gpool + (size_t) G.node_cap * 8), *gch = gc + G.node_cap;
+        for (int j = tid; j < n_live; j += NT) { gb[j] = nbnd[j]; gc[j] = ncnt[j]; gch[j] = nchild[j]; }
+        __syncthreads();
+        nbnd = gb; ncnt = gc; nchild = gch; cap_cur = G.node_cap;
+    };
 
     // ---- 1. candidates of this level in reference order: exclusive scan of the per-cell counts, then gather
     int n = 0;
@@ -533,6 +543,7 @@ __global__ void __launch_bounds__(NT) k_octree(const __grid_constant__ LevelSet 
     const int n_ini = (int) ceilf((float) W / (float) H);                   // ORBExtractor.cpp:645
     const int h_x = (int) ceilf((float) W / (float) n_ini);                 // :646
     if (n_ini * 5 > G.node_cap) { if (tid == 0) atomicExch(a.err, 2); return; }
+    if (n_ini * 5 > cap_cur) use_global_pool(0);
     for (int r = tid; r < n_ini; r += NT) {                                 // :652-670 (last root ends at maxX, sic)
         NodeBounds b; b.x0 = (short) (h_x * r); b.x1 = (short) (r == n_ini - 1 ? G.w - kEdge : h_x * (r + 1)); b.y0 = 0; b.y1 = (short) H;
         nbnd[r] = b; ncnt[r] = 0; nchild[r] = 0;
@@ -600,7 +611,10 @@ __global__ void __launch_bounds__(NT) k_octree(const __grid_constant__ LevelSet 
             __syncthreads();
         }
         if (ns == 0) break;                                    // nothing expandable: size == prevSize (:750 / :806)
-        if (pool_top + 4 * ns > G.node_cap) { if (tid == 0) atomicExch(a.err, 3); return; }
+        if (pool_top + 4 * ns > cap_cur) {
+            if (pool_top + 4 * ns > G.node_cap) { if (tid == 0) atomicExch(a.err, 3); return; }
+            use_global_pool(pool_top);
+        }
         // ---- A. allocate 4 child slots per node of the split list (DivideNode geometry, :367-395)
         for (int j = tid; j < ns; j += NT) {
             const int nd = S[j];

@@ -939,8 +939,6 @@ static int launch_resolve(Handle *h, const ResolveArgs &ra, int n2, cudaStream_t
     if (kVariant != 0 && !serial) {
         const size_t state = sizeof(int) * 2 * (size_t) n2 + sizeof(uint32_t) * (((size_t) ra.nq + 31) / 32) + 64;
         if (state <= 200 * 1024) {
-            static bool attr_par = false;
-            if (!attr_par) { cudaFuncSetAttribute(k_resolve_par<kVariant>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_par = true; }
             ResolveArgs rb = ra;
             rb.smem_entries = (int) ((200 * 1024 - state) / sizeof(uint32_t));
             k_resolve_par<kVariant><<<1, 1024, 200 * 1024, st>>>(rb);
@@ -951,9 +949,21 @@ static int launch_resolve(Handle *h, const ResolveArgs &ra, int n2, cudaStream_t
     if (smem > 200 * 1024)
         return set_error(h, ORBFE_E_ARG, "matcher: %d key points in the searched frame exceed the resolve kernel's shared-memory state (limit about %d)", n2,
                          kVariant == 0 ? 13000 : 20000);
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_resolve<kVariant>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
     k_resolve<kVariant><<<1, 256, smem, st>>>(ra);
+    return ORBFE_OK;
+}
+
+// The resolves use up to 200 KB of dynamic shared memory.  The opt-in is a per-device function attribute, so orbfe_create calls
+// this for the handle's device (after cudaSetDevice) instead of a process-wide "done once" flag.
+template <int kVariant>
+static cudaError_t resolve_attrs() {
+    cudaError_t e = cudaFuncSetAttribute(k_resolve<kVariant>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess && kVariant != 0) e = cudaFuncSetAttribute(k_resolve_par<kVariant>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    return e;
+}
+int match_device_setup(Handle *h) {
+    ORBFE_CUDA(h, resolve_attrs<0>()); ORBFE_CUDA(h, resolve_attrs<1>()); ORBFE_CUDA(h, resolve_attrs<2>());
+    ORBFE_CUDA(h, resolve_attrs<3>()); ORBFE_CUDA(h, resolve_attrs<4>());
     return ORBFE_OK;
 }
 

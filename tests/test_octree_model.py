@@ -84,6 +84,44 @@ def gpu_formulation(xs, ys, sc, W, H, max_x, nF):
     return np.array(best, np.int32), pool_top
 
 
+def node_pool_bound(W, H, nF):
+    """Size of the kernel's global node pool (configure() in csrc/orbfe_extract.cu): every pass that does not end the loop splits all
+    expandable nodes, so there are at most ceil(log2(max(W, H))) + 1 passes of at most max(quota, roots) splits, 4 slots each."""
+    n_ini = math.ceil(W / H)
+    depth = 1
+    while (1 << depth) < max(W, H):
+        depth += 1
+    return 4 * max(nF + 4, 4 * n_ini + 4) * (depth + 2) + 5 * n_ini + 64
+
+
+def tight_pairs(W, H, gx, gy, cluster, gap=2):
+    """Sparse pairs of key points `gap` px apart on a gx x gy lattice plus a dense little cluster: every pair keeps splitting (four
+    slots per split, three of them empty) until the pair separates, which is what exhausts an empirically sized pool."""
+    pts = []
+    for j in range(gy):
+        for i in range(gx):
+            x, y = int((i + 0.5) * W / gx), int((j + 0.5) * H / gy)
+            pts += [(x, y), (x + gap, y)]
+    pts += [(5 + 2 * i, 5 + 2 * j) for j in range(cluster) for i in range(cluster)]
+    pts = np.unique(np.array(pts), axis=0)
+    return pts[np.lexsort((pts[:, 0], pts[:, 1], pts[:, 0] // 30, pts[:, 1] // 30))]
+
+
+@pytest.mark.parametrize("gx,gy,cluster", [(26, 16, 8), (26, 16, 4), (29, 15, 8), (20, 20, 16)])
+def test_sparse_tight_pairs_stay_within_the_proven_pool(oracle, gx, gy, cluster):
+    """Level 0 of a 1920x1080 / 4000-feature frame (W=1882, H=1042, quota 868): these inputs need 7300-7950 node slots, more than
+    the 7050 of the formula the kernel used in round 1 (8 * (quota + 4) + 5 * roots + 64); the proven bound holds them, and the
+    slot formulation still equals the list formulation."""
+    W, H, nF = 1882, 1042, 868
+    pts = tight_pairs(W, H, gx, gy, cluster)
+    c = np.zeros(len(pts), oracle.CORNER_DTYPE)
+    c["x"], c["y"], c["score"] = pts[:, 0], pts[:, 1], 50
+    ref = oracle.distribute_octree(c, 19, W + 19, 19, H + 19, nF)
+    got, top = gpu_formulation(c["x"].astype(int), c["y"].astype(int), c["score"].astype(int), W, H, W + 19, nF)
+    assert np.array_equal(ref, got)
+    assert 8 * (nF + 4) + 5 * 2 + 64 < top <= node_pool_bound(W, H, nF)
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_slot_formulation_equals_list_formulation(oracle, seed):
     rng = np.random.default_rng(seed)
@@ -106,4 +144,4 @@ def test_slot_formulation_equals_list_formulation(oracle, seed):
         ref = oracle.distribute_octree(c, 19, W + 19, 19, H + 19, nF)
         got, top = gpu_formulation(c["x"].astype(int), c["y"].astype(int), c["score"].astype(int), W, H, W + 19, nF)
         assert np.array_equal(ref, got), (trial, W, H, len(pts), nF)
-        assert top <= 8 * (nF + 4) + 5 * math.ceil(W / H) + 64        # the node-pool bound used by the kernel
+        assert top <= node_pool_bound(W, H, nF)
