@@ -198,14 +198,25 @@ int orbfe_descriptor_distance(orbfe_handle *h, const uint8_t *a, int na, const u
 
 /* Brute-force best / second-best over all pairs (BASELINE configs 4/5): for each query row the train index of the
  * minimum distance (first minimum wins), that distance and the second-smallest distance (257 if none). Host memory.
- * Problems of at least 256 x 256 run as an int8 GEMM on the tensor cores (hamming = (256 - <a, b>) / 2 over +-1 vectors, exact),
- * smaller ones on the popc kernel; the results are identical (ORBFE_ALLPAIRS_POPC=1 forces the popc kernel). */
+ * Problems of at least 256 x 256 run as an int8 GEMM on the tensor cores (hamming = (256 - <a, b>) / 2 over +-1 vectors, exact):
+ * tcgen05.mma kind::i8 with TMA-staged operands and accumulators in tensor memory (csrc/orbfe_allpairs_tc.cu); smaller ones on
+ * the popc kernel; the results are identical.  ORBFE_ALLPAIRS=popc|imma|tc selects a kernel for A/B runs (imma = the warp-level
+ * mma.sync kernel of round 1); ORBFE_ALLPAIRS_POPC=1 is the older spelling of popc. */
 int orbfe_hamming_allpairs(orbfe_handle *h, const uint8_t *q, int nq, const uint8_t *t, int nt,
                            int32_t *best_idx, int32_t *best_dist, int32_t *second_dist);
 /* Device-resident variant (asynchronous on `stream` unless sync). */
 int orbfe_hamming_allpairs_device(orbfe_handle *h, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt,
                                   int32_t *d_best_idx, int32_t *d_best_dist, int32_t *d_second_dist,
                                   void *stream, int sync);
+
+/* The same with a per-query exclusion range: excl[2*i], excl[2*i+1] = train indices [lo, hi) that query i skips (lo >= hi: none).
+ * This is how a key-frame window is matched against itself (BASELINE configs 4/5): the table holds the window's key frames back to
+ * back and every descriptor skips the block of its own key frame, so best / second-best are its nearest neighbours in the OTHER
+ * key frames (without it every row finds itself at distance 0).  excl == NULL is orbfe_hamming_allpairs. */
+int orbfe_hamming_allpairs_excl(orbfe_handle *h, const uint8_t *q, int nq, const uint8_t *t, int nt, const int32_t *excl,
+                                int32_t *best_idx, int32_t *best_dist, int32_t *second_dist);
+int orbfe_hamming_allpairs_excl_device(orbfe_handle *h, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, const int32_t *d_excl,
+                                       int32_t *d_best_idx, int32_t *d_best_dist, int32_t *d_second_dist, void *stream, int sync);
 
 /* Best / second-best over caller-supplied candidate lists (SURVEY.md section 8b `orbfe_hamming_window`): the candidates of
  * query i are t[cand_idx[cand_offsets[i] .. cand_offsets[i+1])], scanned in list order like the `if (dist < bestDist)` loops of

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "liborbfe.so")
-SOURCES = ["orbfe_extract.cu", "orbfe_match.cu", "orbfe_frame.cu", "orbfe_bow.cu", "orbfe_geom.cu"]
+SOURCES = ["orbfe_extract.cu", "orbfe_match.cu", "orbfe_allpairs_tc.cu", "orbfe_frame.cu", "orbfe_bow.cu", "orbfe_geom.cu"]
 HEADERS = ["orbfe_internal.cuh", "orbfe_kernels.cuh", "brief_pattern.inc", os.path.join("..", "..", "include", "orbfe.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "-shared", "-cudart", "static"]

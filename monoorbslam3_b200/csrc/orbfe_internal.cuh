@@ -142,6 +142,11 @@ int ensure_match_scratch(Handle *h, size_t bytes);
 // per-device kernel attributes (dynamic shared-memory opt-ins) of the matcher and frame kernels; called by orbfe_create
 int match_device_setup(Handle *h);
 int frame_device_setup(Handle *h);
+// all-pairs search on tcgen05 (orbfe_allpairs_tc.cu): scratch size for a problem, launch (partial results for k_allpairs_merge)
+int allpairs_tc_device_setup(Handle *h);
+size_t allpairs_tc_scratch_bytes(int nq, int nt, int *n_split_out);
+int allpairs_tc_launch(Handle *h, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, const int2 *d_excl, uint8_t *d_scratch,
+                       uint2 **partial_out, int *n_split_out, cudaStream_t st);
 // Frame grid (CSR) of one device-resident key-point array; d_n holds the count (orbfe_frame.cu)
 int frame_grid_launch(Handle *h, const orbfe_keypoint *d_kps, const int *d_n, int cap, int img_w, int img_h, int *d_grid_off, int *d_grid_idx, cudaStream_t st);
 

@@ -86,7 +86,8 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(256) k_hamming_allpairs(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, int nt,
+template <bool kExcl>
+__global__ void __launch_bounds__(256) k_hamming_allpairs(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, int nt, const int2 *__restrict__ excl,
                                                            int *best_idx, int *best_dist, int *second_dist) {
     __shared__ __align__(128) uint4 tile[2][kApTile * 2];
     __shared__ __align__(8) uint64_t bar[2];
@@ -100,6 +101,11 @@ __global__ void __launch_bounds__(256) k_hamming_allpairs(const uint4 *__restric
         qa[r][0] = __ldg(q + 2 * (size_t) qi); qa[r][1] = __ldg(q + 2 * (size_t) qi + 1);
     }
     uint32_t k1[2] = {kApNone, kApNone}, k2[2] = {kApNone, kApNone};
+    int2 ex[2] = {make_int2(0, 0), make_int2(0, 0)};            // train indices [x, y) this query skips (its own key frame's block)
+    if (kExcl) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) ex[r] = __ldg(excl + min(q0 + lane + 32 * r, nq - 1));
+    }
     const int n_tiles = (nt + kApTile - 1) / kApTile;
     if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_barrier_init(); }
     __syncthreads();
@@ -125,7 +131,8 @@ __global__ void __launch_bounds__(256) k_hamming_allpairs(const uint4 *__restric
             const uint4 b0 = tile[buf][2 * j], b1 = tile[buf][2 * j + 1];
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                const uint32_t key = ((uint32_t) hamming256(qa[r][0], qa[r][1], b0, b1) << 22) | (uint32_t) (jbase + j);
+                uint32_t key = ((uint32_t) hamming256(qa[r][0], qa[r][1], b0, b1) << 22) | (uint32_t) (jbase + j);
+                if (kExcl && jbase + j >= ex[r].x && jbase + j < ex[r].y) key = kApNone;
                 k2[r] = min(k2[r], max(key, k1[r]));
                 k1[r] = min(k1[r], key);
             }
@@ -964,7 +971,7 @@ static cudaError_t resolve_attrs() {
 int match_device_setup(Handle *h) {
     ORBFE_CUDA(h, resolve_attrs<0>()); ORBFE_CUDA(h, resolve_attrs<1>()); ORBFE_CUDA(h, resolve_attrs<2>());
     ORBFE_CUDA(h, resolve_attrs<3>()); ORBFE_CUDA(h, resolve_attrs<4>());
-    return ORBFE_OK;
+    return allpairs_tc_device_setup(h);
 }
 
 // pinned host staging of the matcher (one upload and one download per search instead of a dozen small copies)
@@ -1227,19 +1234,33 @@ int orbfe_descriptor_distance(orbfe_handle *h, const uint8_t *a, int na, const u
     return ORBFE_OK;
 }
 
-int orbfe_hamming_allpairs_device(orbfe_handle *h, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, int32_t *d_best_idx, int32_t *d_best_dist,
-                                  int32_t *d_second_dist, void *stream, int sync) {
-    if (!h) return ORBFE_E_ARG;
-    if (nq < 0 || nt < 0 || (nq && (!d_q || !d_best_idx || !d_best_dist || !d_second_dist)) || (nt && !d_t)) return set_error(h, ORBFE_E_ARG, "invalid argument");
-    if (nt >= (1 << 22)) return set_error(h, ORBFE_E_ARG, "at most %d train descriptors per call", (1 << 22) - 1);
-    if (((uintptr_t) d_q | (uintptr_t) d_t) & 15) return set_error(h, ORBFE_E_ARG, "descriptor arrays must be 16-byte aligned");
-    if (nq == 0) return ORBFE_OK;
-    ORBFE_CUDA(h, cudaSetDevice(h->device));
-    cudaStream_t st = stream ? (cudaStream_t) stream : h->stream;
-    // large problems go to the tensor-core formulation (ORBFE_ALLPAIRS_POPC=1 keeps the popc kernel, for A/B runs)
-    const char *popc_env = getenv("ORBFE_ALLPAIRS_POPC");             // read per call: bench.py times both kernels in one process
-    const bool force_popc = popc_env && *popc_env == '1';
-    if (!force_popc && nq >= 2 * kImM && nt >= 4 * kImN) {
+// Kernel choice of the brute-force search.  Problems of at least 256 x 512 run on the tensor cores — tcgen05 (k_allpairs_tc) by default,
+// the legacy warp-level IMMA kernel with ORBFE_ALLPAIRS=imma — smaller ones and ORBFE_ALLPAIRS=popc (or ORBFE_ALLPAIRS_POPC=1) on the
+// popc kernel.  The environment is read per call: bench.py and the tests time / compare the kernels in one process.
+static int allpairs_dispatch(Handle *h, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, const int2 *d_excl, int32_t *d_best_idx, int32_t *d_best_dist,
+                             int32_t *d_second_dist, cudaStream_t st) {
+    const char *popc_env = getenv("ORBFE_ALLPAIRS_POPC"), *kern_env = getenv("ORBFE_ALLPAIRS");
+    int kern = 2;                                                      // 0 popc, 1 mma.sync IMMA, 2 tcgen05
+    if (kern_env && !strcmp(kern_env, "popc")) kern = 0; else if (kern_env && !strcmp(kern_env, "imma")) kern = 1;
+    if (popc_env && *popc_env == '1') kern = 0;
+    if (nq < 2 * kImM || nt < 4 * kImN) kern = 0;
+    if (kern == 1 && d_excl) kern = 2;                                 // the IMMA kernel has no exclusion path
+    auto ensure_ap = [&](size_t need) -> int {
+        if (h->ap_bytes >= need) return ORBFE_OK;
+        ORBFE_CUDA(h, cudaDeviceSynchronize());
+        cudaFree(h->d_ap); h->d_ap = nullptr; h->ap_bytes = 0;
+        ORBFE_CUDA(h, cudaMalloc(&h->d_ap, need));
+        h->ap_bytes = need;
+        return ORBFE_OK;
+    };
+    if (kern == 2) {
+        int rc = ensure_ap(allpairs_tc_scratch_bytes(nq, nt, nullptr));
+        if (rc) return rc;
+        uint2 *partial = nullptr; int n_split = 1;
+        if ((rc = allpairs_tc_launch(h, d_q, nq, d_t, nt, d_excl, (uint8_t *) h->d_ap, &partial, &n_split, st))) return rc;
+        k_allpairs_merge<<<(nq + 255) / 256, 256, 0, st>>>(partial, n_split, nq, d_best_idx, d_best_dist, d_second_dist);
+        h->launches++;
+    } else if (kern == 1) {
         const int n_mt = (nq + kImM - 1) / kImM, n_tiles = (nt + kImN - 1) / kImN;
         const int slots = std::max(h->sm_count, 1) * 3;                      // resident CTAs (about 160 registers x 128 threads, 37 KB)
         int n_split = 1; double best_eff = 0;
@@ -1252,13 +1273,8 @@ int orbfe_hamming_allpairs_device(orbfe_handle *h, const uint8_t *d_q, int nq, c
         const int tiles_per_split = (n_tiles + n_split - 1) / n_split;
         n_split = (n_tiles + tiles_per_split - 1) / tiles_per_split;
         const size_t qe_bytes = ((size_t) nq * kImStride + 255) & ~(size_t) 255, te_bytes = ((size_t) nt * kImStride + 255) & ~(size_t) 255;
-        const size_t need = qe_bytes + te_bytes + (size_t) n_split * nq * sizeof(uint2) + 256;
-        if (h->ap_bytes < need) {
-            ORBFE_CUDA(h, cudaDeviceSynchronize());
-            cudaFree(h->d_ap); h->d_ap = nullptr; h->ap_bytes = 0;
-            ORBFE_CUDA(h, cudaMalloc(&h->d_ap, need));
-            h->ap_bytes = need;
-        }
+        int rc = ensure_ap(qe_bytes + te_bytes + (size_t) n_split * nq * sizeof(uint2) + 256);
+        if (rc) return rc;
         uint8_t *qe = (uint8_t *) h->d_ap, *te = qe + qe_bytes;
         uint2 *partial = reinterpret_cast<uint2 *>(te + te_bytes);
         k_expand_pm1<<<(nq * 36 + 255) / 256, 256, 0, st>>>(d_q, nq, qe);
@@ -1267,36 +1283,64 @@ int orbfe_hamming_allpairs_device(orbfe_handle *h, const uint8_t *d_q, int nq, c
         k_allpairs_merge<<<(nq + 255) / 256, 256, 0, st>>>(partial, n_split, nq, d_best_idx, d_best_dist, d_second_dist);
         h->launches += 4;
     } else {
-        k_hamming_allpairs<<<(nq + kApQ - 1) / kApQ, 256, 0, st>>>((const uint4 *) d_q, nq, (const uint4 *) d_t, nt, d_best_idx, d_best_dist, d_second_dist);
+        if (d_excl) k_hamming_allpairs<true><<<(nq + kApQ - 1) / kApQ, 256, 0, st>>>((const uint4 *) d_q, nq, (const uint4 *) d_t, nt, d_excl, d_best_idx, d_best_dist, d_second_dist);
+        else k_hamming_allpairs<false><<<(nq + kApQ - 1) / kApQ, 256, 0, st>>>((const uint4 *) d_q, nq, (const uint4 *) d_t, nt, nullptr, d_best_idx, d_best_dist, d_second_dist);
         h->launches++;
     }
     ORBFE_CUDA(h, cudaGetLastError());
+    return ORBFE_OK;
+}
+
+int orbfe_hamming_allpairs_excl_device(orbfe_handle *h, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, const int32_t *d_excl, int32_t *d_best_idx,
+                                       int32_t *d_best_dist, int32_t *d_second_dist, void *stream, int sync) {
+    if (!h) return ORBFE_E_ARG;
+    if (nq < 0 || nt < 0 || (nq && (!d_q || !d_best_idx || !d_best_dist || !d_second_dist)) || (nt && !d_t)) return set_error(h, ORBFE_E_ARG, "invalid argument");
+    if (nt >= (1 << 22)) return set_error(h, ORBFE_E_ARG, "at most %d train descriptors per call", (1 << 22) - 1);
+    if (((uintptr_t) d_q | (uintptr_t) d_t) & 15) return set_error(h, ORBFE_E_ARG, "descriptor arrays must be 16-byte aligned");
+    if ((uintptr_t) d_excl & 7) return set_error(h, ORBFE_E_ARG, "exclusion ranges must be 8-byte aligned");
+    if (nq == 0) return ORBFE_OK;
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t) stream : h->stream;
+    int rc = allpairs_dispatch(h, d_q, nq, d_t, nt, reinterpret_cast<const int2 *>(d_excl), d_best_idx, d_best_dist, d_second_dist, st);
+    if (rc) return rc;
     if (sync) ORBFE_CUDA(h, cudaStreamSynchronize(st));
     return ORBFE_OK;
 }
 
-int orbfe_hamming_allpairs(orbfe_handle *h, const uint8_t *q, int nq, const uint8_t *t, int nt, int32_t *best_idx, int32_t *best_dist, int32_t *second_dist) {
+int orbfe_hamming_allpairs_device(orbfe_handle *h, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, int32_t *d_best_idx, int32_t *d_best_dist,
+                                  int32_t *d_second_dist, void *stream, int sync) {
+    return orbfe_hamming_allpairs_excl_device(h, d_q, nq, d_t, nt, nullptr, d_best_idx, d_best_dist, d_second_dist, stream, sync);
+}
+
+int orbfe_hamming_allpairs_excl(orbfe_handle *h, const uint8_t *q, int nq, const uint8_t *t, int nt, const int32_t *excl, int32_t *best_idx, int32_t *best_dist,
+                                int32_t *second_dist) {
     if (!h) return ORBFE_E_ARG;
     if (nq < 0 || nt < 0 || (nq && (!q || !best_idx || !best_dist || !second_dist)) || (nt && !t)) return set_error(h, ORBFE_E_ARG, "invalid argument");
     if (nq == 0) return ORBFE_OK;
     ORBFE_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     Bump probe{nullptr};
-    probe.take<uint4>(2 * (size_t) nq); probe.take<uint4>(2 * (size_t) std::max(nt, 1)); probe.take<int>(nq); probe.take<int>(nq); probe.take<int>(nq);
+    probe.take<uint4>(2 * (size_t) nq); probe.take<uint4>(2 * (size_t) std::max(nt, 1)); probe.take<int>(nq); probe.take<int>(nq); probe.take<int>(nq); probe.take<int2>(nq);
     int rc = ensure_match_scratch(h, probe.off + 1024);
     if (rc) return rc;
     Bump bp{(uint8_t *) h->d_match};
     uint4 *dq = bp.take<uint4>(2 * (size_t) nq), *dt = bp.take<uint4>(2 * (size_t) std::max(nt, 1));
     int *bi = bp.take<int>(nq), *bd = bp.take<int>(nq), *sd = bp.take<int>(nq);
+    int2 *dex = bp.take<int2>(nq);
     ORBFE_CUDA(h, cudaMemcpyAsync(dq, q, 32 * (size_t) nq, cudaMemcpyHostToDevice, st));
     if (nt) ORBFE_CUDA(h, cudaMemcpyAsync(dt, t, 32 * (size_t) nt, cudaMemcpyHostToDevice, st));
-    rc = orbfe_hamming_allpairs_device(h, (const uint8_t *) dq, nq, (const uint8_t *) dt, nt, bi, bd, sd, st, 0);
+    if (excl) ORBFE_CUDA(h, cudaMemcpyAsync(dex, excl, sizeof(int2) * (size_t) nq, cudaMemcpyHostToDevice, st));
+    rc = orbfe_hamming_allpairs_excl_device(h, (const uint8_t *) dq, nq, (const uint8_t *) dt, nt, excl ? (const int32_t *) dex : nullptr, bi, bd, sd, st, 0);
     if (rc) return rc;
     ORBFE_CUDA(h, cudaMemcpyAsync(best_idx, bi, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
     ORBFE_CUDA(h, cudaMemcpyAsync(best_dist, bd, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
     ORBFE_CUDA(h, cudaMemcpyAsync(second_dist, sd, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
     ORBFE_CUDA(h, cudaStreamSynchronize(st));
     return ORBFE_OK;
+}
+
+int orbfe_hamming_allpairs(orbfe_handle *h, const uint8_t *q, int nq, const uint8_t *t, int nt, int32_t *best_idx, int32_t *best_dist, int32_t *second_dist) {
+    return orbfe_hamming_allpairs_excl(h, q, nq, t, nt, nullptr, best_idx, best_dist, second_dist);
 }
 
 int orbfe_hamming_window(orbfe_handle *h, const uint8_t *q, int nq, const uint8_t *t, int nt, const int32_t *cand_offsets, const int32_t *cand_idx,

@@ -83,11 +83,18 @@ class ORBMatcher:
         return v.value
 
     # ---- brute force best / second best (BASELINE configs 4/5)
-    def hamming_allpairs(self, q, t):
+    def hamming_allpairs(self, q, t, excl=None):
+        """Best index / best distance / second-best distance of every query row over all train rows.  excl ([nq, 2] int32, optional):
+        train indices [lo, hi) query i skips — its own key frame's block when a key-frame window is matched against itself."""
         q = _c(q, np.uint8); t = _c(t, np.uint8)
         bi = np.zeros(len(q), np.int32); bd = np.zeros(len(q), np.int32); sd = np.zeros(len(q), np.int32)
-        _capi.check(self._h, self._lib.orbfe_hamming_allpairs(self._h, _capi.ptr(q), len(q), _capi.ptr(t), len(t), _capi.ptr(bi), _capi.ptr(bd),
-                                                              _capi.ptr(sd)))
+        ex = None
+        if excl is not None:
+            ex = _c(excl, np.int32).reshape(-1, 2)
+            if len(ex) != len(q):
+                raise ValueError("excl must have one [lo, hi) pair per query")
+        _capi.check(self._h, self._lib.orbfe_hamming_allpairs_excl(self._h, _capi.ptr(q), len(q), _capi.ptr(t), len(t), _capi.ptr(ex), _capi.ptr(bi),
+                                                                   _capi.ptr(bd), _capi.ptr(sd)))
         return bi, bd, sd
 
     # ---- best / second best over caller-supplied candidate lists (CSR)
@@ -103,9 +110,9 @@ class ORBMatcher:
                                                             _capi.ptr(bi), _capi.ptr(bd), _capi.ptr(sd)))
         return bi, bd, sd
 
-    def hamming_allpairs_device(self, d_q, nq, d_t, nt, d_bi, d_bd, d_sd, stream=None, sync=True):
-        _capi.check(self._h, self._lib.orbfe_hamming_allpairs_device(self._h, _capi.ptr(d_q), nq, _capi.ptr(d_t), nt, _capi.ptr(d_bi), _capi.ptr(d_bd),
-                                                                     _capi.ptr(d_sd), C.c_void_p(stream) if stream else None, int(sync)))
+    def hamming_allpairs_device(self, d_q, nq, d_t, nt, d_bi, d_bd, d_sd, stream=None, sync=True, d_excl=None):
+        _capi.check(self._h, self._lib.orbfe_hamming_allpairs_excl_device(self._h, _capi.ptr(d_q), nq, _capi.ptr(d_t), nt, _capi.ptr(d_excl), _capi.ptr(d_bi),
+                                                                          _capi.ptr(d_bd), _capi.ptr(d_sd), C.c_void_p(stream) if stream else None, int(sync)))
 
     # ---- int SearchForInitialization(frame1, frame2, vecPreMatched, matches12, windowSize=100) — ORBMatcher.cpp:33-116
     def SearchForInitialization(self, frame1, frame2, vecPreMatched, windowSize=100):

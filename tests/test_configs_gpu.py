@@ -166,7 +166,7 @@ def dots_image(h, w, pts):
     return img
 
 
-@pytest.mark.parametrize("gx,gy,cluster", [(26, 16, 8), (20, 20, 16)])
+@pytest.mark.parametrize("gx,gy,cluster", [(26, 16, 8), (20, 20, 8)])
 def test_quadtree_inputs_beyond_the_typical_pool(mods, oracle, gx, gy, cluster):
     """The sparse tight-pair inputs of tests/test_octree_model.py as an image: level 0 needs more node slots than the round-1 pool
     formula allowed (the call failed with ORBFE_E_INTERNAL); the pool now grows into the proven-size global pool."""
@@ -174,10 +174,15 @@ def test_quadtree_inputs_beyond_the_typical_pool(mods, oracle, gx, gy, cluster):
     m, _ = mods
     pts = tight_pairs(1882, 1042, gx, gy, cluster)
     img = dots_image(1080, 1920, pts)
-    ex = m.ORBExtractor(4000, 1.2, 8, 20, 7, keep_stages=True)
+    ex = m.ORBExtractor(2687, 1.2, 8, 20, 7, keep_stages=True)                # level-0 quota 868
+    assert ex.getFeaturesPerLevel(0) == 868
     kps, desc = ex(img)
-    okps, odesc = oracle.Extractor(4000, 1.2, 8, 20, 7)(img)
-    assert len(ex.level_candidates(0)) == len(pts)
+    okps, odesc = oracle.Extractor(2687, 1.2, 8, 20, 7)(img)
+    cand = ex.level_candidates(0)
+    assert np.array_equal(cand[:, :2], pts)                                  # every dot, and nothing else, is a level-0 candidate
+    from test_octree_model import gpu_formulation
+    _, slots = gpu_formulation(cand[:, 0].astype(int), cand[:, 1].astype(int), cand[:, 2].astype(int), 1882, 1042, 1882 + 19, ex.getFeaturesPerLevel(0))
+    assert slots > 8 * (ex.getFeaturesPerLevel(0) + 4) + 5 * 2 + 64          # more than round 1's pool held
     same_keypoints(kps, desc, okps, odesc)
     ex.close()
 

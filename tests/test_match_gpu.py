@@ -54,7 +54,71 @@ def test_allpairs_tensor_core_and_popc_kernels_agree(ctx, monkeypatch):
     ref = m.hamming_allpairs(q, t)
     monkeypatch.delenv("ORBFE_ALLPAIRS_POPC")
     assert all(np.array_equal(a, b) for a, b in zip(got, ref))
+    monkeypatch.setenv("ORBFE_ALLPAIRS", "imma")
+    assert all(np.array_equal(a, b) for a, b in zip(m.hamming_allpairs(q, t), ref))
+    monkeypatch.delenv("ORBFE_ALLPAIRS")
     assert got[1][5] == 0 and got[0][5] <= 100 and got[2][5] == 0
+
+
+def numpy_allpairs(q, t, excl=None):
+    """Brute force in numpy (small shapes): first minimum wins; 257 where there is no (second) candidate."""
+    d = np.unpackbits(q[:, None, :] ^ t[None, :, :], axis=2).sum(2).astype(np.int32)
+    if excl is not None:
+        cols = np.arange(len(t))[None, :]
+        d[(cols >= excl[:, :1]) & (cols < excl[:, 1:2])] = 1000
+    bi = d.argmin(1).astype(np.int32); bd = d.min(1)
+    d2 = d.copy(); d2[np.arange(len(q)), bi] = 1000
+    sd = d2.min(1)
+    bi[bd >= 1000] = -1
+    return bi, np.where(bd >= 1000, 257, bd).astype(np.int32), np.where(sd >= 1000, 257, sd).astype(np.int32)
+
+
+@pytest.mark.parametrize("kernel", ["tc", "imma", "popc"])
+@pytest.mark.parametrize("nq,nt", [(256, 512), (257, 513), (700, 900), (1025, 3000), (2600, 641), (511, 12800)])
+def test_allpairs_every_kernel_against_numpy(ctx, monkeypatch, kernel, nq, nt):
+    """tcgen05 (k_allpairs_tc), mma.sync (k_allpairs_imma) and popc (k_hamming_allpairs) kernels on shapes with ragged query / train
+    tiles, one and several train splits, exact duplicates (ties: the first index wins) and complementary rows (distance 256)."""
+    m = ctx["ORBMatcher"]()
+    rng = np.random.default_rng(nq * 13 + nt)
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8); t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    t[rng.integers(0, nt, nt // 8)] = q[rng.integers(0, nq, nt // 8)]
+    t[nt // 2:nt // 2 + 40] = t[nt // 2]; q[3] = t[nt // 2]; q[4] = ~t[nt // 2]
+    monkeypatch.setenv("ORBFE_ALLPAIRS", kernel)
+    got = m.hamming_allpairs(q, t)
+    exp = numpy_allpairs(q, t) if nq * nt <= 4_000_000 else None
+    if exp is None:
+        monkeypatch.setenv("ORBFE_ALLPAIRS", "popc")
+        exp = m.hamming_allpairs(q, t)
+    for a, b, what in zip(got, exp, ("index", "best", "second")):
+        assert np.array_equal(a, b), (kernel, what)
+
+
+@pytest.mark.parametrize("kernel", ["tc", "popc"])
+def test_allpairs_with_keyframe_block_exclusion(ctx, oracle, monkeypatch, kernel):
+    """A key-frame window matched against itself: every descriptor skips the block of its own key frame (orbfe_hamming_allpairs_excl).
+    Blocks of uneven size that straddle tile boundaries, an empty range, a range covering everything (no candidate: -1 / 257)."""
+    m = ctx["ORBMatcher"]()
+    rng = np.random.default_rng(5)
+    sizes = [130, 257, 1, 400, 128, 383, 64, 300]
+    n = sum(sizes)
+    table = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    table[rng.integers(0, n, 200)] = table[rng.integers(0, n, 200)]                    # duplicates inside and across blocks
+    starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    blk = np.repeat(np.arange(len(sizes)), sizes)
+    excl = np.stack([starts[blk], starts[blk + 1]], 1).astype(np.int32)
+    excl[5] = (7, 7); excl[6] = (0, n)
+    monkeypatch.setenv("ORBFE_ALLPAIRS", kernel)
+    got = m.hamming_allpairs(table, table, excl)
+    exp = numpy_allpairs(table, table, excl)
+    for a, b, what in zip(got, exp, ("index", "best", "second")):
+        assert np.array_equal(a, b), (kernel, what)
+    assert got[0][6] == -1 and got[1][6] == 257 and got[1][5] == 0
+    own = (got[0] >= excl[:, 0]) & (got[0] < excl[:, 1])
+    own[5] = False
+    assert not own.any()                                                               # nobody matched inside its own block
+    # without exclusion every row finds itself
+    bi, bd, _ = m.hamming_allpairs(table, table)
+    assert (bd == 0).all()
 
 
 def test_allpairs_real_descriptors_and_empty(ctx, oracle):
