@@ -10,11 +10,13 @@
 //   warp 1         TMEM allocation (512 columns = 2 accumulator stages x 2 M tiles x 128 columns) and the MMA issue:
 //                  one elected thread, 16 x tcgen05.mma.cta_group::1.kind::i8 (M 128, N 128, K 32) per train tile,
 //                  tcgen05.commit releases the shared-memory stage and publishes the accumulator stage
-//   warps 2..9     epilogue: a thread owns one query row (= one TMEM lane) of one M tile, reads its 128 accumulators of the stage
-//                  with tcgen05.ld, turns two neighbouring columns into one u16x2 word of 16-bit keys
-//                  (distance * 128 + column within the tile: one multiply-add per column, on the FMA pipe) and keeps the two
-//                  smallest keys of both halves with packed min / max (5 ALU instructions per 4 columns); per tile the four
-//                  16-bit candidates are merged into the row's 32-bit (distance << 22 | train index) pair
+//   warps 2..17    epilogue, 16 warps = 4 per scheduler: a thread owns one query row (= one TMEM lane) of one M tile for the even or
+//                  for the odd train tiles (so one half of the warps computes while the other half waits for / loads its stage),
+//                  reads the row's 128 accumulators of the stage with tcgen05.ld.x32,
+//                  turns two neighbouring columns into one u16x2 word of 16-bit keys (distance * 128 + column within the tile:
+//                  one multiply-add per column, on the FMA pipe) and keeps the two smallest keys of both halves with packed
+//                  min / max (5 ALU instructions per 4 columns, two independent chains); per tile the best two of the four 16-bit
+//                  candidates are merged into the row's 32-bit (distance << 22 | train index) pair, if they can improve it
 // The first minimum wins ties, as in the sequential `if (dist < bestDist)` loops: keys order by (distance, index).
 // Train ranges are split over blockIdx.y to fill the machine; k_allpairs_merge (orbfe_match.cu) merges the partial pairs.
 // Optional per-row exclusion range [lo, hi) of train indices: a query never matches its own key frame's block.
@@ -26,14 +28,19 @@
 #include <cstdio>
 #include <cstdlib>
 
+#ifndef ORBFE_TC_STAGES
+#define ORBFE_TC_STAGES 5
+#endif
+
 namespace orbfe {
 
 constexpr int kTcM = 128;                 // rows of one accumulator tile (TMEM lanes)
 constexpr int kTcRows = 2 * kTcM;         // query rows per CTA
 constexpr int kTcN = 128;                 // train rows per tile (accumulator columns)
-constexpr int kTcStages = 3;              // train tiles in flight in shared memory
+constexpr int kTcStages = ORBFE_TC_STAGES;   // train tiles in flight in shared memory (5 x 32 KB + the 64 KB query tile = 224 KB)
 constexpr int kTcHalf = 128 * 128;        // bytes of one (128 rows x 128 K-bytes) swizzled operand block
-constexpr int kTcThreads = 320;
+constexpr int kTcEpiWarps = 16;           // 2 M tiles x 4 lane quarters x 2 tile parities
+constexpr int kTcThreads = 32 * (2 + kTcEpiWarps);
 constexpr uint32_t kTcNone = (257u << 22) | 0x3fffffu;       // == kApNone of orbfe_match.cu
 constexpr size_t kTcSmem = (size_t) (4 + 2 * kTcStages) * kTcHalf + 1024 /* alignment slack */ + 256 /* barriers */;
 
@@ -127,7 +134,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_allpairs_tc(const __grid_cons
 
     if (tid == 0) {
         for (int s = 0; s < kTcStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&b_tfull[s], 1); mbar_init(&b_tempty[s], 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&b_tfull[s], 1); mbar_init(&b_tempty[s], kTcEpiWarps / 2); }
         mbar_init(b_q, 1);
         fence_barrier_init();
     }
@@ -154,21 +161,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_allpairs_tc(const __grid_cons
             }
         }
     } else if (wid == 1) {
-        // ===== MMA issue
+        // ===== MMA issue.  The descriptors of a tile differ only in the start-address field: the low words are precomputed and a k step
+        // is one add (32 bytes = 2 in the >> 4 encoding; the second K half starts kTcHalf bytes further on)
         if (lane == 0 && my_tiles > 0) {
+            const uint64_t desc_hi = (uint64_t) (1024 >> 4) << 32 | (1ull << 46) | (2ull << 61);
+            auto desc_lo = [](uint32_t saddr) -> uint32_t { return ((saddr & 0x3ffffu) >> 4) | (1u << 16); };
+            const uint32_t a_lo0 = desc_lo(smem_u32(s_q)), a_lo1 = desc_lo(smem_u32(s_q + 2 * kTcHalf)), b_lo0 = desc_lo(smem_u32(s_t));
             mbar_wait(b_q, 0);
             for (int i = 0; i < my_tiles; ++i) {
                 const int s = i % kTcStages, ac = i & 1;
                 mbar_wait(&b_tempty[ac], (uint32_t) (((i >> 1) & 1) ^ 1));
                 mbar_wait(&b_full[s], (uint32_t) ((i / kTcStages) & 1));
                 tc_fence_after();
+                const uint32_t b_lo = b_lo0 + (uint32_t) (s * 2 * kTcHalf >> 4);
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
                     const uint32_t d = tmem + (uint32_t) (ac * 2 * kTcN + mt * kTcN);
+                    const uint32_t a_lo = mt ? a_lo1 : a_lo0;
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
-                        const uint32_t ko = (uint32_t) ((ks >> 2) * kTcHalf + (ks & 3) * 32);
-                        tc_mma_i8(d, tc_smem_desc(smem_u32(s_q + mt * 2 * kTcHalf) + ko), tc_smem_desc(smem_u32(s_t + s * 2 * kTcHalf) + ko), kTcIdesc, ks ? 1u : 0u);
+                        const uint32_t ko = (uint32_t) (((ks >> 2) * kTcHalf + (ks & 3) * 32) >> 4);
+                        tc_mma_i8(d, desc_hi | (a_lo + ko), desc_hi | (b_lo + ko), kTcIdesc, ks ? 1u : 0u);
                     }
                 }
                 tc_commit(&b_empty[s]);          // the stage's train tile may be overwritten once these MMAs have read it
@@ -176,8 +189,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_allpairs_tc(const __grid_cons
             }
         }
     } else {
-        // ===== epilogue: warps 2..9; TMEM lane quarter = wid % 4 (hardware rule), M tile = (wid - 2) / 4
-        const int lq = wid & 3, mt = (wid - 2) >> 2;
+        // ===== epilogue: warps 2..17; TMEM lane quarter = wid % 4 (hardware rule); the four warps of a quarter take (M tile, tile parity):
+        // the warps of the even tiles compute while those of the odd tiles wait for / load their accumulators, and vice versa
+        const int lq = wid & 3, grp = (wid - 2) >> 2, mt = grp & 1, par = grp >> 1;
         const int row = row0 + mt * kTcM + lq * 32 + lane;
         int2 ex = make_int2(0, 0);
         if (a.excl && row < a.nq) ex = a.excl[row];
@@ -186,49 +200,59 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_allpairs_tc(const __grid_cons
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { w_lo = min(w_lo, __shfl_xor_sync(0xffffffffu, w_lo, o)); w_hi = max(w_hi, __shfl_xor_sync(0xffffffffu, w_hi, o)); }
         uint32_t K1 = kTcNone, K2 = kTcNone;
-        for (int i = 0; i < my_tiles; ++i) {
-            const int ac = i & 1;
+        for (int i = par; i < my_tiles; i += 2) {
             const int col0 = (t_begin + i) * kTcN;
-            mbar_wait(&b_tfull[ac], (uint32_t) ((i >> 1) & 1));
+            mbar_wait(&b_tfull[par], (uint32_t) ((i >> 1) & 1));
             tc_fence_after();
-            const uint32_t taddr = tmem + ((uint32_t) (lq * 32) << 16) + (uint32_t) (ac * 2 * kTcN + mt * kTcN);
-            const bool slow = col0 + kTcN > a.nt || (col0 < w_hi && col0 + kTcN > w_lo);
-            uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;           // per half: the two smallest 16-bit keys of the even / odd columns
+            const uint32_t taddr = tmem + ((uint32_t) (lq * 32) << 16) + (uint32_t) (par * 2 * kTcN + mt * kTcN);
+            const bool slow = col0 + kTcN > a.nt || (col0 < w_hi && col0 + kTcN > w_lo);      // ragged last tile / a row's own key-frame block
+            // two independent (smallest, second) chains, per 16-bit half
+            uint32_t a1 = 0xffffffffu, a2 = 0xffffffffu, b1 = 0xffffffffu, b2 = 0xffffffffu;
 #pragma unroll
-            for (int c0 = 0; c0 < kTcN; c0 += 32) {
-                uint32_t v[32];
-                tc_ld32(taddr + (uint32_t) c0, v);
+            for (int ch = 0; ch < 2; ++ch) {
+                uint32_t va[32], vb[32];
+                tc_ld32(taddr + (uint32_t) (ch * 64), va);
+                tc_ld32(taddr + (uint32_t) (ch * 64 + 32), vb);
                 tc_ld_wait();
-                uint32_t p[16];
+                if (ch == 1) {      // every accumulator this warp needs from the stage is in registers: hand the stage back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&b_tempty[par]);
+                }
+                // key16 = distance * 128 + column = 16384 - 64 * dot + column, two columns per word; neither half borrows or carries
+                uint32_t pa[16], pb[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    // key16 = distance * 128 + column = 16384 - 64 * dot + column, two columns per word; neither half borrows or carries
-                    const uint32_t cst = (uint32_t) (16384 + c0 + 2 * j) | ((uint32_t) (16384 + c0 + 2 * j + 1) << 16);
-                    p[j] = v[2 * j + 1] * 0xFFC00000u + (v[2 * j] * 0xFFFFFFC0u + cst);
+                    const uint32_t ca = (uint32_t) (16384 + ch * 64 + 2 * j) | ((uint32_t) (16384 + ch * 64 + 2 * j + 1) << 16);
+                    pa[j] = va[2 * j + 1] * 0xFFC00000u + (va[2 * j] * 0xFFFFFFC0u + ca);
+                    pb[j] = vb[2 * j + 1] * 0xFFC00000u + (vb[2 * j] * 0xFFFFFFC0u + (ca + 0x00200020u));
                 }
                 if (slow) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const int ca = col0 + c0 + 2 * j, cb = ca + 1;
-                        if (ca >= a.nt || (ca >= ex.x && ca < ex.y)) p[j] |= 0x0000ffffu;
-                        if (cb >= a.nt || (cb >= ex.x && cb < ex.y)) p[j] |= 0xffff0000u;
+                        const int c = col0 + ch * 64 + 2 * j;
+                        if (c >= a.nt || (c >= ex.x && c < ex.y)) pa[j] |= 0x0000ffffu;
+                        if (c + 1 >= a.nt || (c + 1 >= ex.x && c + 1 < ex.y)) pa[j] |= 0xffff0000u;
+                        if (c + 32 >= a.nt || (c + 32 >= ex.x && c + 32 < ex.y)) pb[j] |= 0x0000ffffu;
+                        if (c + 33 >= a.nt || (c + 33 >= ex.x && c + 33 < ex.y)) pb[j] |= 0xffff0000u;
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) two_smallest_u16x2(k1, k2, p[j], p[j + 1]);
+                for (int j = 0; j < 16; j += 2) { two_smallest_u16x2(a1, a2, pa[j], pa[j + 1]); two_smallest_u16x2(b1, b2, pb[j], pb[j + 1]); }
             }
-            // every accumulator of this stage has been read: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&b_tempty[ac]);
-            // the tile's four 16-bit candidates -> 32-bit keys (distance << 22 | train index)
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                const uint32_t k16 = h == 0 ? (k1 & 0xffffu) : h == 1 ? (k1 >> 16) : h == 2 ? (k2 & 0xffffu) : (k2 >> 16);
-                if (k16 != 0xffffu) merge_key(K1, K2, ((k16 >> 7) << 22) | (uint32_t) (col0 + (int) (k16 & 127u)));
+            const uint32_t k1 = __vminu2(a1, b1), k2 = __vimin3_u16x2(__vmaxu2(a1, b1), a2, b2);
+            // across the two halves: smallest = min(lo, hi); second = min3(max(lo, hi), k2.lo, k2.hi)
+            const uint32_t k1s = __byte_perm(k1, 0, 0x1032), k2s = __byte_perm(k2, 0, 0x1032);
+            const uint32_t m1 = __vminu2(k1, k1s) & 0xffffu, m2 = __vimin3_u16x2(__vmaxu2(k1, k1s), k2, k2s) & 0xffffu;
+            // 16-bit candidates -> 32-bit keys (distance << 22 | train index); most tiles cannot improve the row's pair
+            const uint32_t key1 = ((m1 >> 7) << 22) | (uint32_t) (col0 + (int) (m1 & 127u));
+            if (key1 < K2) {
+                const uint32_t key2 = ((m2 >> 7) << 22) | (uint32_t) (col0 + (int) (m2 & 127u));
+                merge_key(K1, K2, key1);
+                merge_key(K1, K2, key2);
             }
         }
-        if (row < a.nq) a.partial[(size_t) blockIdx.y * a.nq + row] = make_uint2(K1, K2);
+        if (row < a.nq) a.partial[(size_t) (blockIdx.y * 2 + par) * a.nq + row] = make_uint2(K1, K2);
     }
     tc_fence_before();
     __syncthreads();
@@ -280,7 +304,7 @@ size_t allpairs_tc_scratch_bytes(int nq, int nt, int *n_split_out) {
     }
     if (n_split_out) *n_split_out = best;
     auto up = [](size_t v) { return (v + 255) & ~(size_t) 255; };
-    return up((size_t) nq * 256) + up((size_t) nt * 256) + up((size_t) best * nq * sizeof(uint2)) + 1024;
+    return up((size_t) nq * 256) + up((size_t) nt * 256) + up((size_t) 2 * best * nq * sizeof(uint2)) + 1024;    // even / odd tiles of a split report separately
 }
 
 // d_scratch: allpairs_tc_scratch_bytes(nq, nt) bytes.  The results go through `partial` and the caller's merge kernel.
@@ -303,7 +327,7 @@ int allpairs_tc_launch(Handle *h, const uint8_t *d_q, int nq, const uint8_t *d_t
     k_allpairs_tc<<<dim3((nq + kTcRows - 1) / kTcRows, n_split), kTcThreads, kTcSmem, st>>>(mq, mt, ta);
     h->launches += (te == qe) ? 2 : 3;
     ORBFE_CUDA(h, cudaGetLastError());
-    *partial_out = partial; *n_split_out = n_split;
+    *partial_out = partial; *n_split_out = 2 * n_split;          // the even and the odd tiles of every split report separately
     return ORBFE_OK;
 }
 
