@@ -276,12 +276,20 @@ int orbfe_search_by_bow(orbfe_handle *h,
 /* Search half of the fuse ORBMatcher::SearchByProjection(KeyFrame, mapPoints, Map*, th) (ORBMatcher.cpp:524-571), SURVEY.md 8f rank 3:
  * for every map point the adapter projected into the key frame (q_valid, u, v, radius = th * scale[predictLevel], predictLevel) the best
  * key point within KeyFrame::getFeaturesInArea (strict "< r", KeyFrame.cpp:181-211; levels [predict-1, predict]) that passes the
- * chi-square gate (:563-564, square_sigmas of the handle's scale table) with dist <= TH_LOW.  best_idx1[i] = -1 if none; best_dist may
+ * chi-square gate (:563-564, square_sigmas of the handle's own scale table: scale_factor / n_levels of its orbfe_config) with dist <= TH_LOW.  best_idx1[i] = -1 if none; best_dist may
  * be NULL.  The observation / replace bookkeeping of :573-586 is the adapter's. */
 int orbfe_search_fuse(orbfe_handle *h, const float *q_u, const float *q_v, const float *q_radius, const int32_t *q_level,
                       const uint8_t *q_desc, const uint8_t *q_valid, int nq,
                       const orbfe_keypoint *kps1, const uint8_t *desc1, int n1, int img_w, int img_h,
                       int32_t *best_idx1, int32_t *best_dist, int *n_matches);
+
+/* The same with the gate's sigma table passed explicitly (ORBExtractor::getSquareSigma(octave), n_levels entries): use this form when the
+ * matcher's handle was not created with the extractor's scaleFactor / nLevels.  A key point whose octave lies outside the table is
+ * rejected with ORBFE_E_ARG (the reference would index past its vector). */
+int orbfe_search_fuse_sigma(orbfe_handle *h, const float *q_u, const float *q_v, const float *q_radius, const int32_t *q_level,
+                            const uint8_t *q_desc, const uint8_t *q_valid, int nq,
+                            const orbfe_keypoint *kps1, const uint8_t *desc1, int n1, int img_w, int img_h,
+                            const float *square_sigmas, int n_levels, int32_t *best_idx1, int32_t *best_dist, int *n_matches);
 
 /* MapPoint::computeDescriptor (BasicObject/MapPoint.cpp:103-152) for a batch of map points: group g owns the descriptor rows
  * [group_off[g], group_off[g+1]) (its observations in std::map order); best[g] = index within the group of the descriptor with the

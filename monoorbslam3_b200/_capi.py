@@ -86,6 +86,7 @@ SIGNATURES = {
     "orbfe_vocab_words": (_i, [_vp]),
     "orbfe_vocab_transform": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i)]),
     "orbfe_search_fuse": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, C.POINTER(_i)]),
+    "orbfe_search_fuse_sigma": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, C.POINTER(_i)]),
     "orbfe_compute_descriptors": (_i, [_vp, _vp, _vp, _i, _vp]),
     "orbfe_search_by_bow": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _f, _i, C.POINTER(_i)]),
     "orbfe_search_for_triangulation": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i,

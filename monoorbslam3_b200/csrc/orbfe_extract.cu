@@ -597,8 +597,8 @@ int orbfe_features_per_level(const orbfe_handle *h, int level) { return (h && le
 int orbfe_max_keypoints(const orbfe_handle *h) {
     if (!h) return -1;
     if (h->max_kp) return h->max_kp;
-    int s = 0;
-    for (int l = 0; l < h->cfg.n_levels; ++l) s += h->quota[l] + 40;
+    int s = 0;                                  // before the first frame fixes the geometry: a bound that holds for aspect ratios up to 64:1
+    for (int l = 0; l < h->cfg.n_levels; ++l) s += std::max(h->quota[l] + 40, 260);
     return s;
 }
 long long orbfe_launch_count(const orbfe_handle *h) { return h ? h->launches + (h->peer ? h->peer->launches : 0) : 0; }

@@ -1435,9 +1435,23 @@ int orbfe_search_fuse(orbfe_handle *h, const float *q_u, const float *q_v, const
                       const uint8_t *q_valid, int nq, const orbfe_keypoint *kps1, const uint8_t *desc1, int n1, int img_w, int img_h,
                       int32_t *best_idx1, int32_t *best_dist, int *n_matches) {
     if (!h) return ORBFE_E_ARG;
+    float s2[ORBFE_MAX_LEVELS];
+    for (int l = 0; l < h->cfg.n_levels; ++l) s2[l] = h->scale[l] * h->scale[l];                 // square_sigmas (ORBExtractor.cpp:432-436)
+    return orbfe_search_fuse_sigma(h, q_u, q_v, q_radius, q_level, q_desc, q_valid, nq, kps1, desc1, n1, img_w, img_h, s2, h->cfg.n_levels, best_idx1, best_dist,
+                                   n_matches);
+}
+
+int orbfe_search_fuse_sigma(orbfe_handle *h, const float *q_u, const float *q_v, const float *q_radius, const int32_t *q_level, const uint8_t *q_desc,
+                            const uint8_t *q_valid, int nq, const orbfe_keypoint *kps1, const uint8_t *desc1, int n1, int img_w, int img_h,
+                            const float *square_sigmas, int n_levels, int32_t *best_idx1, int32_t *best_dist, int *n_matches) {
+    if (!h) return ORBFE_E_ARG;
     if (!n_matches || nq < 0 || n1 < 0 || (nq && (!q_u || !q_v || !q_radius || !q_level || !q_desc || !q_valid || !best_idx1)) || (n1 && (!kps1 || !desc1)) ||
-        img_w <= 0 || img_h <= 0)
+        img_w <= 0 || img_h <= 0 || !square_sigmas || n_levels < 1 || n_levels > ORBFE_MAX_LEVELS)
         return set_error(h, ORBFE_E_ARG, "invalid argument");
+    // the chi-square gate indexes square_sigmas with the key point's octave (ORBMatcher.cpp:564): an octave outside the table is the caller's error
+    for (int j = 0; j < n1; ++j)
+        if (kps1[j].octave < 0 || kps1[j].octave >= n_levels)
+            return set_error(h, ORBFE_E_ARG, "key point %d has octave %d but the sigma table has %d levels", j, kps1[j].octave, n_levels);
     *n_matches = 0;
     for (int i = 0; i < nq; ++i) { best_idx1[i] = -1; if (best_dist) best_dist[i] = TH_LOW + 1; }
     if (nq == 0 || n1 == 0) return ORBFE_OK;
@@ -1464,8 +1478,8 @@ int orbfe_search_fuse(orbfe_handle *h, const float *q_u, const float *q_v, const
     if ((rc = frame_grid_launch(h, k1, nm + 1, n1, img_w, img_h, coff, cidx, st))) return rc;
     FuseArgs fa; memset(&fa, 0, sizeof fa);
     fa.qx = qx; fa.qy = qy; fa.qr = qr; fa.qlevel = ql; fa.qvalid = qv; fa.qdesc = qd; fa.nq = nq; fa.kps1 = k1; fa.desc1 = d1;
-    fa.cell_off = coff; fa.cell_idx = cidx; fa.cols = cols; fa.rows = rows; fa.n_levels = h->cfg.n_levels;
-    for (int l = 0; l < h->cfg.n_levels; ++l) fa.sigma2[l] = h->scale[l] * h->scale[l];          // square_sigmas (ORBExtractor.cpp:432-436)
+    fa.cell_off = coff; fa.cell_idx = cidx; fa.cols = cols; fa.rows = rows; fa.n_levels = n_levels;
+    for (int l = 0; l < n_levels; ++l) fa.sigma2[l] = square_sigmas[l];
     fa.best_idx = bi; fa.best_dist = bd; fa.n_matches = nm;
     k_fuse<<<(nq + 7) / 8, 256, 0, st>>>(fa);
     h->launches++;

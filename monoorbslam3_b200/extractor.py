@@ -37,6 +37,11 @@ class ORBExtractor:
     def getScaleFactors(self):
         return [self.getScaleFactor(l) for l in range(self.n_levels)]
 
+    def getSquareSigmas(self):
+        """square_sigmas[level] = scale_factors[level]^2 in float32 (ORBExtractor.cpp:432-436)."""
+        sf = np.array(self.getScaleFactors(), np.float32)
+        return (sf * sf).astype(np.float32)
+
     def getMaxScaleFactor(self):
         return self.getScaleFactor(self.n_levels - 1)
 

@@ -1,6 +1,7 @@
 // ORBExtractor.cpp — adapter from the reference's ORBExtractor interface to liborbfe.so (see ORBExtractor.h).
 #include "ORBExtractor.h"
 
+#include <cstdlib>
 #include <iostream>
 
 namespace mono_orb_slam3 {
@@ -24,28 +25,34 @@ namespace mono_orb_slam3 {
     void ORBExtractor::open(float scaleFactor, int nLevels) {
         orbfe_config cfg{};
         cfg.n_features = budget_; cfg.scale_factor = scaleFactor; cfg.n_levels = nLevels;
-        cfg.ini_th_fast = fast_ini_; cfg.min_th_fast = fast_min_; cfg.device = 0; cfg.max_batch = 64; cfg.flags = 0;
+        cfg.ini_th_fast = fast_ini_; cfg.min_th_fast = fast_min_; cfg.device = device_; cfg.max_batch = max_batch_; cfg.flags = 0;
         if (orbfe_create(&cfg, &handle_) != ORBFE_OK) throw std::runtime_error(std::string("orbfe_create: ") + orbfe_last_error(nullptr));
         quota_.resize((size_t) nLevels);
         for (int l = 0; l < nLevels; ++l) quota_[(size_t) l] = orbfe_features_per_level(handle_, l);
         image_pyramid.resize((size_t) nLevels);
     }
 
-    int ORBExtractor::capacity() const {
-        int cap = 0;
-        for (int q : quota_) cap += q + 40;
-        return cap;
+    // the library's own bound (per level max(quota + 4, 4 * roots + 4) once the frame geometry is known, a safe estimate before)
+    int ORBExtractor::capacity() const { return orbfe_max_keypoints(handle_); }
+
+    static int g_default_device = -1;
+    int ORBExtractor::defaultDevice() {
+        if (g_default_device >= 0) return g_default_device;
+        const char *e = std::getenv("ORBFE_DEVICE");
+        return e ? std::atoi(e) : 0;
     }
+    void ORBExtractor::setDefaultDevice(int device) { g_default_device = device; }
 
     // the primary constructor (re)initialises the process-wide pyramid table, like the reference's (ORBExtractor.cpp:427-439)
-    ORBExtractor::ORBExtractor(int nFeatures, float scaleFactor, int nLevels, int iniThFast, int minThFast)
-            : budget_(nFeatures), fast_ini_(iniThFast), fast_min_(minThFast) {
+    ORBExtractor::ORBExtractor(int nFeatures, float scaleFactor, int nLevels, int iniThFast, int minThFast, int device, int maxBatch)
+            : budget_(nFeatures), fast_ini_(iniThFast), fast_min_(minThFast), device_(device >= 0 ? device : defaultDevice()), max_batch_(maxBatch > 0 ? maxBatch : 64) {
         open(scaleFactor, nLevels);
         detail::pyramid().fill(handle_, scaleFactor, nLevels);
     }
 
     ORBExtractor::ORBExtractor(int nFeatures, const ORBExtractor &orbExtractor)
-            : budget_(nFeatures), fast_ini_(orbExtractor.fast_ini_), fast_min_(orbExtractor.fast_min_) {
+            : budget_(nFeatures), fast_ini_(orbExtractor.fast_ini_), fast_min_(orbExtractor.fast_min_), device_(orbExtractor.device_),
+              max_batch_(orbExtractor.max_batch_) {
         open(detail::pyramid().factor, detail::pyramid().levels);
     }
 

@@ -31,7 +31,9 @@ namespace mono_orb_slam3 {
     class ORBExtractor {
     public:
         // ---- what the reference's callers use
-        explicit ORBExtractor(int nFeatures = 1000, float scaleFactor = 1.2, int nLevels = 8, int iniThFast = 20, int minThFast = 10);
+        // device / maxBatch are additions with defaults (the reference has five arguments): device < 0 = defaultDevice()
+        explicit ORBExtractor(int nFeatures = 1000, float scaleFactor = 1.2, int nLevels = 8, int iniThFast = 20, int minThFast = 10, int device = -1,
+                              int maxBatch = 64);
         ORBExtractor(int nFeatures, const ORBExtractor &orbExtractor);       // Tracking.cpp:24: the initial extractor, another feature budget
         void operator()(const cv::Mat &image, std::vector<cv::KeyPoint> &keyPoints, cv::Mat &descriptors);
 
@@ -56,6 +58,10 @@ namespace mono_orb_slam3 {
         // equally sized frames in one call (offline workloads); outputs per frame
         void extractBatch(const std::vector<cv::Mat> &frames, std::vector<std::vector<cv::KeyPoint>> &keyPoints, std::vector<cv::Mat> &descriptors);
         orbfe_handle *handle() const { return handle_; }
+        // CUDA device of extractors (and of the matcher's per-thread handles) created without an explicit one: setDefaultDevice(), else the
+        // environment variable ORBFE_DEVICE, else 0
+        static int defaultDevice();
+        static void setDefaultDevice(int device);
         const std::vector<int> &featuresPerLevel() const { return quota_; }
 
         ~ORBExtractor();
@@ -67,6 +73,7 @@ namespace mono_orb_slam3 {
         int capacity() const;                   // key points one frame can produce: the quotas plus the quadtree's slack
 
         int budget_, fast_ini_, fast_min_;      // nFeatures, iniThFast, minThFast
+        int device_ = 0, max_batch_ = 64;
         std::vector<int> quota_;                // per-level feature quota, as the library computed it
         orbfe_handle *handle_ = nullptr;
     };

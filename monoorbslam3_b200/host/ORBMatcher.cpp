@@ -3,16 +3,28 @@
 
 namespace mono_orb_slam3 {
 
+    // One handle (= one CUDA stream + scratch) per host thread: the reference runs ORBMatcher on the tracking and on the local-mapping
+    // thread at the same time (System.cpp:55).  The handle follows the extractor's process-wide pyramid (scale factor, levels) and
+    // device, and is re-created when an extractor with other values has been constructed since.
     orbfe_handle *ORBMatcher::handle() {
         struct Holder {
             orbfe_handle *h = nullptr;
-            Holder() {
-                orbfe_config cfg{1000, 1.2f, 8, 20, 7, 0, 1, 0};      // the matcher entry points use only the handle's stream and scratch
+            float factor = 0.f; int levels = 0, device = -1;
+            void open() {
+                const detail::PyramidTable &p = detail::pyramid();
+                const float f = p.factor > 1.f ? p.factor : 1.2f;
+                const int l = p.scale.empty() ? 8 : p.levels, d = ORBExtractor::defaultDevice();
+                if (h && f == factor && l == levels && d == device) return;
+                if (h) orbfe_destroy(h);
+                h = nullptr;
+                orbfe_config cfg{1000, f, l, 20, 7, d, 1, 0};
                 if (orbfe_create(&cfg, &h) != ORBFE_OK) throw std::runtime_error(std::string("orbfe_create: ") + orbfe_last_error(nullptr));
+                factor = f; levels = l; device = d;
             }
-            ~Holder() { orbfe_destroy(h); }
+            ~Holder() { if (h) orbfe_destroy(h); }
         };
         static thread_local Holder holder;
+        holder.open();
         return holder.h;
     }
 

@@ -168,16 +168,25 @@ class ORBMatcher:
                                                            int(self.be_check_orientation), C.byref(n)))
         return n.value, asg[:len(d2)]
 
-    def SearchFuse(self, keyframe, q_u, q_v, q_radius, q_level, q_desc, q_valid):
+    def SearchFuse(self, keyframe, q_u, q_v, q_radius, q_level, q_desc, q_valid, square_sigmas=None):
         """Search half of the fuse SearchByProjection(KeyFrame, mapPoints, Map*, th) (ORBMatcher.cpp:524-571): per projected map point the
-        best key-frame key point (or -1) and its distance.  `keyframe` is a FrameView of the key frame (undistorted key points)."""
+        best key-frame key point (or -1) and its distance.  `keyframe` is a FrameView of the key frame (undistorted key points).
+        square_sigmas = ORBExtractor.getSquareSigmas() of the extractor that produced the key points (the chi-square gate of :564 is
+        5.991 * square_sigmas[octave]); without it the table of the matcher's own handle (scale 1.2, 8 levels by default) is used."""
         u = _c(q_u, np.float32); v = _c(q_v, np.float32); r = _c(q_radius, np.float32); lv = _c(q_level, np.int32)
         qd = _c(q_desc, np.uint8); qv = _c(q_valid, np.uint8)
         bi = np.full(max(len(u), 1), -1, np.int32); bd = np.zeros(max(len(u), 1), np.int32)
         n = C.c_int()
-        _capi.check(self._h, self._lib.orbfe_search_fuse(self._h, _capi.ptr(u), _capi.ptr(v), _capi.ptr(r), _capi.ptr(lv), _capi.ptr(qd), _capi.ptr(qv), len(u),
-                                                         _capi.ptr(_c(keyframe.key_points, KP_DTYPE)), _capi.ptr(_c(keyframe.descriptors, np.uint8)), keyframe.num_kps, keyframe.width, keyframe.height,
-                                                         _capi.ptr(bi), _capi.ptr(bd), C.byref(n)))
+        kp = _c(keyframe.key_points, KP_DTYPE); kd = _c(keyframe.descriptors, np.uint8)
+        if square_sigmas is None:
+            _capi.check(self._h, self._lib.orbfe_search_fuse(self._h, _capi.ptr(u), _capi.ptr(v), _capi.ptr(r), _capi.ptr(lv), _capi.ptr(qd), _capi.ptr(qv), len(u),
+                                                             _capi.ptr(kp), _capi.ptr(kd), keyframe.num_kps, keyframe.width, keyframe.height,
+                                                             _capi.ptr(bi), _capi.ptr(bd), C.byref(n)))
+        else:
+            s2 = _c(square_sigmas, np.float32)
+            _capi.check(self._h, self._lib.orbfe_search_fuse_sigma(self._h, _capi.ptr(u), _capi.ptr(v), _capi.ptr(r), _capi.ptr(lv), _capi.ptr(qd), _capi.ptr(qv),
+                                                                   len(u), _capi.ptr(kp), _capi.ptr(kd), keyframe.num_kps, keyframe.width, keyframe.height,
+                                                                   _capi.ptr(s2), len(s2), _capi.ptr(bi), _capi.ptr(bd), C.byref(n)))
         return n.value, bi[:len(u)], bd[:len(u)]
 
     def compute_descriptors(self, desc, group_off):
