@@ -44,28 +44,3 @@ def build_cpp_adapter_test(out=None):
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", out] + srcs + ["-L" + os.path.dirname(LIB), "-lorbfe", "-Wl,-rpath," + os.path.dirname(LIB)])
     return out
 
-
-def build_cpp_matcher_ref_test(out=None):
-    """g++ build of tests/cpp/matcher_ref_test.cpp: the matcher adapter with ORBFE_REFERENCE_TYPES against the stand-in Frame / KeyFrame /
-    MapPoint headers of oracle/matchshim (test infrastructure) and the reference's vendored DBoW2 FeatureVector, which is compiled from
-    where it lies under /root/reference — so the binary is built in the build container and travels to the GPU box prebuilt."""
-    root = os.path.dirname(HERE)
-    out = out or os.path.join(HERE, "lib", "matcher_ref_test")
-    ref = os.environ.get("ORBFE_REFERENCE", "/root/reference")
-    dbow = os.path.join(ref, "thirdParty", "DBoW2")
-    if not os.path.exists(os.path.join(dbow, "DBoW2", "FeatureVector.cpp")):
-        if os.path.exists(out):
-            return out
-        raise FileNotFoundError("matcher_ref_test is not built and %s is not present" % dbow)
-    host, orc = os.path.join(HERE, "host"), os.path.join(root, "oracle")
-    srcs = [os.path.join(root, "tests", "cpp", "matcher_ref_test.cpp"), os.path.join(host, "ORBExtractor.cpp"), os.path.join(host, "ORBMatcher.cpp"),
-            os.path.join(dbow, "DBoW2", "FeatureVector.cpp"), os.path.join(dbow, "DBoW2", "BowVector.cpp")]
-    deps = srcs + [LIB, os.path.join(host, "ORBMatcher.h"), os.path.join(host, "ORBExtractor.h"), os.path.join(orc, "matchshim", "BasicObject", "Frame.h")]
-    if os.path.exists(out) and all(os.path.getmtime(s) < os.path.getmtime(out) for s in deps):
-        return out
-    subprocess.check_call(["make", "-s", "-C", orc, os.path.join(orc, "liborb_oracle.so")])
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-w", "-DORBFE_REFERENCE_TYPES", "-I" + host, "-I" + os.path.join(orc, "matchshim"),
-                           "-I" + os.path.join(orc, "eigenshim"), "-I" + os.path.join(orc, "cvshim"), "-I" + os.path.join(orc, "boostshim"), "-I" + orc,
-                           "-I" + dbow, "-o", out] + srcs +
-                          ["-L" + os.path.dirname(LIB), "-lorbfe", "-L" + orc, "-lorb_oracle", "-Wl,-rpath," + os.path.dirname(LIB), "-Wl,-rpath," + orc])
-    return out

@@ -46,7 +46,10 @@ def test_reference_signatures_equal_the_verbatim_matcher(tmp_path, oracle):
     from oracle import ref_matcher as ref
     if not ref.available():
         pytest.skip("oracle/_ref/libref_matcher.so is not built")
-    exe = build.build_cpp_matcher_ref_test()
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp"))
+    import build_matcher_ref_test
+    exe = build_matcher_ref_test.build()
     ex = ORBExtractor(1200, 1.2, 8, 20, 7)
     a, b = synth.shifted_pair(H, W, 2025)
     ka, da = ex(a); kb, db = ex(b)
