@@ -29,8 +29,39 @@ def build(force=False, verbose=False):
     return LIB
 
 
+DIST_LIB = os.path.join(HERE, "lib", "liborbfe_dist.so")
+
+
+def build_dist(force=False):
+    """liborbfe_dist.so: the multi-GPU entry points (include/orbfe_dist.h) — host C++ over liborbfe.so and NCCL."""
+    src = os.path.join(CSRC, "orbfe_dist.cpp")
+    deps = [src, LIB, os.path.join(HERE, "..", "include", "orbfe_dist.h"), os.path.join(HERE, "..", "include", "orbfe.h")]
+    if not force and os.path.exists(DIST_LIB) and all(os.path.getmtime(d) < os.path.getmtime(DIST_LIB) for d in deps):
+        return DIST_LIB
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-I" + os.path.join(cuda, "include"), "-o", DIST_LIB, src,
+                           "-L" + os.path.dirname(LIB), "-lorbfe", "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-lnccl", "-lpthread",
+                           "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + os.path.join(cuda, "lib64")])
+    return DIST_LIB
+
+
+def build_cpp_dist_test(out=None):
+    """g++ build of tests/cpp/dist_test.cpp against liborbfe_dist.so / liborbfe.so (used by the multi-GPU test)."""
+    root = os.path.dirname(HERE)
+    out = out or os.path.join(HERE, "lib", "dist_test")
+    src = os.path.join(root, "tests", "cpp", "dist_test.cpp")
+    build_dist()
+    if os.path.exists(out) and all(os.path.getmtime(s) < os.path.getmtime(out) for s in (src, LIB, DIST_LIB)):
+        return out
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(cuda, "include"), "-o", out, src, "-L" + os.path.dirname(LIB), "-lorbfe_dist", "-lorbfe",
+                           "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath," + os.path.dirname(LIB), "-Wl,-rpath," + os.path.join(cuda, "lib64")])
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_dist(force="--force" in sys.argv))
 
 
 def build_cpp_adapter_test(out=None):

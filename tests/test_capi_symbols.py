@@ -17,8 +17,8 @@ def capi():
     return _capi
 
 
-def header_symbols():
-    txt = open(os.path.join(ROOT, "include", "orbfe.h")).read()
+def header_symbols(name="orbfe.h"):
+    txt = open(os.path.join(ROOT, "include", name)).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     return sorted(set(re.findall(r"\b(orbfe_[a-z_0-9]+)\s*\(", txt)))
 
@@ -36,6 +36,16 @@ def test_library_exports_every_declared_symbol(capi):
     for s in header_symbols():
         assert hasattr(lib, s), s
     assert set(header_symbols()) == set(capi.SIGNATURES)          # the ctypes table covers the header, nothing more
+
+
+def test_multi_gpu_library_exports_every_declared_symbol(capi):
+    """include/orbfe_dist.h / liborbfe_dist.so: the multi-GPU entry points (NCCL from C++)."""
+    from monoorbslam3_b200 import build
+    out = subprocess.run(["nm", "-D", "--defined-only", build.build_dist()], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (orbfe_[a-z_0-9]+)", out))
+    declared = set(header_symbols("orbfe_dist.h"))
+    assert declared and declared == exported, (declared ^ exported)
+    assert {"orbfe_dist_init", "orbfe_extract_batch_sharded", "orbfe_extract_batch_sharded_device", "orbfe_allpairs_sharded"} <= declared
 
 
 def test_library_contains_sm100a_code_only(capi):
