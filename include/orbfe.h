@@ -235,6 +235,35 @@ int orbfe_search_for_initialization(orbfe_handle *h,
                                     int img_w, int img_h, float *prematched_xy, int32_t *matches12,
                                     int window, float nn_ratio, int check_orientation, int *n_matches);
 
+/* ---------------------------------------------------------------- device-resident frames
+ * What Frame::Frame leaves behind for the matchers (Frame.cpp:20-51) kept in HBM: undistorted key points, descriptors and the 40-px
+ * grid.  Tracking calls the matcher several times per frame on the same frames (Tracking.cpp:284-296 calls SearchByProjection twice
+ * on one frame pair, :412-425 searches the local map in the current frame): with a frame object the key points and descriptors are
+ * uploaded and the grid is built once, and the orbfe_search_*_f entry points only move the queries and the result.
+ *   orbfe_frame_upload       copies host arrays (n key points, n x 32 descriptor bytes) to the device and builds the grid
+ *   orbfe_frame_wrap_device  borrows buffers that are already on the device — the outputs of orbfe_extract_batch_device /
+ *                            orbfe_frame_postprocess_device for one frame (pass its grid, or NULL, NULL to have one built); the
+ *                            buffers must outlive the frame object.  n is the frame's key-point count (d_n_per_frame[b] read back).
+ * A frame belongs to the device of the handle that made it; the searches require a handle on the same device. */
+typedef struct orbfe_frame orbfe_frame;
+int  orbfe_frame_upload(orbfe_handle *h, const orbfe_keypoint *kps, const uint8_t *desc, int n, int img_w, int img_h, orbfe_frame **out);
+int  orbfe_frame_wrap_device(orbfe_handle *h, const orbfe_keypoint *d_kps, const uint8_t *d_desc, int n, int img_w, int img_h,
+                             const int32_t *d_grid_off, const int32_t *d_grid_idx, orbfe_frame **out);
+void orbfe_frame_destroy(orbfe_frame *f);
+int  orbfe_frame_size(const orbfe_frame *f);
+
+/* The window searches on device-resident frames: same semantics and results as the host-array forms below. */
+int orbfe_search_for_initialization_f(orbfe_handle *h, const orbfe_frame *frame1, const orbfe_frame *frame2, float *prematched_xy,
+                                      int32_t *matches12, int window, float nn_ratio, int check_orientation, int *n_matches);
+int orbfe_search_by_projection_f(orbfe_handle *h,
+                                 const float *q_u, const float *q_v, const float *q_radius, const int32_t *q_level,
+                                 const float *q_angle, const uint8_t *q_desc, const uint8_t *q_valid, int nq,
+                                 const orbfe_frame *frame2, const uint8_t *occupied, int32_t *assigned, int check_orientation, int *n_matches);
+int orbfe_search_local_points_f(orbfe_handle *h,
+                                const float *q_u, const float *q_v, const float *q_radius, const int32_t *q_level,
+                                const uint8_t *q_desc, const uint8_t *q_valid, int nq,
+                                const orbfe_frame *frame2, const uint8_t *occupied, int32_t *assigned, float nn_ratio, int *n_matches);
+
 /* ORBMatcher::SearchByProjection(Frame|KeyFrame -> Frame) (ORBMatcher.cpp:203-348) after the adapter projected the
  * map points: query i is considered iff q_valid[i]; window centre (q_u,q_v), radius q_radius (= th * kp.size),
  * octave window [q_level-1, q_level+1]; occupied[j] != 0 marks current-frame slots that already hold a map point;

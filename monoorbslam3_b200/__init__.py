@@ -5,9 +5,9 @@ of the reference's ORBExtractor / ORBMatcher interfaces.  No CPU fallback: witho
 entry points raise."""
 from ._capi import KP_DTYPE, OrbfeError, lib      # noqa: F401
 from .extractor import ORBExtractor               # noqa: F401
-from .matcher import ORBMatcher, FrameView        # noqa: F401
+from .matcher import ORBMatcher, FrameView, DeviceFrame   # noqa: F401
 from .bow import ORBVocabulary                   # noqa: F401
 from .frame import Camera, FramePost, frame_postprocess, frame_postprocess_device, grid_size   # noqa: F401
 
-__all__ = ["ORBExtractor", "ORBMatcher", "FrameView", "KP_DTYPE", "OrbfeError", "lib", "Camera", "FramePost", "frame_postprocess",
+__all__ = ["ORBExtractor", "ORBMatcher", "FrameView", "DeviceFrame", "KP_DTYPE", "OrbfeError", "lib", "Camera", "FramePost", "frame_postprocess",
            "frame_postprocess_device", "grid_size", "ORBVocabulary"]

@@ -77,6 +77,13 @@ SIGNATURES = {
     "orbfe_hamming_window": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "orbfe_hamming_allpairs_device": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i]),
     "orbfe_search_for_initialization": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _f, _i, C.POINTER(_i)]),
+    "orbfe_frame_upload": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(_vp)]),
+    "orbfe_frame_wrap_device": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, C.POINTER(_vp)]),
+    "orbfe_frame_destroy": (None, [_vp]),
+    "orbfe_frame_size": (_i, [_vp]),
+    "orbfe_search_for_initialization_f": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _f, _i, C.POINTER(_i)]),
+    "orbfe_search_by_projection_f": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, C.POINTER(_i)]),
+    "orbfe_search_local_points_f": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _f, C.POINTER(_i)]),
     "orbfe_search_by_projection": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, C.POINTER(_i)]),
     "orbfe_search_local_points": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _f, C.POINTER(_i)]),
     "orbfe_check_homography": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _f, _vp, _vp]),

@@ -159,3 +159,13 @@ int frame_grid_launch(Handle *h, const orbfe_keypoint *d_kps, const int *d_n, in
 }  // namespace orbfe
 
 struct orbfe_handle : orbfe::Handle {};
+
+// Device-resident frame (include/orbfe.h): what Frame::Frame leaves behind for the matchers.  Buffers are owned (orbfe_frame_upload)
+// or borrowed from the caller (orbfe_frame_wrap_device); the host keeps a copy of the key points (octaves and angles drive the
+// query lists of SearchForInitialization).
+struct orbfe_frame {
+    int device = 0, n = 0, img_w = 0, img_h = 0, cols = 0, rows = 0;
+    const orbfe_keypoint *d_kps = nullptr; const uint8_t *d_desc = nullptr; const int *d_grid_off = nullptr, *d_grid_idx = nullptr;
+    void *owned = nullptr;                       // one allocation behind every buffer this object owns
+    std::vector<orbfe_keypoint> kps;             // host mirror
+};

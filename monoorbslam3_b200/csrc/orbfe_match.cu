@@ -812,33 +812,34 @@ static void fill_int(Handle *h, int *p, int v, int n, cudaStream_t st) {
 struct WindowProblem {
     const float *q_u, *q_v, *q_r; const int *q_min, *q_max; const uint8_t *q_valid; const uint8_t *q_desc; const float *q_angle; int nq;
     const orbfe_keypoint *kps2; const uint8_t *desc2; int n2; int img_w, img_h; const uint8_t *occupied;
+    // device-resident operands (orbfe_frame): the searched frame with its grid, and — SearchForInitialization — the query frame's descriptors
+    const orbfe_frame *frame2 = nullptr, *frame1 = nullptr;
 };
 
 // ------------------------------------------------------------------------------------------------
 // Parallel resolve of the searches whose frame-2 slots are exclusive (variants 1, 2, 3, 4: a slot that holds a match is skipped by
-// every later query).  The reference's loop is sequential, but query i's decision only depends on earlier queries through the
-// slots they take, and only its best (and, where a ratio test looks at it, second-best) available slot matters.  Rounds:
-//   1. every undecided query marks all its still-free candidate slots with its index (atomicMin) and finds its best / second-best
-//      free candidate (first minimum in list order, as the sequential loop would);
-//   2. a query is decided when it is the smallest undecided index on its best slot (and on its second-best slot if the variant's
-//      acceptance looks at it): no earlier undecided query can take or change them, and every earlier decided query already has.
-//      It then accepts or rejects exactly as the sequential loop, taking the slot if it accepts.
-// The smallest undecided index is always decided, so the rounds terminate, and by induction over the query index the result is the
-// sequential one (the parity tests compare bit-exactly with a sequential CPU restatement of the reference loops).  One CTA of 1024 threads, thread per query.
+// every later query).  The reference's loop is a serial dictatorship: the queries pick, in index order, their best still-free slot
+// (or nothing, if the acceptance test fails).  Query i's decision is a function of the decisions of the queries before it only —
+// dec[i] = f(dec[0 .. i-1]) — so the sequential result is the unique fixed point of evaluating all queries at once against the
+// previous round's decisions (by induction over i: query 0 depends on nothing, query i is right once all earlier ones are):
+//   1. every query that currently holds a slot marks it with its index (atomicMin: the earliest holder);
+//   2. every query re-evaluates: a candidate is available unless it was occupied before the call or is held by an EARLIER query;
+//      best / second-best available candidate (first minimum in list order), acceptance exactly as in the reference;
+//   3. repeat until no decision changed.
+// The number of rounds is the depth of the chains of actual displacements (6-9 on tracking-sized windows), not the number of queries
+// that merely share a candidate.  One CTA of 1024 threads, thread per query, candidate lists staged in shared memory when they fit.
 // ------------------------------------------------------------------------------------------------
 template <int kVariant>
 __global__ void __launch_bounds__(1024) k_resolve_par(const ResolveArgs a) {
     extern __shared__ __align__(16) uint8_t rp_dyn[];
     __shared__ int hist[HISTO_LENGTH];
-    __shared__ int s_left, s_nmatch;
+    __shared__ int s_changed, s_nmatch;
     const int tid = threadIdx.x;
     const int n2s = kVariant == 3 ? a.n_state : a.n2;
-    int *taken = reinterpret_cast<int *>(rp_dyn);            // -1 free, -2 occupied before the call, else the owner (query / key point)
-    int *minq = taken + n2s;
-    uint32_t *done = reinterpret_cast<uint32_t *>(minq + n2s);   // bit per query
-    const int n_words = (a.nq + 31) / 32;
+    int *held = reinterpret_cast<int *>(rp_dyn);             // earliest query holding the slot; -1: occupied before the call; INT_MAX: free
+    int *dec = held + n2s;                                   // slot query i takes, or -1
     // candidate lists (dist << 16 | idx) staged once when they fit: the rounds then never touch global memory for them
-    uint32_t *s_pack = done + n_words;
+    uint32_t *s_pack = reinterpret_cast<uint32_t *>(dec + a.nq);
     const int total = a.n_cand ? *a.n_cand : 0;
     const bool staged = a.n_cand && total <= a.smem_entries;
     if (staged) for (int k = tid; k < total; k += 1024) s_pack[k] = ((uint32_t) a.c_dist[k] << 16) | (uint32_t) a.c_idx[k];
@@ -846,82 +847,77 @@ __global__ void __launch_bounds__(1024) k_resolve_par(const ResolveArgs a) {
     auto cand_dist = [&](int k) -> int { return staged ? (int) (s_pack[k] >> 16) : a.c_dist[k]; };
     if (tid < HISTO_LENGTH) hist[tid] = 0;
     if (tid == 0) s_nmatch = 0;
-    for (int j = tid; j < n2s; j += 1024) taken[j] = (kVariant == 3 ? a.has_mp2[j] : a.occupied[j]) ? -2 : -1;
-    for (int w = tid; w < n_words; w += 1024) done[w] = 0;
-    __syncthreads();
-    // queries without candidates (or invalid) are decided from the start
-    for (int qi = tid; qi < a.nq; qi += 1024) {
-        const bool live = (kVariant >= 3 || a.qvalid[qi]) && a.q_end[qi] > a.q_beg[qi];
-        if (!live) atomicOr(&done[qi >> 5], 1u << (qi & 31));
-    }
+    for (int qi = tid; qi < a.nq; qi += 1024) dec[qi] = -1;
     __syncthreads();
     int round = 0;
     while (true) {
-        if (tid == 0) s_left = 0;
-        for (int j = tid; j < n2s; j += 1024) minq[j] = INT_MAX;
+        for (int j = tid; j < n2s; j += 1024) held[j] = (kVariant == 3 ? a.has_mp2[j] : a.occupied[j]) ? -1 : INT_MAX;
+        if (tid == 0) s_changed = 0;
         __syncthreads();
-        for (int qi = tid; qi < a.nq; qi += 1024) {
-            if ((done[qi >> 5] >> (qi & 31)) & 1u) continue;
-            for (int k = a.q_beg[qi]; k < a.q_end[qi]; ++k) {
-                const int s = cand_idx(k);
-                if (taken[s] == -1) atomicMin(&minq[s], qi);
-            }
-        }
+        for (int qi = tid; qi < a.nq; qi += 1024) { const int s = dec[qi]; if (s >= 0) atomicMin(&held[s], qi); }
         __syncthreads();
+        bool changed = false;
         for (int qi = tid; qi < a.nq; qi += 1024) {
-            if ((done[qi >> 5] >> (qi & 31)) & 1u) continue;
-            const int beg = a.q_beg[qi], end = a.q_end[qi];
-            uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
-            for (int k = beg; k < end; ++k) {
-                if (taken[cand_idx(k)] != -1) continue;
-                const uint32_t key = ((uint32_t) cand_dist(k) << 22) | (uint32_t) (k - beg);
-                k2 = min(k2, max(key, k1));
-                k1 = min(k1, key);
-            }
-            bool decided, accept = false;
-            int best_idx2 = -1;
-            if (k1 == 0xffffffffu) decided = true;                               // nothing free: bestDist stays at its initial value
-            else {
-                const int best = (int) (k1 >> 22);
-                best_idx2 = cand_idx(beg + (int) (k1 & 0x3fffffu));
-                const int s2 = k2 == 0xffffffffu ? -1 : cand_idx(beg + (int) (k2 & 0x3fffffu));
-                const bool uses_second = kVariant == 2 || kVariant == 4;
-                decided = minq[best_idx2] == qi && (!uses_second || s2 < 0 || minq[s2] == qi);
-                if (decided) {
-                    if (kVariant == 1) accept = best <= TH_HIGH;                                              // :245
+            int nd = -1;
+            if (kVariant >= 3 || a.qvalid[qi]) {
+                const int beg = a.q_beg[qi], end = a.q_end[qi];
+                uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
+                for (int k = beg; k < end; ++k) {
+                    if (held[cand_idx(k)] < qi) continue;                               // occupied, or taken by an earlier query
+                    const uint32_t key = ((uint32_t) cand_dist(k) << 22) | (uint32_t) (k - beg);
+                    k2 = min(k2, max(key, k1));
+                    k1 = min(k1, key);
+                }
+                if (k1 != 0xffffffffu) {
+                    const int best = (int) (k1 >> 22), best_idx2 = cand_idx(beg + (int) (k1 & 0x3fffffu));
+                    const int s2 = k2 == 0xffffffffu ? -1 : cand_idx(beg + (int) (k2 & 0x3fffffu));
+                    bool accept;
+                    if (kVariant == 1) accept = best <= TH_HIGH;                                                  // :245
                     else if (kVariant == 2) {
                         accept = best <= TH_HIGH;
                         if (accept && s2 >= 0) {
                             const int second = (int) (k2 >> 22);
                             if (a.kps2[best_idx2].octave == a.kps2[s2].octave && (float) best > __fmul_rn(a.nn_ratio, (float) second)) accept = false;   // :401-405
                         }
-                    } else if (kVariant == 3) accept = best < TH_LOW && best_idx2 > 0;                        // :464-484 (sic)
+                    } else if (kVariant == 3) accept = best < TH_LOW && best_idx2 > 0;                            // :464-484 (sic)
                     else {
                         const int second = s2 < 0 ? 256 : (int) (k2 >> 22);
-                        accept = best <= TH_LOW && (float) best < __fmul_rn(a.nn_ratio, (float) second);      // :164
+                        accept = best <= TH_LOW && (float) best < __fmul_rn(a.nn_ratio, (float) second);          // :164
                     }
+                    if (accept) nd = best_idx2;
                 }
             }
-            if (!decided) { atomicAdd(&s_left, 1); continue; }
-            atomicOr(&done[qi >> 5], 1u << (qi & 31));
-            if (accept) {
-                const int owner = (kVariant == 3 || kVariant == 4) ? a.q_out_idx[qi] : qi;
-                taken[best_idx2] = kVariant == 3 ? 1 : owner;
-                if (kVariant == 3) a.matches12[owner] = best_idx2;
-                atomicAdd(&s_nmatch, 1);
-                if (a.check_orientation && kVariant != 2) {
-                    const int bn = rot_bin(a.q_angle[qi], a.kps2[best_idx2].angle);
-                    atomicAdd(&hist[bn], 1);
-                    a.bin_of[kVariant == 3 ? owner : best_idx2] = bn;
-                }
-            }
+            if (nd != dec[qi]) { dec[qi] = nd; changed = true; }
         }
+        if (changed) s_changed = 1;
         __syncthreads();
         ++round;
-        if (tid == 0 && a.dbg) { if (round == 2) a.dbg[0] = s_left; if (round == 8) a.dbg[1] = s_left; a.dbg[2] = round; }
-        if (s_left == 0) break;
+        if (tid == 0 && a.dbg) a.dbg[2] = round;
+        const bool more = s_changed != 0;
         __syncthreads();
+        if (!more) break;
     }
+    // fixed point reached: held[] is the unique holder of every taken slot.  Owners, match count, rotation histogram
+    for (int qi = tid; qi < a.nq; qi += 1024) {
+        const int s = dec[qi];
+        if (s < 0) continue;
+        const int owner = (kVariant == 3 || kVariant == 4) ? a.q_out_idx[qi] : qi;
+        if (kVariant == 3) a.matches12[owner] = s;
+        atomicAdd(&s_nmatch, 1);
+        if (a.check_orientation && kVariant != 2) {
+            const int bn = rot_bin(a.q_angle[qi], a.kps2[s].angle);
+            atomicAdd(&hist[bn], 1);
+            a.bin_of[kVariant == 3 ? owner : s] = bn;
+        }
+    }
+    __syncthreads();
+    // slot -> owner (the variants with q_out_idx report the owner's key-point index)
+    int *taken = held;
+    for (int j = tid; j < n2s; j += 1024) {
+        const int q = held[j];
+        taken[j] = (q >= 0 && q != INT_MAX) ? ((kVariant == 3 || kVariant == 4) ? a.q_out_idx[q] : q) : (q == -1 ? -2 : -1);
+    }
+    __syncthreads();
     // rotation consistency (ORBMatcher.cpp:95-108 and copies), then the slot owners go back to global memory
     if (a.check_orientation && kVariant != 2) {
         int i1, i2, i3;
@@ -944,7 +940,7 @@ static int launch_resolve(Handle *h, const ResolveArgs &ra, int n2, cudaStream_t
     static const bool serial = [] { const char *e = getenv("ORBFE_SERIAL_RESOLVE"); return e && *e == '1'; }();      // A/B aid
     if (n2 >= 65536) return set_error(h, ORBFE_E_ARG, "matcher: %d key points in the searched frame (limit 65535)", n2);
     if (kVariant != 0 && !serial) {
-        const size_t state = sizeof(int) * 2 * (size_t) n2 + sizeof(uint32_t) * (((size_t) ra.nq + 31) / 32) + 64;
+        const size_t state = sizeof(int) * ((size_t) n2 + (size_t) ra.nq) + 64;      // earliest holder per slot + decision per query
         if (state <= 200 * 1024) {
             ResolveArgs rb = ra;
             rb.smem_entries = (int) ((200 * 1024 - state) / sizeof(uint32_t));
@@ -1005,8 +1001,11 @@ static int run_window_search(Handle *h, const WindowProblem &p, float nn_ratio, 
     auto layout = [&](Bump &b, size_t cand_cap) {
         hdr = b.take<int>(4);
         qx = b.take<float>(nq); qy = b.take<float>(nq); qr = b.take<float>(nq); qmin = b.take<int>(nq); qmax = b.take<int>(nq);
-        qvalid = b.take<uint8_t>(nq); qang = b.take<float>(nq); occ = b.take<uint8_t>(n2); qdesc = b.take<uint4>(2 * (size_t) nq);
-        kps2 = b.take<orbfe_keypoint>(n2); desc2 = b.take<uint4>(2 * (size_t) n2);
+        qvalid = b.take<uint8_t>(nq); qang = b.take<float>(nq); occ = b.take<uint8_t>(n2);
+        // operands that live in a device-resident frame are neither staged nor uploaded
+        qdesc = p.frame1 ? (uint4 *) p.frame1->d_desc : b.take<uint4>(2 * (size_t) nq);
+        kps2 = p.frame2 ? (orbfe_keypoint *) p.frame2->d_kps : b.take<orbfe_keypoint>(n2);
+        desc2 = p.frame2 ? (uint4 *) p.frame2->d_desc : b.take<uint4>(2 * (size_t) n2);
         const size_t pre_off = (b.off + 255) & ~(size_t) 255;
         pre = b.take<float>(2 * (size_t) nq);
         up_end = b.off;
@@ -1014,7 +1013,8 @@ static int run_window_search(Handle *h, const WindowProblem &p, float nn_ratio, 
         nmatch = b.take<int>(4);
         if (kVariant == 0) { m12 = b.take<int>(nq); down_end = b.off; assigned = b.take<int>(n2); }
         else { assigned = b.take<int>(n2); down_end = b.off; m12 = b.take<int>(nq); }
-        coff = b.take<int>(n_off); cidx = b.take<int>(n_gidx); qbeg = b.take<int>(nq); qend = b.take<int>(nq);
+        coff = p.frame2 ? (int *) p.frame2->d_grid_off : b.take<int>(n_off); cidx = p.frame2 ? (int *) p.frame2->d_grid_idx : b.take<int>(n_gidx);
+        qbeg = b.take<int>(nq); qend = b.take<int>(nq);
         m21 = b.take<int>(n2); mdist = b.take<int>(n2); binof = b.take<int>(std::max(nq, n2));
         cand_idx = b.take<int>(cand_cap); cand_dist = b.take<int>(cand_cap);
     };
@@ -1033,11 +1033,11 @@ static int run_window_search(Handle *h, const WindowProblem &p, float nn_ratio, 
         memcpy(H(qmin), p.q_min, sizeof(int) * nq); memcpy(H(qmax), p.q_max, sizeof(int) * nq); memcpy(H(qvalid), p.q_valid, nq);
         if (p.q_angle) memcpy(H(qang), p.q_angle, sizeof(float) * nq); else memset(H(qang), 0, sizeof(float) * nq);
         if (p.occupied) memcpy(H(occ), p.occupied, n2); else memset(H(occ), 0, n2);
-        memcpy(H(qdesc), p.q_desc, 32 * (size_t) nq);
-        memcpy(H(kps2), p.kps2, sizeof(orbfe_keypoint) * (size_t) n2); memcpy(H(desc2), p.desc2, 32 * (size_t) n2);
+        if (!p.frame1) memcpy(H(qdesc), p.q_desc, 32 * (size_t) nq);
+        if (!p.frame2) { memcpy(H(kps2), p.kps2, sizeof(orbfe_keypoint) * (size_t) n2); memcpy(H(desc2), p.desc2, 32 * (size_t) n2); }
         if (prematched) memcpy(H(pre), prematched, sizeof(float) * 2 * (size_t) nq);
         ORBFE_CUDA(h, cudaMemcpyAsync(db, hp, up_end, cudaMemcpyHostToDevice, st));
-        if ((rc = frame_grid_launch(h, kps2, hdr, std::max(n2, 1), p.img_w, p.img_h, coff, cidx, st))) return rc;
+        if (!p.frame2 && (rc = frame_grid_launch(h, kps2, hdr, std::max(n2, 1), p.img_w, p.img_h, coff, cidx, st))) return rc;
         const int n_init = std::max(std::max(nq, n2), 4);
         k_window_init<<<(n_init + 255) / 256, 256, 0, st>>>(binof, std::max(nq, n2), m12, nq, m21, mdist, assigned, n2, nmatch);
         WinArgs wa;
@@ -1397,6 +1397,144 @@ int orbfe_search_for_initialization(orbfe_handle *h, const orbfe_keypoint *kps1,
     }
     WindowProblem p{qx.data(), qy.data(), qr.data(), qmin.data(), qmax.data(), qv.data(), desc1, qa.data(), n1, kps2, desc2, n2, img_w, img_h, nullptr};
     return run_window_search<0>(h, p, nn_ratio, check_orientation, nullptr, matches12, prematched_xy, n_matches);
+}
+
+// ---------------------------------------------------------------- device-resident frames
+int orbfe_frame_upload(orbfe_handle *h, const orbfe_keypoint *kps, const uint8_t *desc, int n, int img_w, int img_h, orbfe_frame **out) {
+    if (!h) return ORBFE_E_ARG;
+    if (!out || n < 0 || (n && (!kps || !desc)) || img_w <= 0 || img_h <= 0) return set_error(h, ORBFE_E_ARG, "orbfe_frame_upload: invalid argument");
+    *out = nullptr;
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    int cols, rows; grid_dims(img_w, img_h, cols, rows);
+    Bump b{nullptr};
+    auto layout = [&](Bump &bp, orbfe_keypoint *&dk, uint8_t *&dd, int *&off, int *&idx, int *&cnt) {
+        dk = bp.take<orbfe_keypoint>(std::max(n, 1)); dd = bp.take<uint8_t>(32 * (size_t) std::max(n, 1)); off = bp.take<int>((size_t) cols * rows + 1);
+        idx = bp.take<int>(std::max(n, 1)); cnt = bp.take<int>(4);
+    };
+    orbfe_keypoint *dk; uint8_t *dd; int *off, *idx, *cnt;
+    layout(b, dk, dd, off, idx, cnt);
+    void *mem = nullptr;
+    ORBFE_CUDA(h, cudaMalloc(&mem, b.off + 256));
+    Bump bp{(uint8_t *) mem}; layout(bp, dk, dd, off, idx, cnt);
+    cudaStream_t st = h->stream;
+    cudaError_t e = cudaSuccess;
+    if (n) { e = cudaMemcpyAsync(dk, kps, sizeof(orbfe_keypoint) * (size_t) n, cudaMemcpyHostToDevice, st); if (e == cudaSuccess) e = cudaMemcpyAsync(dd, desc, 32 * (size_t) n, cudaMemcpyHostToDevice, st); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(cnt, &n, sizeof(int), cudaMemcpyHostToDevice, st);
+    int rc = e == cudaSuccess ? frame_grid_launch(h, dk, cnt, std::max(n, 1), img_w, img_h, off, idx, st) : set_error(h, ORBFE_E_CUDA, "orbfe_frame_upload: %s", cudaGetErrorString(e));
+    if (rc == ORBFE_OK && (e = cudaStreamSynchronize(st)) != cudaSuccess) rc = set_error(h, ORBFE_E_CUDA, "orbfe_frame_upload: %s", cudaGetErrorString(e));
+    if (rc != ORBFE_OK) { cudaFree(mem); return rc; }
+    orbfe_frame *f = new orbfe_frame();
+    f->device = h->device; f->n = n; f->img_w = img_w; f->img_h = img_h; f->cols = cols; f->rows = rows;
+    f->d_kps = dk; f->d_desc = dd; f->d_grid_off = off; f->d_grid_idx = idx; f->owned = mem;
+    f->kps.assign(kps, kps + n);
+    *out = f;
+    return ORBFE_OK;
+}
+
+int orbfe_frame_wrap_device(orbfe_handle *h, const orbfe_keypoint *d_kps, const uint8_t *d_desc, int n, int img_w, int img_h, const int32_t *d_grid_off,
+                            const int32_t *d_grid_idx, orbfe_frame **out) {
+    if (!h) return ORBFE_E_ARG;
+    if (!out || n < 0 || (n && (!d_kps || !d_desc)) || img_w <= 0 || img_h <= 0 || (!d_grid_off) != (!d_grid_idx) || ((uintptr_t) d_desc & 15))
+        return set_error(h, ORBFE_E_ARG, "orbfe_frame_wrap_device: invalid argument (descriptors must be 16-byte aligned; grid offsets and indices come together)");
+    *out = nullptr;
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    int cols, rows; grid_dims(img_w, img_h, cols, rows);
+    orbfe_frame *f = new orbfe_frame();
+    f->device = h->device; f->n = n; f->img_w = img_w; f->img_h = img_h; f->cols = cols; f->rows = rows;
+    f->d_kps = d_kps; f->d_desc = d_desc; f->d_grid_off = d_grid_off; f->d_grid_idx = d_grid_idx;
+    f->kps.resize((size_t) n);
+    cudaStream_t st = h->stream;
+    cudaError_t e = n ? cudaMemcpyAsync(f->kps.data(), d_kps, sizeof(orbfe_keypoint) * (size_t) n, cudaMemcpyDeviceToHost, st) : cudaSuccess;
+    int rc = e == cudaSuccess ? ORBFE_OK : set_error(h, ORBFE_E_CUDA, "orbfe_frame_wrap_device: %s", cudaGetErrorString(e));
+    if (rc == ORBFE_OK && !d_grid_off) {            // no grid given: build one into buffers this object owns
+        Bump b{nullptr}; b.take<int>((size_t) cols * rows + 1); b.take<int>(std::max(n, 1)); b.take<int>(4);
+        void *mem = nullptr;
+        if ((e = cudaMalloc(&mem, b.off + 256)) != cudaSuccess) rc = set_error(h, ORBFE_E_CUDA, "orbfe_frame_wrap_device: %s", cudaGetErrorString(e));
+        else {
+            Bump bp{(uint8_t *) mem};
+            int *off = bp.take<int>((size_t) cols * rows + 1), *idx = bp.take<int>(std::max(n, 1)), *cnt = bp.take<int>(4);
+            f->owned = mem; f->d_grid_off = off; f->d_grid_idx = idx;
+            if ((e = cudaMemcpyAsync(cnt, &n, sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) rc = set_error(h, ORBFE_E_CUDA, "orbfe_frame_wrap_device: %s", cudaGetErrorString(e));
+            else rc = frame_grid_launch(h, d_kps, cnt, std::max(n, 1), img_w, img_h, off, idx, st);
+        }
+    }
+    if (rc == ORBFE_OK && (e = cudaStreamSynchronize(st)) != cudaSuccess) rc = set_error(h, ORBFE_E_CUDA, "orbfe_frame_wrap_device: %s", cudaGetErrorString(e));
+    if (rc != ORBFE_OK) { cudaFree(f->owned); delete f; return rc; }
+    *out = f;
+    return ORBFE_OK;
+}
+
+void orbfe_frame_destroy(orbfe_frame *f) {
+    if (!f) return;
+    if (f->owned) { cudaSetDevice(f->device); cudaFree(f->owned); }
+    delete f;
+}
+
+int orbfe_frame_size(const orbfe_frame *f) { return f ? f->n : -1; }
+
+static int check_frame(orbfe_handle *h, const orbfe_frame *f, const char *what) {
+    if (!f) return set_error(h, ORBFE_E_ARG, "%s: frame is null", what);
+    if (f->device != h->device) return set_error(h, ORBFE_E_ARG, "%s: the frame lives on device %d, the handle on device %d", what, f->device, h->device);
+    return ORBFE_OK;
+}
+
+int orbfe_search_for_initialization_f(orbfe_handle *h, const orbfe_frame *frame1, const orbfe_frame *frame2, float *prematched_xy, int32_t *matches12,
+                                      int window, float nn_ratio, int check_orientation, int *n_matches) {
+    if (!h) return ORBFE_E_ARG;
+    int rc;
+    if ((rc = check_frame(h, frame1, "orbfe_search_for_initialization_f")) || (rc = check_frame(h, frame2, "orbfe_search_for_initialization_f"))) return rc;
+    const int n1 = frame1->n, n2 = frame2->n;
+    if (!n_matches || (n1 && (!prematched_xy || !matches12))) return set_error(h, ORBFE_E_ARG, "invalid argument");
+    *n_matches = 0;
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    if (n1 == 0 || n2 == 0) return ORBFE_OK;
+    std::vector<float> qx(n1), qy(n1), qr(n1, (float) window), qa(n1);
+    std::vector<int> qmin(n1), qmax(n1); std::vector<uint8_t> qv(n1);
+    const orbfe_keypoint *kps1 = frame1->kps.data();
+    for (int i = 0; i < n1; ++i) {                               // ORBMatcher.cpp:46-52
+        qx[i] = prematched_xy[2 * i]; qy[i] = prematched_xy[2 * i + 1]; qa[i] = kps1[i].angle;
+        qmin[i] = qmax[i] = kps1[i].octave; qv[i] = kps1[i].octave <= 0;
+    }
+    WindowProblem p{qx.data(), qy.data(), qr.data(), qmin.data(), qmax.data(), qv.data(), nullptr, qa.data(), n1, nullptr, nullptr, n2, frame2->img_w, frame2->img_h, nullptr};
+    p.frame1 = frame1; p.frame2 = frame2;
+    return run_window_search<0>(h, p, nn_ratio, check_orientation, nullptr, matches12, prematched_xy, n_matches);
+}
+
+int orbfe_search_by_projection_f(orbfe_handle *h, const float *q_u, const float *q_v, const float *q_radius, const int32_t *q_level, const float *q_angle,
+                                 const uint8_t *q_desc, const uint8_t *q_valid, int nq, const orbfe_frame *frame2, const uint8_t *occupied, int32_t *assigned,
+                                 int check_orientation, int *n_matches) {
+    if (!h) return ORBFE_E_ARG;
+    int rc;
+    if ((rc = check_frame(h, frame2, "orbfe_search_by_projection_f"))) return rc;
+    const int n2 = frame2->n;
+    if (!n_matches || nq < 0 || (nq && (!q_u || !q_v || !q_radius || !q_level || !q_angle || !q_desc || !q_valid)) || (n2 && !assigned))
+        return set_error(h, ORBFE_E_ARG, "invalid argument");
+    *n_matches = 0;
+    for (int j = 0; j < n2; ++j) assigned[j] = -1;
+    if (nq == 0 || n2 == 0) return ORBFE_OK;
+    std::vector<int> qmin(nq), qmax(nq);
+    for (int i = 0; i < nq; ++i) { qmin[i] = q_level[i] - 1; qmax[i] = q_level[i] + 1; }             // ORBMatcher.cpp:229
+    WindowProblem p{q_u, q_v, q_radius, qmin.data(), qmax.data(), q_valid, q_desc, q_angle, nq, nullptr, nullptr, n2, frame2->img_w, frame2->img_h, occupied};
+    p.frame2 = frame2;
+    return run_window_search<1>(h, p, 0.f, check_orientation, assigned, nullptr, nullptr, n_matches);
+}
+
+int orbfe_search_local_points_f(orbfe_handle *h, const float *q_u, const float *q_v, const float *q_radius, const int32_t *q_level, const uint8_t *q_desc,
+                                const uint8_t *q_valid, int nq, const orbfe_frame *frame2, const uint8_t *occupied, int32_t *assigned, float nn_ratio,
+                                int *n_matches) {
+    if (!h) return ORBFE_E_ARG;
+    int rc;
+    if ((rc = check_frame(h, frame2, "orbfe_search_local_points_f"))) return rc;
+    const int n2 = frame2->n;
+    if (!n_matches || nq < 0 || (nq && (!q_u || !q_v || !q_radius || !q_level || !q_desc || !q_valid)) || (n2 && !assigned)) return set_error(h, ORBFE_E_ARG, "invalid argument");
+    *n_matches = 0;
+    for (int j = 0; j < n2; ++j) assigned[j] = -1;
+    if (nq == 0 || n2 == 0) return ORBFE_OK;
+    std::vector<int> qmin(nq), qmax(nq);
+    for (int i = 0; i < nq; ++i) { qmin[i] = q_level[i] - 1; qmax[i] = q_level[i]; }                 // ORBMatcher.cpp:366-369
+    WindowProblem p{q_u, q_v, q_radius, qmin.data(), qmax.data(), q_valid, q_desc, nullptr, nq, nullptr, nullptr, n2, frame2->img_w, frame2->img_h, occupied};
+    p.frame2 = frame2;
+    return run_window_search<2>(h, p, nn_ratio, 0, assigned, nullptr, nullptr, n_matches);
 }
 
 int orbfe_search_by_projection(orbfe_handle *h, const float *q_u, const float *q_v, const float *q_radius, const int32_t *q_level, const float *q_angle,

@@ -30,6 +30,39 @@ class FrameView:
         return len(self.key_points)
 
 
+class DeviceFrame:
+    """orbfe_frame: a frame whose key points, descriptors and 40-px grid stay in HBM between matcher calls (Tracking calls the matcher
+    several times per frame: Tracking.cpp:284-296, 412-425).  Built from host arrays (upload) or from device buffers
+    (wrap: torch tensors / raw pointers, e.g. one frame's slab of ORBExtractor.extract_batch_device + frame_postprocess_device)."""
+
+    def __init__(self, handle, ptr, n, width, height, keep=()):
+        self._h, self._f, self.num_kps, self.width, self.height, self._keep = handle, ptr, int(n), int(width), int(height), keep
+        self._lib = _capi.lib()
+
+    @classmethod
+    def upload(cls, key_points, descriptors, width, height, handle=None, device=0):
+        h = handle if handle is not None else _handle(device)
+        k = _c(key_points, KP_DTYPE); d = _c(descriptors, np.uint8)
+        f = C.c_void_p()
+        _capi.check(h, _capi.lib().orbfe_frame_upload(h, _capi.ptr(k), _capi.ptr(d), len(k), int(width), int(height), C.byref(f)))
+        return cls(h, f, len(k), width, height)
+
+    @classmethod
+    def wrap(cls, d_kps, d_desc, n, width, height, d_grid_off=None, d_grid_idx=None, handle=None, device=0):
+        h = handle if handle is not None else _handle(device)
+        f = C.c_void_p()
+        _capi.check(h, _capi.lib().orbfe_frame_wrap_device(h, _capi.ptr(d_kps), _capi.ptr(d_desc), int(n), int(width), int(height), _capi.ptr(d_grid_off),
+                                                           _capi.ptr(d_grid_idx), C.byref(f)))
+        return cls(h, f, n, width, height, keep=(d_kps, d_desc, d_grid_off, d_grid_idx))
+
+    def close(self):
+        if getattr(self, "_f", None):
+            self._lib.orbfe_frame_destroy(self._f)
+            self._f = None
+
+    __del__ = close
+
+
 _tls = threading.local()
 
 
@@ -117,11 +150,19 @@ class ORBMatcher:
     # ---- int SearchForInitialization(frame1, frame2, vecPreMatched, matches12, windowSize=100) — ORBMatcher.cpp:33-116
     def SearchForInitialization(self, frame1, frame2, vecPreMatched, windowSize=100):
         """Returns (numMatches, matches12); vecPreMatched ([n1,2] float32) is updated in place like the reference's reference argument."""
+        pre = _c(vecPreMatched, np.float32).reshape(-1, 2).copy()
+        n = C.c_int()
+        if isinstance(frame1, DeviceFrame) or isinstance(frame2, DeviceFrame):
+            if not (isinstance(frame1, DeviceFrame) and isinstance(frame2, DeviceFrame)):
+                raise TypeError("SearchForInitialization: both frames must be DeviceFrame objects, or neither")
+            m12 = np.full(max(frame1.num_kps, 1), -1, np.int32)
+            _capi.check(self._h, self._lib.orbfe_search_for_initialization_f(self._h, frame1._f, frame2._f, _capi.ptr(pre), _capi.ptr(m12), int(windowSize),
+                                                                             self.nn_ratio, int(self.be_check_orientation), C.byref(n)))
+            vecPreMatched[...] = pre.reshape(np.shape(vecPreMatched))
+            return n.value, m12[:frame1.num_kps]
         k1 = _c(frame1.key_points, KP_DTYPE); k2 = _c(frame2.key_points, KP_DTYPE)
         d1 = _c(frame1.descriptors, np.uint8); d2 = _c(frame2.descriptors, np.uint8)
-        pre = _c(vecPreMatched, np.float32).reshape(-1, 2).copy()
         m12 = np.full(max(len(k1), 1), -1, np.int32)
-        n = C.c_int()
         _capi.check(self._h, self._lib.orbfe_search_for_initialization(self._h, _capi.ptr(k1), _capi.ptr(d1), len(k1), _capi.ptr(k2), _capi.ptr(d2), len(k2),
                                                                        frame2.width, frame2.height, _capi.ptr(pre), _capi.ptr(m12), int(windowSize),
                                                                        self.nn_ratio, int(self.be_check_orientation), C.byref(n)))
@@ -131,10 +172,16 @@ class ORBMatcher:
     # ---- SearchByProjection(lastFrame|lastKF, curFrame, th) — ORBMatcher.cpp:203-348, after the adapter projected the map points
     def SearchByProjection(self, q_u, q_v, q_radius, q_level, q_angle, q_desc, q_valid, curFrame, occupied):
         """Returns (numMatch, assigned) where assigned[j] = query index written into curFrame.map_points[j] or -1."""
-        k2 = _c(curFrame.key_points, KP_DTYPE); d2 = _c(curFrame.descriptors, np.uint8)
         args = [_c(q_u, np.float32), _c(q_v, np.float32), _c(q_radius, np.float32), _c(q_level, np.int32), _c(q_angle, np.float32),
                 _c(q_desc, np.uint8), _c(q_valid, np.uint8)]
         occ = _c(occupied, np.uint8)
+        if isinstance(curFrame, DeviceFrame):
+            assigned = np.full(max(curFrame.num_kps, 1), -1, np.int32)
+            n = C.c_int()
+            _capi.check(self._h, self._lib.orbfe_search_by_projection_f(self._h, *[_capi.ptr(a) for a in args], len(args[0]), curFrame._f, _capi.ptr(occ),
+                                                                        _capi.ptr(assigned), int(self.be_check_orientation), C.byref(n)))
+            return n.value, assigned[:curFrame.num_kps]
+        k2 = _c(curFrame.key_points, KP_DTYPE); d2 = _c(curFrame.descriptors, np.uint8)
         assigned = np.full(max(len(k2), 1), -1, np.int32)
         n = C.c_int()
         _capi.check(self._h, self._lib.orbfe_search_by_projection(self._h, *[_capi.ptr(a) for a in args], len(args[0]), _capi.ptr(k2), _capi.ptr(d2), len(k2),
@@ -144,9 +191,15 @@ class ORBMatcher:
 
     # ---- SearchByProjection(frame, mapPoints, th) — ORBMatcher.cpp:350-415
     def SearchLocalPoints(self, q_u, q_v, q_radius, q_level, q_desc, q_valid, frame, occupied):
-        k2 = _c(frame.key_points, KP_DTYPE); d2 = _c(frame.descriptors, np.uint8)
         args = [_c(q_u, np.float32), _c(q_v, np.float32), _c(q_radius, np.float32), _c(q_level, np.int32), _c(q_desc, np.uint8), _c(q_valid, np.uint8)]
         occ = _c(occupied, np.uint8)
+        if isinstance(frame, DeviceFrame):
+            assigned = np.full(max(frame.num_kps, 1), -1, np.int32)
+            n = C.c_int()
+            _capi.check(self._h, self._lib.orbfe_search_local_points_f(self._h, *[_capi.ptr(a) for a in args], len(args[0]), frame._f, _capi.ptr(occ),
+                                                                       _capi.ptr(assigned), self.nn_ratio, C.byref(n)))
+            return n.value, assigned[:frame.num_kps]
+        k2 = _c(frame.key_points, KP_DTYPE); d2 = _c(frame.descriptors, np.uint8)
         assigned = np.full(max(len(k2), 1), -1, np.int32)
         n = C.c_int()
         _capi.check(self._h, self._lib.orbfe_search_local_points(self._h, *[_capi.ptr(a) for a in args], len(args[0]), _capi.ptr(k2), _capi.ptr(d2), len(k2),

@@ -365,3 +365,66 @@ def test_matchers_reproduce_the_reference_matcher_golden(ctx):
 
     assert replay(dict(search_for_initialization=init, search_by_projection=proj, search_local_points=local, search_for_triangulation=tri,
                        search_by_bow=bow, search_fuse=fuse)) == 13
+
+
+def test_device_resident_frames_give_the_host_results(ctx, oracle):
+    """orbfe_frame (uploaded once, or wrapped around the device outputs of orbfe_extract_batch_device + orbfe_frame_postprocess_device):
+    SearchForInitialization, SearchByProjection (twice on the same pair, as Tracking.cpp:284-296 does) and the local-map search equal
+    the host-array entry points and the oracle."""
+    import torch
+    from monoorbslam3_b200 import DeviceFrame, Camera, frame_postprocess_device, KP_DTYPE
+    M = ctx["ORBMatcher"]; ka, da, kb, db, W, H = ctx["ka"], ctx["da"], ctx["kb"], ctx["db"], ctx["w"], ctx["h"]
+    f1h, f2h = ctx["FrameView"](ka, da, W, H), ctx["FrameView"](kb, db, W, H)
+    f1, f2 = DeviceFrame.upload(ka, da, W, H), DeviceFrame.upload(kb, db, W, H)
+    assert f1.num_kps == len(ka)
+    pre = np.stack([ka["x"], ka["y"]], 1).astype(np.float32)
+    for window, ratio, orient in ((100, 0.9, True), (40, 0.7, False)):
+        m = M(ratio, orient)
+        p1, p2 = pre.copy(), pre.copy()
+        n1, m1 = m.SearchForInitialization(f1, f2, p1, window)
+        n2, m2 = m.SearchForInitialization(f1h, f2h, p2, window)
+        on, om, op = oracle.search_for_initialization(ka, da, kb, db, W, H, pre.copy(), window, ratio, orient)
+        assert n1 == n2 == on and np.array_equal(m1, m2) and np.array_equal(m1, om) and np.array_equal(p1, p2) and np.array_equal(p1, op)
+    rng = np.random.default_rng(3)
+    nq = len(ka)
+    q_u = (ka["x"] - 7 + rng.normal(0, 1.0, nq)).astype(np.float32); q_v = (ka["y"] - 3 + rng.normal(0, 1.0, nq)).astype(np.float32)
+    q_valid = (rng.random(nq) < 0.85).astype(np.uint8); occ = (rng.random(len(kb)) < 0.1).astype(np.uint8)
+    for th in (15, 30):                                          # the second, wider search of Tracking.cpp:294 on the same frame object
+        q_r = (np.float32(th) * ka["size"]).astype(np.float32)
+        m = M(0.9, True)
+        got = m.SearchByProjection(q_u, q_v, q_r, ka["octave"], ka["angle"], da, q_valid, f2, occ)
+        host = m.SearchByProjection(q_u, q_v, q_r, ka["octave"], ka["angle"], da, q_valid, f2h, occ)
+        exp = oracle.search_by_projection(q_u, q_v, q_r, ka["octave"], ka["angle"], da, q_valid, kb, db, W, H, occ, True)
+        assert got[0] == host[0] == exp[0] and np.array_equal(got[1], host[1]) and np.array_equal(got[1], exp[1]) and got[0] > 300
+    sf = np.array([ctx["ex"].getScaleFactor(int(l)) for l in ka["octave"]], np.float32)
+    q_r = (np.float32(2) * np.float32(4.0) * sf).astype(np.float32)
+    m = M(0.8, True)
+    got = m.SearchLocalPoints(q_u, q_v, q_r, ka["octave"], da, q_valid, f2, occ)
+    exp = oracle.search_local_points(q_u, q_v, q_r, ka["octave"], da, q_valid, kb, db, W, H, occ, 0.8)
+    assert got[0] == exp[0] and np.array_equal(got[1], exp[1]) and got[0] > 300
+
+    # no host round trip between extractor and matcher: extract on the device, post-process on the device, wrap, search
+    ex = ctx["ex"]
+    a, b = ctx["synth"].shifted_pair(480, 752, 1000)
+    dev = torch.device("cuda", 0)
+    frames = torch.from_numpy(np.stack([a, b])).to(dev)
+    cap = 2300
+    d_kps = torch.zeros((2, cap, 7), dtype=torch.float32, device=dev); d_desc = torch.zeros((2, cap, 32), dtype=torch.uint8, device=dev)
+    d_n = torch.zeros(2, dtype=torch.int32, device=dev)
+    ex.extract_batch_device(frames, 2, 480, 752, d_kps, d_desc, cap, d_n, sync=True)
+    cam = Camera(458.654, 457.296, 367.215, 248.375, [0.0, 0.0, 0.0, 0.0])        # no distortion: the undistorted key points are the raw ones
+    from monoorbslam3_b200 import grid_size
+    gc, gr = grid_size(752, 480)
+    d_un = torch.zeros_like(d_kps); d_goff = torch.zeros((2, gc * gr + 1), dtype=torch.int32, device=dev); d_gidx = torch.zeros((2, cap), dtype=torch.int32, device=dev)
+    frame_postprocess_device(ex, cam, d_kps, d_un, d_n, 2, cap, 752, 480, d_goff, d_gidx)
+    n_host = d_n.cpu().numpy()
+    assert n_host[0] == len(ka) and n_host[1] == len(kb)
+    w1 = DeviceFrame.wrap(d_un[0], d_desc[0], int(n_host[0]), 752, 480, d_goff[0], d_gidx[0], handle=ex._h)
+    w2 = DeviceFrame.wrap(d_un[1], d_desc[1], int(n_host[1]), 752, 480, handle=ex._h)          # grid built by the wrap
+    m = M(0.9, True, handle=ex._h)
+    p1 = pre.copy()
+    n1, m1 = m.SearchForInitialization(w1, w2, p1, 100)
+    on, om, op = oracle.search_for_initialization(ka, da, kb, db, W, H, pre.copy(), 100, 0.9, True)
+    assert n1 == on and np.array_equal(m1, om) and np.array_equal(p1, op)
+    for f in (f1, f2, w1, w2):
+        f.close()
