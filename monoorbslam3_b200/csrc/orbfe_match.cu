@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <algorithm>
 #include <climits>
+#include <cmath>
 #include <cstring>
 
 namespace orbfe {
@@ -586,6 +587,8 @@ struct ResolveArgs {
     int n_state;                     // variant 3: key points of frame 2 (n2 carries n1 there)
     const int *n_cand;               // device: total candidate entries in c_idx / c_dist (parallel resolve stages them in shared memory if they fit)
     int smem_entries;                // capacity of that staging area
+    int acc_far;                     // variant 0: distances from here on only matter by existing (see k_resolve_init_par)
+    int acc_limit;                   // variant 0: acceptors a slot may collect per round before the parallel resolve gives up (0 = kInitAcc)
     int *dbg;                        // optional: undecided queries after rounds 2 and 8, number of rounds (parallel resolve)
     int *n_matches;
 };
@@ -609,7 +612,8 @@ static size_t resolve_smem_bytes(int n2) {
 __device__ __forceinline__ void loaders_sync() { asm volatile("bar.sync 1, 224;" ::: "memory"); }     // warps 1..7
 
 template <int kVariant>
-__global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
+__global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a, const int *run_if) {
+    if (run_if && *run_if == 0) return;                       // launched behind the parallel resolve: only runs when that one gave up
     extern __shared__ __align__(16) uint8_t rs_dyn[];
     __shared__ int hist[HISTO_LENGTH];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -935,9 +939,162 @@ __global__ void __launch_bounds__(1024) k_resolve_par(const ResolveArgs a) {
     if (tid == 0) *a.n_matches = s_nmatch;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Parallel resolve of SearchForInitialization (variant 0).  Here a slot is not exclusive: a later query takes it from its owner if its
+// distance is smaller (ORBMatcher.cpp:63, 75-78), and a candidate is skipped when the slot's current matched distance is <= the
+// candidate's.  The decision of query i is still a function of the decisions of the queries before it only, so the same fixed-point
+// iteration applies: every round each slot collects its acceptors (query, distance) of the previous round; query i then sees, for a
+// candidate slot, the smallest distance among the acceptors EARLIER than i — which is the matched distance the sequential loop would
+// hold when it reaches i — and re-evaluates best / second-best / the ratio test.  At the fixed point the owner of a slot is its
+// latest acceptor; the earlier ones are the stolen matches (they still count in the rotation histogram, as in the reference, where
+// rotHist keeps their entries).  A slot keeps at most kInitAcc acceptors per round; if one ever needs more the kernel raises
+// `fallback` and the sequential kernel k_resolve<0> runs instead.
+// ------------------------------------------------------------------------------------------------
+constexpr int kInitAcc = 4;
+
+// Candidates at distance d_far or more never decide anything by their value: an accepted best is <= TH_LOW, so the ratio test
+// best < cvRound(second * ratio) holds for every second >= d_far (d_far = the smallest distance with cvRound(d * ratio) > TH_LOW, computed
+// on the host with the same float operations), and such a candidate can never be the best of an accepted match.  What matters is only
+// whether an eligible one EXISTS when fewer than two near candidates are eligible (a lone candidate is tested against
+// cvRound(INT_MAX * ratio), which saturates to INT_MIN for ratios from about 1.0 on, :74).  The kernel therefore keeps each query's near candidates (d < d_far; a handful) in
+// shared memory with their list positions and scans the far ones in global memory only until the first eligible one.
+__global__ void __launch_bounds__(1024) k_resolve_init_par(const ResolveArgs a, int *fallback) {
+    extern __shared__ __align__(16) uint8_t ri_dyn[];
+    __shared__ int hist[HISTO_LENGTH];
+    __shared__ int s_changed, s_nmatch, s_overflow, s_near;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int *cnt = reinterpret_cast<int *>(ri_dyn);                              // acceptors of the slot in the previous round
+    uint32_t *acc = reinterpret_cast<uint32_t *>(cnt + a.n2);                // [slot][kInitAcc]: query << 9 | distance
+    int *dec = reinterpret_cast<int *>(acc + (size_t) a.n2 * kInitAcc);      // slot | distance << 16, or -1
+    int *nbeg = dec + a.nq;                                                  // near candidates of query i: arena[nbeg[i] .. nbeg[i] + ncnt[i])
+    int *ncnt = nbeg + a.nq;
+    uint2 *arena = reinterpret_cast<uint2 *>(((uintptr_t) (ncnt + a.nq) + 7) & ~(uintptr_t) 7);      // (distance << 16 | slot, position in the query's list)
+    const int arena_cap = a.smem_entries;
+    const int d_far = a.acc_far;
+    if (tid < HISTO_LENGTH) hist[tid] = 0;
+    if (tid == 0) { s_nmatch = 0; s_overflow = 0; s_near = 0; }
+    for (int qi = tid; qi < a.nq; qi += 1024) { dec[qi] = -1; ncnt[qi] = 0; nbeg[qi] = 0; }
+    __syncthreads();
+    // ---- near candidates -> shared memory, one warp per query (coalesced reads, ballot compaction, list order kept)
+    for (int qi = wid; qi < a.nq; qi += 32) {
+        if (!a.qvalid[qi]) continue;
+        const int beg = a.q_beg[qi], end = a.q_end[qi];
+        int n_near = 0;
+        for (int k0 = beg; k0 < end; k0 += 32) n_near += __popc(__ballot_sync(0xffffffffu, k0 + lane < end && a.c_dist[k0 + lane] < d_far));
+        if (n_near == 0) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_near, n_near);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base + n_near > arena_cap) { if (lane == 0) s_overflow = 1; continue; }
+        if (lane == 0) { nbeg[qi] = base; ncnt[qi] = n_near; }
+        int run = 0;
+        for (int k0 = beg; k0 < end; k0 += 32) {
+            const int k = k0 + lane;
+            const int d = k < end ? a.c_dist[k] : INT_MAX;
+            const unsigned bal = __ballot_sync(0xffffffffu, d < d_far);
+            if (d < d_far) arena[base + run + __popc(bal & ((1u << lane) - 1u))] = make_uint2(((uint32_t) d << 16) | (uint32_t) a.c_idx[k], (uint32_t) (k - beg));
+            run += __popc(bal);
+        }
+    }
+    __syncthreads();
+    if (s_overflow) { if (tid == 0) *fallback = 1; return; }
+    const int acc_limit = a.acc_limit ? a.acc_limit : kInitAcc;
+    // matchedDistance[c] <= d when the sequential loop reaches query qi (:63): some acceptor earlier than qi holds c at distance <= d
+    auto blocked = [&](int c, int d, int qi) -> bool {
+        const int m = min(cnt[c], kInitAcc);
+        bool b = false;
+        for (int t = 0; t < m; ++t) { const uint32_t ae = acc[(size_t) c * kInitAcc + t]; if ((int) (ae >> 9) < qi && (int) (ae & 0x1ffu) <= d) b = true; }
+        return b;
+    };
+    while (true) {
+        for (int j = tid; j < a.n2; j += 1024) cnt[j] = 0;
+        if (tid == 0) s_changed = 0;
+        __syncthreads();
+        for (int qi = tid; qi < a.nq; qi += 1024) {
+            const int d = dec[qi];
+            if (d < 0) continue;
+            const int c = d & 0xffff, pos = atomicAdd(&cnt[c], 1);
+            if (pos < acc_limit) acc[(size_t) c * kInitAcc + pos] = ((uint32_t) qi << 9) | (uint32_t) (d >> 16);
+            else s_overflow = 1;
+        }
+        __syncthreads();
+        if (s_overflow) { if (tid == 0) *fallback = 1; return; }
+        bool changed = false;
+        for (int qi = tid; qi < a.nq; qi += 1024) {
+            int nd = -1;
+            const int nn = ncnt[qi];
+            if (nn) {                                                       // without a near candidate the best is > TH_LOW: no match
+                uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu; int c1 = -1;
+                const uint2 *e = arena + nbeg[qi];
+                for (int t = 0; t < nn; ++t) {
+                    const int c = (int) (e[t].x & 0xffffu), d = (int) (e[t].x >> 16);
+                    if (blocked(c, d, qi)) continue;
+                    const uint32_t key = ((uint32_t) d << 22) | e[t].y;
+                    if (key < k1) { k2 = k1; k1 = key; c1 = c; } else if (key < k2) k2 = key;
+                }
+                if (k1 != 0xffffffffu && (int) (k1 >> 22) <= TH_LOW) {
+                    const int best = (int) (k1 >> 22);
+                    bool accept;
+                    if (k2 != 0xffffffffu) accept = best < cv_round_sat(__fmul_rn((float) (int) (k2 >> 22), a.nn_ratio));        // :74, near second
+                    else {                                                  // the second-best, if any, is a far candidate: it only has to exist
+                        accept = false;
+                        for (int k = a.q_beg[qi], end = a.q_end[qi]; k < end && !accept; ++k) {
+                            const int d = a.c_dist[k];
+                            if (d >= d_far && !blocked(a.c_idx[k], d, qi)) accept = true;
+                        }
+                        // a lone candidate: bestDist2 keeps its initial INT_MAX (saturates to INT_MIN for ratios from about 1.0 on)
+                        if (!accept) accept = best < cv_round_sat(__fmul_rn((float) INT_MAX, a.nn_ratio));
+                    }
+                    if (accept) nd = c1 | (best << 16);
+                }
+            }
+            if (nd != dec[qi]) { dec[qi] = nd; changed = true; }
+        }
+        if (changed) s_changed = 1;
+        __syncthreads();
+        const bool more = s_changed != 0;
+        if (tid == 0 && a.dbg) a.dbg[2]++;
+        __syncthreads();
+        if (!more) break;
+    }
+    // fixed point: cnt / acc hold the acceptors of the final decisions.  Every acceptor enters the rotation histogram (:84-91); the
+    // latest acceptor of a slot owns it (:75-78)
+    for (int qi = tid; qi < a.nq; qi += 1024) {
+        const int d = dec[qi];
+        if (d < 0) continue;
+        const int c = d & 0xffff;
+        bool owner = true;
+        const int m = min(cnt[c], kInitAcc);
+        for (int t = 0; t < m; ++t) if ((int) (acc[(size_t) c * kInitAcc + t] >> 9) > qi) owner = false;
+        if (owner) { a.matches12[qi] = c; atomicAdd(&s_nmatch, 1); }
+        if (a.check_orientation) {
+            const int bn = rot_bin(a.q_angle[qi], a.kps2[c].angle);
+            atomicAdd(&hist[bn], 1);
+            a.bin_of[qi] = bn;
+        }
+    }
+    __syncthreads();
+    if (a.check_orientation) {                                              // :95-108
+        int i1, i2, i3;
+        three_maxima(hist, i1, i2, i3);
+        for (int i = tid; i < a.nq; i += 1024) {
+            const int bn = a.bin_of[i];
+            if (bn < 0 || bn == i1 || bn == i2 || bn == i3) continue;
+            if (a.matches12[i] >= 0) { a.matches12[i] = -1; atomicSub(&s_nmatch, 1); }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < a.nq; i += 1024) {                                // update previous match (:111-113)
+        const int m = a.matches12[i];
+        if (m >= 0) { a.prematched[2 * i] = a.kps2[m].x; a.prematched[2 * i + 1] = a.kps2[m].y; }
+    }
+    if (tid == 0) *a.n_matches = s_nmatch;
+}
+
 template <int kVariant>
 static int launch_resolve(Handle *h, const ResolveArgs &ra, int n2, cudaStream_t st) {
-    static const bool serial = [] { const char *e = getenv("ORBFE_SERIAL_RESOLVE"); return e && *e == '1'; }();      // A/B aid
+    const char *serial_env = getenv("ORBFE_SERIAL_RESOLVE");                       // A/B aid, read per call
+    const bool serial = serial_env && *serial_env == '1';
     if (n2 >= 65536) return set_error(h, ORBFE_E_ARG, "matcher: %d key points in the searched frame (limit 65535)", n2);
     if (kVariant != 0 && !serial) {
         const size_t state = sizeof(int) * ((size_t) n2 + (size_t) ra.nq) + 64;      // earliest holder per slot + decision per query
@@ -952,7 +1109,27 @@ static int launch_resolve(Handle *h, const ResolveArgs &ra, int n2, cudaStream_t
     if (smem > 200 * 1024)
         return set_error(h, ORBFE_E_ARG, "matcher: %d key points in the searched frame exceed the resolve kernel's shared-memory state (limit about %d)", n2,
                          kVariant == 0 ? 13000 : 20000);
-    k_resolve<kVariant><<<1, 256, smem, st>>>(ra);
+    if (kVariant == 0 && !serial) {
+        const size_t state = sizeof(int) * ((size_t) n2 * (1 + kInitAcc) + 3 * (size_t) ra.nq + 2) + 64;
+        if (state + 8 * 1024 <= 200 * 1024) {
+            ResolveArgs rb = ra;
+            rb.smem_entries = (int) ((200 * 1024 - state) / sizeof(uint2));          // near-candidate arena
+            rb.acc_far = 257;                                                        // smallest distance with cvRound(d * ratio) > TH_LOW
+            for (int d = 256; d >= 0; --d) {
+                const float v = (float) d * ra.nn_ratio;
+                const int r = (!(v < 2147483648.f) || v < -2147483648.f) ? INT_MIN : (int) lrintf(v);
+                if (r > TH_LOW) rb.acc_far = d; else break;
+            }
+            rb.acc_far = std::max(rb.acc_far, TH_LOW + 1);                          // a candidate that could be an accepted best is always "near"
+            if (const char *e = getenv("ORBFE_INIT_ACC_LIMIT")) rb.acc_limit = std::min(std::max(atoi(e), 1), kInitAcc);    // tests: drive the fallback
+            int *fallback = ra.n_matches + 3;                     // zeroed with the match counter; raised if a slot collects too many acceptors
+            k_resolve_init_par<<<1, 1024, 200 * 1024, st>>>(rb, fallback);
+            k_resolve<kVariant><<<1, 256, smem, st>>>(ra, fallback);
+            h->launches++;
+            return ORBFE_OK;
+        }
+    }
+    k_resolve<kVariant><<<1, 256, smem, st>>>(ra, nullptr);
     return ORBFE_OK;
 }
 
@@ -967,6 +1144,7 @@ static cudaError_t resolve_attrs() {
 int match_device_setup(Handle *h) {
     ORBFE_CUDA(h, resolve_attrs<0>()); ORBFE_CUDA(h, resolve_attrs<1>()); ORBFE_CUDA(h, resolve_attrs<2>());
     ORBFE_CUDA(h, resolve_attrs<3>()); ORBFE_CUDA(h, resolve_attrs<4>());
+    ORBFE_CUDA(h, cudaFuncSetAttribute(k_resolve_init_par, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return allpairs_tc_device_setup(h);
 }
 
@@ -1059,8 +1237,8 @@ static int run_window_search(Handle *h, const WindowProblem &p, float nn_ratio, 
         if (trace) {
             int dbg[4] = {0, 0, 0, 0};
             cudaMemcpy(dbg, hdr, sizeof dbg, cudaMemcpyDeviceToHost);
-            fprintf(stderr, "[orbfe trace] window search variant %d: nq %d n2 %d, issued %.1f us, results on host %.1f us; resolve rounds %d (undecided after 2: %d, after 8: %d)\n",
-                    kVariant, nq, n2, t_issue, us(), dbg[3], dbg[1], dbg[2]);
+            fprintf(stderr, "[orbfe trace] window search variant %d: nq %d n2 %d, issued %.1f us, results on host %.1f us; resolve rounds %d, %d candidate entries, sequential fallback %d\n",
+                    kVariant, nq, n2, t_issue, us(), dbg[3], ((const int *) H(nmatch))[1], ((const int *) H(nmatch))[3]);
         }
         const int *nm_h = (const int *) H(nmatch);
         if (nm_h[2]) {                                    // candidate lists did not fit: nm_h[1] is the exact total

@@ -428,3 +428,28 @@ def test_device_resident_frames_give_the_host_results(ctx, oracle):
     assert n1 == on and np.array_equal(m1, om) and np.array_equal(p1, op)
     for f in (f1, f2, w1, w2):
         f.close()
+
+
+def test_init_search_parallel_resolve_and_its_fallback(ctx, oracle, monkeypatch):
+    """SearchForInitialization resolves as a fixed-point iteration (k_resolve_init_par); when a slot collects more acceptors than the
+    kernel keeps it hands over to the sequential kernel.  Both paths, and the forced-serial one, equal the oracle; duplicated
+    descriptors produce steal chains (several acceptors per slot)."""
+    M = ctx["ORBMatcher"]; ka, da, kb, W, H = ctx["ka"], ctx["da"], ctx["kb"], ctx["w"], ctx["h"]
+    rng = np.random.default_rng(21)
+    db = ctx["db"].copy()
+    lvl0 = np.nonzero(kb["octave"] == 0)[0]
+    for _ in range(60):                                          # many near-identical level-0 descriptors in frame 2: contested slots
+        src = rng.choice(lvl0); dst = rng.choice(lvl0, 4)
+        db[dst] = db[src]; db[dst[0], rng.integers(0, 32)] ^= 1
+    f1, f2 = ctx["FrameView"](ka, da, W, H), ctx["FrameView"](kb, db, W, H)
+    pre = np.stack([ka["x"], ka["y"]], 1).astype(np.float32)
+    for window, ratio, orient in ((100, 0.9, True), (200, 0.95, True), (60, 0.8, False)):
+        exp = oracle.search_for_initialization(ka, da, kb, db, W, H, pre.copy(), window, ratio, orient)
+        for env in ({}, {"ORBFE_INIT_ACC_LIMIT": "1"}, {"ORBFE_SERIAL_RESOLVE": "1"}):
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            p = pre.copy()
+            n, m12 = M(ratio, orient).SearchForInitialization(f1, f2, p, window)
+            for k in env:
+                monkeypatch.delenv(k)
+            assert n == exp[0] and np.array_equal(m12, exp[1]) and np.array_equal(p, exp[2]), (window, env)
