@@ -218,6 +218,14 @@ int orbfe_hamming_allpairs_excl(orbfe_handle *h, const uint8_t *q, int nq, const
 int orbfe_hamming_allpairs_excl_device(orbfe_handle *h, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, const int32_t *d_excl,
                                        int32_t *d_best_idx, int32_t *d_best_dist, int32_t *d_second_dist, void *stream, int sync);
 
+/* A key-frame window matched against itself straight from the extractor's output slabs (orbfe_extract_batch_device): d_desc holds
+ * n_frames blocks of `cap` descriptor rows of which the first d_n_per_frame[f] are key points.  Every key point's best / second-best
+ * among the key points of the OTHER frames of the window; padding rows neither match nor are matched (their outputs are -1 / 257 /
+ * 257).  Outputs have n_frames * cap entries and best_idx is a slab row (frame * cap + key point).  No compaction pass and no host
+ * synchronisation for the counts: the call chains behind the extraction on the same stream.  Runs on the tensor cores for every size. */
+int orbfe_hamming_allpairs_slab_device(orbfe_handle *h, const uint8_t *d_desc, const int *d_n_per_frame, int n_frames, int cap,
+                                       int32_t *d_best_idx, int32_t *d_best_dist, int32_t *d_second_dist, void *stream, int sync);
+
 /* Best / second-best over caller-supplied candidate lists (SURVEY.md section 8b `orbfe_hamming_window`): the candidates of
  * query i are t[cand_idx[cand_offsets[i] .. cand_offsets[i+1])], scanned in list order like the `if (dist < bestDist)` loops of
  * ORBMatcher.cpp:60-72 / :237-248 (first minimum wins).  best_idx is the train index of the minimum (-1 and 257 for an

@@ -74,6 +74,7 @@ SIGNATURES = {
     "orbfe_hamming_allpairs": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "orbfe_hamming_allpairs_excl": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "orbfe_hamming_allpairs_excl_device": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i]),
+    "orbfe_hamming_allpairs_slab_device": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i]),
     "orbfe_hamming_window": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "orbfe_hamming_allpairs_device": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i]),
     "orbfe_search_for_initialization": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _f, _i, C.POINTER(_i)]),

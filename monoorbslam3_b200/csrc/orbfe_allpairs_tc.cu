@@ -115,6 +115,9 @@ struct TcArgs {
     int nq, nt, tiles_per_split;
     const int2 *excl;        // per query row: train indices [x, y) are skipped; NULL = none
     uint2 *partial;          // [split][nq] (best key, second key)
+    // slab mode (key-frame window straight from the extractor's output slabs): the table is n_frames blocks of `cap` rows of which
+    // the first slab_n[f] are key points; the padding rows never match and are never matched, and a row skips its own block
+    const int *slab_n; int cap;
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1) k_allpairs_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_t, const TcArgs a) {
@@ -195,6 +198,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_allpairs_tc(const __grid_cons
         const int row = row0 + mt * kTcM + lq * 32 + lane;
         int2 ex = make_int2(0, 0);
         if (a.excl && row < a.nq) ex = a.excl[row];
+        bool row_live = row < a.nq;
+        if (a.slab_n && row < a.nq) { const int f = row / a.cap; ex = make_int2(f * a.cap, (f + 1) * a.cap); row_live = row - f * a.cap < a.slab_n[f]; }
         // warp-wide hull of the exclusion ranges: tiles outside it take the fast path
         int w_lo = ex.x < ex.y ? ex.x : 0x7fffffff, w_hi = ex.x < ex.y ? ex.y : 0;
 #pragma unroll
@@ -205,7 +210,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_allpairs_tc(const __grid_cons
             mbar_wait(&b_tfull[par], (uint32_t) ((i >> 1) & 1));
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t) (lq * 32) << 16) + (uint32_t) (par * 2 * kTcN + mt * kTcN);
-            const bool slow = col0 + kTcN > a.nt || (col0 < w_hi && col0 + kTcN > w_lo);      // ragged last tile / a row's own key-frame block
+            bool slow = col0 + kTcN > a.nt || (col0 < w_hi && col0 + kTcN > w_lo);            // ragged last tile / a row's own key-frame block
+            int f0 = 0, f_split = 0x7fffffff, n0 = 0x7fffffff, n1 = 0x7fffffff;              // slab mode: the (at most two) blocks the tile touches
+            if (a.slab_n) {
+                f0 = col0 / a.cap; f_split = (f0 + 1) * a.cap;
+                n0 = f0 * a.cap + a.slab_n[f0];                                               // first padding row of block f0
+                if (f_split < col0 + kTcN && f_split < a.nt) n1 = f_split + a.slab_n[f0 + 1];
+                slow = slow || col0 + kTcN > n0;                                              // reaches block f0's padding (or the next block)
+            }
             // two independent (smallest, second) chains, per 16-bit half
             uint32_t a1 = 0xffffffffu, a2 = 0xffffffffu, b1 = 0xffffffffu, b2 = 0xffffffffu;
 #pragma unroll
@@ -231,10 +243,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_allpairs_tc(const __grid_cons
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int c = col0 + ch * 64 + 2 * j;
-                        if (c >= a.nt || (c >= ex.x && c < ex.y)) pa[j] |= 0x0000ffffu;
-                        if (c + 1 >= a.nt || (c + 1 >= ex.x && c + 1 < ex.y)) pa[j] |= 0xffff0000u;
-                        if (c + 32 >= a.nt || (c + 32 >= ex.x && c + 32 < ex.y)) pb[j] |= 0x0000ffffu;
-                        if (c + 33 >= a.nt || (c + 33 >= ex.x && c + 33 < ex.y)) pb[j] |= 0xffff0000u;
+                        auto dead = [&](int cc) { return cc >= a.nt || (cc >= ex.x && cc < ex.y) || (cc < f_split ? cc >= n0 : cc >= n1); };
+                        if (dead(c)) pa[j] |= 0x0000ffffu;
+                        if (dead(c + 1)) pa[j] |= 0xffff0000u;
+                        if (dead(c + 32)) pb[j] |= 0x0000ffffu;
+                        if (dead(c + 33)) pb[j] |= 0xffff0000u;
                     }
                 }
 #pragma unroll
@@ -252,7 +265,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_allpairs_tc(const __grid_cons
                 merge_key(K1, K2, key2);
             }
         }
-        if (row < a.nq) a.partial[(size_t) (blockIdx.y * 2 + par) * a.nq + row] = make_uint2(K1, K2);
+        if (row < a.nq) a.partial[(size_t) (blockIdx.y * 2 + par) * a.nq + row] = row_live ? make_uint2(K1, K2) : make_uint2(kTcNone, kTcNone);
     }
     tc_fence_before();
     __syncthreads();
@@ -309,7 +322,7 @@ size_t allpairs_tc_scratch_bytes(int nq, int nt, int *n_split_out) {
 
 // d_scratch: allpairs_tc_scratch_bytes(nq, nt) bytes.  The results go through `partial` and the caller's merge kernel.
 int allpairs_tc_launch(Handle *h, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, const int2 *d_excl, uint8_t *d_scratch,
-                       uint2 **partial_out, int *n_split_out, cudaStream_t st) {
+                       uint2 **partial_out, int *n_split_out, cudaStream_t st, const int *d_slab_n, int slab_cap) {
     int n_split = 1;
     allpairs_tc_scratch_bytes(nq, nt, &n_split);
     auto up = [](size_t v) { return (v + 255) & ~(size_t) 255; };
@@ -324,6 +337,7 @@ int allpairs_tc_launch(Handle *h, const uint8_t *d_q, int nq, const uint8_t *d_t
     const int n_tiles = (nt + kTcN - 1) / kTcN;
     TcArgs ta;
     ta.nq = nq; ta.nt = nt; ta.tiles_per_split = (n_tiles + n_split - 1) / n_split; ta.excl = d_excl; ta.partial = partial;
+    ta.slab_n = d_slab_n; ta.cap = slab_cap;
     k_allpairs_tc<<<dim3((nq + kTcRows - 1) / kTcRows, n_split), kTcThreads, kTcSmem, st>>>(mq, mt, ta);
     h->launches += (te == qe) ? 2 : 3;
     ORBFE_CUDA(h, cudaGetLastError());

@@ -146,7 +146,7 @@ int frame_device_setup(Handle *h);
 int allpairs_tc_device_setup(Handle *h);
 size_t allpairs_tc_scratch_bytes(int nq, int nt, int *n_split_out);
 int allpairs_tc_launch(Handle *h, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, const int2 *d_excl, uint8_t *d_scratch,
-                       uint2 **partial_out, int *n_split_out, cudaStream_t st);
+                       uint2 **partial_out, int *n_split_out, cudaStream_t st, const int *d_slab_n = nullptr, int slab_cap = 0);
 // Frame grid (CSR) of one device-resident key-point array; d_n holds the count (orbfe_frame.cu)
 int frame_grid_launch(Handle *h, const orbfe_keypoint *d_kps, const int *d_n, int cap, int img_w, int img_h, int *d_grid_off, int *d_grid_idx, cudaStream_t st);
 

@@ -1485,6 +1485,35 @@ int orbfe_hamming_allpairs_excl_device(orbfe_handle *h, const uint8_t *d_q, int 
     return ORBFE_OK;
 }
 
+// Key-frame window straight from the extractor's output slabs: no compaction, no host synchronisation for the counts.
+int orbfe_hamming_allpairs_slab_device(orbfe_handle *h, const uint8_t *d_desc, const int *d_n_per_frame, int n_frames, int cap, int32_t *d_best_idx,
+                                       int32_t *d_best_dist, int32_t *d_second_dist, void *stream, int sync) {
+    if (!h) return ORBFE_E_ARG;
+    if (n_frames < 0 || cap < 1 || (n_frames && (!d_desc || !d_n_per_frame || !d_best_idx || !d_best_dist || !d_second_dist)))
+        return set_error(h, ORBFE_E_ARG, "orbfe_hamming_allpairs_slab_device: invalid argument");
+    if ((long long) n_frames * cap >= (1 << 22)) return set_error(h, ORBFE_E_ARG, "at most %d descriptor rows per window", (1 << 22) - 1);
+    if ((uintptr_t) d_desc & 15) return set_error(h, ORBFE_E_ARG, "descriptor slab must be 16-byte aligned");
+    if (n_frames == 0) return ORBFE_OK;
+    ORBFE_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t) stream : h->stream;
+    const int n = n_frames * cap;
+    const size_t need = allpairs_tc_scratch_bytes(n, n, nullptr);
+    if (h->ap_bytes < need) {
+        ORBFE_CUDA(h, cudaDeviceSynchronize());
+        cudaFree(h->d_ap); h->d_ap = nullptr; h->ap_bytes = 0;
+        ORBFE_CUDA(h, cudaMalloc(&h->d_ap, need));
+        h->ap_bytes = need;
+    }
+    uint2 *partial = nullptr; int n_split = 1;
+    int rc = allpairs_tc_launch(h, d_desc, n, d_desc, n, nullptr, (uint8_t *) h->d_ap, &partial, &n_split, st, d_n_per_frame, cap);
+    if (rc) return rc;
+    k_allpairs_merge<<<(n + 255) / 256, 256, 0, st>>>(partial, n_split, n, d_best_idx, d_best_dist, d_second_dist);
+    h->launches++;
+    ORBFE_CUDA(h, cudaGetLastError());
+    if (sync) ORBFE_CUDA(h, cudaStreamSynchronize(st));
+    return ORBFE_OK;
+}
+
 int orbfe_hamming_allpairs_device(orbfe_handle *h, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, int32_t *d_best_idx, int32_t *d_best_dist,
                                   int32_t *d_second_dist, void *stream, int sync) {
     return orbfe_hamming_allpairs_excl_device(h, d_q, nq, d_t, nt, nullptr, d_best_idx, d_best_dist, d_second_dist, stream, sync);

@@ -147,6 +147,11 @@ class ORBMatcher:
         _capi.check(self._h, self._lib.orbfe_hamming_allpairs_excl_device(self._h, _capi.ptr(d_q), nq, _capi.ptr(d_t), nt, _capi.ptr(d_excl), _capi.ptr(d_bi),
                                                                           _capi.ptr(d_bd), _capi.ptr(d_sd), C.c_void_p(stream) if stream else None, int(sync)))
 
+    def hamming_allpairs_slab_device(self, d_desc, d_n, n_frames, cap, d_bi, d_bd, d_sd, stream=None, sync=True):
+        """A key-frame window matched against itself straight from the extractor's slabs (orbfe_hamming_allpairs_slab_device)."""
+        _capi.check(self._h, self._lib.orbfe_hamming_allpairs_slab_device(self._h, _capi.ptr(d_desc), _capi.ptr(d_n), int(n_frames), int(cap), _capi.ptr(d_bi),
+                                                                          _capi.ptr(d_bd), _capi.ptr(d_sd), C.c_void_p(stream) if stream else None, int(sync)))
+
     # ---- int SearchForInitialization(frame1, frame2, vecPreMatched, matches12, windowSize=100) — ORBMatcher.cpp:33-116
     def SearchForInitialization(self, frame1, frame2, vecPreMatched, windowSize=100):
         """Returns (numMatches, matches12); vecPreMatched ([n1,2] float32) is updated in place like the reference's reference argument."""

@@ -453,3 +453,34 @@ def test_init_search_parallel_resolve_and_its_fallback(ctx, oracle, monkeypatch)
             for k in env:
                 monkeypatch.delenv(k)
             assert n == exp[0] and np.array_equal(m12, exp[1]) and np.array_equal(p, exp[2]), (window, env)
+
+
+@pytest.mark.parametrize("n_frames,cap", [(5, 700), (3, 257), (2, 128), (7, 401)])
+def test_allpairs_on_extractor_slabs(ctx, oracle, n_frames, cap):
+    """orbfe_hamming_allpairs_slab_device: a key-frame window matched against itself straight from fixed-capacity slabs (counts on the
+    device, padding rows in between): equals the compacted table searched with per-row exclusion of the own frame."""
+    import torch
+    m = ctx["ORBMatcher"]()
+    rng = np.random.default_rng(n_frames * 1000 + cap)
+    pool = np.concatenate([ctx["da"], ctx["db"]])
+    counts = rng.integers(cap // 2, cap + 1, n_frames).astype(np.int32)
+    counts[0] = cap; counts[-1] = max(1, cap // 3)                         # a full block and a short one
+    slab = rng.integers(0, 256, (n_frames, cap, 32), dtype=np.uint8)       # padding rows hold garbage that must never match
+    for f in range(n_frames):
+        slab[f, :counts[f]] = pool[rng.integers(0, len(pool), counts[f])]
+    dev = torch.device("cuda", 0)
+    d_slab = torch.from_numpy(slab).to(dev); d_n = torch.from_numpy(counts).to(dev)
+    bi = torch.zeros(n_frames * cap, dtype=torch.int32, device=dev); bd = torch.zeros_like(bi); sd = torch.zeros_like(bi)
+    m.hamming_allpairs_slab_device(d_slab, d_n, n_frames, cap, bi, bd, sd)
+    bi, bd, sd = (t.cpu().numpy().reshape(n_frames, cap) for t in (bi, bd, sd))
+    table = np.concatenate([slab[f, :counts[f]] for f in range(n_frames)])
+    starts = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    blk = np.repeat(np.arange(n_frames), counts)
+    excl = np.stack([starts[blk], starts[blk + 1]], 1).astype(np.int32)
+    ebi, ebd, esd = m.hamming_allpairs(table, table, excl)                 # parity-tested against numpy / the oracle above
+    row_of = np.concatenate([f * cap + np.arange(counts[f]) for f in range(n_frames)])          # compact index -> slab row
+    for f in range(n_frames):
+        sl = slice(starts[f], starts[f + 1])
+        exp_idx = np.where(ebi[sl] >= 0, row_of[np.maximum(ebi[sl], 0)], -1)
+        assert np.array_equal(bi[f, :counts[f]], exp_idx) and np.array_equal(bd[f, :counts[f]], ebd[sl]) and np.array_equal(sd[f, :counts[f]], esd[sl]), f
+        assert (bi[f, counts[f]:] == -1).all() and (bd[f, counts[f]:] == 257).all()
