@@ -3,13 +3,20 @@
 1.2 / 8 levels / FAST 20,7), plus all-pairs Hamming GMatch/s, on N B200s of one node.
 
 A step = one pass of the hot path (pyramid, FAST, quadtree, blur, descriptors) over one batch of B synthetic frames per GPU.
-  value : frames/s with the frames already resident in HBM (device API), CUDA events on the launching stream, max over ranks
+  value : frames/s with the frames already resident in HBM (device API), CUDA events on the launching stream, max over ranks.
+          N > 1: frames are sharded by rank (weak scaling) and every rank's result slabs land on rank 0 inside the timed region —
+          written there directly by the descriptor kernel through peer-mapped memory over NVLink (torch symmetric memory), or, when
+          that is not available, gathered to rank 0 with NCCL send / recv on a side stream
   e2e   : frames/s through the host C-ABI with pinned HOST buffers — H2D and D2H of every step inside the timed region; the streaming
           form orbfe_extract_batch_submit / _wait with two batches in flight (e2e.value) and one blocking orbfe_extract_batch call
-          per step (e2e.sync_call_value)
+          per step (e2e.sync_call_value); e2e.h2d_ceiling is what the host can feed to the N GPUs at once (concurrent pinned uploads)
   roofline : the dominant stage, algorithmic bytes per launch / its CUDA-event duration, against MEASURED_PEAKS.json
-  cpu_baseline : the reference's own ORBExtractor.cpp (oracle/_ref, compiled verbatim) on the host cores, bounded sample
-`--impl reference` runs only that CPU arm.  N > 1: frames are sharded by rank (weak scaling), results gathered with NCCL."""
+  match : all-pairs best / second-best at 40 000 x 40 000 on tcgen05 (k_allpairs_tc), against the int8 tensor peak
+  c5    : BASELINE config 5 (strong scaling): 4096 x 1920x1080 frames extracted and matched inside 20-key-frame windows, sharded by
+          window block, match results landing on rank 0
+  cpu_baseline : the reference's own ORBExtractor.cpp (oracle/_ref, compiled verbatim) on the host cores, bounded sample, beside a
+          composite with cv2's primitives (the faster one is the baseline), at one thread and at all cores
+`--impl reference` runs only that CPU arm."""
 import argparse
 import json
 import os
@@ -26,6 +33,13 @@ sys.path.insert(0, ROOT)
 W, H, NF = 752, 480, 1000
 ORB = dict(nFeatures=NF, scaleFactor=1.2, nLevels=8, iniThFast=20, minThFast=7)
 WORKLOAD = "C1: %dx%d grayscale frames, %d features, 8 levels, scale 1.2, FAST 20/7 (euroc-shaped), dense synthetic profile" % (W, H, NF)
+METRIC = "ORB extract+describe frames/s (752x480, 1000 kp)"
+
+
+def make_config(batch, distinct):
+    """Identical in both arms: what is extracted.  (How each arm runs it is reported outside `config`.)"""
+    return {"workload": WORKLOAD, "frames_per_step_per_gpu": batch, "distinct_scenes": distinct, "scene_seeds": "1000 + k (rank 0)",
+            "l2": "inputs larger than L2 (%.0f MB of frames per step)" % (batch * H * W / 1e6)}
 
 
 def level_sizes(w, h, n_levels=8, sf=1.2):
@@ -80,16 +94,19 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+# ------------------------------------------------------------------------------------------------------------------------------
+# CPU arm
+# ------------------------------------------------------------------------------------------------------------------------------
 def cpu_reference_fps(frames, threads, min_seconds=8.0, max_frames=None):
     """Time the reference's own extractor (oracle/_ref/libref_orb.so = ORBExtractor.cpp compiled verbatim + cv shim) frame-parallel
-    on `threads` host threads; falls back to the C oracle port when the verbatim build is not there.  Returns (fps, kind, sample)."""
+    on `threads` host threads; falls back to the C oracle port when the verbatim build is not there.  Returns (fps, kind, sample, threads)."""
     from oracle import orb_oracle as orc
     kind = "reference"
     try:
         ref = orc.ReferenceExtractor(NF, 1.2, 8, 20, 7, canonical=False)
     except (FileNotFoundError, OSError):
         ref, kind = None, "port"
-    n = max(threads, 8)
+    n = max(threads, 8) if threads > 1 else 4
     total_t, total_n = 0.0, 0
     while True:
         idx = [i % len(frames) for i in range(total_n, total_n + n)]
@@ -109,6 +126,73 @@ def cpu_reference_fps(frames, threads, min_seconds=8.0, max_frames=None):
         n = min(4 * n, max(n, int(n * (min_seconds - total_t) / max(sec, 1e-6)) + threads))
     used = threads if ref is not None else 1
     return total_n / total_t, kind, "%d frames of the workload in %.1f s on %d thread(s)" % (total_n, total_t, used), used
+
+
+def cpu_composite_ms_per_frame(frames):
+    """BASELINE.md section 2's fairness rule: the per-frame time of a composite that uses cv2's SIMD primitives for pyramid / FAST /
+    blur and the reference's algorithm for the rest (quadtree, orientation, descriptors, copies).  The rest is measured inside the
+    oracle port (the same algorithm as the verbatim code, bit for bit; its extract call reports its own stage split); FAST is timed
+    per whole level with cv2 — faster than the reference's per-cell calls, i.e. in the CPU's favour.  One thread.
+    Returns (ms per frame, parts) or None without cv2."""
+    try:
+        import cv2
+    except Exception:
+        return None
+    from oracle import orb_oracle as orc
+    cv2.setNumThreads(1)
+    det = cv2.FastFeatureDetector_create(20, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    sizes = level_sizes(W, H)
+    t = {"pyramid": 0.0, "fast": 0.0, "blur": 0.0}
+    reps = 6
+    for r in range(reps):
+        lv = [frames[r % len(frames)]]
+        t0 = time.perf_counter()
+        for (w, h) in sizes[1:]:
+            lv.append(cv2.resize(lv[-1], (w, h), interpolation=cv2.INTER_LINEAR))
+        t1 = time.perf_counter()
+        for im in lv:
+            det.detect(im)
+        t2 = time.perf_counter()
+        for im in lv:
+            cv2.GaussianBlur(im, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+        t3 = time.perf_counter()
+        t["pyramid"] += t1 - t0; t["fast"] += t2 - t1; t["blur"] += t3 - t2
+    cvp = {k: 1e3 * v / reps for k, v in t.items()}
+    ex = orc.Extractor(NF, 1.2, 8, 20, 7)
+    port = np.zeros(4)
+    for r in range(4):
+        ex(frames[r % len(frames)])
+        port += np.array(ex.last_stage_ms())
+    port /= 4
+    parts = {"cv2_ms": cvp, "port_ms": dict(zip(("pyramid", "fast", "blur", "rest"), port.tolist())), "rest_ms": float(port[3])}
+    return sum(cvp.values()) + float(port[3]), parts
+
+
+_composite_cache = {}
+
+
+def cpu_baseline_record(frames, seconds):
+    """verbatim_shim / composite_cv2 at one thread and at all cores; `value` = the faster all-cores figure."""
+    cores = host_cores()
+    fps_all, kind, sample_all, used = cpu_reference_fps(frames, cores, min_seconds=seconds)
+    fps_1, _, sample_1, _ = cpu_reference_fps(frames, 1, min_seconds=min(seconds, 2.0), max_frames=32)
+    rec = {"unit": "frames/s", "cores": used, "kind": kind,
+           "verbatim_shim": {"value": fps_all, "one_thread": fps_1, "sample": sample_all, "sample_one_thread": sample_1,
+                             "what": "ORBExtractor.cpp compiled verbatim + scalar cv:: shim (oracle/_ref), frame-parallel"}}
+    if "parts" not in _composite_cache:                                     # the primitives are timed once per process
+        _composite_cache["parts"] = cpu_composite_ms_per_frame(frames)
+    comp = _composite_cache.get("parts")
+    if comp is not None:
+        ms, parts = comp
+        scale = fps_all / (fps_1 * used) if used > 1 else 1.0           # the all-cores figure inherits the verbatim run's parallel efficiency
+        rec["composite_cv2"] = {"one_thread": 1e3 / ms, "value": 1e3 / ms * used * scale, "ms_per_frame_one_thread": ms, "parts": parts,
+                                "what": "cv2 4.x SIMD resize / FAST (whole level) / GaussianBlur timed here + quadtree / orientation / descriptors as timed inside the CPU port; "
+                                        "all-cores = one thread x cores x the verbatim run's measured parallel efficiency (%.2f)" % scale}
+    best = max(("verbatim_shim", "composite_cv2"), key=lambda k: rec.get(k, {}).get("value", 0.0))
+    rec["value"] = rec[best]["value"]; rec["one_thread"] = rec[best]["one_thread"]; rec["faster"] = best
+    rec["sample"] = "%s; baseline = the faster of verbatim_shim (%.0f frames/s) and composite_cv2 (%s) on %d threads" % (
+        sample_all, fps_all, ("%.0f frames/s" % rec["composite_cv2"]["value"]) if "composite_cv2" in rec else "not available", used)
+    return rec
 
 
 def cpu_hamming_gmatch(threads, nt=40000, q_per_thread=1024):
@@ -133,31 +217,36 @@ def run_reference(args):
     if rank != 0:
         return
     from monoorbslam3_b200 import synth
+    distinct = min(args.distinct, args.batch)
+    frames = synth.frames(distinct, H, W, 1000, "dense")                 # the scenes rank 0 of the GPU arm extracts
     cores = host_cores()
-    frames = synth.frames(16, H, W, 1000, "dense")
     for _ in range(max(args.warmup, 0)):
         cpu_reference_fps(frames, cores, min_seconds=0.5)
-    vals, samples = [], []
+    vals = []
     t_all = time.perf_counter()
-    kind = used = None
+    rec = None
     for _ in range(args.steps):
-        fps, kind, sample, used = cpu_reference_fps(frames, cores, min_seconds=args.ref_seconds)
-        vals.append(fps); samples.append(sample)
+        rec = cpu_baseline_record(frames, args.ref_seconds)
+        vals.append(rec["value"])
     v = float(np.mean(vals))
-    line = {"impl": "reference", "metric": "ORB extract+describe frames/s (752x480, 1000 kp)", "value": v, "unit": "frames/s",
+    rec["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (time.perf_counter() - t_all) / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": "bounded CPU sample of the same frames (%s)" % samples[-1],
-                       "sharding": "rank 0 only, all host threads", "l2": "n/a (CPU arm)"},
-            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": used, "kind": kind, "sample": samples[-1]},
+            "config": make_config(args.batch, distinct),
+            "how": "rank 0 only, all host threads; each step is a bounded sample of the workload's frames (%s)" % rec["sample"],
+            "cpu_baseline": rec,
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from monoorbslam3_b200 import ORBExtractor, ORBMatcher, KP_DTYPE, synth
+    from monoorbslam3_b200 import ORBExtractor, ORBMatcher, KP_DTYPE, synth, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -182,7 +271,42 @@ def run_ours(args):
             os.close(saved)
     B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
 
-    # synthetic frames: `distinct` different scenes, repeated to fill the batch (B*H*W = 185 MB at B=512 > the 126 MB L2)
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # Result slabs of all ranks on rank 0.  Preferred: one symmetric (peer-mapped) allocation per buffer set — every rank passes the
+    # address of ITS block inside rank 0's buffer as the extractor's output pointer, so k_describe's stores travel over NVLink and the
+    # gather costs no kernel and no copy.  Fallback: local slabs + NCCL send / recv to rank 0 on a side stream.
+    def peer_buffers(nbytes, n_sets):
+        """-> list (per set) of (base address of rank 0's buffer as seen from this rank, keep-alive objects), or None."""
+        if world == 1 or args.no_peer_store:
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            out = []
+            for _ in range(n_sets):
+                buf = symm.empty(nbytes, dtype=torch.uint8, device=dev)
+                hdl = symm.rendezvous(buf, dist.group.WORLD)
+                root = buf if rank == 0 else hdl.get_buffer(0, (nbytes,), torch.uint8)
+                out.append((root.data_ptr(), (buf, hdl, root)))
+            ok = torch.ones(1, device=dev)
+        except Exception as e:                                             # symmetric memory not available on this box / build
+            if rank == 0:
+                print("[bench] peer-mapped result buffers unavailable (%s: %s): NCCL gather to rank 0 instead" % (type(e).__name__, e), file=sys.stderr)
+            out, ok = None, torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        return out if float(ok.item()) > 0 else None
+
+    # ---------------------------------------------------------------- C1 (the headline): frames resident in HBM
     distinct = min(args.distinct, B)
     base = synth.frames(distinct, H, W, 1000 + 100000 * rank, "dense")
     reps = (B + distinct - 1) // distinct
@@ -191,59 +315,83 @@ def run_ours(args):
 
     ex = ORBExtractor(device=local, max_batch=B, **ORB)
     cap = NF + 64
-    # a real (non-default) stream: the library launches on it and the timing events are recorded on it
-    tstream = torch.cuda.Stream(device=dev)
+    tstream = torch.cuda.Stream(device=dev)                                # a real (non-default) stream: launches and timing events go on it
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     assert stream != 0
 
-    # Output slabs.  N > 1: two sets, so that the NCCL gather of step k (fixed-capacity slabs) runs on a side stream
-    # while step k+1 computes into the other set — the gather is inside the timed region but off the compute stream's critical path.
     n_sets = 2 if world > 1 else 1
-    outs = [(torch.zeros((B, cap, 7), dtype=torch.float32, device=dev), torch.zeros((B, cap, 32), dtype=torch.uint8, device=dev),
-             torch.zeros(B, dtype=torch.int32, device=dev)) for _ in range(n_sets)]
-    d_kps, d_desc, d_n = outs[0]
-    gather_bufs = comm_stream = None
-    if world > 1:
-        gather_bufs = [(torch.empty((world,) + tuple(d_kps.shape), dtype=d_kps.dtype, device=dev),
-                        torch.empty((world,) + tuple(d_desc.shape), dtype=d_desc.dtype, device=dev),
-                        torch.empty((world, B), dtype=torch.int32, device=dev)) for _ in range(n_sets)]
+    kp_b, ds_b, n_b = B * cap * 28, B * cap * 32, B * 4
+    blk = (kp_b + ds_b + n_b + 255) // 256 * 256                          # one rank's block of a buffer set
+    peers = peer_buffers(world * blk, n_sets)
+    gather_mode = "single GPU" if world == 1 else ("peer-store: k_describe writes each rank's result slabs into rank 0's peer-mapped buffer over NVLink "
+                                                    "(no gather kernel, no copy)" if peers else "NCCL send/recv gather of the result slabs to rank 0 on a side stream, double-buffered")
+    outs = []                                                              # per set: (kps ptr/tensor, desc, n) this rank's extractor writes
+    local_sets = [(torch.zeros((B, cap, 7), dtype=torch.float32, device=dev), torch.zeros((B, cap, 32), dtype=torch.uint8, device=dev),
+                   torch.zeros(B, dtype=torch.int32, device=dev)) for _ in range(n_sets if not peers else 0)]
+    for k in range(n_sets):
+        if peers:
+            b0 = peers[k][0] + rank * blk
+            outs.append((b0, b0 + kp_b, b0 + kp_b + ds_b))
+        else:
+            outs.append(local_sets[k])
+    root_bufs = comm_stream = None
+    if world > 1 and not peers:
         comm_stream = torch.cuda.Stream(device=dev)
         ev_computed = [torch.cuda.Event() for _ in range(n_sets)]
         ev_gathered = [torch.cuda.Event() for _ in range(n_sets)]
+        if rank == 0:
+            root_bufs = [[tuple(torch.empty_like(t) for t in local_sets[k]) for _ in range(world - 1)] for k in range(n_sets)]
     step_no = [0]
 
     def step_device():
         k = step_no[0] % n_sets
         step_no[0] += 1
         o = outs[k]
-        if world > 1 and step_no[0] > n_sets:
-            tstream.wait_event(ev_gathered[k])             # the gather that read this set two steps ago has finished
+        if comm_stream is not None and step_no[0] > n_sets:
+            tstream.wait_event(ev_gathered[k])                             # the gather that read this set two steps ago has finished
         ex.extract_batch_device(d_frames, B, H, W, o[0], o[1], cap, o[2], stream=stream, sync=False)
-        if world > 1:
+        if comm_stream is not None:
             ev_computed[k].record(tstream)
             with torch.cuda.stream(comm_stream):
                 comm_stream.wait_event(ev_computed[k])
-                dist.all_gather_into_tensor(gather_bufs[k][0], o[0])
-                dist.all_gather_into_tensor(gather_bufs[k][1], o[1])
-                dist.all_gather_into_tensor(gather_bufs[k][2], o[2])
+                if rank == 0:
+                    ops = [dist.P2POp(dist.irecv, t, p + 1) for p in range(world - 1) for t in root_bufs[k][p]]
+                else:
+                    ops = [dist.P2POp(dist.isend, t, 0) for t in o]
+                for w_ in dist.batch_isend_irecv(ops):
+                    w_.wait()
                 ev_gathered[k].record(comm_stream)
 
     def drain():
         """the timed region ends when the last gather has landed: the compute stream waits for the side stream"""
-        if world > 1:
+        if comm_stream is not None:
             tstream.wait_stream(comm_stream)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def read_counts():
+        """key-point counts of this rank's last batch (from rank 0's buffer when the slabs are peer-stored there)"""
+        k = (step_no[0] - 1) % n_sets
+        if not peers:
+            return outs[k][2].clone()
+        view = torch.empty(B, dtype=torch.int32, device=dev)
+        src = peers[k][1][2]                                               # tensor over rank 0's buffer
+        off = rank * blk + kp_b + ds_b
+        view.copy_(src[off:off + n_b].view(torch.int32))
+        return view
 
     for _ in range(Wm):
         step_device()
-    barrier()
+    drain(); barrier()
+    d_n = read_counts()
     n_kp_mean = float(d_n.float().mean().item())
     assert n_kp_mean > 900, n_kp_mean
+    if peers and world > 1:                                                # rank 0 sees every rank's counts in its own buffer
+        if rank == 0:
+            root_t = peers[(step_no[0] - 1) % n_sets][1][2]
+            for r in range(world):
+                off = r * blk + kp_b + ds_b
+                assert float(root_t[off:off + n_b].view(torch.int32).float().mean().item()) > 900, "rank %d's slab did not land on rank 0" % r
+        barrier()
 
     # ---- timed region 1: frames resident in HBM
     sampler = ClockSampler(local); sampler.start()
@@ -273,29 +421,22 @@ def run_ours(args):
     ms_prof = p0.elapsed_time(p1)
     stage_ms, passes = ex.profile_read(reset=True)
     ex.profile(False)
-    if world > 1:
-        t = torch.tensor([ms_dev], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev = float(t.item())
+    ms_dev = max_over_ranks(ms_dev)
     value = world * B * K / (ms_dev * 1e-3)
 
-    # ---- timed region 2: end to end through the host C-ABI with pinned host buffers (H2D + kernels + D2H every step)
+    # ---------------------------------------------------------------- e2e: host C-ABI, pinned host buffers, H2D + kernels + D2H every step
     h_n = torch.zeros(B, dtype=torch.int32).pin_memory()
     h_kps = torch.zeros((B, cap, 7), dtype=torch.float32).pin_memory()
     h_desc = torch.zeros((B, cap, 32), dtype=torch.uint8).pin_memory()
     frames_np = host_frames.numpy()
     out = (h_n.numpy(), h_kps.numpy().view(KP_DTYPE).reshape(B, cap), h_desc.numpy())
+
     def timed(run):
         barrier()
         t0 = time.perf_counter()
         run()
         barrier()
-        sec = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([sec], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            sec = float(t.item())
-        return world * B * K / sec
+        return world * B * K / max_over_ranks(time.perf_counter() - t0)
 
     # (a) one synchronous orbfe_extract_batch call per step: every call pays the pipeline's fill (first upload) and drain (last pass + download)
     def run_sync():
@@ -312,59 +453,78 @@ def run_ours(args):
     h_n2 = torch.zeros(B, dtype=torch.int32).pin_memory()
     h_kps2 = torch.zeros((B, cap, 7), dtype=torch.float32).pin_memory()
     h_desc2 = torch.zeros((B, cap, 32), dtype=torch.uint8).pin_memory()
-    outs = (out, (h_n2.numpy(), h_kps2.numpy().view(KP_DTYPE).reshape(B, cap), h_desc2.numpy()))
+    houts = (out, (h_n2.numpy(), h_kps2.numpy().view(KP_DTYPE).reshape(B, cap), h_desc2.numpy()))
 
     def run_stream():
         prev = None
         for k in range(K):
-            t = ex.extract_batch_submit(frames_np, outs[k & 1], cap=cap)
+            t = ex.extract_batch_submit(frames_np, houts[k & 1], cap=cap)
             if prev is not None:
                 ex.extract_batch_wait(prev)
-                _ = int(outs[(k - 1) & 1][0][0])
+                _ = int(houts[(k - 1) & 1][0][0])
             prev = t
         ex.extract_batch_wait(prev)
-        _ = int(outs[(K - 1) & 1][0][0])
+        _ = int(houts[(K - 1) & 1][0][0])
     run_stream()
     e2e = timed(run_stream)
     # both buffer sets hold the results of the same frames (rows beyond n[b] are unspecified)
-    assert np.array_equal(outs[0][0], outs[1][0]), "streamed batches disagree on the key-point counts"
+    assert np.array_equal(houts[0][0], houts[1][0]), "streamed batches disagree on the key-point counts"
     for b in range(B):
-        nb_ = int(outs[0][0][b])
-        assert np.array_equal(outs[0][2][b, :nb_], outs[1][2][b, :nb_]) and outs[0][1][b, :nb_].tobytes() == outs[1][1][b, :nb_].tobytes()
+        nb_ = int(houts[0][0][b])
+        assert np.array_equal(houts[0][2][b, :nb_], houts[1][2][b, :nb_]) and houts[0][1][b, :nb_].tobytes() == houts[1][1][b, :nb_].tobytes()
+
+    # (c) what the host can feed: every rank uploads its pinned batch back to back at the same time (nothing else running).  The e2e
+    # path can not exceed this many frames/s however fast the kernels are: it shows whether a multi-GPU e2e figure is host-bound.
+    up_dst = torch.empty_like(d_frames)
+    for _ in range(2):
+        up_dst.copy_(host_frames, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(K, 10)):
+        up_dst.copy_(host_frames, non_blocking=True)
+    barrier()
+    h2d_sec = max_over_ranks(time.perf_counter() - t0)
+    h2d_gbs = world * max(K, 10) * B * H * W / h2d_sec / 1e9
+    h2d_ceiling = h2d_gbs * 1e9 / (H * W)
+    del up_dst
     sampler.stop_flag = True; sampler.join(timeout=2)
 
-    # ---- all-pairs Hamming (BASELINE config 4: 20 key frames x 2000 descriptors = 40k x 40k), device resident
+    # ---------------------------------------------------------------- all-pairs Hamming (BASELINE config 4: 40k x 40k), device resident
     nq = 40000
     g = torch.Generator(device="cpu"); g.manual_seed(7 + rank)
     descs = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, generator=g).to(dev)
+    train = descs[torch.randperm(nq, generator=g).to(dev)].contiguous()   # a shuffled copy: every query has one exact match somewhere else
     bi = torch.zeros(nq, dtype=torch.int32, device=dev); bd = torch.zeros_like(bi); sd = torch.zeros_like(bi)
     mt = ORBMatcher(0.6, False, handle=ex._h)
 
-    def time_allpairs():
-        for _ in range(2):
-            mt.hamming_allpairs_device(descs, nq, descs, nq, bi, bd, sd, stream=stream, sync=False)
-        torch.cuda.synchronize()
-        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps_m = 5
-        m0.record()
-        for _ in range(reps_m):
-            mt.hamming_allpairs_device(descs, nq, descs, nq, bi, bd, sd, stream=stream, sync=False)
-        m1.record()
-        torch.cuda.synchronize()
-        return m0.elapsed_time(m1) / reps_m, (bi.clone(), bd.clone(), sd.clone())
+    def time_allpairs(kernel):
+        os.environ["ORBFE_ALLPAIRS"] = kernel
+        try:
+            l0 = ex.launch_count()
+            for _ in range(2):
+                mt.hamming_allpairs_device(descs, nq, train, nq, bi, bd, sd, stream=stream, sync=False)
+            per_call = (ex.launch_count() - l0) // 2
+            torch.cuda.synchronize()
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps_m = 5
+            m0.record()
+            for _ in range(reps_m):
+                mt.hamming_allpairs_device(descs, nq, train, nq, bi, bd, sd, stream=stream, sync=False)
+            m1.record()
+            torch.cuda.synchronize()
+            return m0.elapsed_time(m1) / reps_m, (bi.clone(), bd.clone(), sd.clone()), per_call
+        finally:
+            del os.environ["ORBFE_ALLPAIRS"]
 
-    # the int8 tensor-core formulation (default for problems of this size), then the popc kernel on the same inputs
-    ms_match, res_tc = time_allpairs()
-    gmatch = nq * nq / (ms_match * 1e-3) / 1e9
-    os.environ["ORBFE_ALLPAIRS_POPC"] = "1"
-    ms_popc, res_popc = time_allpairs()
-    del os.environ["ORBFE_ALLPAIRS_POPC"]
-    gmatch_popc = nq * nq / (ms_popc * 1e-3) / 1e9
-    assert all(torch.equal(a, b) for a, b in zip(res_tc, res_popc)), "tensor-core and popc all-pairs disagree"
-    imma_peak = mt.imma_peak()            # measured 10^9 pairs/s of the mma.sync int8 instruction
+    ms_match, res_tc, match_launches = time_allpairs("tc")                 # tcgen05 (the default for problems of this size)
+    ms_imma, res_imma, _ = time_allpairs("imma")                           # round 1's warp-level mma.sync kernel
+    ms_popc, res_popc, _ = time_allpairs("popc")
+    gmatch, gmatch_imma, gmatch_popc = (nq * nq / (m * 1e-3) / 1e9 for m in (ms_match, ms_imma, ms_popc))
+    assert all(torch.equal(a, b) for a, b in zip(res_tc, res_popc)) and all(torch.equal(a, b) for a, b in zip(res_imma, res_popc)), "all-pairs kernels disagree"
+    assert int((res_tc[1] == 0).sum()) == nq                               # every row found its shuffled copy
     popc_peak = mt.popc_peak()            # measured 10^9 popc/s; one match = 8 popc
 
-    # ---- single-frame latency through the reference-shaped call (ORBExtractor::operator(), host image in, host vectors out)
+    # ---------------------------------------------------------------- single-frame latency through the reference-shaped call
     one = base[0]
     ex1 = ORBExtractor(device=local, max_batch=1, **ORB)
     for _ in range(5):
@@ -374,25 +534,55 @@ def run_ours(args):
         ex1(one)
     ms_single = (time.perf_counter() - t0) * 1e3 / 100
 
-    # ---- SearchForInitialization on a frame pair of the workload (window 100, ratio 0.9), GPU call vs the CPU restatement
-    init = None
+    # ---------------------------------------------------------------- matcher calls of the tracking loop on a frame pair of the workload
+    init = track = None
     if rank == 0:
-        from monoorbslam3_b200 import FrameView
+        from monoorbslam3_b200 import FrameView, DeviceFrame
         fa_, fb_ = synth.shifted_pair(H, W, 1000)
         ex2 = ORBExtractor(device=local, max_batch=1, **dict(ORB, nFeatures=2 * NF))       # the initial extractor uses 2 x nFeatures (Tracking.cpp:24)
         ka, da = ex2(fa_); kb, db = ex2(fb_)
-        f1, f2 = FrameView(ka, da, W, H), FrameView(kb, db, W, H)
+        hf1, hf2 = FrameView(ka, da, W, H), FrameView(kb, db, W, H)
+        df1, df2 = DeviceFrame.upload(ka, da, W, H, handle=ex2._h), DeviceFrame.upload(kb, db, W, H, handle=ex2._h)
         mi = ORBMatcher(0.9, True, handle=ex2._h)
         pre0 = np.stack([ka["x"], ka["y"]], 1).astype(np.float32)
-        for _ in range(3):
-            mi.SearchForInitialization(f1, f2, pre0.copy(), 100)
-        t0 = time.perf_counter()
-        for _ in range(20):
-            n_init, _ = mi.SearchForInitialization(f1, f2, pre0.copy(), 100)
-        ms_init = (time.perf_counter() - t0) * 1e3 / 20
-        init = {"matches": int(n_init), "gpu_ms_per_call": ms_init, "queries": int((ka["octave"] == 0).sum())}
 
-    # ---- the other single-GPU BASELINE configs, frames resident in HBM (reported next to the headline, not the headline)
+        def _ms(f, reps):
+            for _ in range(3):
+                f()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                r = f()
+            return (time.perf_counter() - t0) * 1e3 / reps, r
+        g_i, (n_init, _) = _ms(lambda: mi.SearchForInitialization(df1, df2, pre0.copy(), 100), 50)
+        g_ih, (n_init_h, _) = _ms(lambda: mi.SearchForInitialization(hf1, hf2, pre0.copy(), 100), 20)
+        assert n_init == n_init_h
+        init = {"matches": int(n_init), "queries": int((ka["octave"] == 0).sum()), "gpu_ms_per_call": g_i, "gpu_ms_per_call_host_arrays": g_ih,
+                "api": "orbfe_search_for_initialization_f on device-resident frames (orbfe_frame); _host_arrays = orbfe_search_for_initialization, "
+                       "which uploads both frames and builds the grid on every call"}
+        rng = np.random.default_rng(0)
+        nqk = len(ka)
+        q_u = (ka["x"] - 7 + rng.normal(0, 1.0, nqk)).astype(np.float32); q_v = (ka["y"] - 3 + rng.normal(0, 1.0, nqk)).astype(np.float32)
+        q_l = ka["octave"].astype(np.int32); q_a = ka["angle"].astype(np.float32); q_ok = (rng.random(nqk) < 0.9).astype(np.uint8)
+        occ = np.zeros(len(kb), np.uint8)
+        sfac = np.array([ex2.getScaleFactor(int(l)) for l in q_l], np.float32)
+        r_proj = (np.float32(15) * ka["size"]).astype(np.float32); r_loc = (np.float32(2) * np.float32(4.0) * sfac).astype(np.float32)
+        mt1 = ORBMatcher(0.9, True, handle=ex2._h); mt2 = ORBMatcher(0.8, True, handle=ex2._h)
+        g1, (n1_, _) = _ms(lambda: mt1.SearchByProjection(q_u, q_v, r_proj, q_l, q_a, da, q_ok, df2, occ), 50)
+        g1h, (n1h, _) = _ms(lambda: mt1.SearchByProjection(q_u, q_v, r_proj, q_l, q_a, da, q_ok, hf2, occ), 20)
+        g2, (n2_, _) = _ms(lambda: mt2.SearchLocalPoints(q_u, q_v, r_loc, q_l, da, q_ok, df2, occ), 50)
+        g2h, (n2h, _) = _ms(lambda: mt2.SearchLocalPoints(q_u, q_v, r_loc, q_l, da, q_ok, hf2, occ), 20)
+        assert n1_ == n1h and n2_ == n2h
+        track = {"queries": int(nqk),
+                 "search_by_projection_th15": {"gpu_ms_per_call": g1, "gpu_ms_per_call_host_arrays": g1h, "matches": int(n1_)},
+                 "search_local_points_th2": {"gpu_ms_per_call": g2, "gpu_ms_per_call_host_arrays": g2h, "matches": int(n2_)}}
+        if world == 1 and not args.no_cpu:
+            from oracle import orb_oracle as orc
+            c1, (cn1, _) = _ms(lambda: orc.search_by_projection(q_u, q_v, r_proj, q_l, q_a, da, q_ok, kb, db, W, H, occ, True), 5)
+            c2, (cn2, _) = _ms(lambda: orc.search_local_points(q_u, q_v, r_loc, q_l, da, q_ok, kb, db, W, H, occ, 0.8), 5)
+            track["search_by_projection_th15"].update(cpu_port_ms_per_call=c1, cpu_matches=int(cn1))
+            track["search_local_points_th2"].update(cpu_port_ms_per_call=c2, cpu_matches=int(cn2))
+
+    # ---------------------------------------------------------------- the other single-GPU BASELINE configs, frames resident in HBM
     other = None
     if rank == 0:
         other = {}
@@ -414,36 +604,14 @@ def run_ours(args):
             oms = o0.elapsed_time(o1) / 5
             other[name] = {"frames_per_s": ob / oms * 1e3, "ms_per_pass": oms, "frames_per_pass": ob, "mean_keypoints_per_frame": float(on_.float().mean().item())}
             oex.close(); del ob_frames, okps, odesc, on_
+    ex1.close()
+    del d_frames, host_frames, descs, train
+    torch.cuda.empty_cache()
 
-    # ---- tracking-loop matchers on the same frame pair: SearchByProjection (frame -> frame, th 15) and the local-map search (th 2)
-    track = None
-    if rank == 0:
-        rng = np.random.default_rng(0)
-        nq = len(ka)
-        q_u = (ka["x"] - 7 + rng.normal(0, 1.0, nq)).astype(np.float32); q_v = (ka["y"] - 3 + rng.normal(0, 1.0, nq)).astype(np.float32)
-        q_l = ka["octave"].astype(np.int32); q_a = ka["angle"].astype(np.float32); q_ok = (rng.random(nq) < 0.9).astype(np.uint8)
-        occ = np.zeros(len(kb), np.uint8)
-        sfac = np.array([ex2.getScaleFactor(int(l)) for l in q_l], np.float32)
-        r_proj = (np.float32(15) * ka["size"]).astype(np.float32); r_loc = (np.float32(2) * np.float32(4.0) * sfac).astype(np.float32)
-        mt1 = ORBMatcher(0.9, True, handle=ex2._h); mt2 = ORBMatcher(0.8, True, handle=ex2._h)
-
-        def _ms(f, reps):
-            for _ in range(3):
-                f()
-            t0 = time.perf_counter()
-            for _ in range(reps):
-                r = f()
-            return (time.perf_counter() - t0) * 1e3 / reps, r
-        g1, (n1_, _) = _ms(lambda: mt1.SearchByProjection(q_u, q_v, r_proj, q_l, q_a, da, q_ok, f2, occ), 20)
-        g2, (n2_, _) = _ms(lambda: mt2.SearchLocalPoints(q_u, q_v, r_loc, q_l, da, q_ok, f2, occ), 20)
-        track = {"queries": int(nq), "search_by_projection_th15": {"gpu_ms_per_call": g1, "matches": int(n1_)},
-                 "search_local_points_th2": {"gpu_ms_per_call": g2, "matches": int(n2_)}}
-        if world == 1 and not args.no_cpu:
-            from oracle import orb_oracle as orc
-            c1, (cn1, _) = _ms(lambda: orc.search_by_projection(q_u, q_v, r_proj, q_l, q_a, da, q_ok, kb, db, W, H, occ, True), 5)
-            c2, (cn2, _) = _ms(lambda: orc.search_local_points(q_u, q_v, r_loc, q_l, da, q_ok, kb, db, W, H, occ, 0.8), 5)
-            track["search_by_projection_th15"].update(cpu_port_ms_per_call=c1, cpu_matches=int(cn1))
-            track["search_local_points_th2"].update(cpu_port_ms_per_call=c2, cpu_matches=int(cn2))
+    # ---------------------------------------------------------------- BASELINE config 5 (strong scaling)
+    c5 = None
+    if not args.no_c5:
+        c5 = run_c5(args, torch, dist, dev, local, rank, world, tstream, barrier, max_over_ranks, peer_buffers)
 
     if rank == 0:
         peaks = {}
@@ -452,6 +620,9 @@ def run_ours(args):
         except Exception:
             pass
         peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+        bf16_tf, bf16_src = (peaks["bf16_tflops"], "measured (MEASURED_PEAKS.json, burst)") if "bf16_tflops" in peaks else (1590.0, "fallback (B200_PROFILING.md)")
+        # dense int8 runs at twice the bf16 rate on the tensor cores (4.5 vs 2.25 POP/s nominal); one 256-bit match = 256 MACs = 512 ops
+        i8_peak_gmatch = 2.0 * bf16_tf * 1e12 / 512 / 1e9
         ab = algorithmic_bytes(W, H, n_kp_mean)
         per_launch_ms = {k: v / max(passes, 1) for k, v in stage_ms.items()}
         hbm_stages = ("pyramid", "fast", "blur")
@@ -462,13 +633,15 @@ def run_ours(args):
                         for k in stage_ms}
         traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
         issue = None            # why the HBM fraction is low: the stage kernels are bound by instruction issue, not by bytes
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if tj.get("batch") == B:
+        for prof in ("r02_traffic.json", "r01_traffic.json"):
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", prof)))
+                if tj.get("batch") != B:
+                    continue
                 traffic = tj["stages"][dom]["dram_read_bytes"] + tj["stages"][dom]["dram_write_bytes"]
                 clk = (sampler.summary().get("sm_mhz") or 1965.0) * 1e6
                 slots_per_s = 148 * 4 * clk                       # warp instructions the SM sub-partitions can issue per second
-                issue = {}
+                issue = {"source": "profiles/" + prof}
                 for k, d in tj["stages"].items():
                     if "warp_instructions" not in d or per_launch_ms.get(k, 0) <= 0:
                         continue
@@ -477,17 +650,22 @@ def run_ours(args):
                                 "issue_frac": floor_ms / per_launch_ms[k], "ncu_issue_active_pct": d.get("issue_active_pct"),
                                 "ncu_alu_pipe_pct": d.get("alu_pipe_pct"),
                                 "thread_instructions_per_pixel": (d["warp_instructions"] * 32 / (ab["fast"] * B)) if k in ("fast", "blur") else None}
-        except Exception:
-            pass
+                break
+            except Exception:
+                pass
         line = {
-            "metric": "ORB extract+describe frames/s (752x480, 1000 kp)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "distinct_scenes": distinct, "sharding": "frames by rank, NCCL all_gather of result slabs on a side stream (double-buffered, inside the timed region)" if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2 (%.0f MB of frames per step)" % (B * H * W / 1e6), "mean_keypoints_per_frame": n_kp_mean},
+            "config": make_config(B, distinct),
+            "how": {"sharding": "frames by rank (weak scaling: %d frames per rank per step)" % B if world > 1 else "single GPU",
+                    "results_on_rank0": gather_mode, "mean_keypoints_per_frame": n_kp_mean, "scene_seeds_other_ranks": "1000 + 100000 * rank + k"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * H * W, "d2h_bytes_per_step": B * (4 + cap * 60),
                     "api": "orbfe_extract_batch_submit / _wait (host C-ABI, pinned host buffers, two batches in flight)",
-                    "sync_call_value": e2e_sync, "sync_call_api": "orbfe_extract_batch, one blocking call per step"},
+                    "sync_call_value": e2e_sync, "sync_call_api": "orbfe_extract_batch, one blocking call per step",
+                    "h2d_ceiling": {"frames_per_s": h2d_ceiling, "GBps": h2d_gbs, "frac": e2e / h2d_ceiling,
+                                    "what": "all %d rank(s) uploading their pinned %d-frame batch at the same time, nothing else running: "
+                                            "the most frames/s the host can feed; frac = e2e.value / that" % (world, B)}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab[dom] * B,
@@ -495,14 +673,19 @@ def run_ours(args):
             "stages": stage_report, "ms_per_step_serialised_with_stage_events": ms_prof / K,
             "issue_roofline": {"note": "warp instructions per step (committed ncu capture) / (148 SMs x 4 schedulers x SM clock): the time the stage would "
                                        "take at one instruction per scheduler per cycle; issue_frac = that / measured stage time", "stages": issue},
-            "match": {"metric": "Hamming GMatch/s (all-pairs 40000 x 40000, best/second-best)", "value": gmatch, "unit": "GMatch/s", "ms": ms_match,
-                      "kernel": "k_allpairs_imma: +-1 int8 GEMM on the tensor cores (mma.sync m16n8k32), hamming = (256 - dot) / 2, fused (min, second-min) epilogue; identical results to the popc kernel (checked in this run)",
-                      "roofline": {"bound": "tensor (int8 IMMA via mma.sync)", "achieved": gmatch, "peak": imma_peak, "unit": "GMatch/s", "frac": gmatch / imma_peak,
-                                   "peak_source": "measured IMMA micro-benchmark (orbfe_imma_peak), 256 int8 multiply-adds per match"},
+            "match": {"metric": "Hamming GMatch/s (all-pairs 40000 x 40000, best/second-best; the train table is a shuffled copy of the queries)",
+                      "value": gmatch, "unit": "GMatch/s", "ms": ms_match, "gpu_launches_per_call": int(match_launches),
+                      "kernel": "k_allpairs_tc: +-1 int8 GEMM on tcgen05 (tcgen05.mma kind::i8, TMA-staged 128-byte-swizzled operands, accumulators in TMEM, "
+                                "(min, second-min) epilogue from tcgen05.ld on packed 16-bit keys); hamming = (256 - dot) / 2; identical to the mma.sync "
+                                "and popc kernels (checked in this run) and to the oracle (tests)",
+                      "roofline": {"bound": "tensor", "achieved": gmatch, "peak": i8_peak_gmatch, "unit": "GMatch/s", "frac": gmatch / i8_peak_gmatch,
+                                   "peak_source": "2 x the bf16 GEMM peak (%s: %.1f TFLOP/s) = dense int8 rate, / 512 ops per 256-bit pair" % (bf16_src, bf16_tf)},
+                      "imma_kernel": {"value": gmatch_imma, "unit": "GMatch/s", "ms": ms_imma, "what": "round 1's k_allpairs_imma (mma.sync m16n8k32.s8), ORBFE_ALLPAIRS=imma"},
                       "popc_kernel": {"value": gmatch_popc, "unit": "GMatch/s", "ms": ms_popc,
                                       "roofline": {"bound": "integer pipe (popc)", "achieved": gmatch_popc, "peak": popc_peak / 8, "unit": "GMatch/s",
                                                    "frac": gmatch_popc / (popc_peak / 8),
                                                    "peak_source": "measured popc micro-benchmark (orbfe_popc_peak), 8 popc per 256-bit match"}}},
+            "c5": c5,
             "single_frame": {"ms_per_call": ms_single, "frames_per_s": 1e3 / ms_single, "api": "ORBExtractor.__call__ -> orbfe_extract (host image in, host key points out)"},
             "search_for_initialization": init,
             "tracking_matchers": track,
@@ -510,8 +693,7 @@ def run_ours(args):
             "clocks": sampler.summary(),
         }
         if world == 1 and not args.no_cpu:
-            fps, kind, sample, used = cpu_reference_fps(base, host_cores(), min_seconds=args.ref_seconds)
-            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": used, "kind": kind, "sample": sample}
+            line["cpu_baseline"] = cpu_baseline_record(base, args.ref_seconds)
             line["match"]["cpu_baseline"] = cpu_hamming_gmatch(host_cores())
             if init is not None:
                 from oracle import orb_oracle as orc
@@ -526,6 +708,100 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_c5(args, torch, dist, dev, local, rank, world, tstream, barrier, max_over_ranks, peer_buffers):
+    """BASELINE config 5, STRONG scaling: F synthetic 1920x1080 frames (phone.yaml shape, 4000 features) extracted and every key point
+    matched against the other key frames of its window of 20 (orbfe_hamming_allpairs_slab_device: straight from the extractor's slabs,
+    own key frame excluded).  A rank owns a contiguous block of windows, so extraction and matching need no data-path collective; the
+    match results (best slab row, best and second-best distance per descriptor row) land on rank 0 — peer-stored by the merge kernel
+    or gathered with NCCL send / recv at the end.  The whole step runs on one stream without a host synchronisation."""
+    from monoorbslam3_b200 import ORBExtractor, ORBMatcher, synth, sharding
+    F, Hc, Wc, NFc, WIN, PASS = args.c5_frames, 1080, 1920, 4000, 20, 128
+    n_win = (F + WIN - 1) // WIN
+    w_lo, w_hi = sharding.shard_range(n_win, rank, world)
+    f_lo, f_hi = w_lo * WIN, min(w_hi * WIN, F)
+    nb = f_hi - f_lo
+    cap = NFc + 128
+    base = synth.frames(8, Hc, Wc, 1000 + 100 * rank, "dense")                  # 8 distinct scenes per rank, repeated
+    frames = torch.from_numpy(base).to(dev)[torch.arange(max(nb, 1), device=dev) % 8].contiguous()
+    ex = ORBExtractor(NFc, 1.2, 8, 20, 7, device=local, max_batch=PASS)
+    mt = ORBMatcher(handle=ex._h)
+    kps = torch.zeros((max(nb, 1), cap, 7), dtype=torch.float32, device=dev); desc = torch.zeros((max(nb, 1), cap, 32), dtype=torch.uint8, device=dev)
+    n = torch.zeros(max(nb, 1), dtype=torch.int32, device=dev)
+    rows_total = F * cap
+    peers = peer_buffers(3 * rows_total * 4, 1)
+    if peers:
+        root0 = peers[0][0]
+        res = tuple(root0 + a * rows_total * 4 + f_lo * cap * 4 for a in range(3))       # this rank's rows inside rank 0's three arrays
+        res_t = None
+    else:
+        res_t = tuple(torch.zeros(max(nb, 1) * cap, dtype=torch.int32, device=dev) for _ in range(3))
+        res = tuple(t.data_ptr() for t in res_t)
+        root_t = tuple(torch.zeros(rows_total, dtype=torch.int32, device=dev) for _ in range(3)) if (rank == 0 and world > 1) else None
+    stream = tstream.cuda_stream
+
+    def run():
+        if nb:
+            ex.extract_batch_device(frames, nb, Hc, Wc, kps, desc, cap, n, stream=stream, sync=False)
+        for wi in range(w_hi - w_lo):
+            lo = wi * WIN; hi = min(lo + WIN, nb)
+            o = lo * cap * 4
+            mt.hamming_allpairs_slab_device(desc[lo:hi], n[lo:hi], hi - lo, cap, res[0] + o, res[1] + o, res[2] + o, stream=stream, sync=False)
+        if world > 1 and not peers:                                             # results to rank 0 in window order
+            if rank == 0:
+                ops = []
+                for p in range(1, world):
+                    plo, phi = sharding.shard_range(n_win, p, world)
+                    a, b = plo * WIN * cap, min(phi * WIN, F) * cap
+                    ops += [dist.P2POp(dist.irecv, root_t[k][a:b], p) for k in range(3) if b > a]
+                for k in range(3):
+                    root_t[k][:nb * cap].copy_(res_t[k][:nb * cap], non_blocking=True)
+            else:
+                ops = [dist.P2POp(dist.isend, res_t[k][:nb * cap], 0) for k in range(3)] if nb else []
+            for w_ in (dist.batch_isend_irecv(ops) if ops else []):
+                w_.wait()
+
+    l0 = ex.launch_count()
+    run()
+    launches = ex.launch_count() - l0
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(1, args.c5_steps)
+    e0.record()
+    for _ in range(steps):
+        run()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+    counts = n[:nb].long() if nb else torch.zeros(0, dtype=torch.long, device=dev)
+    pairs = 0.0
+    for wi in range(w_hi - w_lo):
+        c = counts[wi * WIN:min(wi * WIN + WIN, nb)]
+        pairs += float(c.sum()) ** 2 - float((c * c).sum())                      # every key point against the other key frames of its window
+    stat = torch.tensor([pairs, float(nb), float(counts.sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stat)
+    # a look at the result: with 8 repeated scenes per rank every key point has an exact twin in another key frame of its window
+    bd_first = None
+    if nb:
+        if peers:
+            src = peers[0][1][2] if rank != 0 else peers[0][1][0]
+            off = (rows_total + f_lo * cap) * 4
+            bd_first = src[off:off + cap * 4].view(torch.int32)[:int(n[0])]
+        else:
+            bd_first = res_t[1][:int(n[0])]
+        assert int((bd_first == 0).sum()) == int(n[0]), "C5 matching did not find the repeated scenes"
+    ex.close()
+    if rank != 0:
+        return None
+    return {"workload": "C5: %d frames 1920x1080 / 4000 features, every key point matched against the other key frames of its %d-key-frame window" % (F, WIN),
+            "n_gpus": world, "scaling": "strong", "ms_per_step": ms, "steps": steps, "frames_per_s": F / ms * 1e3, "gmatch_per_s": float(stat[0]) / ms / 1e6,
+            "descriptor_pairs": float(stat[0]), "mean_keypoints_per_frame": float(stat[2]) / max(float(stat[1]), 1), "gpu_launches_per_step": int(launches),
+            "sharding": "contiguous blocks of key-frame windows per rank, no data-path collective",
+            "results_on_rank0": ("peer-store: the all-pairs merge kernel writes into rank 0's peer-mapped arrays over NVLink" if peers else
+                                 "NCCL send/recv gather at the end of the step") if world > 1 else "single GPU",
+            "host_syncs_inside_step": 0, "frames_resident": True}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -534,7 +810,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU")
     ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic scenes per rank (repeated to fill the batch)")
-    ap.add_argument("--ref-seconds", type=float, default=10.0, help="CPU work per reference step / cpu_baseline sample")
+    ap.add_argument("--ref-seconds", type=float, default=7.0, help="all-cores CPU work per reference step / cpu_baseline sample (plus about 2 s at one thread)")
+    ap.add_argument("--c5-frames", type=int, default=4096)
+    ap.add_argument("--c5-steps", type=int, default=2)
+    ap.add_argument("--no-c5", action="store_true")
+    ap.add_argument("--no-peer-store", action="store_true", help="gather the result slabs with NCCL instead of writing them into rank 0's peer-mapped buffer")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -490,7 +490,7 @@ struct OctArgs {
 struct NodeBounds { short x0, x1, y0, y1; };
 
 template <int NT>
-__global__ void __launch_bounds__(NT) k_octree(const __grid_constant__ LevelSet L, const OctArgs a) {
+__global__ void __launch_bounds__(NT, 2048 / NT) k_octree(const __grid_constant__ LevelSet L, const OctArgs a) {
     extern __shared__ __align__(16) uint8_t dyn[];
     __shared__ int s_warp[NT / 32];
     __shared__ int s_bcast[4];
@@ -511,18 +511,19 @@ __global__ void __launch_bounds__(NT) k_octree(const __grid_constant__ LevelSet 
     // slot counts frames produce in practice) and moves to the level's global pool — sized by the proven bound, see configure() —
     // the first time a pass would not fit, so a valid image can never exhaust it.
     unsigned long long *skey = reinterpret_cast<unsigned long long *>(dyn);
-    uint8_t *gpool = a.nodes + ((size_t) frame * a.nodes_per_frame + G.node_off) * 16;
+    // The pool is one base pointer and its capacity: [bounds 8 B x cap][count 4 B x cap][first child 4 B x cap]
     int cap_cur = min(a.smem_node_cap, G.node_cap);
     uint8_t *pool = dyn + (size_t) a.sort_cap * 8;
-    NodeBounds *nbnd = reinterpret_cast<NodeBounds *>(pool);
-    int *ncnt = reinterpret_cast<int *>(pool + (size_t) cap_cur * 8);
-    int *nchild = ncnt + cap_cur;
+#define nbnd (reinterpret_cast<NodeBounds *>(pool))
+#define ncnt (reinterpret_cast<int *>(pool + (size_t) cap_cur * 8))
+#define nchild (reinterpret_cast<int *>(pool + (size_t) cap_cur * 12))
     auto use_global_pool = [&](int n_live) {            // block-uniform; copies the n_live slots in use
+        uint8_t *gpool = a.nodes + ((size_t) frame * a.nodes_per_frame + G.node_off) * 16;
         NodeBounds *gb = reinterpret_cast<NodeBounds *>(gpool);
         int *gc = reinterpret_cast<int *>(gpool + (size_t) G.node_cap * 8), *gch = gc + G.node_cap;
         for (int j = tid; j < n_live; j += NT) { gb[j] = nbnd[j]; gc[j] = ncnt[j]; gch[j] = nchild[j]; }
         __syncthreads();
-        nbnd = gb; ncnt = gc; nchild = gch; cap_cur = G.node_cap;
+        pool = gpool; cap_cur = G.node_cap;
     };
 
     // ---- 1. candidates of this level in reference order: exclusive scan of the per-cell counts, then gather
@@ -758,6 +759,9 @@ __global__ void __launch_bounds__(NT) k_octree(const __grid_constant__ LevelSet 
         kp_out[j] = ((v & 0xfffu) + kEdge) | ((((v >> 12) & 0xfffu) + kEdge) << 12) | (v & 0xff000000u);   // :625-632
     }
     if (tid == 0) a.nkp[frame * ORBFE_MAX_LEVELS + l] = len;
+#undef nbnd
+#undef ncnt
+#undef nchild
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,3 +1,5 @@
+#define _POSIX_C_SOURCE 200809L      /* clock_gettime (stage timers of orc_extract) under -std=c99 */
+#include <time.h>
 /*
  * orb_oracle.c — CPU oracle (plain C99) for the ORB front-end hot path.  TEST INFRASTRUCTURE ONLY:
  * see the header of orb_oracle.h for who may call this and how parity is pinned.
@@ -500,9 +502,19 @@ void orc_brief_descriptor(const uint8_t *blurred, size_t stride, int x, int y, f
  * operator() — ORBExtractor.cpp:495-547 with ComputePyramid :559-570 and
  * ComputeKeyPointsOctTree :572-638
  * ------------------------------------------------------------------------------------------ */
+/* Wall-clock split of the last orc_extract call on this thread: [0] pyramid (resize), [1] FAST per cell, [2] Gaussian blur,
+ * [3] everything else (quadtree, orientation, descriptors, copies).  bench.py's cv2 composite uses [3] as the part of a frame that
+ * OpenCV's SIMD primitives do not speed up. */
+static __thread double g_stage_ms[4];
+static double now_ms(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; }
+void orc_last_stage_ms(double out[4]) { for (int i = 0; i < 4; ++i) out[i] = g_stage_ms[i]; }
+
 int orc_extract(orc_extractor *ex, const uint8_t *img, int w, int h, size_t stride,
                 orc_keypoint *kps, uint8_t *desc, int cap) {
     if (!img || w <= 0 || h <= 0) return 0;                                          /* :497 */
+    const double t_begin = now_ms();
+    double t_pyr = 0, t_fast = 0, t_blur = 0, t0;
+    g_stage_ms[0] = g_stage_ms[1] = g_stage_ms[2] = g_stage_ms[3] = 0;
     free_stage(ex);
     const int nl = ex->n_levels;
     /* pyramid: level l is resized from level l-1 to a size derived from the ORIGINAL size (:563-565) */
@@ -511,7 +523,7 @@ int orc_extract(orc_extractor *ex, const uint8_t *img, int w, int h, size_t stri
         else { ex->lw[l] = orc_roundf((float) w * ex->inv_scale[l]); ex->lh[l] = orc_roundf((float) h * ex->inv_scale[l]); }
         ex->img[l] = (uint8_t *) malloc((size_t) ex->lw[l] * (size_t) ex->lh[l]);
         if (l == 0) for (int y = 0; y < h; ++y) memcpy(ex->img[0] + (size_t) y * w, img + (size_t) y * stride, (size_t) w);
-        else orc_resize_linear_u8(ex->img[l - 1], ex->lw[l - 1], ex->lh[l - 1], (size_t) ex->lw[l - 1], ex->img[l], ex->lw[l], ex->lh[l], (size_t) ex->lw[l]);
+        else { t0 = now_ms(); orc_resize_linear_u8(ex->img[l - 1], ex->lw[l - 1], ex->lh[l - 1], (size_t) ex->lw[l - 1], ex->img[l], ex->lw[l], ex->lh[l], (size_t) ex->lw[l]); t_pyr += now_ms() - t0; }
     }
     int total = 0;
     for (int l = 0; l < nl; ++l) {
@@ -524,6 +536,7 @@ int orc_extract(orc_extractor *ex, const uint8_t *img, int w, int h, size_t stri
         int cap_c = 1024, n_c = 0;
         orc_corner *cand = (orc_corner *) malloc(sizeof(orc_corner) * (size_t) cap_c);
         orc_corner cell[36 * 36];
+        t0 = now_ms();
         for (int i = 0; i < n_rows; ++i) {
             const int ini_y = min_by + i * ORC_CELL, max_y = ini_y + ORC_CELL < max_by ? ini_y + ORC_CELL : max_by;
             for (int j = 0; j < n_cols; ++j) {
@@ -540,6 +553,7 @@ int orc_extract(orc_extractor *ex, const uint8_t *img, int w, int h, size_t stri
                 }
             }
         }
+        t_fast += now_ms() - t0;
         ex->cand[l] = cand; ex->n_cand[l] = n_c;
         int *sel = (int *) malloc(sizeof(int) * (size_t) (n_c > 0 ? n_c : 1));
         const int n_sel = n_c ? orc_distribute_octree(cand, n_c, min_bx, max_bx, min_by, max_by, ex->quota[l], sel, n_c) : 0;  /* :622 */
@@ -560,6 +574,7 @@ int orc_extract(orc_extractor *ex, const uint8_t *img, int w, int h, size_t stri
     for (int l = 0; l < nl; ++l)                                                                        /* :636-637 */
         for (int k = 0; k < ex->n_kp[l]; ++k)
             ex->kp[l][k].angle = ic_angle_umax(ex->img[l], (size_t) ex->lw[l], orc_roundf(ex->kp[l][k].x), orc_roundf(ex->kp[l][k].y), ex->u_max);
+    g_stage_ms[0] = t_pyr; g_stage_ms[1] = t_fast; g_stage_ms[3] = now_ms() - t_begin - t_pyr - t_fast;
     if (total == 0) return 0;                                                                           /* :512 */
     if (total > cap) return -1;
     int off = 0;
@@ -567,7 +582,7 @@ int orc_extract(orc_extractor *ex, const uint8_t *img, int w, int h, size_t stri
         if (ex->n_kp[l] == 0) continue;
         const int lw = ex->lw[l], lh = ex->lh[l];
         ex->blur[l] = (uint8_t *) malloc((size_t) lw * (size_t) lh);
-        orc_gaussian_blur7_u8(ex->img[l], lw, lh, (size_t) lw, ex->blur[l], (size_t) lw);
+        t0 = now_ms(); orc_gaussian_blur7_u8(ex->img[l], lw, lh, (size_t) lw, ex->blur[l], (size_t) lw); t_blur += now_ms() - t0;
         for (int k = 0; k < ex->n_kp[l]; ++k) {
             orc_keypoint kp = ex->kp[l][k];
             orc_brief_descriptor(ex->blur[l], (size_t) lw, orc_roundf(kp.x), orc_roundf(kp.y), kp.angle, desc + (size_t) (off + k) * 32);
@@ -576,6 +591,7 @@ int orc_extract(orc_extractor *ex, const uint8_t *img, int w, int h, size_t stri
         }
         off += ex->n_kp[l];
     }
+    g_stage_ms[2] = t_blur; g_stage_ms[3] = now_ms() - t_begin - t_pyr - t_fast - t_blur;
     return total;
 }
 

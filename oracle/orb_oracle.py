@@ -147,6 +147,12 @@ class Extractor:
         assert n >= 0, "oracle capacity"
         return kps[:n].copy(), desc[:n].copy()
 
+    def last_stage_ms(self):
+        """Wall-clock split of the last call on this thread: (pyramid, FAST per cell, blur, everything else) in ms."""
+        out = (C.c_double * 4)()
+        lib().orc_last_stage_ms(out)
+        return tuple(out)
+
     def _img(self, fn, level):
         w, h, st = C.c_int(), C.c_int(), C.c_size_t()
         p = fn(self._h, level, C.byref(w), C.byref(h), C.byref(st))
