@@ -288,7 +288,7 @@ def run_ours(args):
     # gather costs no kernel and no copy.  Fallback: local slabs + NCCL send / recv to rank 0 on a side stream.
     def peer_buffers(nbytes, n_sets):
         """-> list (per set) of (base address of rank 0's buffer as seen from this rank, keep-alive objects), or None."""
-        if world == 1 or args.no_peer_store:
+        if world == 1:
             return None
         try:
             import torch.distributed._symmetric_memory as symm
@@ -322,26 +322,28 @@ def run_ours(args):
 
     n_sets = 2 if world > 1 else 1
     kp_b, ds_b, n_b = B * cap * 28, B * cap * 32, B * 4
-    blk = (kp_b + ds_b + n_b + 255) // 256 * 256                          # one rank's block of a buffer set
-    peers = peer_buffers(world * blk, n_sets)
-    gather_mode = "single GPU" if world == 1 else ("peer-store: k_describe writes each rank's result slabs into rank 0's peer-mapped buffer over NVLink "
-                                                    "(no gather kernel, no copy)" if peers else "NCCL send/recv gather of the result slabs to rank 0 on a side stream, double-buffered")
-    outs = []                                                              # per set: (kps ptr/tensor, desc, n) this rank's extractor writes
-    local_sets = [(torch.zeros((B, cap, 7), dtype=torch.float32, device=dev), torch.zeros((B, cap, 32), dtype=torch.uint8, device=dev),
-                   torch.zeros(B, dtype=torch.int32, device=dev)) for _ in range(n_sets if not peers else 0)]
+    blk = (kp_b + ds_b + n_b + 255) // 256 * 256                          # one rank's block of a buffer set: [key points][descriptors][counts]
+    peers = peer_buffers(world * blk, n_sets) if args.gather != "nccl" else None
+    # peer-store: the extractor's output pointers ARE this rank's block inside rank 0's buffer (k_describe's stores cross NVLink);
+    # peer-copy : the extractor writes a local block, one copy-engine transfer per step moves it into rank 0's buffer on a side stream;
+    # nccl      : local slabs, NCCL send / recv to rank 0 on a side stream
+    mode = "single" if world == 1 else ("nccl" if not peers else args.gather)
+    gather_mode = {"single": "single GPU",
+                   "peer-store": "peer-store: k_describe writes each rank's result slabs into rank 0's peer-mapped buffer over NVLink (no gather kernel, no copy)",
+                   "peer-copy": "peer-copy: one copy-engine transfer per step and rank into rank 0's peer-mapped buffer, on a side stream (no kernel on the SMs)",
+                   "nccl": "NCCL send/recv gather of the result slabs to rank 0 on a side stream, double-buffered"}[mode]
+    outs = []                                                              # per set: (kps, desc, n) addresses / tensors this rank's extractor writes
+    local_blocks = [torch.zeros(blk, dtype=torch.uint8, device=dev) for _ in range(n_sets if mode != "peer-store" else 0)]
     for k in range(n_sets):
-        if peers:
-            b0 = peers[k][0] + rank * blk
-            outs.append((b0, b0 + kp_b, b0 + kp_b + ds_b))
-        else:
-            outs.append(local_sets[k])
+        b0 = peers[k][0] + rank * blk if mode == "peer-store" else local_blocks[k].data_ptr()
+        outs.append((b0, b0 + kp_b, b0 + kp_b + ds_b))
     root_bufs = comm_stream = None
-    if world > 1 and not peers:
+    if mode in ("nccl", "peer-copy"):
         comm_stream = torch.cuda.Stream(device=dev)
         ev_computed = [torch.cuda.Event() for _ in range(n_sets)]
         ev_gathered = [torch.cuda.Event() for _ in range(n_sets)]
-        if rank == 0:
-            root_bufs = [[tuple(torch.empty_like(t) for t in local_sets[k]) for _ in range(world - 1)] for k in range(n_sets)]
+        if mode == "nccl" and rank == 0:
+            root_bufs = [[torch.empty(blk, dtype=torch.uint8, device=dev) for _ in range(world - 1)] for k in range(n_sets)]
     step_no = [0]
 
     def step_device():
@@ -355,12 +357,15 @@ def run_ours(args):
             ev_computed[k].record(tstream)
             with torch.cuda.stream(comm_stream):
                 comm_stream.wait_event(ev_computed[k])
-                if rank == 0:
-                    ops = [dist.P2POp(dist.irecv, t, p + 1) for p in range(world - 1) for t in root_bufs[k][p]]
+                if mode == "peer-copy":
+                    peers[k][1][2][rank * blk:(rank + 1) * blk].copy_(local_blocks[k], non_blocking=True)
                 else:
-                    ops = [dist.P2POp(dist.isend, t, 0) for t in o]
-                for w_ in dist.batch_isend_irecv(ops):
-                    w_.wait()
+                    if rank == 0:
+                        ops = [dist.P2POp(dist.irecv, root_bufs[k][p], p + 1) for p in range(world - 1)]
+                    else:
+                        ops = [dist.P2POp(dist.isend, local_blocks[k], 0)]
+                    for w_ in dist.batch_isend_irecv(ops):
+                        w_.wait()
                 ev_gathered[k].record(comm_stream)
 
     def drain():
@@ -371,8 +376,8 @@ def run_ours(args):
     def read_counts():
         """key-point counts of this rank's last batch (from rank 0's buffer when the slabs are peer-stored there)"""
         k = (step_no[0] - 1) % n_sets
-        if not peers:
-            return outs[k][2].clone()
+        if mode in ("single", "nccl"):
+            return local_blocks[k][kp_b + ds_b:kp_b + ds_b + n_b].view(torch.int32).clone()
         view = torch.empty(B, dtype=torch.int32, device=dev)
         src = peers[k][1][2]                                               # tensor over rank 0's buffer
         off = rank * blk + kp_b + ds_b
@@ -385,7 +390,7 @@ def run_ours(args):
     d_n = read_counts()
     n_kp_mean = float(d_n.float().mean().item())
     assert n_kp_mean > 900, n_kp_mean
-    if peers and world > 1:                                                # rank 0 sees every rank's counts in its own buffer
+    if mode in ("peer-store", "peer-copy"):                                # rank 0 sees every rank's counts in its own buffer
         if rank == 0:
             root_t = peers[(step_no[0] - 1) % n_sets][1][2]
             for r in range(world):
@@ -423,6 +428,13 @@ def run_ours(args):
     ex.profile(False)
     ms_dev = max_over_ranks(ms_dev)
     value = world * B * K / (ms_dev * 1e-3)
+    if args.only_c1:
+        sampler.stop_flag = True
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": ms_dev / K, "n_gpus": world, "results_on_rank0": gather_mode, "clocks": sampler.summary()}), flush=True)
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
 
     # ---------------------------------------------------------------- e2e: host C-ABI, pinned host buffers, H2D + kernels + D2H every step
     h_n = torch.zeros(B, dtype=torch.int32).pin_memory()
@@ -473,19 +485,30 @@ def run_ours(args):
         nb_ = int(houts[0][0][b])
         assert np.array_equal(houts[0][2][b, :nb_], houts[1][2][b, :nb_]) and houts[0][1][b, :nb_].tobytes() == houts[1][1][b, :nb_].tobytes()
 
-    # (c) what the host can feed: every rank uploads its pinned batch back to back at the same time (nothing else running).  The e2e
-    # path can not exceed this many frames/s however fast the kernels are: it shows whether a multi-GPU e2e figure is host-bound.
-    up_dst = torch.empty_like(d_frames)
-    for _ in range(2):
-        up_dst.copy_(host_frames, non_blocking=True)
+    # (c) what the host can move: every rank uploads its pinned batch and downloads a result-sized block back to back at the same time,
+    # on two streams, nothing else running.  The e2e path can not exceed this many frames/s however fast the kernels are: it shows
+    # whether a multi-GPU e2e figure is host-bound.
+    up_dst = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+    dn_src = torch.zeros(B * (4 + cap * 60), dtype=torch.uint8, device=dev)
+    dn_dst = torch.zeros(B * (4 + cap * 60), dtype=torch.uint8).pin_memory()
+    s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    reps_c = max(K, 10)
+
+    def copies(n):
+        for _ in range(n):
+            with torch.cuda.stream(s_up):
+                up_dst.copy_(host_frames, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                dn_dst.copy_(dn_src, non_blocking=True)
+    copies(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(max(K, 10)):
-        up_dst.copy_(host_frames, non_blocking=True)
+    copies(reps_c)
     barrier()
     h2d_sec = max_over_ranks(time.perf_counter() - t0)
-    h2d_gbs = world * max(K, 10) * B * H * W / h2d_sec / 1e9
+    h2d_gbs = world * reps_c * B * H * W / h2d_sec / 1e9
     h2d_ceiling = h2d_gbs * 1e9 / (H * W)
+    del dn_src, dn_dst
     del up_dst
     sampler.stop_flag = True; sampler.join(timeout=2)
 
@@ -664,8 +687,9 @@ def run_ours(args):
                     "api": "orbfe_extract_batch_submit / _wait (host C-ABI, pinned host buffers, two batches in flight)",
                     "sync_call_value": e2e_sync, "sync_call_api": "orbfe_extract_batch, one blocking call per step",
                     "h2d_ceiling": {"frames_per_s": h2d_ceiling, "GBps": h2d_gbs, "frac": e2e / h2d_ceiling,
-                                    "what": "all %d rank(s) uploading their pinned %d-frame batch at the same time, nothing else running: "
-                                            "the most frames/s the host can feed; frac = e2e.value / that" % (world, B)}},
+                                    "what": "all %d rank(s) uploading their pinned %d-frame batch and downloading a result-sized block at the same time "
+                                            "(two streams per rank), nothing else running: the most frames/s the host can move; frac = e2e.value / that; "
+                                            "GBps = the upload direction" % (world, B)}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab[dom] * B,
@@ -814,7 +838,9 @@ def main():
     ap.add_argument("--c5-frames", type=int, default=4096)
     ap.add_argument("--c5-steps", type=int, default=2)
     ap.add_argument("--no-c5", action="store_true")
-    ap.add_argument("--no-peer-store", action="store_true", help="gather the result slabs with NCCL instead of writing them into rank 0's peer-mapped buffer")
+    ap.add_argument("--gather", default="peer-copy", choices=["peer-store", "peer-copy", "nccl"],
+                    help="how every rank's result slabs reach rank 0 at N > 1 (peer-mapped symmetric memory, else NCCL)")
+    ap.add_argument("--only-c1", action="store_true", help="stop after the resident C1 measurement (tuning aid; prints a short line)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
