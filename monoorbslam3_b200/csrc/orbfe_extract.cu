@@ -409,7 +409,8 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
     // K2 FAST + per-cell NMS
     FastArgs fa; fa.slots = h->d_slots; fa.cell_cnt = h->d_cell_cnt; fa.blk_tab = h->d_fast_tab; fa.cells_per_frame = g.cells_per_frame;
     fa.t_ini = h->cfg.ini_th_fast; fa.t_min = h->cfg.min_th_fast;
-    fa.one = 1; fa.flags = h->fast_exact_cmp ? 1 : 0;
+    fa.one = 1; fa.flags = (h->fast_exact_cmp ? 1 : 0) | (h->fast_fma_shift ? 2 : 0);
+    fa.shift_mul = make_uint3(1u << 24, 1u << 16, 1u << 8);
     k_fast<kTMA><<<dim3(g.fast_blocks, nb), 256, 0, st>>>(LS, TF, fa);
     ORBFE_AFTER_LAUNCH(h, st, "k_fast");
     ORBFE_PROF_MARK(h, st, 2);
@@ -532,6 +533,7 @@ int orbfe_create(const orbfe_config *cfg, orbfe_handle **out) {
     h->use_tma = !(cfg->flags & ORBFE_FLAG_NO_TMA);
     h->keep_stages = (cfg->flags & ORBFE_FLAG_KEEP_STAGES) != 0;
     if (const char *ev = getenv("ORBFE_FAST_EXACT")) h->fast_exact_cmp = *ev == '1';
+    if (const char *ev = getenv("ORBFE_FAST_FMA_SHIFT")) h->fast_fma_shift = *ev == '1';
     build_ctor_tables(h);
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaMalloc(&h->d_err, sizeof(int))) != cudaSuccess || (e = cudaMemset(h->d_err, 0, sizeof(int))) != cudaSuccess) {

@@ -288,11 +288,23 @@ __device__ __forceinline__ uint32_t pair_gt(uint32_t v, uint32_t pa, uint32_t pb
     }
 }
 
+// Funnel shift right by 8 / 16 / 24 bits, (lo >> s) | (hi << (32 - s)).  kFma: on the FMA pipe as hi * 2^(32-s) + umulhi(lo, 2^(32-s))
+// (IMAD + IMAD.HI; the two terms share no bit, so the add is an or; the multipliers are kernel arguments — as immediates the compiler
+// turns the multiplies back into shifts).  An experiment kept behind ORBFE_FAST_FMA_SHIFT=1: k_fast executes 58 % of its instructions
+// on the ALU pipe against 17 % on the FMA pipe, but it is as close to the issue limit as to the ALU limit, and two instructions for
+// one cost more than the pipe change wins (measured: stage 1.456 -> 1.541 ms per 512 C1 frames).
+template <bool kFma>
+__device__ __forceinline__ uint32_t fsr(uint32_t lo, uint32_t hi, int s, uint32_t m) {
+    if constexpr (kFma) return hi * m + __umulhi(lo, m);
+    else return __funnelshift_r(lo, hi, s);
+}
+
 // Stage A of k_fast for one strip row y: a lane owns the aligned words 2*lane and 2*lane+1 (8 pixels).  A 9-arc of the 16-ring
 // holds ring k or ring k+8 for every k, so a corner needs |p_k - v| > t or |p_(k+8) - v| > t for all eight opposite pairs.
 // Returns the pass flags of the two words in bit 7 of each byte.
-template <int kMode>
-__device__ __forceinline__ void fast_pairs_row(const uint8_t *tile, int y, int lane, uint32_t k7, uint32_t one, uint32_t &acc0, uint32_t &acc1) {
+template <int kMode, bool kFma>
+__device__ __forceinline__ void fast_pairs_row(const uint8_t *tile, int y, int lane, uint32_t k7, uint32_t one, uint3 sm, uint32_t &acc0, uint32_t &acc1) {
+#define __funnelshift_r(a, b, s) fsr<kFma>((a), (b), (s), (s) == 8 ? sm.x : (s) == 16 ? sm.y : sm.z)
     constexpr int SP = kBoxW;
     const uint8_t *base = tile + y * SP + 8 * lane;
     const int lo = lane == 0 ? 0 : -4, hi = lane == 31 ? 4 : 8;          // clamp the neighbour words at the box edge (never candidates)
@@ -330,6 +342,7 @@ __device__ __forceinline__ void fast_pairs_row(const uint8_t *tile, int y, int l
     }
 #undef ORBFE_PAIR
 #undef ORBFE_ROW
+#undef __funnelshift_r
 }
 
 // bytes [0, n) set, n in [0, 4]
@@ -339,7 +352,8 @@ struct FastArgs {
     uint32_t *slots; int *cell_cnt; const int *blk_tab;
     int cells_per_frame, t_ini, t_min;
     int one;        // 1: multiplier that keeps the stage-A adds on the FMA pipe (an immediate would be folded into an IADD)
-    int flags;      // bit 0: exact (masked) stage-A compares, for A/B testing
+    int flags;      // bit 0: exact (masked) stage-A compares, for A/B testing; bit 1: funnel shifts of stage A on the FMA pipe instead of SHF (experiment)
+    uint3 shift_mul; // 2^24, 2^16, 2^8: the multipliers of the FMA-pipe funnel shifts by 8, 16, 24 bits
 };
 
 template <bool kTMA>
@@ -387,12 +401,13 @@ __global__ void __launch_bounds__(256, 6) k_fast(const __grid_constant__ LevelSe
                     if (!((open >> ((x * 2185) >> 16)) & 1u)) { if (p < 4) vm0 &= ~(0x80u << (8 * p)); else vm1 &= ~(0x80u << (8 * (p - 4))); }
                 }
             }
-            const int mode = t >= 128 ? 2 : (a.flags & 1) ? 1 : 0;
+            const int mode = t >= 128 ? 2 : (a.flags & 1) ? 1 : (a.flags & 2) ? 0 : 3;
             for (int y = wid; y < ch; y += 8) {
                 uint32_t a0, a1;
-                if (mode == 0) fast_pairs_row<0>(tile, y, lane, k7, one, a0, a1);
-                else if (mode == 1) fast_pairs_row<1>(tile, y, lane, k7, one, a0, a1);
-                else fast_pairs_row<2>(tile, y, lane, k7, one, a0, a1);
+                if (mode == 0) fast_pairs_row<0, true>(tile, y, lane, k7, one, a.shift_mul, a0, a1);
+                else if (mode == 3) fast_pairs_row<0, false>(tile, y, lane, k7, one, a.shift_mul, a0, a1);
+                else if (mode == 1) fast_pairs_row<1, false>(tile, y, lane, k7, one, a.shift_mul, a0, a1);
+                else fast_pairs_row<2, false>(tile, y, lane, k7, one, a.shift_mul, a0, a1);
                 *reinterpret_cast<uint2 *>(mmap + y * SP + 8 * lane) = make_uint2(a0 & vm0, a1 & vm1);
             }
         }
