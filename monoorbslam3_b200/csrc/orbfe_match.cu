@@ -842,8 +842,11 @@ __global__ void __launch_bounds__(1024) k_resolve_par(const ResolveArgs a) {
     const int n2s = kVariant == 3 ? a.n_state : a.n2;
     int *held = reinterpret_cast<int *>(rp_dyn);             // earliest query holding the slot; -1: occupied before the call; INT_MAX: free
     int *dec = held + n2s;                                   // slot query i takes, or -1
+    int *s_beg = dec + a.nq, *s_end = s_beg + a.nq;          // candidate list of query i (empty for an invalid query): read every round
+    uint8_t *s_occ = reinterpret_cast<uint8_t *>(s_end + a.nq);   // slots occupied before the call
     // candidate lists (dist << 16 | idx) staged once when they fit: the rounds then never touch global memory for them
-    uint32_t *s_pack = reinterpret_cast<uint32_t *>(dec + a.nq);
+    uint8_t *s_oct = s_occ + n2s;                            // variant 2: octave of every slot (the same-level ratio test reads two per query and round)
+    uint32_t *s_pack = reinterpret_cast<uint32_t *>(s_oct + n2s + ((4 - ((2 * n2s) & 3)) & 3));
     const int total = a.n_cand ? *a.n_cand : 0;
     const bool staged = a.n_cand && total <= a.smem_entries;
     if (staged) for (int k = tid; k < total; k += 1024) s_pack[k] = ((uint32_t) a.c_dist[k] << 16) | (uint32_t) a.c_idx[k];
@@ -851,11 +854,20 @@ __global__ void __launch_bounds__(1024) k_resolve_par(const ResolveArgs a) {
     auto cand_dist = [&](int k) -> int { return staged ? (int) (s_pack[k] >> 16) : a.c_dist[k]; };
     if (tid < HISTO_LENGTH) hist[tid] = 0;
     if (tid == 0) s_nmatch = 0;
-    for (int qi = tid; qi < a.nq; qi += 1024) dec[qi] = -1;
+    for (int qi = tid; qi < a.nq; qi += 1024) {
+        dec[qi] = -1;
+        const bool live = kVariant >= 3 || a.qvalid[qi];
+        const int b = a.q_beg[qi];
+        s_beg[qi] = b; s_end[qi] = live ? a.q_end[qi] : b;
+    }
+    for (int j = tid; j < n2s; j += 1024) {
+        s_occ[j] = (kVariant == 3 ? a.has_mp2[j] : a.occupied[j]) ? 1 : 0;
+        if (kVariant == 2) s_oct[j] = (uint8_t) a.kps2[j].octave;
+    }
     __syncthreads();
     int round = 0;
     while (true) {
-        for (int j = tid; j < n2s; j += 1024) held[j] = (kVariant == 3 ? a.has_mp2[j] : a.occupied[j]) ? -1 : INT_MAX;
+        for (int j = tid; j < n2s; j += 1024) held[j] = s_occ[j] ? -1 : INT_MAX;
         if (tid == 0) s_changed = 0;
         __syncthreads();
         for (int qi = tid; qi < a.nq; qi += 1024) { const int s = dec[qi]; if (s >= 0) atomicMin(&held[s], qi); }
@@ -863,8 +875,8 @@ __global__ void __launch_bounds__(1024) k_resolve_par(const ResolveArgs a) {
         bool changed = false;
         for (int qi = tid; qi < a.nq; qi += 1024) {
             int nd = -1;
-            if (kVariant >= 3 || a.qvalid[qi]) {
-                const int beg = a.q_beg[qi], end = a.q_end[qi];
+            const int beg = s_beg[qi], end = s_end[qi];
+            if (end > beg) {
                 uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
                 for (int k = beg; k < end; ++k) {
                     if (held[cand_idx(k)] < qi) continue;                               // occupied, or taken by an earlier query
@@ -881,7 +893,7 @@ __global__ void __launch_bounds__(1024) k_resolve_par(const ResolveArgs a) {
                         accept = best <= TH_HIGH;
                         if (accept && s2 >= 0) {
                             const int second = (int) (k2 >> 22);
-                            if (a.kps2[best_idx2].octave == a.kps2[s2].octave && (float) best > __fmul_rn(a.nn_ratio, (float) second)) accept = false;   // :401-405
+                            if (s_oct[best_idx2] == s_oct[s2] && (float) best > __fmul_rn(a.nn_ratio, (float) second)) accept = false;   // :401-405
                         }
                     } else if (kVariant == 3) accept = best < TH_LOW && best_idx2 > 0;                            // :464-484 (sic)
                     else {
@@ -1097,7 +1109,7 @@ static int launch_resolve(Handle *h, const ResolveArgs &ra, int n2, cudaStream_t
     const bool serial = serial_env && *serial_env == '1';
     if (n2 >= 65536) return set_error(h, ORBFE_E_ARG, "matcher: %d key points in the searched frame (limit 65535)", n2);
     if (kVariant != 0 && !serial) {
-        const size_t state = sizeof(int) * ((size_t) n2 + (size_t) ra.nq) + 64;      // earliest holder per slot + decision per query
+        const size_t state = sizeof(int) * ((size_t) n2 + 3 * (size_t) ra.nq) + 2 * (size_t) n2 + 64;  // holder, occupancy, octave per slot; decision + list bounds per query
         if (state <= 200 * 1024) {
             ResolveArgs rb = ra;
             rb.smem_entries = (int) ((200 * 1024 - state) / sizeof(uint32_t));
