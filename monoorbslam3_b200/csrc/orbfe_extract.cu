@@ -411,8 +411,15 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
     fa.t_ini = h->cfg.ini_th_fast; fa.t_min = h->cfg.min_th_fast;
     fa.one = 1; fa.flags = (h->fast_exact_cmp ? 1 : 0) | (h->fast_fma_shift ? 2 : 0);
     fa.shift_mul = make_uint3(1u << 24, 1u << 16, 1u << 8);
-    k_fast<kTMA><<<dim3(g.fast_blocks, nb), 256, 0, st>>>(LS, TF, fa);
-    ORBFE_AFTER_LAUNCH(h, st, "k_fast");
+    if (h->fast_v1) {
+        k_fast<kTMA><<<dim3(g.fast_blocks, nb), 256, 0, st>>>(LS, TF, fa);
+        ORBFE_AFTER_LAUNCH(h, st, "k_fast");
+    } else {
+        Fast2Args f2; f2.slots = fa.slots; f2.cell_cnt = fa.cell_cnt; f2.blk_tab = fa.blk_tab; f2.cells_per_frame = fa.cells_per_frame;
+        f2.t_ini = fa.t_ini; f2.t_min = fa.t_min; f2.one = 1u; f2.gather = 0x00204081u; f2.exact = h->fast_exact_cmp ? 1 : 0;
+        k_fast_planes<kTMA><<<dim3(g.fast_blocks, nb), kF2Threads, 0, st>>>(LS, TF, f2);
+        ORBFE_AFTER_LAUNCH(h, st, "k_fast_planes");
+    }
     ORBFE_PROF_MARK(h, st, 2);
     // K4 quadtree
     OctArgs oa;
@@ -534,6 +541,7 @@ int orbfe_create(const orbfe_config *cfg, orbfe_handle **out) {
     h->keep_stages = (cfg->flags & ORBFE_FLAG_KEEP_STAGES) != 0;
     if (const char *ev = getenv("ORBFE_FAST_EXACT")) h->fast_exact_cmp = *ev == '1';
     if (const char *ev = getenv("ORBFE_FAST_FMA_SHIFT")) h->fast_fma_shift = *ev == '1';
+    if (const char *ev = getenv("ORBFE_FAST_V1")) h->fast_v1 = *ev == '1';
     build_ctor_tables(h);
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaMalloc(&h->d_err, sizeof(int))) != cudaSuccess || (e = cudaMemset(h->d_err, 0, sizeof(int))) != cudaSuccess) {

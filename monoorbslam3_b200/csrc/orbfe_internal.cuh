@@ -66,6 +66,7 @@ struct Handle {
     cudaStream_t stream = nullptr;
     bool use_tma = true, keep_stages = false;
     bool fast_fma_shift = false;     // ORBFE_FAST_FMA_SHIFT=1: FAST stage-A funnel shifts as IMAD + IMAD.HI on the FMA pipe instead of SHF (experiment, slower)
+    bool fast_v1 = false;            // ORBFE_FAST_V1=1: k_fast (per-pixel pair tests) instead of k_fast_planes (difference planes), for A/B measurements
     bool fast_exact_cmp = false;     // ORBFE_FAST_EXACT=1: masked (exact) byte compares in FAST stage A, for A/B measurements
     float scale[ORBFE_MAX_LEVELS], inv_scale[ORBFE_MAX_LEVELS];
     int quota[ORBFE_MAX_LEVELS];

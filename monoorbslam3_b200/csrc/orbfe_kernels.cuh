@@ -490,6 +490,270 @@ __global__ void __launch_bounds__(256, 6) k_fast(const __grid_constant__ LevelSe
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2 (second formulation)  k_fast_planes: the same four stages, with stage A rebuilt around two observations.
+//   1. |I(q) - I(p)| is symmetric: ring pixel k+8 of centre p is p - D_k, and its test against p is the test of ring pixel k of centre
+//      p - D_k.  So only EIGHT difference planes F_D(p) = [|I(p + D) - I(p)| > t] exist (one per opposite pair), and the pair test of
+//      (k, k+8) at p is F_D(p) | F_D(p - D).  Half the absolute differences and threshold adds of the per-pixel formulation.
+//   2. Once a plane is packed one bit per pixel, the realignment by D costs one funnel shift per 32 pixels instead of one per 4,
+//      and the AND over the eight pairs runs on 32 pixels per LOP3.
+// Phase 1 (thread = 16 pixels of one row, all eight directions): directions are chosen with Dy >= 0, so a task reads rows r .. r+3;
+// a direction with Dx > 0 displaces the ring row, one with Dx < 0 displaces the centre row instead (its plane is then stored |Dx| bits
+// to the left; phase 2 compensates), which lets the displaced rows be shared: 24 byte funnel shifts per task.  Per 4 pixels and
+// direction: VABSDIFF4, the threshold add as IMAD (FMA pipe), LOP3 (y | x) & 0x80808080, IMAD by 0x00204081 (gathers the four bit-7
+// flags into bits 28..31; the partial products never collide) and one funnel shift that appends the nibble to the row word.
+// Phase 2 (thread = 32 pixels): the eight pair terms from the planes of rows y, y-1, y-2, y-3 -> pass bits (natural order).
+// A2 takes four bytes of pass bits from four distant places per thread (corner-rich regions are compact, so a thread that owns 32
+// adjacent pixels has 3x the mean load in the worst lane; spread out it is 2x) and needs no position decode: the byte index is the
+// queue entry >> 3; queue offsets come from a warp scan and one shared-memory atomic per warp (the order is irrelevant).
+// B / C / D are k_fast's, with the score map laid out cell by cell (32-byte cell stride, one zero column either side) so that the
+// non-max test needs no cell-border predicates, and B leaves the score-map position of each corner in its queue entry (0 = rejected)
+// so that C touches only corners.  The planes are dead after phase 2; the score map lives there.
+// 288 threads = 33 plane rows x 16 tasks in two even passes; 5 CTAs per SM (34 KB, 40 registers).
+// ------------------------------------------------------------------------------------------------
+constexpr int kF2Threads = 288;
+constexpr int kF2PlaneRows = kCell + 3;                 // strip rows -3 .. 29
+constexpr int kF2Tile = kFastBoxH * kBoxW;              // bytes of the staged box
+constexpr int kF2PlaneHalves = kF2PlaneRows * 16;       // u16 entries of one plane
+
+// 16 pass bits of one direction: bit 4j + i = |c - r| > t for byte i of word j.  kMode as in pair_gt.
+template <int kMode>
+__device__ __forceinline__ uint32_t diff_nibble(uint32_t c, uint32_t r, uint32_t k7, uint32_t one, uint32_t gather, uint32_t acc) {
+    const uint32_t x = __vabsdiffu4(c, r);
+    uint32_t f;
+    if constexpr (kMode == 0) f = ((x * one + k7) | x) & 0x80808080u;
+    else if constexpr (kMode == 1) f = (((x & 0x7f7f7f7fu) + k7) | x) & 0x80808080u;
+    else f = (((x & 0x7f7f7f7fu) + k7) & x) & 0x80808080u;
+    return __funnelshift_l(f * gather, acc, 4);                       // (acc << 4) | flags of this word
+}
+template <int kMode>
+__device__ __forceinline__ uint16_t diff_bits(const uint4 c, const uint4 r, uint32_t k7, uint32_t one, uint32_t gather) {
+    uint32_t acc = diff_nibble<kMode>(c.w, r.w, k7, one, gather, 0u);
+    acc = diff_nibble<kMode>(c.z, r.z, k7, one, gather, acc);
+    acc = diff_nibble<kMode>(c.y, r.y, k7, one, gather, acc);
+    acc = diff_nibble<kMode>(c.x, r.x, k7, one, gather, acc);
+    return (uint16_t) acc;
+}
+// 16 bytes starting s bytes to the right of v (nx = the word after v)
+__device__ __forceinline__ uint4 bytes_right(const uint4 v, uint32_t nx, int s) {
+    return make_uint4(__funnelshift_r(v.x, v.y, 8 * s), __funnelshift_r(v.y, v.z, 8 * s), __funnelshift_r(v.z, v.w, 8 * s), __funnelshift_r(v.w, nx, 8 * s));
+}
+
+// phase 1 for the plane rows [0, kF2PlaneRows): tile = the staged box (pitch kBoxW; readable up to 4 bytes past its end), planes[d][row][16] u16
+template <int kMode>
+__device__ __forceinline__ void fast_planes(const uint8_t *tile, uint16_t *planes, int tid, uint32_t k7, uint32_t one, uint32_t gather) {
+    constexpr int SP = kBoxW, PH = kF2PlaneHalves;
+    for (int task = tid; task < kF2PlaneRows * 16; task += kF2Threads) {
+        const uint8_t *p = tile + (task >> 4) * SP + 16 * (task & 15);           // centre row r = task >> 4
+        uint16_t *out = planes + task;
+#define ORBFE_LD(off) (*reinterpret_cast<const uint4 *>(p + (off)))
+#define ORBFE_NX(off) (*reinterpret_cast<const uint32_t *>(p + (off) + 16))
+        const uint4 c0 = ORBFE_LD(0); const uint32_t c0n = ORBFE_NX(0);
+        {
+            const uint4 r3 = ORBFE_LD(3 * SP); const uint32_t r3n = ORBFE_NX(3 * SP);
+            out[0 * PH] = diff_bits<kMode>(c0, r3, k7, one, gather);                               // ( 0, 3)  ring 0 / 8
+            out[1 * PH] = diff_bits<kMode>(c0, bytes_right(r3, r3n, 1), k7, one, gather);          // ( 1, 3)  ring 1 / 9
+            out[7 * PH] = diff_bits<kMode>(bytes_right(c0, c0n, 1), r3, k7, one, gather);          // (-1, 3)  ring 15 / 7, stored 1 bit left
+        }
+        {
+            const uint4 r2 = ORBFE_LD(2 * SP); const uint32_t r2n = ORBFE_NX(2 * SP);
+            out[2 * PH] = diff_bits<kMode>(c0, bytes_right(r2, r2n, 2), k7, one, gather);          // ( 2, 2)  ring 2 / 10
+            out[6 * PH] = diff_bits<kMode>(bytes_right(c0, c0n, 2), r2, k7, one, gather);          // (-2, 2)  ring 14 / 6, stored 2 bits left
+        }
+        {
+            const uint4 r1 = ORBFE_LD(SP); const uint32_t r1n = ORBFE_NX(SP);
+            const uint4 c3 = bytes_right(c0, c0n, 3);
+            out[3 * PH] = diff_bits<kMode>(c0, bytes_right(r1, r1n, 3), k7, one, gather);          // ( 3, 1)  ring 3 / 11
+            out[4 * PH] = diff_bits<kMode>(c0, c3, k7, one, gather);                               // ( 3, 0)  ring 4 / 12
+            out[5 * PH] = diff_bits<kMode>(c3, r1, k7, one, gather);                               // (-3, 1)  ring 13 / 5, stored 3 bits left
+        }
+#undef ORBFE_LD
+#undef ORBFE_NX
+    }
+}
+
+// the most significant set bit of a non-zero word (bfind: one FLO)
+__device__ __forceinline__ int top_bit(uint32_t v) { int b; asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(v)); return b; }
+
+struct Fast2Args {
+    uint32_t *slots; int *cell_cnt; const int *blk_tab;
+    int cells_per_frame, t_ini, t_min;
+    uint32_t one;       // 1: keeps the threshold add an IMAD (an immediate would be folded into an IADD on the ALU pipe)
+    uint32_t gather;    // 0x00204081: bit 8i+7 -> bit 28+i (as an argument so that the multiply stays an IMAD)
+    int exact;          // masked (exact) threshold adds also below 128, for A/B measurements
+};
+
+template <bool kTMA>
+__global__ void __launch_bounds__(kF2Threads, 5) k_fast_planes(const __grid_constant__ LevelSet L, const __grid_constant__ TmapSet T, const Fast2Args a) {
+    constexpr int SP = kBoxW, NT = kF2Threads;
+    __shared__ __align__(128) uint8_t tile[kF2Tile + 16];              // phase 1 reads the word after a 16-byte group
+    // the eight planes; from stage A2 on the score map: cell c, column cx, strip row y at [(y+1)*SP + 32*c + cx + 1], zero elsewhere
+    __shared__ __align__(16) uint16_t planes[8 * kF2PlaneHalves];
+    __shared__ uint16_t queue[kStripW * kCell];                          // y << 8 | tile column; after stage B: score-map position or 0
+    __shared__ __align__(16) uint32_t passw[kCell * 8];                  // pass bits of strip row y: word w = tile columns 32w .. 32w+31
+    __shared__ uint32_t rowmask[kCellsPerBlk][32];
+    __shared__ int s_n;
+    __shared__ __align__(8) uint64_t bar;
+    static_assert(sizeof(planes) >= 32 * SP, "score map fits the planes");
+    uint8_t *mmap = reinterpret_cast<uint8_t *>(planes);
+
+    const int frame = blockIdx.y, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int packed = __ldg(&a.blk_tab[blockIdx.x]);                                   // level | cell row << 4 | strip << 16
+    const int l = packed & 15, ci = (packed >> 4) & 0xfff, cg = packed >> 16;
+    const LevelGeom &G = L.lv[l];
+    const int px = kEdge - 3 + kStripW * cg, py = kEdge - 3 + kCell * ci;               // tile column c = strip x + 3, tile row = strip y + 3
+    stage_box<kTMA, NT>(tile, &bar, &T.m[l], L.img[l] + (size_t) frame * G.frame_stride, G.pitch, G.h, px, py, frame, kFastBoxH);
+
+    const int strip_w = min(kStripW, G.w - kEdge - (kEdge + kStripW * cg));             // pixels of this strip inside maxBorderX
+    const int ch = min(kCell, G.h - kEdge - (kEdge + kCell * ci));                      // rows inside maxBorderY
+    unsigned open = (1u << ((strip_w + kCell - 1) / kCell)) - 1u;                       // cells that still need a result
+
+#pragma unroll 1
+    for (int round = 0; round < 2; ++round) {
+        const int t = round == 0 ? a.t_ini : a.t_min;
+        if (tid < kCellsPerBlk * 32) rowmask[wid][lane] = 0;
+        if (tid == 0) s_n = 0;
+        // ---- A, phase 1: the eight difference planes
+        {
+            const uint32_t k7 = (uint32_t) (127 - (t & 127)) * 0x01010101u;
+            if (t >= 128) fast_planes<2>(tile, planes, tid, k7, a.one, a.gather);
+            else if (a.exact) fast_planes<1>(tile, planes, tid, k7, a.one, a.gather);
+            else fast_planes<0>(tile, planes, tid, k7, a.one, a.gather);
+        }
+        __syncthreads();
+        // ---- A, phase 2: pair terms and their AND, 32 pixels per thread
+        if (tid < kCell * 8) {
+            const int y = tid >> 3, w = tid & 7;
+            uint32_t pass = 0;
+            if (y < ch) {
+                const uint32_t *P = reinterpret_cast<const uint32_t *>(planes) + (y + 3) * 8 + w;      // plane row of strip row y
+                constexpr int PW = kF2PlaneRows * 8;                                                      // words per plane
+#define ORBFE_AT(d, dy) P[(d) * PW - (dy) * 8]
+#define ORBFE_SHL(d, dy, s) __funnelshift_l(w ? P[(d) * PW - (dy) * 8 - 1] : 0u, P[(d) * PW - (dy) * 8], s)
+                pass = ORBFE_AT(0, 0) | ORBFE_AT(0, 3);
+                pass &= ORBFE_AT(1, 0) | ORBFE_SHL(1, 3, 1);
+                pass &= ORBFE_AT(2, 0) | ORBFE_SHL(2, 2, 2);
+                pass &= ORBFE_AT(3, 0) | ORBFE_SHL(3, 1, 3);
+                pass &= ORBFE_AT(4, 0) | ORBFE_SHL(4, 0, 3);
+                pass &= ORBFE_SHL(5, 0, 3) | ORBFE_AT(5, 1);
+                pass &= ORBFE_SHL(6, 0, 2) | ORBFE_AT(6, 2);
+                pass &= ORBFE_SHL(7, 0, 1) | ORBFE_AT(7, 3);
+#undef ORBFE_AT
+#undef ORBFE_SHL
+                // candidate columns: c - 3 in [0, strip_w), in a cell that is still open
+                const int c0 = 32 * w - 3;                                                  // strip x of bit 0
+                const int hi0 = strip_w - c0;
+                uint32_t valid = hi0 <= 0 ? 0u : (hi0 >= 32 ? 0xffffffffu : (1u << hi0) - 1u);
+                if (w == 0) valid &= ~7u;
+                if (round) {
+#pragma unroll 1
+                    for (int c = 0; c < kCellsPerBlk; ++c) {
+                        if (!((open >> c) & 1u)) {
+                            const int lo = max(kCell * c - c0, 0), hi = min(kCell * (c + 1) - c0, 32);
+                            if (hi > lo) valid &= ~((hi >= 32 ? 0xffffffffu : (1u << hi) - 1u) & ~((1u << lo) - 1u));
+                        }
+                    }
+                }
+                pass &= valid;
+            }
+            passw[tid] = pass;
+        }
+        __syncthreads();
+        // ---- A2: pass bits -> queue (order is irrelevant); a thread owns the bytes tid, tid + 240, tid + 480, tid + 720.
+        // The planes are dead: zero the score map on the way.
+        for (int i = tid; i < 32 * SP / 16; i += NT) reinterpret_cast<uint4 *>(mmap)[i] = make_uint4(0, 0, 0, 0);
+        {
+            uint32_t bits = 0;
+            if (tid < 240) {
+                const uint8_t *pb = reinterpret_cast<const uint8_t *>(passw);
+                bits = (uint32_t) pb[tid] | ((uint32_t) pb[tid + 240] << 8) | ((uint32_t) pb[tid + 480] << 16) | ((uint32_t) pb[tid + 720] << 24);
+            }
+            const int cnt = __popc(bits);
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+            int base = 0;
+            if (lane == 31 && inc) base = atomicAdd(&s_n, inc);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            uint16_t *q = queue + base + inc - cnt;
+            const int pos0 = 8 * tid;
+            while (bits) {
+                const int b = top_bit(bits);
+                bits ^= 1u << b;
+                *q++ = (uint16_t) (pos0 + b + 1912 * (b >> 3));                          // byte index * 8 + bit = y << 8 | tile column
+            }
+        }
+        __syncthreads();
+        const int n = s_n;
+
+        // ---- B: exact measure of the queued pixels; corners (m > t) go into the score map, their map position into the queue entry
+        for (int k = tid; k < n; k += NT) {
+            const int pos = queue[k];
+            const int m = fast_measure1(tile + 3 * SP + pos);
+            int mp = 0;
+            if (m > t) {
+                const int x = (pos & 255) - 3;
+                mp = (pos & 0xff00) + SP + x + 2 * ((x * 2185) >> 16) + 1;
+                mmap[mp] = (uint8_t) m;
+            }
+            queue[k] = (uint16_t) mp;
+        }
+        __syncthreads();
+
+        // ---- C: non-max suppression inside the cell (strictly greater than the 8 neighbours; the cell's border columns / rows are 0)
+        for (int k = tid; k < n; k += NT) {
+            const int mp = queue[k];
+            if (mp == 0) continue;
+            const uint8_t *p = mmap + mp;
+            const uint32_t m = p[0];
+            const uint32_t n0 = __vimax3_u32(p[-SP - 1], p[-SP], p[-SP + 1]), n1 = __vimax3_u32(p[-1], p[1], p[SP - 1]);
+            const uint32_t nb = __vimax3_u32(n0, n1, max((uint32_t) p[SP], (uint32_t) p[SP + 1]));
+            if (m > nb) atomicOr(&rowmask[(mp & 255) >> 5][(mp >> 8) - 1], 1u << ((mp & 31) - 1));
+        }
+        __syncthreads();
+
+        // ---- D: one warp per cell, lane = cell row: ordered emission (ORBExtractor.cpp:609-615)
+        bool still_open = false;
+        if (wid < kCellsPerBlk) {
+            unsigned mask = rowmask[wid][lane];
+            const bool has = __any_sync(0xffffffffu, mask != 0);
+            const bool mine = (open >> wid) & 1u;
+            still_open = mine && !has;
+            if (mine && (has || round == 1)) {
+                const int cnt = __popc(mask);
+                int inc = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+                const int total = __shfl_sync(0xffffffffu, inc, 31);
+                const int cj = cg * kCellsPerBlk + wid;
+                const int cell = G.cell_base + ci * G.n_cols + cj;
+                uint32_t *slot = a.slots + ((size_t) frame * a.cells_per_frame + cell) * kSlotCap + (inc - cnt);
+                while (mask) {
+                    const int cx = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int m = mmap[(lane + 1) * SP + 32 * wid + cx + 1];
+                    *slot++ = (uint32_t) (cj * kCell + cx) | ((uint32_t) (ci * kCell + lane) << 12) | ((uint32_t) (m - 1) << 24);
+                }
+                if (lane == 0) a.cell_cnt[(size_t) frame * a.cells_per_frame + cell] = total;
+            }
+        }
+        if (round) break;
+        // cells without a corner at iniThFAST go through a second round at minThFAST; the barrier also orders stage D's reads of the
+        // score map / row masks before the next round's writes.  Each warp reports its own cell.
+        if (__syncthreads_or(still_open) == 0) break;
+        {
+            // rebuild `open` identically in every thread: warp w's cell stays open iff it was open and had no corner; publish through passw
+            if (lane == 0 && wid < kCellsPerBlk) passw[wid] = still_open;
+            __syncthreads();
+            unsigned o2 = 0;
+#pragma unroll
+            for (int c = 0; c < kCellsPerBlk; ++c) o2 |= passw[c] ? 1u << c : 0u;
+            open = o2;
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4  DistributeOctree.  One CTA per (level, frame).  See DESIGN.md "quadtree" for the derivation:
 // a node is a path prefix, its key points are the candidates (in reference order) whose coordinates descend to it,
 // so no per-node vectors are moved — only per-node counts; list order is recovered from the creation order of slots.
