@@ -501,14 +501,16 @@ __global__ void __launch_bounds__(256, 6) k_fast(const __grid_constant__ LevelSe
 // to the left; phase 2 compensates), which lets the displaced rows be shared: 24 byte funnel shifts per task.  Per 4 pixels and
 // direction: VABSDIFF4, the threshold add as IMAD (FMA pipe), LOP3 (y | x) & 0x80808080, IMAD by 0x00204081 (gathers the four bit-7
 // flags into bits 28..31; the partial products never collide) and one funnel shift that appends the nibble to the row word.
-// Phase 2 (thread = 32 pixels): the eight pair terms from the planes of rows y, y-1, y-2, y-3 -> pass bits (natural order).
-// A2 takes four bytes of pass bits from four distant places per thread (corner-rich regions are compact, so a thread that owns 32
-// adjacent pixels has 3x the mean load in the worst lane; spread out it is 2x) and needs no position decode: the byte index is the
-// queue entry >> 3; queue offsets come from a warp scan and one shared-memory atomic per warp (the order is irrelevant).
+// Phase 2 (thread = 32 pixels): the eight pair terms from the planes of rows y, y-1, y-2, y-3 -> pass bits in pixel order, expanded
+// into the queue by the same thread (queue offsets from a warp scan and one shared-memory atomic per warp; the order across warps is
+// irrelevant).  The order INSIDE a warp matters: a thread's entries are adjacent pixels and a warp's lie in four adjacent rows, so the
+// 17 byte loads per candidate of stage B fall into few words per warp.  (Spreading each thread over four distant bytes of pass bits
+// halves the divergence of the expansion loop but makes stage B's loads hit 3.2 banks-conflicted wavefronts each — the kernel then
+// sits on the shared-memory pipe at 0.9 wavefronts per clock: measured 1.42 ms against 1.27 ms per 512 C1 frames.)
 // B / C / D are k_fast's, with the score map laid out cell by cell (32-byte cell stride, one zero column either side) so that the
 // non-max test needs no cell-border predicates, and B leaves the score-map position of each corner in its queue entry (0 = rejected)
-// so that C touches only corners.  The planes are dead after phase 2; the score map lives there.
-// 288 threads = 33 plane rows x 16 tasks in two even passes; 5 CTAs per SM (34 KB, 40 registers).
+// so that C touches only corners.
+// 288 threads = 33 plane rows x 16 tasks in two even passes; 5 CTAs per SM (41 KB, 40 registers).
 // ------------------------------------------------------------------------------------------------
 constexpr int kF2Threads = 288;
 constexpr int kF2PlaneRows = kCell + 3;                 // strip rows -3 .. 29
@@ -538,7 +540,7 @@ __device__ __forceinline__ uint4 bytes_right(const uint4 v, uint32_t nx, int s) 
     return make_uint4(__funnelshift_r(v.x, v.y, 8 * s), __funnelshift_r(v.y, v.z, 8 * s), __funnelshift_r(v.z, v.w, 8 * s), __funnelshift_r(v.w, nx, 8 * s));
 }
 
-// phase 1 for the plane rows [0, kF2PlaneRows): tile = the staged box (pitch kBoxW; readable up to 4 bytes past its end), planes[d][row][16] u16
+// phase 1 for the plane rows [0, kF2PlaneRows): tile = the staged box (pitch kBoxW), planes[d][row][16] u16
 template <int kMode>
 __device__ __forceinline__ void fast_planes(const uint8_t *tile, uint16_t *planes, int tid, uint32_t k7, uint32_t one, uint32_t gather) {
     constexpr int SP = kBoxW, PH = kF2PlaneHalves;
@@ -546,21 +548,24 @@ __device__ __forceinline__ void fast_planes(const uint8_t *tile, uint16_t *plane
         const uint8_t *p = tile + (task >> 4) * SP + 16 * (task & 15);           // centre row r = task >> 4
         uint16_t *out = planes + task;
 #define ORBFE_LD(off) (*reinterpret_cast<const uint4 *>(p + (off)))
-#define ORBFE_NX(off) (*reinterpret_cast<const uint32_t *>(p + (off) + 16))
-        const uint4 c0 = ORBFE_LD(0); const uint32_t c0n = ORBFE_NX(0);
+        // the word after a 16-byte group is the first word of the next lane's group (the last group of a row gets a word that only
+        // reaches columns >= 253, which are never candidates)
+        const unsigned am = __activemask();
+#define ORBFE_NX(v) __shfl_down_sync(am, (v).x, 1)
+        const uint4 c0 = ORBFE_LD(0); const uint32_t c0n = ORBFE_NX(c0);
         {
-            const uint4 r3 = ORBFE_LD(3 * SP); const uint32_t r3n = ORBFE_NX(3 * SP);
+            const uint4 r3 = ORBFE_LD(3 * SP); const uint32_t r3n = ORBFE_NX(r3);
             out[0 * PH] = diff_bits<kMode>(c0, r3, k7, one, gather);                               // ( 0, 3)  ring 0 / 8
             out[1 * PH] = diff_bits<kMode>(c0, bytes_right(r3, r3n, 1), k7, one, gather);          // ( 1, 3)  ring 1 / 9
             out[7 * PH] = diff_bits<kMode>(bytes_right(c0, c0n, 1), r3, k7, one, gather);          // (-1, 3)  ring 15 / 7, stored 1 bit left
         }
         {
-            const uint4 r2 = ORBFE_LD(2 * SP); const uint32_t r2n = ORBFE_NX(2 * SP);
+            const uint4 r2 = ORBFE_LD(2 * SP); const uint32_t r2n = ORBFE_NX(r2);
             out[2 * PH] = diff_bits<kMode>(c0, bytes_right(r2, r2n, 2), k7, one, gather);          // ( 2, 2)  ring 2 / 10
             out[6 * PH] = diff_bits<kMode>(bytes_right(c0, c0n, 2), r2, k7, one, gather);          // (-2, 2)  ring 14 / 6, stored 2 bits left
         }
         {
-            const uint4 r1 = ORBFE_LD(SP); const uint32_t r1n = ORBFE_NX(SP);
+            const uint4 r1 = ORBFE_LD(SP); const uint32_t r1n = ORBFE_NX(r1);
             const uint4 c3 = bytes_right(c0, c0n, 3);
             out[3 * PH] = diff_bits<kMode>(c0, bytes_right(r1, r1n, 3), k7, one, gather);          // ( 3, 1)  ring 3 / 11
             out[4 * PH] = diff_bits<kMode>(c0, c3, k7, one, gather);                               // ( 3, 0)  ring 4 / 12
@@ -585,16 +590,13 @@ struct Fast2Args {
 template <bool kTMA>
 __global__ void __launch_bounds__(kF2Threads, 5) k_fast_planes(const __grid_constant__ LevelSet L, const __grid_constant__ TmapSet T, const Fast2Args a) {
     constexpr int SP = kBoxW, NT = kF2Threads;
-    __shared__ __align__(128) uint8_t tile[kF2Tile + 16];              // phase 1 reads the word after a 16-byte group
-    // the eight planes; from stage A2 on the score map: cell c, column cx, strip row y at [(y+1)*SP + 32*c + cx + 1], zero elsewhere
+    __shared__ __align__(128) uint8_t tile[kF2Tile];
     __shared__ __align__(16) uint16_t planes[8 * kF2PlaneHalves];
+    __shared__ __align__(16) uint8_t mmap[32 * SP];                      // score of cell c, column cx, strip row y at [(y+1)*SP + 32*c + cx + 1], zero elsewhere
     __shared__ uint16_t queue[kStripW * kCell];                          // y << 8 | tile column; after stage B: score-map position or 0
-    __shared__ __align__(16) uint32_t passw[kCell * 8];                  // pass bits of strip row y: word w = tile columns 32w .. 32w+31
     __shared__ uint32_t rowmask[kCellsPerBlk][32];
-    __shared__ int s_n;
+    __shared__ int s_n, s_open[kCellsPerBlk];
     __shared__ __align__(8) uint64_t bar;
-    static_assert(sizeof(planes) >= 32 * SP, "score map fits the planes");
-    uint8_t *mmap = reinterpret_cast<uint8_t *>(planes);
 
     const int frame = blockIdx.y, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int packed = __ldg(&a.blk_tab[blockIdx.x]);                                   // level | cell row << 4 | strip << 16
@@ -612,6 +614,7 @@ __global__ void __launch_bounds__(kF2Threads, 5) k_fast_planes(const __grid_cons
         const int t = round == 0 ? a.t_ini : a.t_min;
         if (tid < kCellsPerBlk * 32) rowmask[wid][lane] = 0;
         if (tid == 0) s_n = 0;
+        for (int i = tid; i < 32 * SP / 16; i += NT) reinterpret_cast<uint4 *>(mmap)[i] = make_uint4(0, 0, 0, 0);
         // ---- A, phase 1: the eight difference planes
         {
             const uint32_t k7 = (uint32_t) (127 - (t & 127)) * 0x01010101u;
@@ -620,10 +623,11 @@ __global__ void __launch_bounds__(kF2Threads, 5) k_fast_planes(const __grid_cons
             else fast_planes<0>(tile, planes, tid, k7, a.one, a.gather);
         }
         __syncthreads();
-        // ---- A, phase 2: pair terms and their AND, 32 pixels per thread
-        if (tid < kCell * 8) {
-            const int y = tid >> 3, w = tid & 7;
+        // ---- A, phase 2: pair terms and their AND, 32 pixels per thread, and the pass bits -> queue.  Queue entries of a thread are
+        // adjacent pixels and those of a warp lie in four adjacent rows: stage B's ring loads of a warp then fall into few words.
+        {
             uint32_t pass = 0;
+            const int y = tid >> 3, w = tid & 7;
             if (y < ch) {
                 const uint32_t *P = reinterpret_cast<const uint32_t *>(planes) + (y + 3) * 8 + w;      // plane row of strip row y
                 constexpr int PW = kF2PlaneRows * 8;                                                      // words per plane
@@ -655,19 +659,7 @@ __global__ void __launch_bounds__(kF2Threads, 5) k_fast_planes(const __grid_cons
                 }
                 pass &= valid;
             }
-            passw[tid] = pass;
-        }
-        __syncthreads();
-        // ---- A2: pass bits -> queue (order is irrelevant); a thread owns the bytes tid, tid + 240, tid + 480, tid + 720.
-        // The planes are dead: zero the score map on the way.
-        for (int i = tid; i < 32 * SP / 16; i += NT) reinterpret_cast<uint4 *>(mmap)[i] = make_uint4(0, 0, 0, 0);
-        {
-            uint32_t bits = 0;
-            if (tid < 240) {
-                const uint8_t *pb = reinterpret_cast<const uint8_t *>(passw);
-                bits = (uint32_t) pb[tid] | ((uint32_t) pb[tid + 240] << 8) | ((uint32_t) pb[tid + 480] << 16) | ((uint32_t) pb[tid + 720] << 24);
-            }
-            const int cnt = __popc(bits);
+            const int cnt = __popc(pass);
             int inc = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
@@ -675,11 +667,11 @@ __global__ void __launch_bounds__(kF2Threads, 5) k_fast_planes(const __grid_cons
             if (lane == 31 && inc) base = atomicAdd(&s_n, inc);
             base = __shfl_sync(0xffffffffu, base, 31);
             uint16_t *q = queue + base + inc - cnt;
-            const int pos0 = 8 * tid;
-            while (bits) {
-                const int b = top_bit(bits);
-                bits ^= 1u << b;
-                *q++ = (uint16_t) (pos0 + b + 1912 * (b >> 3));                          // byte index * 8 + bit = y << 8 | tile column
+            const int pos0 = 32 * tid;                                                      // y << 8 | 32 * w
+            while (pass) {
+                const int b = top_bit(pass);
+                pass ^= 1u << b;
+                *q++ = (uint16_t) (pos0 + b);
             }
         }
         __syncthreads();
@@ -741,12 +733,12 @@ __global__ void __launch_bounds__(kF2Threads, 5) k_fast_planes(const __grid_cons
         // score map / row masks before the next round's writes.  Each warp reports its own cell.
         if (__syncthreads_or(still_open) == 0) break;
         {
-            // rebuild `open` identically in every thread: warp w's cell stays open iff it was open and had no corner; publish through passw
-            if (lane == 0 && wid < kCellsPerBlk) passw[wid] = still_open;
+            // rebuild `open` identically in every thread: warp w's cell stays open iff it was open and had no corner; publish through s_open
+            if (lane == 0 && wid < kCellsPerBlk) s_open[wid] = still_open;
             __syncthreads();
             unsigned o2 = 0;
 #pragma unroll
-            for (int c = 0; c < kCellsPerBlk; ++c) o2 |= passw[c] ? 1u << c : 0u;
+            for (int c = 0; c < kCellsPerBlk; ++c) o2 |= s_open[c] ? 1u << c : 0u;
             open = o2;
             __syncthreads();
         }
