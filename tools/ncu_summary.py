@@ -35,7 +35,7 @@ if __name__ == "__main__" and sys.argv[1] != "--traffic":
     print("wrote", out_csv, len(allrows), "kernels")
 
 
-def traffic_json(rep, out_json, batch, note=""):
+def traffic_json(rep, out_json, batch, note="", whole=False):
     """profiles/rNN_traffic.json: per stage of the LAST pass in `rep` (tools/profile_run.py runs the pass twice) the kernel time,
     DRAM bytes, executed warp instructions and issue / pipe utilisation — what bench.py's roofline.traffic and issue figures read."""
     import json
@@ -45,7 +45,8 @@ def traffic_json(rep, out_json, batch, note=""):
     seq = [(s, r) for s, r in seq if s]
     n_desc = sum(1 for s, _ in seq if s == "describe")
     # keep the kernels after the second-to-last describe launch (= the last pass)
-    if n_desc > 1:
+    # whole: the capture already holds exactly one pass (e.g. --launch-skip 22 -c 22: the two half passes of a split batch)
+    if n_desc > 1 and not whole:
         seen = 0
         for i, (s, _) in enumerate(seq):
             if s == "describe":
@@ -70,4 +71,5 @@ def traffic_json(rep, out_json, batch, note=""):
 
 
 if __name__ == "__main__" and sys.argv[1] == "--traffic":
-    traffic_json(sys.argv[2], sys.argv[3], int(sys.argv[4]), " ".join(sys.argv[5:]))
+    rest = sys.argv[5:]
+    traffic_json(sys.argv[2], sys.argv[3], int(sys.argv[4]), " ".join(a for a in rest if a != "--whole"), whole="--whole" in rest)
