@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Per-stage device times for any BASELINE config: stage_probe.py <w> <h> <n_features> <batch> [profile]"""
+"""Per-stage device times for any BASELINE config: stage_probe.py <w> <h> <n_features> <batch> [dense|natural|photo]"""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,7 +9,13 @@ from monoorbslam3_b200 import ORBExtractor, synth
 w, h, nf, batch = (int(v) for v in sys.argv[1:5])
 profile = sys.argv[5] if len(sys.argv) > 5 else "dense"
 dev = torch.device("cuda", 0)
-base = synth.frames(min(batch, 8), h, w, 1000, profile)
+if profile == "photo":      # the recorded 752x480 photograph of tests/golden/photos_ref.npz and seven flipped / shifted variants of it
+    img = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "photos_ref.npz"))["img_china"]
+    assert img.shape == (h, w), img.shape
+    base = np.stack([img, img[::-1], img[:, ::-1], img[::-1, ::-1], np.roll(img, 37, 1), np.roll(img, 53, 0), np.roll(img[::-1], 91, 1), np.roll(img[:, ::-1], 17, 0)])[:min(batch, 8)]
+    base = np.ascontiguousarray(base)
+else:
+    base = synth.frames(min(batch, 8), h, w, 1000, profile)
 fr = torch.from_numpy(np.concatenate([base] * ((batch + len(base) - 1) // len(base)))[:batch]).to(dev)
 ex = ORBExtractor(nf, 1.2, 8, 20, 7, max_batch=batch)
 cap = nf + 128
