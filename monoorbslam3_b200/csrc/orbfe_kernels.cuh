@@ -499,8 +499,8 @@ __global__ void __launch_bounds__(256, 6) k_fast(const __grid_constant__ LevelSe
 // Phase 1 (thread = 16 pixels of one row, all eight directions): directions are chosen with Dy >= 0, so a task reads rows r .. r+3;
 // a direction with Dx > 0 displaces the ring row, one with Dx < 0 displaces the centre row instead (its plane is then stored |Dx| bits
 // to the left; phase 2 compensates), which lets the displaced rows be shared: 24 byte funnel shifts per task.  Per 4 pixels and
-// direction: VABSDIFF4, the threshold add as IMAD (FMA pipe), LOP3 (y | x) & 0x80808080, IMAD by 0x00204081 (gathers the four bit-7
-// flags into bits 28..31; the partial products never collide) and one funnel shift that appends the nibble to the row word.
+// direction: VABSDIFF4, the threshold add as IMAD (FMA pipe), LOP3 (y | x) & 0x80808080 and one IDP4A (FMA pipe) that gathers the four
+// bit-7 flags with the byte weights 1, 2, 4, 8 / 16, 32, 64, 128 into the row word: 2 ALU + 2 FMA instructions.
 // Phase 2 (thread = 32 pixels): the eight pair terms from the planes of rows y, y-1, y-2, y-3 -> pass bits in pixel order, expanded
 // into the queue by the same thread (queue offsets from a warp scan and one shared-memory atomic per warp; the order across warps is
 // irrelevant).  The order INSIDE a warp matters: a thread's entries are adjacent pixels and a warp's lie in four adjacent rows, so the
@@ -518,22 +518,25 @@ constexpr int kF2Tile = kFastBoxH * kBoxW;              // bytes of the staged b
 constexpr int kF2PlaneHalves = kF2PlaneRows * 16;       // u16 entries of one plane
 
 // 16 pass bits of one direction: bit 4j + i = |c - r| > t for byte i of word j.  kMode as in pair_gt.
+// The flag bytes (0x80 / 0) of a word are gathered by a dot product with the byte weights (1, 2, 4, 8) or (16, 32, 64, 128): IDP4A runs
+// on the FMA pipe and accumulates, so two words cost two instructions there and nothing on the ALU pipe (as IMAD by 0x00204081 +
+// funnel shift the gather took one FMA and one ALU instruction per word; the ALU pipe is the one that binds).
 template <int kMode>
-__device__ __forceinline__ uint32_t diff_nibble(uint32_t c, uint32_t r, uint32_t k7, uint32_t one, uint32_t gather, uint32_t acc) {
+__device__ __forceinline__ uint32_t diff_flags(uint32_t c, uint32_t r, uint32_t k7, uint32_t one) {
     const uint32_t x = __vabsdiffu4(c, r);
-    uint32_t f;
-    if constexpr (kMode == 0) f = ((x * one + k7) | x) & 0x80808080u;
-    else if constexpr (kMode == 1) f = (((x & 0x7f7f7f7fu) + k7) | x) & 0x80808080u;
-    else f = (((x & 0x7f7f7f7fu) + k7) & x) & 0x80808080u;
-    return __funnelshift_l(f * gather, acc, 4);                       // (acc << 4) | flags of this word
+    if constexpr (kMode == 0) return ((x * one + k7) | x) & 0x80808080u;
+    else if constexpr (kMode == 1) return (((x & 0x7f7f7f7fu) + k7) | x) & 0x80808080u;
+    else return (((x & 0x7f7f7f7fu) + k7) & x) & 0x80808080u;
 }
 template <int kMode>
 __device__ __forceinline__ uint16_t diff_bits(const uint4 c, const uint4 r, uint32_t k7, uint32_t one, uint32_t gather) {
-    uint32_t acc = diff_nibble<kMode>(c.w, r.w, k7, one, gather, 0u);
-    acc = diff_nibble<kMode>(c.z, r.z, k7, one, gather, acc);
-    acc = diff_nibble<kMode>(c.y, r.y, k7, one, gather, acc);
-    acc = diff_nibble<kMode>(c.x, r.x, k7, one, gather, acc);
-    return (uint16_t) acc;
+    constexpr uint32_t W0 = 0x08040201u, W1 = 0x80402010u;
+    (void) gather;
+    uint32_t lo = __dp4a(diff_flags<kMode>(c.x, r.x, k7, one), W0, 0u);          // flags * 128: bits 7 .. 14
+    lo = __dp4a(diff_flags<kMode>(c.y, r.y, k7, one), W1, lo);
+    uint32_t hi = __dp4a(diff_flags<kMode>(c.z, r.z, k7, one), W0, 0u);
+    hi = __dp4a(diff_flags<kMode>(c.w, r.w, k7, one), W1, hi);
+    return (uint16_t) ((lo >> 7) + hi * 2u);
 }
 // 16 bytes starting s bytes to the right of v (nx = the word after v)
 __device__ __forceinline__ uint4 bytes_right(const uint4 v, uint32_t nx, int s) {
@@ -583,7 +586,7 @@ struct Fast2Args {
     uint32_t *slots; int *cell_cnt; const int *blk_tab;
     int cells_per_frame, t_ini, t_min;
     uint32_t one;       // 1: keeps the threshold add an IMAD (an immediate would be folded into an IADD on the ALU pipe)
-    uint32_t gather;    // 0x00204081: bit 8i+7 -> bit 28+i (as an argument so that the multiply stays an IMAD)
+    uint32_t gather;    // unused (round-2 experiment: IMAD by 0x00204081 moves bit 8i+7 to bit 28+i; the IDP4A gather replaced it)
     int exact;          // masked (exact) threshold adds also below 128, for A/B measurements
 };
 
