@@ -544,31 +544,37 @@ __device__ __forceinline__ uint4 bytes_right(const uint4 v, uint32_t nx, int s) 
 }
 
 // phase 1 for the plane rows [0, kF2PlaneRows): tile = the staged box (pitch kBoxW), planes[d][row][16] u16
-template <int kMode>
-__device__ __forceinline__ void fast_planes(const uint8_t *tile, uint16_t *planes, int tid, uint32_t k7, uint32_t one, uint32_t gather) {
+// kCompact (the minThFAST round): only the 16-pixel groups in `segs` (bit = group of a row) are computed — those that hold plane
+// bits of a cell that is still open; tasks are (row, n-th listed group), so the lanes stay dense.
+template <int kMode, bool kCompact>
+__device__ __forceinline__ void fast_planes(const uint8_t *tile, uint16_t *planes, int tid, uint32_t k7, uint32_t one, uint32_t gather, uint32_t segs) {
     constexpr int SP = kBoxW, PH = kF2PlaneHalves;
-    for (int task = tid; task < kF2PlaneRows * 16; task += kF2Threads) {
-        const uint8_t *p = tile + (task >> 4) * SP + 16 * (task & 15);           // centre row r = task >> 4
-        uint16_t *out = planes + task;
+    const int nseg = kCompact ? __popc(segs) : 16;
+    for (int task = tid; task < kF2PlaneRows * nseg; task += kF2Threads) {
+        int row, seg;
+        if constexpr (kCompact) { row = task / nseg; seg = __fns(segs, 0, task - row * nseg + 1); }
+        else { row = task >> 4; seg = task & 15; }
+        const uint8_t *p = tile + row * SP + 16 * seg;                           // centre row
+        uint16_t *out = planes + row * 16 + seg;
 #define ORBFE_LD(off) (*reinterpret_cast<const uint4 *>(p + (off)))
         // the word after a 16-byte group is the first word of the next lane's group (the last group of a row gets a word that only
-        // reaches columns >= 253, which are never candidates)
+        // reaches columns >= 253, which are never candidates); compact tasks have no such neighbour and load it (the tile is padded)
         const unsigned am = __activemask();
-#define ORBFE_NX(v) __shfl_down_sync(am, (v).x, 1)
-        const uint4 c0 = ORBFE_LD(0); const uint32_t c0n = ORBFE_NX(c0);
+#define ORBFE_NX(off, v) (kCompact ? *reinterpret_cast<const uint32_t *>(p + (off) + 16) : __shfl_down_sync(am, (v).x, 1))
+        const uint4 c0 = ORBFE_LD(0); const uint32_t c0n = ORBFE_NX(0, c0);
         {
-            const uint4 r3 = ORBFE_LD(3 * SP); const uint32_t r3n = ORBFE_NX(r3);
+            const uint4 r3 = ORBFE_LD(3 * SP); const uint32_t r3n = ORBFE_NX(3 * SP, r3);
             out[0 * PH] = diff_bits<kMode>(c0, r3, k7, one, gather);                               // ( 0, 3)  ring 0 / 8
             out[1 * PH] = diff_bits<kMode>(c0, bytes_right(r3, r3n, 1), k7, one, gather);          // ( 1, 3)  ring 1 / 9
             out[7 * PH] = diff_bits<kMode>(bytes_right(c0, c0n, 1), r3, k7, one, gather);          // (-1, 3)  ring 15 / 7, stored 1 bit left
         }
         {
-            const uint4 r2 = ORBFE_LD(2 * SP); const uint32_t r2n = ORBFE_NX(r2);
+            const uint4 r2 = ORBFE_LD(2 * SP); const uint32_t r2n = ORBFE_NX(2 * SP, r2);
             out[2 * PH] = diff_bits<kMode>(c0, bytes_right(r2, r2n, 2), k7, one, gather);          // ( 2, 2)  ring 2 / 10
             out[6 * PH] = diff_bits<kMode>(bytes_right(c0, c0n, 2), r2, k7, one, gather);          // (-2, 2)  ring 14 / 6, stored 2 bits left
         }
         {
-            const uint4 r1 = ORBFE_LD(SP); const uint32_t r1n = ORBFE_NX(r1);
+            const uint4 r1 = ORBFE_LD(SP); const uint32_t r1n = ORBFE_NX(SP, r1);
             const uint4 c3 = bytes_right(c0, c0n, 3);
             out[3 * PH] = diff_bits<kMode>(c0, bytes_right(r1, r1n, 3), k7, one, gather);          // ( 3, 1)  ring 3 / 11
             out[4 * PH] = diff_bits<kMode>(c0, c3, k7, one, gather);                               // ( 3, 0)  ring 4 / 12
@@ -593,7 +599,7 @@ struct Fast2Args {
 template <bool kTMA>
 __global__ void __launch_bounds__(kF2Threads, 5) k_fast_planes(const __grid_constant__ LevelSet L, const __grid_constant__ TmapSet T, const Fast2Args a) {
     constexpr int SP = kBoxW, NT = kF2Threads;
-    __shared__ __align__(128) uint8_t tile[kF2Tile];
+    __shared__ __align__(128) uint8_t tile[kF2Tile + 16];                // + the word a compact phase-1 task reads after the last group
     __shared__ __align__(16) uint16_t planes[8 * kF2PlaneHalves];
     __shared__ __align__(16) uint8_t mmap[32 * SP];                      // score of cell c, column cx, strip row y at [(y+1)*SP + 32*c + cx + 1], zero elsewhere
     __shared__ uint16_t queue[kStripW * kCell];                          // y << 8 | tile column; after stage B: score-map position or 0
@@ -621,9 +627,21 @@ __global__ void __launch_bounds__(kF2Threads, 5) k_fast_planes(const __grid_cons
         // ---- A, phase 1: the eight difference planes
         {
             const uint32_t k7 = (uint32_t) (127 - (t & 127)) * 0x01010101u;
-            if (t >= 128) fast_planes<2>(tile, planes, tid, k7, a.one, a.gather);
-            else if (a.exact) fast_planes<1>(tile, planes, tid, k7, a.one, a.gather);
-            else fast_planes<0>(tile, planes, tid, k7, a.one, a.gather);
+            if (round == 0) {
+                if (t >= 128) fast_planes<2, false>(tile, planes, tid, k7, a.one, a.gather, 0xffffu);
+                else if (a.exact) fast_planes<1, false>(tile, planes, tid, k7, a.one, a.gather, 0xffffu);
+                else fast_planes<0, false>(tile, planes, tid, k7, a.one, a.gather, 0xffffu);
+            } else {
+                // plane columns read for the candidates of cell c (tile columns 30c+3 .. 30c+32): 30c .. 30c+32
+                uint32_t segs = 0;
+#pragma unroll
+                for (int c = 0; c < kCellsPerBlk; ++c)
+                    if ((open >> c) & 1u) segs |= (2u << ((kCell * c + 32) >> 4)) - (1u << ((kCell * c) >> 4));
+                segs &= 0xffffu;
+                if (t >= 128) fast_planes<2, true>(tile, planes, tid, k7, a.one, a.gather, segs);
+                else if (a.exact) fast_planes<1, true>(tile, planes, tid, k7, a.one, a.gather, segs);
+                else fast_planes<0, true>(tile, planes, tid, k7, a.one, a.gather, segs);
+            }
         }
         __syncthreads();
         // ---- A, phase 2: pair terms and their AND, 32 pixels per thread, and the pass bits -> queue.  Queue entries of a thread are
