@@ -255,3 +255,28 @@ def test_bench_sized_batch_properties(mods):
             x = np.rint(sel["x"] / s); y = np.rint(sel["y"] / s)
             assert (x >= 19).all() and (y >= 19).all() and (x < lw - 19).all() and (y < lh - 19).all()
     ex.close(); ex1.close()
+
+
+# ---------------------------------------------------------------- both FAST formulations
+@pytest.mark.parametrize("w,h,nf,profile,th", [(752, 480, 1000, "dense", (20, 7)), (752, 480, 1000, "natural", (20, 7)), (1241, 376, 2000, "natural", (20, 7)),
+                                               (752, 480, 1000, "dense", (140, 130)), (752, 480, 1000, "natural", (60, 3))])
+def test_fast_formulations_agree(mods, oracle, monkeypatch, w, h, nf, profile, th):
+    """k_fast_planes (difference planes, the default) and round 1's k_fast (ORBFE_FAST_V1=1, kept for A/B measurements) give the oracle's
+    candidate lists, order included: dense and natural profiles (the natural one drives the compact minThFAST round), thresholds on both
+    sides of 128, with and without TMA staging."""
+    ORBExtractor, synth, _ = mods
+    img = synth.frame(h, w, 1234, profile)
+    oc = oracle.Extractor(nf, 1.2, 8, th[0], th[1])
+    oc(img)
+    want = []
+    for l in range(8):
+        c = oc.level_candidates(l)
+        want.append(np.stack([c["x"], c["y"], c["score"]], 1).reshape(-1, 3))
+    for v1 in ("0", "1"):
+        monkeypatch.setenv("ORBFE_FAST_V1", v1)                      # read by orbfe_create
+        for use_tma in (True, False):
+            ex = ORBExtractor(nf, 1.2, 8, th[0], th[1], use_tma=use_tma, keep_stages=True)
+            ex(img)
+            for l in range(8):
+                assert np.array_equal(ex.level_candidates(l), want[l]), ("k_fast" if v1 == "1" else "k_fast_planes", use_tma, l)
+            ex.close()
