@@ -204,11 +204,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_allpairs_tc(const __grid_cons
         int w_lo = ex.x < ex.y ? ex.x : 0x7fffffff, w_hi = ex.x < ex.y ? ex.y : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { w_lo = min(w_lo, __shfl_xor_sync(0xffffffffu, w_lo, o)); w_hi = max(w_hi, __shfl_xor_sync(0xffffffffu, w_hi, o)); }
+        // ... and their warp-wide core: a tile inside it is excluded for every row of the warp (a key-frame window matched against itself
+        // spends cap / 128 train tiles per row inside the row's own key frame).  A warp whose rows are all padding has nothing to do at all.
+        int c_lo = ex.x < ex.y ? ex.x : 0x7fffffff, c_hi = ex.x < ex.y ? ex.y : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { c_lo = max(c_lo, __shfl_xor_sync(0xffffffffu, c_lo, o)); c_hi = min(c_hi, __shfl_xor_sync(0xffffffffu, c_hi, o)); }
+        const bool warp_live = __any_sync(0xffffffffu, row_live);
         uint32_t K1 = kTcNone, K2 = kTcNone;
         for (int i = par; i < my_tiles; i += 2) {
             const int col0 = (t_begin + i) * kTcN;
             mbar_wait(&b_tfull[par], (uint32_t) ((i >> 1) & 1));
             tc_fence_after();
+            if (!warp_live || (col0 >= c_lo && col0 + kTcN <= c_hi)) {                       // nothing to read: hand the stage straight back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&b_tempty[par]);
+                continue;
+            }
             const uint32_t taddr = tmem + ((uint32_t) (lq * 32) << 16) + (uint32_t) (par * 2 * kTcN + mt * kTcN);
             bool slow = col0 + kTcN > a.nt || (col0 < w_hi && col0 + kTcN > w_lo);            // ragged last tile / a row's own key-frame block
             int f0 = 0, f_split = 0x7fffffff, n0 = 0x7fffffff, n1 = 0x7fffffff;              // slab mode: the (at most two) blocks the tile touches

@@ -612,8 +612,12 @@ __global__ void __launch_bounds__(kF2Threads, 5) k_fast_planes(const __grid_cons
     const int l = packed & 15, ci = (packed >> 4) & 0xfff, cg = packed >> 16;
     const LevelGeom &G = L.lv[l];
     const int px = kEdge - 3 + kStripW * cg, py = kEdge - 3 + kCell * ci;               // tile column c = strip x + 3, tile row = strip y + 3
-    stage_box<kTMA, NT>(tile, &bar, &T.m[l], L.img[l] + (size_t) frame * G.frame_stride, G.pitch, G.h, px, py, frame, kFastBoxH);
-
+    // the box is requested first; the per-round state of round 0 is cleared while it is in flight
+    if constexpr (kTMA) {
+        if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+        __syncthreads();
+        if (tid == 0) { mbar_expect_tx(&bar, (uint32_t) kF2Tile); tma_load_3d(tile, &T.m[l], &bar, px, py, frame); }
+    }
     const int strip_w = min(kStripW, G.w - kEdge - (kEdge + kStripW * cg));             // pixels of this strip inside maxBorderX
     const int ch = min(kCell, G.h - kEdge - (kEdge + kCell * ci));                      // rows inside maxBorderY
     unsigned open = (1u << ((strip_w + kCell - 1) / kCell)) - 1u;                       // cells that still need a result
@@ -624,6 +628,10 @@ __global__ void __launch_bounds__(kF2Threads, 5) k_fast_planes(const __grid_cons
         if (tid < kCellsPerBlk * 32) rowmask[wid][lane] = 0;
         if (tid == 0) s_n = 0;
         for (int i = tid; i < 32 * SP / 16; i += NT) reinterpret_cast<uint4 *>(mmap)[i] = make_uint4(0, 0, 0, 0);
+        if (round == 0) {
+            if constexpr (kTMA) mbar_wait(&bar, 0);
+            else stage_box<false, NT>(tile, &bar, &T.m[l], L.img[l] + (size_t) frame * G.frame_stride, G.pitch, G.h, px, py, frame, kFastBoxH);
+        }
         // ---- A, phase 1: the eight difference planes
         {
             const uint32_t k7 = (uint32_t) (127 - (t & 127)) * 0x01010101u;
