@@ -744,7 +744,7 @@ def run_c5(args, torch, dist, dev, local, rank, world, tstream, barrier, max_ove
     w_lo, w_hi = sharding.shard_range(n_win, rank, world)
     f_lo, f_hi = w_lo * WIN, min(w_hi * WIN, F)
     nb = f_hi - f_lo
-    cap = NFc + 128
+    cap = (NFc + 128 + 127) // 128 * 128     # 4224: a multiple of the all-pairs kernel's 128-row train tile, so that every key frame's block starts on a tile boundary
     base = synth.frames(8, Hc, Wc, 1000 + 100 * rank, "dense")                  # 8 distinct scenes per rank, repeated
     frames = torch.from_numpy(base).to(dev)[torch.arange(max(nb, 1), device=dev) % 8].contiguous()
     ex = ORBExtractor(NFc, 1.2, 8, 20, 7, device=local, max_batch=PASS)

@@ -222,7 +222,9 @@ int orbfe_hamming_allpairs_excl_device(orbfe_handle *h, const uint8_t *d_q, int 
  * n_frames blocks of `cap` descriptor rows of which the first d_n_per_frame[f] are key points.  Every key point's best / second-best
  * among the key points of the OTHER frames of the window; padding rows neither match nor are matched (their outputs are -1 / 257 /
  * 257).  Outputs have n_frames * cap entries and best_idx is a slab row (frame * cap + key point).  No compaction pass and no host
- * synchronisation for the counts: the call chains behind the extraction on the same stream.  Runs on the tensor cores for every size. */
+ * synchronisation for the counts: the call chains behind the extraction on the same stream.  Runs on the tensor cores for every size.
+ * Any cap works; with cap a multiple of 128 (the kernel's train-tile height) every block starts on a tile boundary, the tiles of a row's
+ * own key frame and the tiles of padding rows are skipped whole, and only one tile per block needs per-column masking. */
 int orbfe_hamming_allpairs_slab_device(orbfe_handle *h, const uint8_t *d_desc, const int *d_n_per_frame, int n_frames, int cap,
                                        int32_t *d_best_idx, int32_t *d_best_dist, int32_t *d_second_dist, void *stream, int sync);
 

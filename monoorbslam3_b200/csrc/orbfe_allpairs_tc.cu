@@ -215,20 +215,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_allpairs_tc(const __grid_cons
             const int col0 = (t_begin + i) * kTcN;
             mbar_wait(&b_tfull[par], (uint32_t) ((i >> 1) & 1));
             tc_fence_after();
-            if (!warp_live || (col0 >= c_lo && col0 + kTcN <= c_hi)) {                       // nothing to read: hand the stage straight back
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&b_tempty[par]);
-                continue;
-            }
-            const uint32_t taddr = tmem + ((uint32_t) (lq * 32) << 16) + (uint32_t) (par * 2 * kTcN + mt * kTcN);
-            bool slow = col0 + kTcN > a.nt || (col0 < w_hi && col0 + kTcN > w_lo);            // ragged last tile / a row's own key-frame block
             int f0 = 0, f_split = 0x7fffffff, n0 = 0x7fffffff, n1 = 0x7fffffff;              // slab mode: the (at most two) blocks the tile touches
             if (a.slab_n) {
                 f0 = col0 / a.cap; f_split = (f0 + 1) * a.cap;
                 n0 = f0 * a.cap + a.slab_n[f0];                                               // first padding row of block f0
                 if (f_split < col0 + kTcN && f_split < a.nt) n1 = f_split + a.slab_n[f0 + 1];
-                slow = slow || col0 + kTcN > n0;                                              // reaches block f0's padding (or the next block)
+            }
+            if (!warp_live || (col0 >= c_lo && col0 + kTcN <= c_hi) || (col0 >= n0 && col0 + kTcN <= f_split)) {
+                tc_fence_before();                                                           // nothing to read (also: a tile of padding rows
+                __syncwarp();                                                                // only, when the slab capacity is a multiple of
+                if (lane == 0) mbar_arrive(&b_tempty[par]);                                  // the tile height): hand the stage straight back
+                continue;
+            }
+            const uint32_t taddr = tmem + ((uint32_t) (lq * 32) << 16) + (uint32_t) (par * 2 * kTcN + mt * kTcN);
+            bool slow = col0 + kTcN > a.nt || (col0 < w_hi && col0 + kTcN > w_lo);            // ragged last tile / a row's own key-frame block
+            if (a.slab_n) slow = slow || col0 + kTcN > n0;                                    // reaches block f0's padding (or the next block)
+            // slow tiles: the dead columns of this row as a 128-bit mask, built from the (at most four) intervals with shifts instead of
+            // six compares per column: beyond the table, the row's own key frame, the padding of block f0, the padding of block f0 + 1
+            uint32_t dm[4] = {0u, 0u, 0u, 0u};
+            if (slow) {
+                auto ge = [](int t, int w) -> uint32_t {                                     // bits b of word w with 32 w + b >= t
+                    const int sft = min(max(t - 32 * w, 0), 32);
+                    return (uint32_t) (0xffffffffull << sft);
+                };
+                const int r_nt = a.nt - col0, r_e0 = ex.x - col0, r_e1 = ex.y - col0, r_n0 = n0 - col0, r_sp = f_split - col0, r_n1 = n1 - col0;
+#pragma unroll
+                for (int w = 0; w < 4; ++w)
+                    dm[w] = ge(r_nt, w) | (ge(r_e0, w) & ~ge(r_e1, w)) | (ge(r_n0, w) & ~ge(r_sp, w)) | (ge(r_sp, w) & ge(r_n1, w));
             }
             // two independent (smallest, second) chains, per 16-bit half
             uint32_t a1 = 0xffffffffu, a2 = 0xffffffffu, b1 = 0xffffffffu, b2 = 0xffffffffu;
@@ -251,15 +264,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_allpairs_tc(const __grid_cons
                     pa[j] = va[2 * j + 1] * 0xFFC00000u + (va[2 * j] * 0xFFFFFFC0u + ca);
                     pb[j] = vb[2 * j + 1] * 0xFFC00000u + (vb[2 * j] * 0xFFFFFFC0u + (ca + 0x00200020u));
                 }
-                if (slow) {
+                if (slow) {                      // pa[j] holds the columns 64 ch + 2 j, + 1 and pb[j] those 32 further on: one test + one predicated OR each
+                    const uint32_t ma = dm[2 * ch], mb = dm[2 * ch + 1];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const int c = col0 + ch * 64 + 2 * j;
-                        auto dead = [&](int cc) { return cc >= a.nt || (cc >= ex.x && cc < ex.y) || (cc < f_split ? cc >= n0 : cc >= n1); };
-                        if (dead(c)) pa[j] |= 0x0000ffffu;
-                        if (dead(c + 1)) pa[j] |= 0xffff0000u;
-                        if (dead(c + 32)) pb[j] |= 0x0000ffffu;
-                        if (dead(c + 33)) pb[j] |= 0xffff0000u;
+                        if (ma & (1u << (2 * j))) pa[j] |= 0x0000ffffu;
+                        if (ma & (2u << (2 * j))) pa[j] |= 0xffff0000u;
+                        if (mb & (1u << (2 * j))) pb[j] |= 0x0000ffffu;
+                        if (mb & (2u << (2 * j))) pb[j] |= 0xffff0000u;
                     }
                 }
 #pragma unroll

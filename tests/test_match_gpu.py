@@ -99,7 +99,7 @@ def test_allpairs_with_keyframe_block_exclusion(ctx, oracle, monkeypatch, kernel
     Blocks of uneven size that straddle tile boundaries, an empty range, a range covering everything (no candidate: -1 / 257)."""
     m = ctx["ORBMatcher"]()
     rng = np.random.default_rng(5)
-    sizes = [130, 257, 1, 400, 128, 383, 64, 300]
+    sizes = [130, 257, 1, 400, 128, 383, 64, 300, 900]                                 # 900: several train tiles lie inside the own block of whole warps
     n = sum(sizes)
     table = rng.integers(0, 256, (n, 32), dtype=np.uint8)
     table[rng.integers(0, n, 200)] = table[rng.integers(0, n, 200)]                    # duplicates inside and across blocks
@@ -455,7 +455,7 @@ def test_init_search_parallel_resolve_and_its_fallback(ctx, oracle, monkeypatch)
             assert n == exp[0] and np.array_equal(m12, exp[1]) and np.array_equal(p, exp[2]), (window, env)
 
 
-@pytest.mark.parametrize("n_frames,cap", [(5, 700), (3, 257), (2, 128), (7, 401)])
+@pytest.mark.parametrize("n_frames,cap", [(5, 700), (3, 257), (2, 128), (7, 401), (4, 512), (6, 384), (3, 1024)])   # the last three: blocks on tile boundaries, train tiles of padding rows only
 def test_allpairs_on_extractor_slabs(ctx, oracle, n_frames, cap):
     """orbfe_hamming_allpairs_slab_device: a key-frame window matched against itself straight from fixed-capacity slabs (counts on the
     device, padding rows in between): equals the compacted table searched with per-row exclusion of the own frame."""
