@@ -416,7 +416,7 @@ static int run_pass_t(Handle *h, int nb, const uint8_t *l0, size_t l0_pitch, siz
         ORBFE_AFTER_LAUNCH(h, st, "k_fast");
     } else {
         Fast2Args f2; f2.slots = fa.slots; f2.cell_cnt = fa.cell_cnt; f2.blk_tab = fa.blk_tab; f2.cells_per_frame = fa.cells_per_frame;
-        f2.t_ini = fa.t_ini; f2.t_min = fa.t_min; f2.one = 1u; f2.gather = 0x00204081u; f2.exact = h->fast_exact_cmp ? 1 : 0;
+        f2.t_ini = fa.t_ini; f2.t_min = fa.t_min; f2.one = 1u; f2.exact = h->fast_exact_cmp ? 1 : 0;
         k_fast_planes<kTMA><<<dim3(g.fast_blocks, nb), kF2Threads, 0, st>>>(LS, TF, f2);
         ORBFE_AFTER_LAUNCH(h, st, "k_fast_planes");
     }

@@ -529,9 +529,8 @@ __device__ __forceinline__ uint32_t diff_flags(uint32_t c, uint32_t r, uint32_t 
     else return (((x & 0x7f7f7f7fu) + k7) & x) & 0x80808080u;
 }
 template <int kMode>
-__device__ __forceinline__ uint16_t diff_bits(const uint4 c, const uint4 r, uint32_t k7, uint32_t one, uint32_t gather) {
+__device__ __forceinline__ uint16_t diff_bits(const uint4 c, const uint4 r, uint32_t k7, uint32_t one) {
     constexpr uint32_t W0 = 0x08040201u, W1 = 0x80402010u;
-    (void) gather;
     uint32_t lo = __dp4a(diff_flags<kMode>(c.x, r.x, k7, one), W0, 0u);          // flags * 128: bits 7 .. 14
     lo = __dp4a(diff_flags<kMode>(c.y, r.y, k7, one), W1, lo);
     uint32_t hi = __dp4a(diff_flags<kMode>(c.z, r.z, k7, one), W0, 0u);
@@ -547,7 +546,7 @@ __device__ __forceinline__ uint4 bytes_right(const uint4 v, uint32_t nx, int s) 
 // kCompact (the minThFAST round): only the 16-pixel groups in `segs` (bit = group of a row) are computed — those that hold plane
 // bits of a cell that is still open; tasks are (row, n-th listed group), so the lanes stay dense.
 template <int kMode, bool kCompact>
-__device__ __forceinline__ void fast_planes(const uint8_t *tile, uint16_t *planes, int tid, uint32_t k7, uint32_t one, uint32_t gather, uint32_t segs) {
+__device__ __forceinline__ void fast_planes(const uint8_t *tile, uint16_t *planes, int tid, uint32_t k7, uint32_t one, uint32_t segs) {
     constexpr int SP = kBoxW, PH = kF2PlaneHalves;
     const int nseg = kCompact ? __popc(segs) : 16;
     for (int task = tid; task < kF2PlaneRows * nseg; task += kF2Threads) {
@@ -564,21 +563,21 @@ __device__ __forceinline__ void fast_planes(const uint8_t *tile, uint16_t *plane
         const uint4 c0 = ORBFE_LD(0); const uint32_t c0n = ORBFE_NX(0, c0);
         {
             const uint4 r3 = ORBFE_LD(3 * SP); const uint32_t r3n = ORBFE_NX(3 * SP, r3);
-            out[0 * PH] = diff_bits<kMode>(c0, r3, k7, one, gather);                               // ( 0, 3)  ring 0 / 8
-            out[1 * PH] = diff_bits<kMode>(c0, bytes_right(r3, r3n, 1), k7, one, gather);          // ( 1, 3)  ring 1 / 9
-            out[7 * PH] = diff_bits<kMode>(bytes_right(c0, c0n, 1), r3, k7, one, gather);          // (-1, 3)  ring 15 / 7, stored 1 bit left
+            out[0 * PH] = diff_bits<kMode>(c0, r3, k7, one);                               // ( 0, 3)  ring 0 / 8
+            out[1 * PH] = diff_bits<kMode>(c0, bytes_right(r3, r3n, 1), k7, one);          // ( 1, 3)  ring 1 / 9
+            out[7 * PH] = diff_bits<kMode>(bytes_right(c0, c0n, 1), r3, k7, one);          // (-1, 3)  ring 15 / 7, stored 1 bit left
         }
         {
             const uint4 r2 = ORBFE_LD(2 * SP); const uint32_t r2n = ORBFE_NX(2 * SP, r2);
-            out[2 * PH] = diff_bits<kMode>(c0, bytes_right(r2, r2n, 2), k7, one, gather);          // ( 2, 2)  ring 2 / 10
-            out[6 * PH] = diff_bits<kMode>(bytes_right(c0, c0n, 2), r2, k7, one, gather);          // (-2, 2)  ring 14 / 6, stored 2 bits left
+            out[2 * PH] = diff_bits<kMode>(c0, bytes_right(r2, r2n, 2), k7, one);          // ( 2, 2)  ring 2 / 10
+            out[6 * PH] = diff_bits<kMode>(bytes_right(c0, c0n, 2), r2, k7, one);          // (-2, 2)  ring 14 / 6, stored 2 bits left
         }
         {
             const uint4 r1 = ORBFE_LD(SP); const uint32_t r1n = ORBFE_NX(SP, r1);
             const uint4 c3 = bytes_right(c0, c0n, 3);
-            out[3 * PH] = diff_bits<kMode>(c0, bytes_right(r1, r1n, 3), k7, one, gather);          // ( 3, 1)  ring 3 / 11
-            out[4 * PH] = diff_bits<kMode>(c0, c3, k7, one, gather);                               // ( 3, 0)  ring 4 / 12
-            out[5 * PH] = diff_bits<kMode>(c3, r1, k7, one, gather);                               // (-3, 1)  ring 13 / 5, stored 3 bits left
+            out[3 * PH] = diff_bits<kMode>(c0, bytes_right(r1, r1n, 3), k7, one);          // ( 3, 1)  ring 3 / 11
+            out[4 * PH] = diff_bits<kMode>(c0, c3, k7, one);                               // ( 3, 0)  ring 4 / 12
+            out[5 * PH] = diff_bits<kMode>(c3, r1, k7, one);                               // (-3, 1)  ring 13 / 5, stored 3 bits left
         }
 #undef ORBFE_LD
 #undef ORBFE_NX
@@ -592,7 +591,6 @@ struct Fast2Args {
     uint32_t *slots; int *cell_cnt; const int *blk_tab;
     int cells_per_frame, t_ini, t_min;
     uint32_t one;       // 1: keeps the threshold add an IMAD (an immediate would be folded into an IADD on the ALU pipe)
-    uint32_t gather;    // unused (round-2 experiment: IMAD by 0x00204081 moves bit 8i+7 to bit 28+i; the IDP4A gather replaced it)
     int exact;          // masked (exact) threshold adds also below 128, for A/B measurements
 };
 
@@ -636,9 +634,9 @@ __global__ void __launch_bounds__(kF2Threads, 5) k_fast_planes(const __grid_cons
         {
             const uint32_t k7 = (uint32_t) (127 - (t & 127)) * 0x01010101u;
             if (round == 0) {
-                if (t >= 128) fast_planes<2, false>(tile, planes, tid, k7, a.one, a.gather, 0xffffu);
-                else if (a.exact) fast_planes<1, false>(tile, planes, tid, k7, a.one, a.gather, 0xffffu);
-                else fast_planes<0, false>(tile, planes, tid, k7, a.one, a.gather, 0xffffu);
+                if (t >= 128) fast_planes<2, false>(tile, planes, tid, k7, a.one, 0xffffu);
+                else if (a.exact) fast_planes<1, false>(tile, planes, tid, k7, a.one, 0xffffu);
+                else fast_planes<0, false>(tile, planes, tid, k7, a.one, 0xffffu);
             } else {
                 // plane columns read for the candidates of cell c (tile columns 30c+3 .. 30c+32): 30c .. 30c+32
                 uint32_t segs = 0;
@@ -646,9 +644,9 @@ __global__ void __launch_bounds__(kF2Threads, 5) k_fast_planes(const __grid_cons
                 for (int c = 0; c < kCellsPerBlk; ++c)
                     if ((open >> c) & 1u) segs |= (2u << ((kCell * c + 32) >> 4)) - (1u << ((kCell * c) >> 4));
                 segs &= 0xffffu;
-                if (t >= 128) fast_planes<2, true>(tile, planes, tid, k7, a.one, a.gather, segs);
-                else if (a.exact) fast_planes<1, true>(tile, planes, tid, k7, a.one, a.gather, segs);
-                else fast_planes<0, true>(tile, planes, tid, k7, a.one, a.gather, segs);
+                if (t >= 128) fast_planes<2, true>(tile, planes, tid, k7, a.one, segs);
+                else if (a.exact) fast_planes<1, true>(tile, planes, tid, k7, a.one, segs);
+                else fast_planes<0, true>(tile, planes, tid, k7, a.one, segs);
             }
         }
         __syncthreads();
