@@ -1,7 +1,7 @@
 // orbfe_kernels.cuh — device code of the ORB extractor path, hand-written for sm_100a.
 //
 //   K1 k_resize    cv::resize INTER_LINEAR 8U, level l-1 -> l        (ORBExtractor.cpp:559-570)
-//   K2 k_fast      per-cell FAST-9/16 + NMS + threshold fallback     (ORBExtractor.cpp:592-617)
+//   K2 k_fast_planes  per-cell FAST-9/16 + NMS + threshold fallback  (ORBExtractor.cpp:592-617); k_fast = round 1's formulation, ORBFE_FAST_V1=1
 //   K4 k_octree    DistributeOctree, deterministic, pointer-free     (ORBExtractor.cpp:367-413, 640-830)
 //   K6 k_blur      GaussianBlur 7x7 sigma 2, 8.8 fixed point         (ORBExtractor.cpp:527-528)
 //   K5/K7 k_describe  IC_Angle + fastAtan2 + rotated BRIEF-256        (ORBExtractor.cpp:18-97)
