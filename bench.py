@@ -744,11 +744,16 @@ def run_c5(args, torch, dist, dev, local, rank, world, tstream, barrier, max_ove
     w_lo, w_hi = sharding.shard_range(n_win, rank, world)
     f_lo, f_hi = w_lo * WIN, min(w_hi * WIN, F)
     nb = f_hi - f_lo
-    cap = (NFc + 128 + 127) // 128 * 128     # 4224: a multiple of the all-pairs kernel's 128-row train tile, so that every key frame's block starts on a tile boundary
     base = synth.frames(8, Hc, Wc, 1000 + 100 * rank, "dense")                  # 8 distinct scenes per rank, repeated
     frames = torch.from_numpy(base).to(dev)[torch.arange(max(nb, 1), device=dev) % 8].contiguous()
     ex = ORBExtractor(NFc, 1.2, 8, 20, 7, device=local, max_batch=PASS)
     mt = ORBMatcher(handle=ex._h)
+    # slab capacity: the extractor's own bound for this frame size (known once a frame has fixed the geometry: 4032 for 1080p / 4000
+    # features), rounded up to the all-pairs kernel's 128-row train tile so that every key frame's block starts on a tile boundary (4096)
+    cap0 = ex.capacity()
+    ex.extract_batch_device(frames[:1], 1, Hc, Wc, torch.zeros((1, cap0, 7), dtype=torch.float32, device=dev), torch.zeros((1, cap0, 32), dtype=torch.uint8, device=dev),
+                            cap0, torch.zeros(1, dtype=torch.int32, device=dev), stream=tstream.cuda_stream, sync=True)
+    cap = (ex.capacity() + 127) // 128 * 128
     kps = torch.zeros((max(nb, 1), cap, 7), dtype=torch.float32, device=dev); desc = torch.zeros((max(nb, 1), cap, 32), dtype=torch.uint8, device=dev)
     n = torch.zeros(max(nb, 1), dtype=torch.int32, device=dev)
     rows_total = F * cap
@@ -823,7 +828,8 @@ def run_c5(args, torch, dist, dev, local, rank, world, tstream, barrier, max_ove
             "sharding": "contiguous blocks of key-frame windows per rank, no data-path collective",
             "results_on_rank0": ("peer-store: the all-pairs merge kernel writes into rank 0's peer-mapped arrays over NVLink" if peers else
                                  "NCCL send/recv gather at the end of the step") if world > 1 else "single GPU",
-            "host_syncs_inside_step": 0, "frames_resident": True}
+            "host_syncs_inside_step": 0, "frames_resident": True,
+            "slab_capacity": int(cap), "slab_capacity_what": "rows per key frame in the extractor's output slabs = orbfe_max_keypoints rounded up to the all-pairs tile height (128)"}
 
 
 def main():
