@@ -69,3 +69,25 @@ def test_product_does_not_import_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 assert "oracle" not in open(os.path.join(dirpath, f), errors="ignore").read().replace("ORBFE", ""), os.path.join(dirpath, f)
+
+
+def test_built_kernels_are_blackwell_native():
+    """The shipped liborbfe.so holds sm_100a code whose all-pairs kernel issues tcgen05 MMAs with the accumulators in tensor memory
+    (UTCIMMA, LDTM) on TMA-staged operands (UTMALDG), and the extractor's tiles come in by TMA as well (cuobjdump -sass, no GPU needed)."""
+    import shutil
+    import subprocess
+    from monoorbslam3_b200 import build as _b
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    lib = _b.build()
+
+    def sass(fn):
+        return subprocess.run([exe, "-sass", "-fun", fn, lib], capture_output=True, text=True).stdout
+
+    tc = sass("_ZN5orbfe13k_allpairs_tcE14CUtensorMap_stS0_NS_6TcArgsE")
+    assert "sm_100a" in tc
+    for mnemonic, at_least in (("UTCIMMA", 16), ("LDTM", 4), ("UTMALDG", 2), ("UTCBAR", 1)):
+        assert tc.count(mnemonic) >= at_least, (mnemonic, tc.count(mnemonic))
+    fast = sass("_ZN5orbfe13k_fast_planesILb1EEEvNS_8LevelSetENS_7TmapSetENS_9Fast2ArgsE")
+    assert fast.count("UTMALDG") >= 1 and fast.count("IDP.4A") >= 32 and fast.count("VABSDIFF4") >= 32
