@@ -96,15 +96,19 @@ __device__ __forceinline__ int block_scan_excl(int v, int &total, int *s_warp) {
     }
     if (lane == 31) s_warp[wid] = inc;
     __syncthreads();
-    int before = 0, tot = 0;
+    // every warp scans the NT / 32 warp totals itself (lane = warp): a handful of shuffles instead of a loop over all totals
+    constexpr int NW = NT / 32;
+    static_assert(NW <= 32, "one lane per warp total");
+    const int x = lane < NW ? s_warp[lane] : 0;
+    int xi = x;
 #pragma unroll
-    for (int w = 0; w < NT / 32; ++w) {
-        const int x = s_warp[w];
-        if (w < wid) before += x;
-        tot += x;
+    for (int o = 1; o < NW; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, xi, o);
+        if (lane >= o) xi += t;
     }
+    const int before = __shfl_sync(0xffffffffu, xi - x, wid);
+    total = __shfl_sync(0xffffffffu, xi, NW - 1);
     __syncthreads();
-    total = tot;
     return before + inc - v;
 }
 
